@@ -1,0 +1,140 @@
+/* scaml_b200.h -- C ABI of the B200-native ScaML-GP hot path (libscaml_b200.so).
+ *
+ * The reference (boschresearch/Scalable-Meta-Learning-with-Gaussian-Processes) is pure
+ * Python: it has no FFI.  The interfaces these entry points replace are therefore the
+ * Python call sites at which the reference hands the arithmetic to botorch/gpytorch
+ * (cited per function as reference file:line).  INTEGRATION.md shows the ctypes stubs a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (torch tensors' data_ptr());
+ *    the library never allocates, frees or retains memory;
+ *  - all floating point data is IEEE binary64, row-major, dense;
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls are
+ *    asynchronous w.r.t. the host and re-entrant;
+ *  - return value: 0 = launched; <0 = bad argument (SCAML_E_*); >0 = cudaError_t.
+ *  - per-evaluation numerical failures never abort a batch: they are reported through
+ *    `info` (LAPACK style: k > 0 = first non-positive pivot, 1-based) with NaN outputs,
+ *    mirroring the NotPSD -> NaN-loss behaviour of the reference's fit closure
+ *    (scamlgp/utils.py:174-198).
+ *
+ * Layouts
+ *   X          [M][n_max][d]     inputs in [0,1]^d, rows >= n_valid[m] ignored
+ *   y          [M][n_max]        per-task standardised targets (botorch Standardize)
+ *   n_valid    [M] int32         points of task m (1..n_max); NULL = n_max everywhere
+ *   theta_raw  [M][R][P]         P = d + 2: raw (pre-sigmoid) lengthscales, outputscale, noise
+ *   "packed factor" (scaml_factorize output, scaml_predict_* input):
+ *       n_pad = 64*ceil(n_max/64), NB = n_pad/32, lower 32x32 tiles (bi >= bj) of L^-1 at
+ *       tile index bi*(bi+1)/2 + bj, each tile 1024 doubles COLUMN-major; stride per task
+ *       = NB*(NB+1)/2*1024 doubles.
+ */
+#ifndef SCAML_B200_H
+#define SCAML_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCAML_KERNEL_RBF 0
+#define SCAML_KERNEL_MATERN12 1
+#define SCAML_KERNEL_MATERN32 2
+#define SCAML_KERNEL_MATERN52 3
+
+#define SCAML_PRIOR_NONE 0
+#define SCAML_PRIOR_GAMMA 1     /* p1 = concentration, p2 = rate   */
+#define SCAML_PRIOR_LOGNORMAL 2 /* p1 = mu,            p2 = sigma  */
+
+#define SCAML_E_ARG (-1)      /* null pointer / non-positive size            */
+#define SCAML_E_WORKSPACE (-2) /* workspace smaller than scaml_fit_workspace_bytes */
+#define SCAML_E_UNSUPPORTED (-3) /* d or n_max beyond what the kernels are built for */
+#define SCAML_E_SMEM (-4)     /* configuration does not fit 227 KB shared memory */
+
+/* Kernel family + gpytorch `Interval` constraints + priors of one GP
+ * (reference scamlgp/model.py:25-33 likelihood, :36-70 source kernel, :73-105 target kernel). */
+typedef struct scaml_hyper_spec {
+  int32_t kernel;      /* SCAML_KERNEL_*                                   */
+  int32_t ls_prior;    /* SCAML_PRIOR_* on each lengthscale                */
+  int32_t os_prior;    /* ... on the outputscale                           */
+  int32_t noise_prior; /* ... on the noise variance                        */
+  double ls_lo, ls_hi; /* Interval(lower, upper) of the lengthscales       */
+  double os_lo, os_hi;
+  double noise_lo, noise_hi;
+  double ls_p1, ls_p2;
+  double os_p1, os_p2;
+  double noise_p1, noise_p2;
+} scaml_hyper_spec;
+
+/* Library / build identification ("scaml_b200 <version> sm_100a"). */
+const char* scaml_version(void);
+
+/* Largest n_max / d the fit kernels accept (shared-memory budget), and the number of
+ * workspace bytes scaml_lml_grad / scaml_factorize need for (n_max, device).  The
+ * workspace is scratch: contents are undefined between calls. */
+int scaml_fit_limits(int* n_max_limit, int* d_limit);
+size_t scaml_fit_workspace_bytes(int n_max, int d);
+
+/* K1 standalone: K[m] = s_m * kappa(X_m / l_m) + noise_m * I for every task, written dense
+ * [M][n_max][n_max] (rows/cols >= n_valid are the identity).  `theta` holds CONSTRAINED
+ * values [M][P].  Replaces `covar_module(X)` + likelihood noise evaluated inside
+ * `mll(model(X), y)` (reference scamlgp/utils.py:175-177; kernels model.py:44-70). */
+int scaml_kernel_matrix(const double* X, const int32_t* n_valid, const double* theta,
+                        double* K, int M, int n_max, int d, int kernel, void* stream);
+
+/* K1-K5 fused: (LML + log priors)/n and its gradient w.r.t. the RAW parameters for
+ * M tasks x R hyper-parameter rows in ONE launch.  Replaces one evaluation of the
+ * closure scipy drives inside `fit.fit_gpytorch_mll(mll)` and of
+ * `mll(model(*model.train_inputs), model.train_targets)` (reference
+ * scamlgp/utils.py:171-177,190-192; loop over tasks model.py:176-188).
+ *   jitter [M][R] or NULL : added to the diagonal (psd_safe_cholesky ladder is driven
+ *                           by the host: 1e-8, 1e-7, 1e-6)
+ *   skip   [M][R] or NULL : non-zero entries are not evaluated and not written
+ *   lml    [M][R], grad [M][R][P], info [M][R]                                    */
+int scaml_lml_grad(const double* X, const double* y, const int32_t* n_valid,
+                   const double* theta_raw, const double* jitter, const int32_t* skip,
+                   double* lml, double* grad, int32_t* info, void* workspace,
+                   size_t workspace_bytes, int M, int R, int n_max, int d,
+                   const scaml_hyper_spec* spec, void* stream);
+
+/* K1-K3 for prediction: factorise K_y of every task at its fitted parameters
+ * (theta_raw [M][P]) and emit the packed L^-1 tiles, alpha = K_y^-1 y~ [M][n_pad], and
+ * the constrained parameters theta [M][P].  Replaces the prediction-strategy caches
+ * gpytorch builds on the first `gp.posterior(x)` (reference scamlgp/model.py:128,281). */
+int scaml_factorize(const double* X, const double* y, const int32_t* n_valid,
+                    const double* theta_raw, const double* jitter, double* linv_packed,
+                    double* alpha, double* theta, int32_t* info, void* workspace,
+                    size_t workspace_bytes, int M, int n_max, int d,
+                    const scaml_hyper_spec* spec, void* stream);
+
+/* Bytes of partial-sum scratch scaml_predict_weighted needs for B candidates. */
+size_t scaml_predict_workspace_bytes(int M, int n_max, int d, int B);
+
+/* K6-K9 fused: weighted ScaML-GP prior prediction at B candidates (q = 1),
+ *   mean[b] = sum_m w_m (ybar_m + ystd_m * k*_m(b)^T alpha_m)
+ *   var[b]  = sum_m w_m^2 ystd_m^2 (s_m - || L_m^-1 k*_m(b) ||^2)
+ * reduced over the M tasks inside the kernel in a fixed order (deterministic).
+ * Tasks with w_m == 0 are skipped (weight pruning, reference model.py:192-215,365-372).
+ * Replaces `_compute_target_prior` (reference scamlgp/model.py:108-135).
+ *   theta [M][P] constrained (from scaml_factorize), Xc [B][d], mean [B], var [B].     */
+int scaml_predict_weighted(const double* X, const int32_t* n_valid, const double* theta,
+                           const double* linv_packed, const double* alpha,
+                           const double* ybar, const double* ystd, const double* w,
+                           const double* Xc, double* mean, double* var, void* workspace,
+                           size_t workspace_bytes, int M, int n_max, int d, int B,
+                           int kernel, void* stream);
+
+/* Per-task (un-reduced) source posteriors at n_t target inputs: mean [n_t][M] and dense
+ * covariance [n_t][n_t][M] in raw-Y units -- the `source_means` / `source_covs` caches of
+ * `ScaMLGP.__init__` (reference scamlgp/model.py:278-289).  n_t <= 64 per call tile. */
+int scaml_predict_cross(const double* X, const int32_t* n_valid, const double* theta,
+                        const double* linv_packed, const double* alpha, const double* ybar,
+                        const double* ystd, const double* Xt, double* source_means,
+                        double* source_covs, int M, int n_max, int d, int n_t, int kernel,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCAML_B200_H */

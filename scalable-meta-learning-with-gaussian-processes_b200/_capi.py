@@ -1,0 +1,201 @@
+"""ctypes binding of the C ABI declared in include/scaml_b200.h.
+
+The binding is address based (plain integers for pointers) so the same code drives
+  * the product library  csrc/libscaml_b200.so  (sm_100a, device pointers), and
+  * in CPU-only CI, the logic-emulation build of the same kernel sources
+    (tests/ only; host pointers) -- see csrc/emu/cuda_emu.h.
+Nothing here falls back to a CPU implementation: `load_cuda_library()` raises if the
+sm_100a library has not been built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+KERNEL_RBF, KERNEL_MATERN12, KERNEL_MATERN32, KERNEL_MATERN52 = 0, 1, 2, 3
+PRIOR_NONE, PRIOR_GAMMA, PRIOR_LOGNORMAL = 0, 1, 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CUDA_LIB_PATH = os.path.join(_HERE, "csrc", "libscaml_b200.so")
+
+
+class CHyperSpec(C.Structure):
+    _fields_ = [
+        ("kernel", C.c_int32),
+        ("ls_prior", C.c_int32),
+        ("os_prior", C.c_int32),
+        ("noise_prior", C.c_int32),
+        ("ls_lo", C.c_double),
+        ("ls_hi", C.c_double),
+        ("os_lo", C.c_double),
+        ("os_hi", C.c_double),
+        ("noise_lo", C.c_double),
+        ("noise_hi", C.c_double),
+        ("ls_p1", C.c_double),
+        ("ls_p2", C.c_double),
+        ("os_p1", C.c_double),
+        ("os_p2", C.c_double),
+        ("noise_p1", C.c_double),
+        ("noise_p2", C.c_double),
+    ]
+
+
+@dataclass
+class HyperSpec:
+    """Kernel family, Interval constraints, priors and initial values of one GP.
+
+    Defaults are the source-GP settings of the reference (scamlgp/model.py:25-70);
+    `HyperSpec.target()` gives the target-GP defaults (model.py:73-105).
+    """
+
+    kernel: int = KERNEL_RBF
+    ls_bounds: Tuple[float, float] = (1e-4, 1e2)
+    os_bounds: Tuple[float, float] = (1e-4, 1e2)
+    noise_bounds: Tuple[float, float] = (1e-8, 1e-2)
+    ls_prior: Tuple[int, float, float] = (PRIOR_GAMMA, 3.0, 6.0)
+    os_prior: Tuple[int, float, float] = (PRIOR_GAMMA, 2.0, 0.15)
+    noise_prior: Tuple[int, float, float] = (PRIOR_LOGNORMAL, -8.0, 2.0)
+    ls_init: float = 0.5
+    os_init: float = 1.0
+    noise_init: float = 1e-3
+
+    @staticmethod
+    def source(kernel: int = KERNEL_RBF) -> "HyperSpec":
+        return HyperSpec(kernel=kernel)
+
+    @staticmethod
+    def target(kernel: int = KERNEL_RBF) -> "HyperSpec":
+        return HyperSpec(
+            kernel=kernel,
+            ls_prior=(PRIOR_LOGNORMAL, 0.5, 1.5),
+            os_prior=(PRIOR_LOGNORMAL, -2.0, 3.0),
+            ls_init=1.0,
+            os_init=0.1,
+        )
+
+    def to_c(self) -> CHyperSpec:
+        return CHyperSpec(
+            int(self.kernel), int(self.ls_prior[0]), int(self.os_prior[0]), int(self.noise_prior[0]),
+            self.ls_bounds[0], self.ls_bounds[1], self.os_bounds[0], self.os_bounds[1],
+            self.noise_bounds[0], self.noise_bounds[1],
+            float(self.ls_prior[1]), float(self.ls_prior[2]),
+            float(self.os_prior[1]), float(self.os_prior[2]),
+            float(self.noise_prior[1]), float(self.noise_prior[2]),
+        )
+
+
+EXPORTED_SYMBOLS = (
+    "scaml_version",
+    "scaml_fit_limits",
+    "scaml_fit_workspace_bytes",
+    "scaml_kernel_matrix",
+    "scaml_lml_grad",
+    "scaml_factorize",
+    "scaml_predict_workspace_bytes",
+    "scaml_predict_weighted",
+    "scaml_predict_cross",
+)
+
+
+class ScamlError(RuntimeError):
+    pass
+
+
+_ERRORS = {-1: "bad argument", -2: "workspace too small", -3: "unsupported size (d or n_max)",
+           -4: "configuration does not fit shared memory"}
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = _ERRORS.get(rc, f"CUDA error {rc}" if rc > 0 else f"error {rc}")
+        raise ScamlError(f"{what}: {msg}")
+
+
+class ScamlLib:
+    """Typed view of one loaded libscaml shared object."""
+
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise ScamlError(
+                f"{path} not found: build the sm_100a library first "
+                "(python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback."
+            )
+        self.path = path
+        self.lib = C.CDLL(path)
+        L = self.lib
+        vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+        L.scaml_version.restype = C.c_char_p
+        L.scaml_fit_limits.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.scaml_fit_workspace_bytes.restype = sz
+        L.scaml_fit_workspace_bytes.argtypes = [i32, i32]
+        L.scaml_kernel_matrix.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
+        L.scaml_lml_grad.argtypes = [vp] * 10 + [sz, i32, i32, i32, i32, C.POINTER(CHyperSpec), vp]
+        L.scaml_factorize.argtypes = [vp] * 10 + [sz, i32, i32, i32, C.POINTER(CHyperSpec), vp]
+        L.scaml_predict_workspace_bytes.restype = sz
+        L.scaml_predict_workspace_bytes.argtypes = [i32, i32, i32, i32]
+        L.scaml_predict_weighted.argtypes = [vp] * 12 + [sz, i32, i32, i32, i32, i32, vp]
+        L.scaml_predict_cross.argtypes = [vp] * 10 + [i32, i32, i32, i32, i32, vp]
+
+    # ---- thin, address-based wrappers ------------------------------------------------ #
+    def version(self) -> str:
+        return self.lib.scaml_version().decode()
+
+    def fit_limits(self) -> Tuple[int, int]:
+        n, d = C.c_int(0), C.c_int(0)
+        self.lib.scaml_fit_limits(C.byref(n), C.byref(d))
+        return n.value, d.value
+
+    def fit_workspace_bytes(self, n_max: int, d: int) -> int:
+        return int(self.lib.scaml_fit_workspace_bytes(n_max, d))
+
+    def predict_workspace_bytes(self, M: int, n_max: int, d: int, B: int) -> int:
+        return int(self.lib.scaml_predict_workspace_bytes(M, n_max, d, B))
+
+    def kernel_matrix(self, X, n_valid, theta, K, M, n_max, d, kernel, stream=0):
+        _check(self.lib.scaml_kernel_matrix(X, n_valid, theta, K, M, n_max, d, kernel, stream), "scaml_kernel_matrix")
+
+    def lml_grad(self, X, y, n_valid, theta_raw, jitter, skip, lml, grad, info, ws, ws_bytes, M, R, n_max, d,
+                 spec: HyperSpec, stream=0):
+        cs = spec.to_c()
+        _check(self.lib.scaml_lml_grad(X, y, n_valid, theta_raw, jitter, skip, lml, grad, info, ws, ws_bytes,
+                                       M, R, n_max, d, C.byref(cs), stream), "scaml_lml_grad")
+
+    def factorize(self, X, y, n_valid, theta_raw, jitter, linv, alpha, theta, info, ws, ws_bytes, M, n_max, d,
+                  spec: HyperSpec, stream=0):
+        cs = spec.to_c()
+        _check(self.lib.scaml_factorize(X, y, n_valid, theta_raw, jitter, linv, alpha, theta, info, ws, ws_bytes,
+                                        M, n_max, d, C.byref(cs), stream), "scaml_factorize")
+
+    def predict_weighted(self, X, n_valid, theta, linv, alpha, ybar, ystd, w, Xc, mean, var, ws, ws_bytes,
+                         M, n_max, d, B, kernel, stream=0):
+        _check(self.lib.scaml_predict_weighted(X, n_valid, theta, linv, alpha, ybar, ystd, w, Xc, mean, var,
+                                               ws, ws_bytes, M, n_max, d, B, kernel, stream),
+               "scaml_predict_weighted")
+
+    def predict_cross(self, X, n_valid, theta, linv, alpha, ybar, ystd, Xt, means, covs, M, n_max, d, n_t,
+                      kernel, stream=0):
+        _check(self.lib.scaml_predict_cross(X, n_valid, theta, linv, alpha, ybar, ystd, Xt, means, covs,
+                                            M, n_max, d, n_t, kernel, stream), "scaml_predict_cross")
+
+
+_cuda_lib: Optional[ScamlLib] = None
+
+
+def load_cuda_library() -> ScamlLib:
+    """The product library. Raises ScamlError when it has not been built."""
+    global _cuda_lib
+    if _cuda_lib is None:
+        _cuda_lib = ScamlLib(CUDA_LIB_PATH)
+    return _cuda_lib
+
+
+def packed_tiles(n_max: int) -> int:
+    """Number of 32x32 tiles in the packed lower-triangular factor of one task."""
+    nb = ((n_max + 63) // 64) * 2
+    return nb * (nb + 1) // 2
+
+
+def pad64(n: int) -> int:
+    return ((n + 63) // 64) * 64

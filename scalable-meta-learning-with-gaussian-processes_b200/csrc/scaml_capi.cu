@@ -1,0 +1,171 @@
+// extern "C" entry points of libscaml_b200.so (see include/scaml_b200.h).
+// No torch types, no allocation: raw device pointers + sizes + stream.
+#include "scaml_fit.cuh"
+#include "scaml_kmat.cuh"
+#include "scaml_predict.cuh"
+
+#ifndef SCAML_EMU
+#include <cuda_runtime.h>
+#endif
+
+namespace {
+
+constexpr size_t kMaxSmem = 227 * 1024;
+
+int g_num_sms = 0;
+int num_sms() {
+#ifdef SCAML_EMU
+  return 2;
+#else
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+#endif
+}
+
+inline int pad64(int n) { return ((n + 63) / 64) * 64; }
+
+// persistent grid of the fit kernels: CTAs per SM allowed by shared memory (<= 2)
+int fit_ctas_per_sm(int n_pad, int d) {
+  const size_t s = scaml::fit_smem_bytes(n_pad, d) + 1024;
+  return (2 * s <= 228 * 1024) ? 2 : 1;
+}
+int fit_grid_slots(int n_pad, int d) { return num_sms() * fit_ctas_per_sm(n_pad, d); }
+
+template <int KIND>
+int launch_fit(const scaml::FitParams& p, int grid, size_t smem, void* stream) {
+#ifdef SCAML_EMU
+  (void)stream;
+  cuemu::launch(dim3(grid), dim3(scaml::kThreads), smem, scaml::scaml_fit_kernel<KIND>, p);
+  return 0;
+#else
+  cudaError_t err = cudaFuncSetAttribute(scaml::scaml_fit_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+  if (err != cudaSuccess) return (int)err;
+  scaml::scaml_fit_kernel<KIND><<<grid, scaml::kThreads, smem, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
+#endif
+}
+
+int dispatch_fit(const scaml::FitParams& p, int grid, size_t smem, void* stream) {
+  switch (p.spec.kernel) {
+    case SCAML_KERNEL_RBF: return launch_fit<SCAML_KERNEL_RBF>(p, grid, smem, stream);
+    case SCAML_KERNEL_MATERN12: return launch_fit<SCAML_KERNEL_MATERN12>(p, grid, smem, stream);
+    case SCAML_KERNEL_MATERN32: return launch_fit<SCAML_KERNEL_MATERN32>(p, grid, smem, stream);
+    case SCAML_KERNEL_MATERN52: return launch_fit<SCAML_KERNEL_MATERN52>(p, grid, smem, stream);
+    default: return SCAML_E_ARG;
+  }
+}
+
+int run_fit(scaml::FitParams p, void* workspace, size_t workspace_bytes, void* stream) {
+  if (p.M <= 0 || p.R <= 0 || p.n_max <= 0 || p.d <= 0) return SCAML_E_ARG;
+  if (p.d > scaml::kMaxP - 2) return SCAML_E_UNSUPPORTED;
+  p.n_pad = pad64(p.n_max);
+  const size_t smem = scaml::fit_smem_bytes(p.n_pad, p.d);
+  if (smem > kMaxSmem) return SCAML_E_SMEM;
+  if (workspace_bytes < scaml_fit_workspace_bytes(p.n_max, p.d)) return SCAML_E_WORKSPACE;
+  p.workspace = static_cast<double*>(workspace);
+  p.ws_stride = scaml::fit_ws_doubles_host(p.n_pad);
+  int grid = fit_grid_slots(p.n_pad, p.d);
+  const long long E = (long long)p.M * p.R;
+  if (E < grid) grid = (int)E;
+  return dispatch_fit(p, grid, smem, stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* scaml_version(void) {
+#ifdef SCAML_EMU
+  return "scaml_b200 0.1.0 cpu-logic-emulation (tests only)";
+#else
+  return "scaml_b200 0.1.0 sm_100a";
+#endif
+}
+
+int scaml_fit_limits(int* n_max_limit, int* d_limit) {
+  if (d_limit) *d_limit = scaml::kMaxP - 2;
+  if (n_max_limit) {
+    int n = 64;
+    while (scaml::fit_smem_bytes(n + 64, 6) <= kMaxSmem) n += 64;
+    *n_max_limit = n;
+  }
+  return 0;
+}
+
+size_t scaml_fit_workspace_bytes(int n_max, int d) {
+  if (n_max <= 0 || d <= 0) return 0;
+  const int n_pad = pad64(n_max);
+  return (size_t)fit_grid_slots(n_pad, d) * (size_t)scaml::fit_ws_doubles_host(n_pad) * sizeof(double);
+}
+
+int scaml_lml_grad(const double* X, const double* y, const int32_t* n_valid, const double* theta_raw,
+                   const double* jitter, const int32_t* skip, double* lml, double* grad, int32_t* info,
+                   void* workspace, size_t workspace_bytes, int M, int R, int n_max, int d,
+                   const scaml_hyper_spec* spec, void* stream) {
+  if (!X || !y || !theta_raw || !lml || !grad || !info || !workspace || !spec) return SCAML_E_ARG;
+  scaml::FitParams p{};
+  p.X = X, p.y = y, p.n_valid = n_valid, p.theta_raw = theta_raw, p.jitter = jitter, p.skip = skip;
+  p.lml = lml, p.grad = grad, p.info = info;
+  p.M = M, p.R = R, p.n_max = n_max, p.d = d, p.mode = scaml::kModeLmlGrad;
+  p.spec = *spec;
+  return run_fit(p, workspace, workspace_bytes, stream);
+}
+
+int scaml_factorize(const double* X, const double* y, const int32_t* n_valid, const double* theta_raw,
+                    const double* jitter, double* linv_packed, double* alpha, double* theta, int32_t* info,
+                    void* workspace, size_t workspace_bytes, int M, int n_max, int d, const scaml_hyper_spec* spec,
+                    void* stream) {
+  if (!X || !y || !theta_raw || !linv_packed || !alpha || !theta || !info || !workspace || !spec) return SCAML_E_ARG;
+  scaml::FitParams p{};
+  p.X = X, p.y = y, p.n_valid = n_valid, p.theta_raw = theta_raw, p.jitter = jitter, p.skip = nullptr;
+  p.info = info, p.linv_out = linv_packed, p.alpha_out = alpha, p.theta_out = theta;
+  p.M = M, p.R = 1, p.n_max = n_max, p.d = d, p.mode = scaml::kModeFactorize;
+  p.spec = *spec;
+  return run_fit(p, workspace, workspace_bytes, stream);
+}
+
+int scaml_kernel_matrix(const double* X, const int32_t* n_valid, const double* theta, double* K, int M, int n_max,
+                        int d, int kernel, void* stream) {
+  if (!X || !theta || !K || M <= 0 || n_max <= 0 || d <= 0) return SCAML_E_ARG;
+  if (d > scaml::kMaxP - 2) return SCAML_E_UNSUPPORTED;
+  if (kernel < 0 || kernel > 3) return SCAML_E_ARG;
+  return scaml::launch_kmat(X, n_valid, theta, K, M, n_max, d, kernel, stream);
+}
+
+size_t scaml_predict_workspace_bytes(int M, int n_max, int d, int B) {
+  return scaml::predict_workspace_bytes(M, pad64(n_max), d, B, num_sms());
+}
+
+int scaml_predict_weighted(const double* X, const int32_t* n_valid, const double* theta, const double* linv_packed,
+                           const double* alpha, const double* ybar, const double* ystd, const double* w,
+                           const double* Xc, double* mean, double* var, void* workspace, size_t workspace_bytes,
+                           int M, int n_max, int d, int B, int kernel, void* stream) {
+  if (!X || !theta || !linv_packed || !alpha || !ybar || !ystd || !w || !Xc || !mean || !var) return SCAML_E_ARG;
+  if (M <= 0 || n_max <= 0 || d <= 0 || B <= 0 || kernel < 0 || kernel > 3) return SCAML_E_ARG;
+  if (d > scaml::kMaxP - 2) return SCAML_E_UNSUPPORTED;
+  if (workspace_bytes < scaml_predict_workspace_bytes(M, n_max, d, B) || (!workspace && workspace_bytes))
+    return SCAML_E_WORKSPACE;
+  return scaml::launch_predict_weighted(X, n_valid, theta, linv_packed, alpha, ybar, ystd, w, Xc, mean, var,
+                                        static_cast<double*>(workspace), M, n_max, pad64(n_max), d, B, kernel,
+                                        num_sms(), stream);
+}
+
+int scaml_predict_cross(const double* X, const int32_t* n_valid, const double* theta, const double* linv_packed,
+                        const double* alpha, const double* ybar, const double* ystd, const double* Xt,
+                        double* source_means, double* source_covs, int M, int n_max, int d, int n_t, int kernel,
+                        void* stream) {
+  if (!X || !theta || !linv_packed || !alpha || !ybar || !ystd || !Xt || !source_means || !source_covs)
+    return SCAML_E_ARG;
+  if (M <= 0 || n_max <= 0 || d <= 0 || n_t <= 0 || kernel < 0 || kernel > 3) return SCAML_E_ARG;
+  if (d > scaml::kMaxP - 2) return SCAML_E_UNSUPPORTED;
+  return scaml::launch_predict_cross(X, n_valid, theta, linv_packed, alpha, ybar, ystd, Xt, source_means,
+                                     source_covs, M, n_max, pad64(n_max), d, n_t, kernel, stream);
+}
+
+}  // extern "C"

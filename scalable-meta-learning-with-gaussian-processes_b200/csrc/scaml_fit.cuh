@@ -1,0 +1,741 @@
+// Fused per-task GP fit kernel: kernel-matrix assembly -> blocked Cholesky -> triangular
+// inverse -> (K^-1 contraction with dK/dtheta) for M tasks x R hyper-parameter rows.
+//
+// One persistent CTA (256 threads) owns one evaluation at a time.  The n_pad x n_pad
+// lower triangle lives in a per-CTA global workspace of 32x32 fp64 tiles (8 KB each,
+// L2-resident: 2 CTAs/SM x 148 SMs x ~0.4 MB < 126 MB), and every n^3-class step is the
+// same register-tiled micro-kernel
+//        acc[4][4] += A[kk][r] * B[kk][c]        (64x64 super-tile, 32-deep chunks)
+// fed by cp.async double-buffered 8 KB tiles.  Tile layouts are chosen per phase so that
+// the contraction index is always the slow index of the staged tile (no transposes):
+//   L   (Cholesky factor, off-diagonal super-tiles)  column-major tiles ("C")
+//   L^-1                                              row-major tiles    ("R")
+//   D^-1 (inverse of a 64x64 diagonal super-tile)     both (C copy in `dinvc` area)
+// K and K^-1 never reach memory: K is recomputed from the (length-scaled) inputs held in
+// shared memory in the epilogues, K^-1 super-tiles are contracted with dK/dtheta straight
+// out of the accumulator registers.
+//
+// Math: SURVEY.md appendix A.3-A.5; reference call sites scamlgp/utils.py:171-177,190-192
+// (objective), scamlgp/model.py:25-70 (constraints/priors), model.py:176-188 (task loop).
+#pragma once
+#include "scaml_device.cuh"
+
+namespace scaml {
+
+enum { kModeLmlGrad = 0, kModeFactorize = 1 };
+
+struct FitParams {
+  const double* X;          // [M][n_max][d]
+  const double* y;          // [M][n_max]
+  const int32_t* n_valid;   // [M] or null
+  const double* theta_raw;  // [M][R][P]
+  const double* jitter;     // [M][R] or null
+  const int32_t* skip;      // [M][R] or null
+  double* lml;              // [M][R]
+  double* grad;             // [M][R][P]
+  int32_t* info;            // [M][R]
+  double* linv_out;         // factorize: [M][ntiles][1024] C-layout
+  double* alpha_out;        // factorize: [M][n_pad]
+  double* theta_out;        // factorize: [M][P] constrained
+  double* workspace;
+  long long ws_stride;  // doubles per CTA slot
+  int M, R, n_max, n_pad, d, mode;
+  scaml_hyper_spec spec;
+};
+
+// workspace slot: [ lower tiles: tri(NB) x 1024 ][ dinvC: NS x 3 x 1024 ]
+SCAML_DEVICE long long fit_ws_doubles(int n_pad) {
+  const int NB = n_pad / kBS, NS = n_pad / kSB;
+  return (long long)tri(NB) * kTile + (long long)NS * 3 * kTile;
+}
+inline long long fit_ws_doubles_host(int n_pad) {
+  const int NB = n_pad / kBS, NS = n_pad / kSB;
+  return (long long)((NB * (NB + 1)) / 2) * kTile + (long long)NS * 3 * kTile;
+}
+// shared memory (doubles): stage 8192 | dinvc 3072 | xs d*n_pad | y,z,alpha 3*n_pad |
+//                          red 256 | gsm 8*kMaxP | par 4*kMaxP+8 | flags
+inline size_t fit_smem_bytes(int n_pad, int d) {
+  return sizeof(double) * (size_t)(8192 + 3072 + (size_t)d * n_pad + 3 * (size_t)n_pad + 256 + 8 * kMaxP +
+                                   4 * kMaxP + 8 + 2);
+}
+
+// per-thread coordinates inside a 64x64 super-tile (16x16 threads of 4x4 elements)
+struct Thr {
+  int tid, warp, lane;
+  int rb, cb;    // tile row / col inside the super-tile (0/1) -- warp-uniform
+  int rin, cin;  // first row / col inside the tile (multiples of 4)
+};
+SCAML_DEVICE Thr make_thr() {
+  Thr t;
+  t.tid = threadIdx.x;
+  t.warp = t.tid >> 5;
+  t.lane = t.tid & 31;
+  const int tyb = t.warp >> 2, txb = t.warp & 3;
+  t.rb = tyb;
+  t.cb = txb >> 1;
+  t.rin = 4 * (t.lane >> 2);
+  t.cin = 16 * (txb & 1) + 4 * (t.lane & 3);
+  return t;
+}
+
+SCAML_DEVICE void acc_zero(double (&acc)[4][4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+}
+
+// acc += A[kk][rin..rin+3] (x) B[kk][cin..cin+3] over one 32-deep chunk
+SCAML_DEVICE void mma_chunk(double (&acc)[4][4], const double* __restrict__ Ap, const double* __restrict__ Bp) {
+#pragma unroll 8
+  for (int kk = 0; kk < kBS; ++kk) {
+    const double2 a01 = *reinterpret_cast<const double2*>(Ap + kk * kBS);
+    const double2 a23 = *reinterpret_cast<const double2*>(Ap + kk * kBS + 2);
+    const double2 b01 = *reinterpret_cast<const double2*>(Bp + kk * kBS);
+    const double2 b23 = *reinterpret_cast<const double2*>(Bp + kk * kBS + 2);
+    const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+    const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+  }
+}
+
+// ---- chunk sources: which global tiles feed chunk `ck` of a super-tile product ------- //
+struct ChunkPtrs {
+  const double* a[2];
+  const double* b[2];
+  int zoff;  // first global row/col index covered by this chunk (piggy-backed GEMV)
+};
+SCAML_DEVICE const double* wtile(const double* W, int bi, int bj) { return W + (size_t)(tri(bi) + bj) * kTile; }
+
+// Cholesky update of super-tile (I,J): sum_{kb < 2J} L(I,kb) L(J,kb)^T  (C-layout tiles)
+struct CholSrc {
+  const double* W;
+  int I, J;
+  SCAML_DEVICE int count() const { return 2 * J; }
+  SCAML_DEVICE bool same() const { return I == J; }
+  SCAML_DEVICE ChunkPtrs get(int ck) const {
+    ChunkPtrs c;
+    c.a[0] = wtile(W, 2 * I, ck);
+    c.a[1] = wtile(W, 2 * I + 1, ck);
+    c.b[0] = wtile(W, 2 * J, ck);
+    c.b[1] = wtile(W, 2 * J + 1, ck);
+    c.zoff = ck * kBS;
+    return c;
+  }
+};
+// Triangular inverse, super-tile (I,J), I>J: S = sum_{K=J}^{I-1} L(I,K) Linv(K,J)
+// A = L tiles (C-layout, contraction over their columns); B = Linv tiles (R-layout, rows)
+struct TrtriSrc {
+  const double* W;
+  int I, J;
+  SCAML_DEVICE int count() const { return 2 * (I - J); }
+  SCAML_DEVICE bool same() const { return false; }
+  SCAML_DEVICE ChunkPtrs get(int ck) const {
+    ChunkPtrs c;
+    const int kcol = 2 * J + ck;
+    c.a[0] = wtile(W, 2 * I, kcol);
+    c.a[1] = wtile(W, 2 * I + 1, kcol);
+    c.b[0] = wtile(W, kcol, 2 * J);
+    c.b[1] = (kcol >= 2 * J + 1) ? wtile(W, kcol, 2 * J + 1) : nullptr;
+    c.zoff = kcol * kBS;
+    return c;
+  }
+};
+// K^-1 super-tile (I,J), I>=J: sum_{K>=I} Linv(K,I)^T Linv(K,J)  (R-layout, contraction over rows)
+struct LauumSrc {
+  const double* W;
+  int I, J, NS;
+  SCAML_DEVICE int count() const { return 2 * (NS - I); }
+  SCAML_DEVICE bool same() const { return I == J; }
+  SCAML_DEVICE ChunkPtrs get(int ck) const {
+    ChunkPtrs c;
+    const int krow = 2 * I + ck;
+    c.a[0] = wtile(W, krow, 2 * I);
+    c.a[1] = (krow >= 2 * I + 1) ? wtile(W, krow, 2 * I + 1) : nullptr;
+    c.b[0] = wtile(W, krow, 2 * J);
+    c.b[1] = (krow >= 2 * J + 1) ? wtile(W, krow, 2 * J + 1) : nullptr;
+    c.zoff = krow * kBS;
+    return c;
+  }
+};
+
+template <class Src>
+SCAML_DEVICE void stage_issue(const Src& src, int ck, double* st, int tid) {
+  const ChunkPtrs c = src.get(ck);
+  if (c.a[0]) tile_async(st, c.a[0], tid);
+  if (c.a[1]) tile_async(st + kTile, c.a[1], tid);
+  if (!src.same()) {
+    if (c.b[0]) tile_async(st + 2 * kTile, c.b[0], tid);
+    if (c.b[1]) tile_async(st + 3 * kTile, c.b[1], tid);
+  }
+  cp_async_commit();
+}
+
+// acc += sum over chunks; optional piggy-backed GEMV  pig[c] += sum_kk A[kk][c] * zv[zoff+kk]
+// (c = tid & 63 over the 64 A columns of the super-tile, kk-quarter = tid >> 6).
+// On return every thread has passed a __syncthreads after its last read of `stage`.
+template <class Src, bool PIGGY>
+SCAML_DEVICE void gemm_global(double (&acc)[4][4], const Src& src, double* stage, const Thr& t, bool skip_tile,
+                              double& pig, const double* zv) {
+  const int n = src.count();
+  if (n <= 0) return;
+  stage_issue(src, 0, stage, t.tid);
+  for (int ck = 0; ck < n; ++ck) {
+    double* st = stage + (ck & 1) * 4 * kTile;
+    if (ck + 1 < n) {
+      stage_issue(src, ck + 1, stage + ((ck + 1) & 1) * 4 * kTile, t.tid);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const ChunkPtrs c = src.get(ck);
+    const double* As = st;
+    const double* Bs = src.same() ? st : st + 2 * kTile;
+    const bool bvalid = src.same() ? (c.a[t.cb] != nullptr) : (c.b[t.cb] != nullptr);
+    if (!skip_tile && c.a[t.rb] != nullptr && bvalid)
+      mma_chunk(acc, As + t.rb * kTile + t.rin, Bs + t.cb * kTile + t.cin);
+    if (PIGGY) {
+      const int col = t.tid & 63, q = t.tid >> 6;
+      if (c.a[col >> 5] != nullptr) {
+        const double* ap = As + (col >> 5) * kTile + (col & 31) + q * 8 * kBS;
+        const double* zp = zv + c.zoff + q * 8;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) pig = fma(ap[kk * kBS], zp[kk], pig);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// product of shared-memory resident 64x64 operands given as 2 chunks x 2 tiles each
+SCAML_DEVICE void gemm_smem(double (&acc)[4][4], const double* const (&A)[2][2], const double* const (&B)[2][2],
+                            const Thr& t) {
+#pragma unroll
+  for (int ck = 0; ck < 2; ++ck) {
+    const double* a = A[ck][t.rb];
+    const double* b = B[ck][t.cb];
+    if (a != nullptr && b != nullptr) mma_chunk(acc, a + t.rin, b + t.cin);
+  }
+}
+
+// 4x4 register tile -> one 32x32 tile, column-major ("C") or row-major ("R")
+SCAML_DEVICE void store_tile_C(double* blk, const double (&acc)[4][4], const Thr& t, double scale) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    double* p = blk + (t.cin + j) * kBS + t.rin;
+    *reinterpret_cast<double2*>(p) = make_double2(scale * acc[0][j], scale * acc[1][j]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(scale * acc[2][j], scale * acc[3][j]);
+  }
+}
+SCAML_DEVICE void store_tile_R(double* blk, const double (&acc)[4][4], const Thr& t, double scale) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double* p = blk + (t.rin + i) * kBS + t.cin;
+    *reinterpret_cast<double2*>(p) = make_double2(scale * acc[i][0], scale * acc[i][1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(scale * acc[i][2], scale * acc[i][3]);
+  }
+}
+
+// ---- epilogue 1: acc <- K_y(I,J) - acc, K recomputed from the scaled inputs ----------- //
+template <int KIND>
+SCAML_DEVICE void assemble_tile(double (&acc)[4][4], int I, int J, const Thr& t, const double* xs, int n_pad, int d,
+                                int nv, double os, double diag_add) {
+  const int a0 = I * kSB + t.rb * kBS + t.rin;
+  const int b0 = J * kSB + t.cb * kBS + t.cin;
+  double r2[4][4];
+  acc_zero(r2);
+  for (int k = 0; k < d; ++k) {
+    const double* xr = xs + k * n_pad;
+    const double2 xa01 = *reinterpret_cast<const double2*>(xr + a0);
+    const double2 xa23 = *reinterpret_cast<const double2*>(xr + a0 + 2);
+    const double2 xb01 = *reinterpret_cast<const double2*>(xr + b0);
+    const double2 xb23 = *reinterpret_cast<const double2*>(xr + b0 + 2);
+    const double xa[4] = {xa01.x, xa01.y, xa23.x, xa23.y};
+    const double xb[4] = {xb01.x, xb01.y, xb23.x, xb23.y};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double df = xa[i] - xb[j];
+        r2[i][j] = fma(df, df, r2[i][j]);
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int a = a0 + i, b = b0 + j;
+      double k = os * kappa_of<KIND>(r2[i][j]);
+      if (a == b) k += diag_add;
+      if (a >= nv || b >= nv) k = (a == b) ? 1.0 : 0.0;
+      acc[i][j] = k - acc[i][j];
+    }
+}
+
+// ---- epilogue 2: contract the K^-1 super-tile in `acc` with dK/dtheta ----------------- //
+// accumulates into gsm[warp][0..d-1] (lengthscales), [d] (outputscale), [d+1] (trace W)
+template <int KIND>
+SCAML_DEVICE void grad_tile(const double (&acc)[4][4], int I, int J, const Thr& t, const double* xs,
+                            const double* av, int n_pad, int d, int nv, double* gsm) {
+  const int a0 = I * kSB + t.rb * kBS + t.rin;
+  const int b0 = J * kSB + t.cb * kBS + t.cin;
+  double r2[4][4];
+  acc_zero(r2);
+  for (int k = 0; k < d; ++k) {
+    const double* xr = xs + k * n_pad;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double df = xr[a0 + i] - xr[b0 + j];
+        r2[i][j] = fma(df, df, r2[i][j]);
+      }
+  }
+  double accS = 0.0, accT = 0.0;
+  double tt[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int a = a0 + i, b = b0 + j;
+      double kap, kd;
+      kappa_pair<KIND>(r2[i][j], kap, kd);
+      const bool use = (a >= b) && (a < nv) && (b < nv);
+      const double wgt = use ? ((a == b) ? 1.0 : 2.0) : 0.0;
+      const double Wab = av[a] * av[b] - acc[i][j];
+      const double wk = wgt * Wab;
+      accS = fma(wk, kap, accS);
+      tt[i][j] = wk * kd;
+      if (use && a == b) accT += Wab;
+    }
+  double* g = gsm + t.warp * kMaxP;
+  for (int k = 0; k < d; ++k) {
+    const double* xr = xs + k * n_pad;
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double df = xr[a0 + i] - xr[b0 + j];
+        s = fma(tt[i][j], df * df, s);
+      }
+    s = warp_sum(s);
+    if (t.lane == 0) g[k] += s;
+  }
+  accS = warp_sum(accS);
+  accT = warp_sum(accT);
+  if (t.lane == 0) {
+    g[d] += accS;
+    g[d + 1] += accT;
+  }
+}
+
+// ---- warp-level 32x32 Cholesky + triangular inverse (row r of the tile per lane) ------ //
+// Dsm: SPD tile, C-layout (lower part valid).  Lc: 1024-double scratch (receives L, C-layout).
+// P: 32x33 scratch.  Outputs: XC (C-layout inverse, shared), XRs (R-layout, shared, optional),
+// XRg (R-layout, global, optional).  Returns 0 or the 1-based failing pivot; adds
+// sum(log L_kk^2) over the tile to *logdet (lane 0).
+SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* P, double* XC, double* XRs, double* XRg,
+                             double* logdet, int lane) {
+  double a[kBS];
+#pragma unroll
+  for (int c = 0; c < kBS; ++c) a[c] = Dsm[c * kBS + lane];
+  int fail = 0;
+  double mydiag = 1.0, myrs = 1.0;
+#pragma unroll
+  for (int k = 0; k < kBS; ++k) {
+    double dkk = __shfl_sync(0xffffffffu, a[k], k);
+    if (!(dkk > 0.0) || !(dkk < 1e300)) {
+      if (fail == 0) fail = k + 1;
+      dkk = 1.0;
+    }
+    const double rs = rsqrt(dkk);
+    if (lane == k) {
+      mydiag = dkk;
+      myrs = rs;
+    }
+    const double lrk = a[k] * rs;
+    Lc[k * kBS + lane] = lrk;
+    __syncwarp();
+#pragma unroll
+    for (int j = k + 1; j < kBS; ++j) a[j] = fma(-lrk, Lc[k * kBS + j], a[j]);
+  }
+  // log det contribution: sum_k log(d_kk)   (= 2 sum log L_kk)
+  double ld = log(mydiag);
+  ld = warp_sum(ld);
+  if (lane == 0) *logdet += ld;
+  // inverse, row `lane` of X = L^-1 by a backward column sweep on L^T
+  double w[kBS];
+#pragma unroll
+  for (int c = 0; c < kBS; ++c) w[c] = (c == lane) ? 1.0 : 0.0;
+#pragma unroll
+  for (int j = kBS - 1; j >= 0; --j) {
+    const double rj = __shfl_sync(0xffffffffu, myrs, j);
+    w[j] *= rj;
+#pragma unroll
+    for (int k = 0; k < j; ++k) w[k] = fma(-Lc[k * kBS + j], w[j], w[k]);
+  }
+#pragma unroll
+  for (int c = 0; c < kBS; ++c) {
+    XC[c * kBS + lane] = w[c];
+    P[lane * 33 + c] = w[c];
+  }
+  __syncwarp();
+  if (XRs != nullptr || XRg != nullptr) {
+#pragma unroll 4
+    for (int r = 0; r < kBS; ++r) {
+      const double v = P[r * 33 + lane];
+      if (XRs) XRs[r * kBS + lane] = v;
+      if (XRg) XRg[r * kBS + lane] = v;
+    }
+  }
+  __syncwarp();
+  return fail;
+}
+
+// 32x32x32 product by the whole CTA: out(r,c) = sum_kk A[kk][r] * B[kk][c]; thread owns a 2x2 patch
+SCAML_DEVICE void small_gemm(double (&o)[2][2], const double* A, const double* B, int tid) {
+  const int r0 = 2 * (tid & 15), c0 = 2 * (tid >> 4);
+  o[0][0] = o[0][1] = o[1][0] = o[1][1] = 0.0;
+#pragma unroll 8
+  for (int kk = 0; kk < kBS; ++kk) {
+    const double2 a = *reinterpret_cast<const double2*>(A + kk * kBS + r0);
+    const double2 b = *reinterpret_cast<const double2*>(B + kk * kBS + c0);
+    o[0][0] = fma(a.x, b.x, o[0][0]);
+    o[0][1] = fma(a.x, b.y, o[0][1]);
+    o[1][0] = fma(a.y, b.x, o[1][0]);
+    o[1][1] = fma(a.y, b.y, o[1][1]);
+  }
+}
+SCAML_DEVICE void small_store_C(double* blk, const double (&o)[2][2], int tid, double scale) {
+  const int r0 = 2 * (tid & 15), c0 = 2 * (tid >> 4);
+  *reinterpret_cast<double2*>(blk + c0 * kBS + r0) = make_double2(scale * o[0][0], scale * o[1][0]);
+  *reinterpret_cast<double2*>(blk + (c0 + 1) * kBS + r0) = make_double2(scale * o[0][1], scale * o[1][1]);
+}
+SCAML_DEVICE void small_store_R(double* blk, const double (&o)[2][2], int tid, double scale) {
+  const int r0 = 2 * (tid & 15), c0 = 2 * (tid >> 4);
+  *reinterpret_cast<double2*>(blk + r0 * kBS + c0) = make_double2(scale * o[0][0], scale * o[0][1]);
+  *reinterpret_cast<double2*>(blk + (r0 + 1) * kBS + c0) = make_double2(scale * o[1][0], scale * o[1][1]);
+}
+
+// ---- factorise + invert the 64x64 diagonal super-tile held in `stage` ----------------- //
+// stage tiles (C-layout): [0]=D00  [1]=scratch (X00 R-layout)  [2]=D10  [3]=D11 ; stage[4096..] scratch.
+// Results: dinvc[0..2] = D^-1 tiles (0,0),(1,0),(1,1) C-layout (shared) + copy in `dinvc_g`;
+//          R-layout tiles of D^-1 written to the workspace diagonal (wd00, wd10, wd11).
+// *logdet (shared scalar) accumulates log det; *flag receives the failing pivot (1-based, tile local + base).
+SCAML_DEVICE void diag_factor(double* stage, double* dinvc, double* dinvc_g, double* wd00, double* wd10,
+                              double* wd11, double* logdet, int* flag, int pivot_base, const Thr& t) {
+  double* D00 = stage;
+  double* XR00 = stage + kTile;
+  double* D10 = stage + 2 * kTile;
+  double* D11 = stage + 3 * kTile;
+  double* P = stage + 4 * kTile;            // 32*33
+  double* T = stage + 4 * kTile + 2 * kTile;  // R-layout temp
+  double* Lc = stage + 4 * kTile + 3 * kTile;
+  if (t.warp == 0) {
+    const int f = chol_inv_32(D00, Lc, P, dinvc, XR00, wd00, logdet, t.lane);
+    if (f && t.lane == 0 && *flag == 0) *flag = pivot_base + f;
+  }
+  __syncthreads();
+  double o[2][2];
+  // L10 = D10 * X00^T      (A = D10 C-layout, B[kk][c] = X00(c,kk) = C-layout X00)
+  small_gemm(o, D10, dinvc, t.tid);
+  __syncthreads();
+  small_store_C(D10, o, t.tid, 1.0);  // D10 now holds L10 (C-layout)
+  __syncthreads();
+  // D11 -= L10 L10^T ;  T = L10 * X00  (B[kk][c] = X00(kk,c) = R-layout X00)
+  small_gemm(o, D10, D10, t.tid);
+  {
+    const int r0 = 2 * (t.tid & 15), c0 = 2 * (t.tid >> 4);
+    D11[c0 * kBS + r0] -= o[0][0];
+    D11[c0 * kBS + r0 + 1] -= o[1][0];
+    D11[(c0 + 1) * kBS + r0] -= o[0][1];
+    D11[(c0 + 1) * kBS + r0 + 1] -= o[1][1];
+  }
+  small_gemm(o, D10, XR00, t.tid);
+  small_store_R(T, o, t.tid, 1.0);
+  __syncthreads();
+  if (t.warp == 0) {
+    const int f = chol_inv_32(D11, Lc, P, dinvc + 2 * kTile, nullptr, wd11, logdet, t.lane);
+    if (f && t.lane == 0 && *flag == 0) *flag = pivot_base + kBS + f;
+  }
+  __syncthreads();
+  // X10 = -X11 * T        (A[kk][r] = X11(r,kk) = C-layout X11, B = T R-layout)
+  small_gemm(o, dinvc + 2 * kTile, T, t.tid);
+  small_store_C(dinvc + kTile, o, t.tid, -1.0);
+  small_store_R(wd10, o, t.tid, -1.0);
+  __syncthreads();
+  // C-layout copy of D^-1 for the triangular-inverse phase
+  for (int i = t.tid; i < 3 * kTile / 2; i += kThreads)
+    reinterpret_cast<double2*>(dinvc_g)[i] = reinterpret_cast<const double2*>(dinvc)[i];
+}
+
+// out[r] = sum_kk D^-1(r,kk) v[kk] over a 64x64 lower-triangular D^-1 held as dinvc (C-layout tiles)
+SCAML_DEVICE void dinv_matvec(double* out, const double* dinvc, const double* v, double* red, const Thr& t) {
+  const int r = t.tid & 63, q = t.tid >> 6;  // q: 16-wide kk quarter
+  double s = 0.0;
+  for (int kk = q * 16; kk < q * 16 + 16; ++kk) {
+    if (kk > r) break;
+    const int rb_ = r >> 5, kb_ = kk >> 5;
+    const double* blk = dinvc + ((rb_ == 0) ? 0 : (kb_ == 0 ? kTile : 2 * kTile));
+    s = fma(blk[(kk & 31) * kBS + (r & 31)], v[kk], s);
+  }
+  red[q * 64 + r] = s;
+  __syncthreads();
+  if (t.tid < 64) out[t.tid] = ((red[t.tid] + red[64 + t.tid]) + red[128 + t.tid]) + red[192 + t.tid];
+  __syncthreads();
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams p) {
+  SCAML_DYN_SMEM(double, sm);
+  const Thr t = make_thr();
+  const int d = p.d, P = p.d + 2, n_pad_max = p.n_pad;
+  double* stage = sm;
+  double* dinvc = stage + 8192;
+  double* xs = dinvc + 3072;
+  double* yv = xs + (size_t)d * n_pad_max;
+  double* zv = yv + n_pad_max;
+  double* av = zv + n_pad_max;
+  double* red = av + n_pad_max;
+  double* gsm = red + 256;
+  double* par = gsm + 8 * kMaxP;  // th | lp | dlp | chain | scalars
+  double* th = par;
+  double* lp = par + kMaxP;
+  double* dlp = par + 2 * kMaxP;
+  double* chain = par + 3 * kMaxP;
+  double* scal = par + 4 * kMaxP;  // [0] logdet
+  int* flag = reinterpret_cast<int*>(scal + 8);
+
+  double* W = p.workspace + (size_t)blockIdx.x * p.ws_stride;
+  const int E = p.M * p.R;
+  const scaml_hyper_spec& sp = p.spec;
+
+  for (int e = blockIdx.x; e < E; e += gridDim.x) {
+    if (p.skip != nullptr && p.skip[e] != 0) continue;
+    const int m = e / p.R;
+    const int nv = p.n_valid ? p.n_valid[m] : p.n_max;
+    if (nv < 1 || nv > p.n_max) {
+      if (t.tid == 0) p.info[e] = -1;
+      continue;
+    }
+    const int NS = (nv + kSB - 1) / kSB, n_pad = NS * kSB;
+    double* dinvc_g = W + (size_t)tri(2 * NS) * kTile;  // NS x 3 tiles
+    __syncthreads();  // previous evaluation fully retired before shared state is rewritten
+
+    // ---- parameters: Interval transform, priors, chain rule -------------------------- //
+    if (t.tid < P) {
+      const double raw = p.theta_raw[(size_t)e * P + t.tid];
+      double lo, hi, p1, p2;
+      int pk;
+      if (t.tid < d) {
+        lo = sp.ls_lo, hi = sp.ls_hi, pk = sp.ls_prior, p1 = sp.ls_p1, p2 = sp.ls_p2;
+      } else if (t.tid == d) {
+        lo = sp.os_lo, hi = sp.os_hi, pk = sp.os_prior, p1 = sp.os_p1, p2 = sp.os_p2;
+      } else {
+        lo = sp.noise_lo, hi = sp.noise_hi, pk = sp.noise_prior, p1 = sp.noise_p1, p2 = sp.noise_p2;
+      }
+      const double sg = sigmoid(raw);
+      const double v = lo + (hi - lo) * sg;
+      th[t.tid] = v;
+      lp[t.tid] = log_prior(pk, p1, p2, v);
+      dlp[t.tid] = dlog_prior(pk, p1, p2, v);
+      chain[t.tid] = (hi - lo) * sg * (1.0 - sg);
+      if (p.mode == kModeFactorize) p.theta_out[(size_t)e * P + t.tid] = v;
+    }
+    if (t.tid == 0) {
+      scal[0] = 0.0;
+      *flag = 0;
+    }
+    for (int i = t.tid; i < 8 * kMaxP; i += kThreads) gsm[i] = 0.0;
+    __syncthreads();
+    const double os = th[d];
+    const double diag_add = th[d + 1] + (p.jitter ? p.jitter[e] : 0.0);
+    // scaled inputs, dimension-major; targets
+    {
+      const double* Xm = p.X + (size_t)m * p.n_max * d;
+      for (int i = t.tid; i < n_pad * d; i += kThreads) {
+        const int a = i / d, k = i - a * d;
+        xs[k * n_pad_max + a] = (a < nv) ? Xm[(size_t)a * d + k] / th[k] : 0.0;
+      }
+      const double* ym = p.y + (size_t)m * p.n_max;
+      for (int i = t.tid; i < n_pad; i += kThreads) yv[i] = (i < nv) ? ym[i] : 0.0;
+    }
+    __syncthreads();
+
+    double acc[4][4], acc2[4][4];
+    double pig = 0.0;
+    bool failed = false;
+
+    // ================= phase B: blocked left-looking Cholesky ========================== //
+    for (int J = 0; J < NS && !failed; ++J) {
+      {  // diagonal super-tile
+        const bool skip_tile = (t.rb == 0 && t.cb == 1);
+        acc_zero(acc);
+        CholSrc src{W, J, J};
+        gemm_global<CholSrc, false>(acc, src, stage, t, skip_tile, pig, nullptr);
+        if (!skip_tile) {
+          assemble_tile<KIND>(acc, J, J, t, xs, n_pad_max, d, nv, os, diag_add);
+          store_tile_C(stage + (t.rb * 2 + t.cb) * kTile, acc, t, 1.0);
+        }
+        __syncthreads();
+        double* wd00 = W + (size_t)(tri(2 * J) + 2 * J) * kTile;
+        double* wd10 = W + (size_t)(tri(2 * J + 1) + 2 * J) * kTile;
+        double* wd11 = W + (size_t)(tri(2 * J + 1) + 2 * J + 1) * kTile;
+        diag_factor(stage, dinvc, dinvc_g + (size_t)J * 3 * kTile, wd00, wd10, wd11, &scal[0], flag, J * kSB, t);
+        __syncthreads();
+        if (*flag != 0) {
+          failed = true;
+          break;
+        }
+      }
+      const double* const TB[2][2] = {{dinvc, dinvc + kTile}, {nullptr, dinvc + 2 * kTile}};
+      for (int I = J + 1; I < NS; ++I) {
+        acc_zero(acc);
+        CholSrc src{W, I, J};
+        gemm_global<CholSrc, false>(acc, src, stage, t, false, pig, nullptr);
+        assemble_tile<KIND>(acc, I, J, t, xs, n_pad_max, d, nv, os, diag_add);
+        store_tile_C(stage + (t.rb * 2 + t.cb) * kTile, acc, t, 1.0);
+        __syncthreads();
+        // L(I,J) = C * D^-T : A chunk kb2 = C tiles (rb,kb2); B[kk][c] = D^-1(c,kk)
+        const double* const TA[2][2] = {{stage, stage + 2 * kTile}, {stage + kTile, stage + 3 * kTile}};
+        acc_zero(acc2);
+        gemm_smem(acc2, TA, TB, t);
+        store_tile_C(W + (size_t)(tri(2 * I + t.rb) + 2 * J + t.cb) * kTile, acc2, t, 1.0);
+        __syncthreads();
+      }
+      __syncthreads();
+    }
+    if (failed) {
+      if (t.tid == 0) {
+        p.info[e] = *flag;
+        if (p.mode == kModeLmlGrad) p.lml[e] = nan("");
+      }
+      if (p.mode == kModeLmlGrad && t.tid < P) p.grad[(size_t)e * P + t.tid] = nan("");
+      continue;
+    }
+
+    // ================= phase C: triangular inverse (row-wise), z = L^-1 y ============== //
+    // row 0: D^-1_0 must be re-staged (dinvc holds the last diagonal super-tile)
+    for (int I = 0; I < NS; ++I) {
+      __syncthreads();
+      for (int i = t.tid; i < 3 * kTile / 2; i += kThreads)
+        reinterpret_cast<double2*>(dinvc)[i] =
+            __ldcg(reinterpret_cast<const double2*>(dinvc_g + (size_t)I * 3 * kTile) + i);
+      __syncthreads();
+      pig = 0.0;
+      const double* const TA[2][2] = {{dinvc, dinvc + kTile}, {nullptr, dinvc + 2 * kTile}};
+      for (int J = 0; J < I; ++J) {
+        acc_zero(acc);
+        TrtriSrc src{W, I, J};
+        if (J == 0)
+          gemm_global<TrtriSrc, true>(acc, src, stage, t, false, pig, zv);
+        else
+          gemm_global<TrtriSrc, false>(acc, src, stage, t, false, pig, nullptr);
+        store_tile_R(stage + (t.rb * 2 + t.cb) * kTile, acc, t, 1.0);  // S, R-layout tiles (kb2, cb)
+        __syncthreads();
+        const double* const TBs[2][2] = {{stage, stage + kTile}, {stage + 2 * kTile, stage + 3 * kTile}};
+        acc_zero(acc2);
+        gemm_smem(acc2, TA, TBs, t);
+        store_tile_R(W + (size_t)(tri(2 * I + t.rb) + 2 * J + t.cb) * kTile, acc2, t, -1.0);
+        if (p.mode == kModeFactorize)
+          store_tile_C(p.linv_out + ((size_t)m * tri(n_pad_max / kBS) + tri(2 * I + t.rb) + 2 * J + t.cb) * kTile, acc2,
+                       t, -1.0);
+        __syncthreads();
+      }
+      // z_I = D_I^-1 (y_I - sum_{K<I} L(I,K) z_K)
+      red[t.tid] = pig;
+      __syncthreads();
+      if (t.tid < 64) {
+        const double u = ((red[t.tid] + red[64 + t.tid]) + red[128 + t.tid]) + red[192 + t.tid];
+        av[t.tid] = yv[I * kSB + t.tid] - u;  // av used as scratch here
+      }
+      __syncthreads();
+      dinv_matvec(zv + I * kSB, dinvc, av, red, t);
+      if (p.mode == kModeFactorize) {
+        // diagonal tiles of L^-1 in C-layout = dinvc
+        double* lo = p.linv_out + (size_t)m * tri(n_pad_max / kBS) * kTile;
+        for (int i = t.tid; i < kTile; i += kThreads) {
+          lo[(size_t)(tri(2 * I) + 2 * I) * kTile + i] = dinvc[i];
+          lo[(size_t)(tri(2 * I + 1) + 2 * I) * kTile + i] = dinvc[kTile + i];
+          lo[(size_t)(tri(2 * I + 1) + 2 * I + 1) * kTile + i] = dinvc[2 * kTile + i];
+        }
+      }
+    }
+    __syncthreads();
+
+    if (p.mode == kModeFactorize) {
+      // alpha = L^-T z : warp w owns 32-columns bj = w, w+8, ... ; lane = column inside the tile
+      const int NB = 2 * NS;
+      for (int bj = t.warp; bj < NB; bj += 8) {
+        double s = 0.0;
+        for (int bi = bj; bi < NB; ++bi) {
+          const double* blk = wtile(W, bi, bj);  // R-layout: (r,c) at r*32+c
+#pragma unroll 8
+          for (int r = 0; r < kBS; ++r) s = fma(__ldcg(blk + r * kBS + t.lane), zv[bi * kBS + r], s);
+        }
+        p.alpha_out[(size_t)m * n_pad_max + bj * kBS + t.lane] = s;
+      }
+      for (int i = n_pad + t.tid; i < n_pad_max; i += kThreads) p.alpha_out[(size_t)m * n_pad_max + i] = 0.0;
+      if (t.tid == 0) p.info[e] = 0;
+      continue;
+    }
+
+    // ================= phase D: K^-1 super-tiles, fused gradient contraction ========== //
+    for (int I = 0; I < NS; ++I) {
+      {
+        const bool skip_tile = (t.rb == 0 && t.cb == 1);
+        acc_zero(acc);
+        pig = 0.0;
+        LauumSrc src{W, I, I, NS};
+        gemm_global<LauumSrc, true>(acc, src, stage, t, skip_tile, pig, zv);
+        red[t.tid] = pig;
+        __syncthreads();
+        if (t.tid < 64) av[I * kSB + t.tid] = ((red[t.tid] + red[64 + t.tid]) + red[128 + t.tid]) + red[192 + t.tid];
+        __syncthreads();
+        if (!skip_tile) grad_tile<KIND>(acc, I, I, t, xs, av, n_pad_max, d, nv, gsm);
+      }
+      for (int J = 0; J < I; ++J) {
+        acc_zero(acc);
+        LauumSrc src{W, I, J, NS};
+        gemm_global<LauumSrc, false>(acc, src, stage, t, false, pig, nullptr);
+        grad_tile<KIND>(acc, I, J, t, xs, av, n_pad_max, d, nv, gsm);
+      }
+    }
+    __syncthreads();
+    // quad = z^T z (fixed order), final scalars
+    {
+      double q = 0.0;
+      for (int i = t.tid; i < n_pad; i += kThreads) q = fma(zv[i], zv[i], q);
+      q = warp_sum(q);
+      if (t.lane == 0) red[t.warp] = q;
+      __syncthreads();
+      if (t.tid < P) {
+        double g = 0.0;
+        for (int w = 0; w < 8; ++w) g += gsm[w * kMaxP + (t.tid < d ? t.tid : t.tid)];
+        double gt;
+        if (t.tid < d)
+          gt = 0.5 * os * g / th[t.tid];
+        else if (t.tid == d)
+          gt = 0.5 * g;
+        else
+          gt = 0.5 * g;
+        p.grad[(size_t)e * P + t.tid] = (gt + dlp[t.tid]) * chain[t.tid] / (double)nv;
+      }
+      if (t.tid == 0) {
+        double quad = 0.0;
+        for (int w = 0; w < 8; ++w) quad += red[w];
+        double prior = 0.0;
+        for (int k = 0; k < P; ++k) prior += lp[k];
+        p.lml[e] = (-0.5 * (quad + scal[0] + (double)nv * kLog2Pi) + prior) / (double)nv;
+        p.info[e] = 0;
+      }
+    }
+  }
+}
+
+}  // namespace scaml
