@@ -1,0 +1,264 @@
+"""Batched GP engine: torch CUDA tensors in, hand-written sm_100a kernels underneath.
+
+This is the host side of the hot path: it owns the device-resident padded task batch,
+the scratch workspaces and the jitter ladder, and calls the C ABI
+(include/scaml_b200.h) with `tensor.data_ptr()` on the caller's current CUDA stream.
+torch is plumbing only (memory, streams, torch.distributed); every n^2 / n^3 operation
+runs in libscaml_b200.so.  There is no CPU or eager fallback: constructing an Engine
+without a GPU or without the built library raises.
+
+Reference call sites replaced:
+  * the per-task loop of meta_fit_scamlgp            scamlgp/model.py:176-188
+  * one LML(+grad) closure evaluation                scamlgp/utils.py:171-177,190-192
+  * per-task posterior loops                         scamlgp/model.py:128-134, 280-289
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from ._capi import HyperSpec, ScamlError, ScamlLib, load_cuda_library, pad64, packed_tiles
+
+JITTER_LADDER = (1e-8, 1e-7, 1e-6)  # linear_operator psd_safe_cholesky (fp64), SURVEY A.5
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def standardize_rows(Y: torch.Tensor, n_valid: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """botorch Standardize(m=1) per task on a padded [M, n_max] batch.
+
+    Unbiased std; std < 1e-8 or NaN (n = 1) -> 1.  Returns (y_std [M,n_max] with zeros in
+    the padding, ybar [M], ystd [M]).
+    """
+    M, n_max = Y.shape
+    idx = torch.arange(n_max, device=Y.device).unsqueeze(0)
+    mask = idx < n_valid.unsqueeze(1)
+    cnt = n_valid.to(Y.dtype)
+    Ym = torch.where(mask, Y, torch.zeros_like(Y))
+    ybar = Ym.sum(1) / cnt
+    dev = torch.where(mask, Y - ybar.unsqueeze(1), torch.zeros_like(Y))
+    var = (dev * dev).sum(1) / (cnt - 1.0)
+    std = torch.sqrt(var)
+    std = torch.where(std >= 1e-8, std, torch.ones_like(std))  # NaN (n=1) fails the test -> 1
+    return dev / std.unsqueeze(1), ybar, std
+
+
+@dataclass
+class SourceBatch:
+    """Device-resident, padded meta-data: the input layout of the kernels.
+
+    X [M, n_max, d], y [M, n_max] (standardised, zero padded), n_valid [M] int32,
+    ybar/ystd [M] (the per-task Standardize state), Y_raw [M, n_max] (raw targets).
+    """
+
+    X: torch.Tensor
+    y: torch.Tensor
+    n_valid: torch.Tensor
+    ybar: torch.Tensor
+    ystd: torch.Tensor
+    Y_raw: torch.Tensor
+
+    @property
+    def M(self) -> int:
+        return self.X.shape[0]
+
+    @property
+    def n_max(self) -> int:
+        return self.X.shape[1]
+
+    @property
+    def d(self) -> int:
+        return self.X.shape[2]
+
+    @staticmethod
+    def from_padded(X: torch.Tensor, Y: torch.Tensor, n_valid: Optional[torch.Tensor] = None) -> "SourceBatch":
+        X = X.to(torch.float64).contiguous()
+        Y = Y.to(torch.float64).reshape(X.shape[0], X.shape[1]).contiguous()
+        if n_valid is None:
+            n_valid = torch.full((X.shape[0],), X.shape[1], dtype=torch.int32, device=X.device)
+        n_valid = n_valid.to(device=X.device, dtype=torch.int32).contiguous()
+        y, ybar, ystd = standardize_rows(Y, n_valid)
+        return SourceBatch(X, y.contiguous(), n_valid, ybar.contiguous(), ystd.contiguous(), Y)
+
+    @staticmethod
+    def from_ragged(tasks: Sequence[Tuple[torch.Tensor, torch.Tensor]], device) -> "SourceBatch":
+        """tasks: sequence of (X_i [n_i, d], Y_i [n_i] or [n_i, 1]) host or device tensors."""
+        M = len(tasks)
+        d = tasks[0][0].shape[-1]
+        n_max = max(int(t[0].shape[-2]) for t in tasks)
+        X = torch.zeros(M, n_max, d, dtype=torch.float64)
+        Y = torch.zeros(M, n_max, dtype=torch.float64)
+        nv = torch.zeros(M, dtype=torch.int32)
+        for i, (xi, yi) in enumerate(tasks):
+            n = int(xi.shape[-2])
+            X[i, :n] = xi.detach().to("cpu", torch.float64)
+            Y[i, :n] = yi.detach().to("cpu", torch.float64).reshape(-1)
+            nv[i] = n
+        return SourceBatch.from_padded(X.to(device), Y.to(device), nv.to(device))
+
+    def slice(self, lo: int, hi: int) -> "SourceBatch":
+        return SourceBatch(self.X[lo:hi].contiguous(), self.y[lo:hi].contiguous(), self.n_valid[lo:hi].contiguous(),
+                           self.ybar[lo:hi].contiguous(), self.ystd[lo:hi].contiguous(), self.Y_raw[lo:hi].contiguous())
+
+
+@dataclass
+class FittedSources:
+    """Prediction state of M fitted source GPs (output of Engine.factorize)."""
+
+    batch: SourceBatch
+    theta_raw: torch.Tensor  # [M, P]
+    theta: torch.Tensor  # [M, P] constrained (lengthscales, outputscale, noise)
+    linv: torch.Tensor  # [M, tiles, 1024] packed L^-1, column-major 32x32 tiles
+    alpha: torch.Tensor  # [M, n_pad]
+    info: torch.Tensor  # [M] int32
+    spec: HyperSpec
+
+
+class Engine:
+    """One engine per process / GPU.  All methods run on torch's current CUDA stream."""
+
+    def __init__(self, device: Optional[torch.device] = None, lib: Optional[ScamlLib] = None):
+        if not torch.cuda.is_available():
+            raise ScamlError("scamlgp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.lib = lib if lib is not None else load_cuda_library()
+        self._ws: Optional[torch.Tensor] = None
+        self._pws: Optional[torch.Tensor] = None
+        self.launches = 0  # kernels launched through this engine (bench.py reports it)
+
+    # ---- workspaces ------------------------------------------------------------------ #
+    def _fit_ws(self, n_max: int, d: int) -> torch.Tensor:
+        need = self.lib.fit_workspace_bytes(n_max, d)
+        if self._ws is None or self._ws.numel() * 8 < need:
+            self._ws = torch.empty((need + 7) // 8, dtype=torch.float64, device=self.device)
+        return self._ws
+
+    def _pred_ws(self, M: int, n_max: int, d: int, B: int) -> Tuple[Optional[torch.Tensor], int]:
+        need = self.lib.predict_workspace_bytes(M, n_max, d, B)
+        if need == 0:
+            return None, 0
+        if self._pws is None or self._pws.numel() * 8 < need:
+            self._pws = torch.empty((need + 7) // 8, dtype=torch.float64, device=self.device)
+        return self._pws, need
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ---- K1 standalone ----------------------------------------------------------------- #
+    def kernel_matrix(self, X: torch.Tensor, theta: torch.Tensor, kernel: int = 0,
+                      n_valid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        M, n_max, d = X.shape
+        if out is None:
+            out = torch.empty(M, n_max, n_max, dtype=torch.float64, device=self.device)
+        self.lib.kernel_matrix(_ptr(X), _ptr(n_valid), _ptr(theta), _ptr(out), M, n_max, d, kernel, self._stream())
+        self.launches += 1
+        return out
+
+    # ---- K1-K5 fused ------------------------------------------------------------------- #
+    def lml_grad_raw(self, batch: SourceBatch, theta_raw: torch.Tensor, spec: HyperSpec,
+                     jitter: Optional[torch.Tensor] = None, skip: Optional[torch.Tensor] = None,
+                     out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):
+        """One launch, no jitter ladder.  theta_raw [M, R, P] -> lml [M,R], grad [M,R,P], info [M,R]."""
+        M, R, P = theta_raw.shape
+        assert M == batch.M and P == batch.d + 2 and theta_raw.is_contiguous()
+        if out is None:
+            lml = torch.empty(M, R, dtype=torch.float64, device=self.device)
+            grad = torch.empty(M, R, P, dtype=torch.float64, device=self.device)
+            info = torch.empty(M, R, dtype=torch.int32, device=self.device)
+        else:
+            lml, grad, info = out
+        ws = self._fit_ws(batch.n_max, batch.d)
+        self.lib.lml_grad(_ptr(batch.X), _ptr(batch.y), _ptr(batch.n_valid), _ptr(theta_raw), _ptr(jitter), _ptr(skip),
+                          _ptr(lml), _ptr(grad), _ptr(info), _ptr(ws), ws.numel() * 8, M, R, batch.n_max, batch.d,
+                          spec, self._stream())
+        self.launches += 1
+        return lml, grad, info
+
+    def lml_grad(self, batch: SourceBatch, theta_raw: torch.Tensor, spec: HyperSpec):
+        """LML+grad with the psd_safe_cholesky jitter ladder (only failed rows are re-run).
+
+        Rows that still fail keep info > 0 and NaN outputs -- the reference hands NaN to
+        scipy in that case."""
+        lml, grad, info = self.lml_grad_raw(batch, theta_raw, spec)
+        if bool((info > 0).any()):
+            for jit in JITTER_LADDER:
+                bad = info > 0
+                if not bool(bad.any()):
+                    break
+                skip = (~bad).to(torch.int32).contiguous()
+                jitter = torch.where(bad, torch.full_like(lml, jit), torch.zeros_like(lml)).contiguous()
+                self.lml_grad_raw(batch, theta_raw, spec, jitter=jitter, skip=skip, out=(lml, grad, info))
+        return lml, grad, info
+
+    # ---- K1-K3 for prediction ------------------------------------------------------------ #
+    def factorize(self, batch: SourceBatch, theta_raw: torch.Tensor, spec: HyperSpec) -> FittedSources:
+        M, P = theta_raw.shape
+        assert M == batch.M and P == batch.d + 2
+        theta_raw = theta_raw.contiguous()
+        n_pad = pad64(batch.n_max)
+        linv = torch.zeros(M, packed_tiles(batch.n_max), 1024, dtype=torch.float64, device=self.device)
+        alpha = torch.zeros(M, n_pad, dtype=torch.float64, device=self.device)
+        theta = torch.empty(M, P, dtype=torch.float64, device=self.device)
+        info = torch.empty(M, dtype=torch.int32, device=self.device)
+        ws = self._fit_ws(batch.n_max, batch.d)
+        jitter = None
+        for attempt in range(len(JITTER_LADDER) + 1):
+            self.lib.factorize(_ptr(batch.X), _ptr(batch.y), _ptr(batch.n_valid), _ptr(theta_raw), _ptr(jitter),
+                               _ptr(linv), _ptr(alpha), _ptr(theta), _ptr(info), _ptr(ws), ws.numel() * 8,
+                               M, batch.n_max, batch.d, spec, self._stream())
+            self.launches += 1
+            bad = info > 0
+            if attempt == len(JITTER_LADDER) or not bool(bad.any()):
+                break
+            # re-run everything with jitter on the failed tasks only (rare path)
+            jitter = torch.where(bad, torch.full((M,), JITTER_LADDER[attempt], dtype=torch.float64, device=self.device),
+                                 torch.zeros(M, dtype=torch.float64, device=self.device) if jitter is None else jitter)
+            jitter = jitter.contiguous()
+        return FittedSources(batch, theta_raw, theta, linv, alpha, info, spec)
+
+    # ---- K6-K9 fused --------------------------------------------------------------------- #
+    def predict_weighted(self, fs: FittedSources, w: torch.Tensor, Xc: torch.Tensor,
+                         out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        """mean[b] = sum_m w_m mu_m(x_b), var[b] = sum_m w_m^2 var_m(x_b) (raw-Y units)."""
+        b = fs.batch
+        Xc = Xc.to(torch.float64).contiguous()
+        B = Xc.shape[0]
+        w = w.to(torch.float64).contiguous()
+        if out is None:
+            mean = torch.empty(B, dtype=torch.float64, device=self.device)
+            var = torch.empty(B, dtype=torch.float64, device=self.device)
+        else:
+            mean, var = out
+        pws, need = self._pred_ws(b.M, b.n_max, b.d, B)
+        self.lib.predict_weighted(_ptr(b.X), _ptr(b.n_valid), _ptr(fs.theta), _ptr(fs.linv), _ptr(fs.alpha),
+                                  _ptr(b.ybar), _ptr(b.ystd), _ptr(w), _ptr(Xc), _ptr(mean), _ptr(var), _ptr(pws), need,
+                                  b.M, b.n_max, b.d, B, fs.spec.kernel, self._stream())
+        self.launches += 2 if need else 1
+        return mean, var
+
+    def predict_cross(self, fs: FittedSources, Xt: torch.Tensor):
+        """source_means [n_t, M] and source_covs [n_t, n_t, M] (reference model.py:278-289)."""
+        b = fs.batch
+        Xt = Xt.to(torch.float64).contiguous()
+        nt = Xt.shape[0]
+        means = torch.empty(nt, b.M, dtype=torch.float64, device=self.device)
+        covs = torch.empty(nt, nt, b.M, dtype=torch.float64, device=self.device)
+        self.lib.predict_cross(_ptr(b.X), _ptr(b.n_valid), _ptr(fs.theta), _ptr(fs.linv), _ptr(fs.alpha),
+                               _ptr(b.ybar), _ptr(b.ystd), _ptr(Xt), _ptr(means), _ptr(covs), b.M, b.n_max, b.d, nt,
+                               fs.spec.kernel, self._stream())
+        self.launches += 1
+        return means, covs
+
+
+_default_engine: Optional[Engine] = None
+
+
+def default_engine() -> Engine:
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine()
+    return _default_engine

@@ -1,0 +1,128 @@
+"""CPU logic-emulation of the CUDA kernel SOURCES (csrc/emu/cuda_emu.h) vs the oracle.
+
+Not a product path and not a fallback: the emulation library is only ever loaded here.
+It proves, in the GPU-less CI container, that the block algorithm (tile layouts, chunk
+schedules, padding, failure codes) of the very same .cuh files is right; the `-m gpu`
+tests repeat the comparisons on the real sm_100a build."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import scaml_oracle as O
+from scamlgp_b200._capi import HyperSpec, packed_tiles, pad64
+from tests.helpers import TOL_GRAD, TOL_LML, TOL_MEAN_VAR, grad_rel_err, lml_rel_err, make_problem, oracle_lml_grad, rel_err
+
+
+def P(a):
+    return None if a is None else a.ctypes.data
+
+
+def emu_lml_grad(lib, pb, jitter=None):
+    M, R, n, d = pb["M"], pb["R"], pb["n"], pb["d"]
+    X = np.ascontiguousarray(pb["X"].numpy())
+    y = np.ascontiguousarray(pb["yt"].numpy())
+    th = np.ascontiguousarray(pb["th"].numpy())
+    lml = np.full((M, R), -7.0)
+    grad = np.full((M, R, d + 2), -7.0)
+    info = np.full((M, R), -9, dtype=np.int32)
+    wsb = lib.fit_workspace_bytes(n, d)
+    ws = np.zeros(wsb // 8 + 8)
+    lib.lml_grad(P(X), P(y), P(pb["nv"]), P(th), P(jitter), None, P(lml), P(grad), P(info), P(ws), wsb, M, R, n, d,
+                 pb["cspec"])
+    return lml, grad, info
+
+
+@pytest.mark.parametrize("M,R,n,d,nv,kernel", [
+    (2, 2, 64, 6, None, 0),
+    (1, 2, 128, 3, None, 0),
+    (3, 1, 192, 6, [130, 1, 64], 0),   # ragged incl. a single-point task
+    (1, 1, 100, 2, None, 3),           # n not a multiple of the 64 grid, Matern-5/2
+    (1, 1, 64, 4, None, 1),
+    (1, 1, 64, 4, None, 2),
+])
+def test_emu_lml_grad_matches_oracle(emu_lib, M, R, n, d, nv, kernel):
+    pb = make_problem(M, R, n, d, seed=3, n_valid=nv, kernel=kernel)
+    lml, grad, info = emu_lml_grad(emu_lib, pb)
+    v, g = oracle_lml_grad(pb)
+    assert (info == 0).all()
+    assert lml_rel_err(lml, v) < TOL_LML
+    assert grad_rel_err(grad, g) < TOL_GRAD
+
+
+def test_emu_reports_non_psd_pivot_and_jitter_recovers(emu_lib):
+    # duplicated inputs + minimal noise + huge outputscale -> K_y numerically singular
+    pb = make_problem(1, 1, 64, 2, seed=1)
+    pb["X"][0, 32:] = pb["X"][0, :32]
+    pb["ospec"].noise_bounds = (1e-30, 1e-2)  # let the noise vanish against the outputscale
+    pb["cspec"].noise_bounds = (1e-30, 1e-2)
+    spec = pb["ospec"]
+    pb["th"][0, 0] = O.pack_theta(torch.full((2,), 50.0, dtype=torch.float64), 99.0, 1e-25, spec)
+    lml, grad, info = emu_lml_grad(emu_lib, pb)
+    assert info[0, 0] > 0 and np.isnan(lml[0, 0]) and np.isnan(grad[0, 0]).all()
+    # the oracle (torch.linalg.cholesky) fails on the same matrix
+    with pytest.raises(Exception):
+        O.lml_and_grad_autograd(pb["X"][0], pb["yt"][0], pb["th"][0, 0], spec)
+    jit = np.full((1, 1), 1e-6)
+    lml, grad, info = emu_lml_grad(emu_lib, pb, jitter=jit)
+    v, g = O.lml_and_grad_autograd(pb["X"][0], pb["yt"][0], pb["th"][0, 0], spec, jitter=1e-6)
+    assert info[0, 0] == 0 and np.isfinite(lml[0, 0])
+    assert abs(lml[0, 0] - float(v)) < 1e-6 * abs(float(v))  # cond ~ 1e8+: loose tolerance, see DESIGN.md
+
+
+def test_emu_factorize_and_weighted_prediction(emu_lib):
+    lib = emu_lib
+    M, n, d, B = 3, 128, 3, 70
+    pb = make_problem(M, 2, n, d, seed=5, n_valid=[128, 77, 5])
+    th = pb["th"][:, 1].contiguous()
+    X = np.ascontiguousarray(pb["X"].numpy())
+    y = np.ascontiguousarray(pb["yt"].numpy())
+    thn = np.ascontiguousarray(th.numpy())
+    linv = np.full((M, packed_tiles(n), 1024), np.nan)
+    alpha = np.full((M, pad64(n)), np.nan)
+    theta = np.zeros((M, d + 2))
+    info = np.full(M, -9, dtype=np.int32)
+    wsb = lib.fit_workspace_bytes(n, d)
+    ws = np.zeros(wsb // 8 + 8)
+    lib.factorize(P(X), P(y), P(pb["nv"]), P(thn), None, P(linv), P(alpha), P(theta), P(info), P(ws), wsb, M, n, d,
+                  pb["cspec"])
+    assert (info == 0).all()
+    states = [O.factorize(pb["X"][m, : pb["nv"][m]], pb["Y"][m, : pb["nv"][m]], th[m], pb["ospec"]) for m in range(M)]
+    for m in range(M):
+        nv = pb["nv"][m]
+        assert rel_err(alpha[m, :nv], states[m].alpha.numpy()) < 1e-9
+        assert (alpha[m, nv:] == 0).all()
+        ls, os_, nz = O.split_theta(th[m], pb["ospec"])
+        assert rel_err(theta[m], torch.cat([ls, os_.reshape(1), nz.reshape(1)]).numpy()) < 1e-14
+    g = torch.Generator().manual_seed(5)
+    Xc = torch.rand(B, d, dtype=torch.float64, generator=g)
+    w = torch.tensor([0.5, 0.0, 0.25], dtype=torch.float64)  # middle task pruned (w = 0)
+    mean, var = np.zeros(B), np.zeros(B)
+    pwb = lib.predict_workspace_bytes(M, n, d, B)
+    pws = np.zeros(pwb // 8 + 8)
+    Xcn, wn = np.ascontiguousarray(Xc.numpy()), w.numpy().copy()
+    lib.predict_weighted(P(X), P(pb["nv"]), P(theta), P(linv), P(alpha), P(pb["ybar"]), P(pb["ystd"]), P(wn), P(Xcn),
+                         P(mean), P(var), P(pws), pwb, M, n, d, B, 0)
+    om, ov = O.scaml_prior_predict(states, w, Xc)
+    assert rel_err(mean, om.numpy()) < TOL_MEAN_VAR
+    assert rel_err(var, ov.numpy()) < TOL_MEAN_VAR
+
+
+def test_emu_kernel_matrix(emu_lib):
+    M, n, d = 2, 70, 3
+    pb = make_problem(M, 1, n, d, seed=2, n_valid=[70, 33])
+    theta = np.zeros((M, d + 2))
+    for m in range(M):
+        ls, os_, nz = O.split_theta(pb["th"][m, 0], pb["ospec"])
+        theta[m] = torch.cat([ls, os_.reshape(1), nz.reshape(1)]).numpy()
+    X = np.ascontiguousarray(pb["X"].numpy())
+    for kernel in (0, 3):
+        K = np.full((M, n, n), np.nan)
+        emu_lib.kernel_matrix(P(X), P(pb["nv"]), P(theta), P(K), M, n, d, kernel)
+        for m in range(M):
+            nv = pb["nv"][m]
+            t = torch.tensor(theta[m])
+            ref = O.kernel_matrix(pb["X"][m, :nv], pb["X"][m, :nv], t[:d], t[d], kernel) + t[d + 1] * torch.eye(nv, dtype=torch.float64)
+            assert np.abs(K[m, :nv, :nv] - ref.numpy()).max() < 1e-14
+            if nv < n:
+                assert np.array_equal(K[m, nv:, nv:], np.eye(n - nv))
+                assert (K[m, :nv, nv:] == 0).all() and (K[m, nv:, :nv] == 0).all()
