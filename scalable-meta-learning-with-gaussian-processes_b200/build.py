@@ -54,6 +54,19 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     return CUDA_LIB
 
 
+def build_prof(force: bool = False) -> str:
+    """Diagnostics variant with per-phase clock64 counters (-DSCAML_PROF); not used by the product path."""
+    out = os.path.join(CSRC, "libscaml_b200_prof.so")
+    deps = [os.path.join(CSRC, s) for s in CUDA_SOURCES + HEADERS]
+    if not force and _newer(out, deps):
+        return out
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-DSCAML_PROF", "-o", out] + CUDA_SOURCES
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc (prof build) failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 def build_emu(force: bool = False) -> str:
     deps = [os.path.join(CSRC, s) for s in ["scaml_capi.cu"] + HEADERS]
     if not force and _newer(EMU_LIB, deps):

@@ -13,6 +13,7 @@ namespace {
 constexpr size_t kMaxSmem = 227 * 1024;
 
 int g_num_sms = 0;
+long long* g_prof = nullptr;  // SCAML_PROF builds: per-CTA phase cycle counters
 int num_sms() {
 #ifdef SCAML_EMU
   return 2;
@@ -70,6 +71,7 @@ int run_fit(scaml::FitParams p, void* workspace, size_t workspace_bytes, void* s
   if (workspace_bytes < scaml_fit_workspace_bytes(p.n_max, p.d)) return SCAML_E_WORKSPACE;
   p.workspace = static_cast<double*>(workspace);
   p.ws_stride = scaml::fit_ws_doubles_host(p.n_pad);
+  p.prof = g_prof;
   int grid = fit_grid_slots(p.n_pad, p.d);
   const long long E = (long long)p.M * p.R;
   if (E < grid) grid = (int)E;
@@ -79,6 +81,11 @@ int run_fit(scaml::FitParams p, void* workspace, size_t workspace_bytes, void* s
 }  // namespace
 
 extern "C" {
+
+#ifdef SCAML_PROF
+// diagnostics build only: device buffer of [grid][16] long long phase counters
+void scaml_debug_set_prof(void* buf) { g_prof = static_cast<long long*>(buf); }
+#endif
 
 const char* scaml_version(void) {
 #ifdef SCAML_EMU

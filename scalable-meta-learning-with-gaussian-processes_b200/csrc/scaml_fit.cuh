@@ -22,6 +22,21 @@
 
 namespace scaml {
 
+#ifdef SCAML_PROF
+#define PROF_MARK(ph)                                   \
+  do {                                                  \
+    if (threadIdx.x == 0) {                             \
+      const long long now_ = clock64();                 \
+      profsm[ph] += now_ - prof_last;                   \
+      prof_last = now_;                                 \
+    }                                                   \
+  } while (0)
+#else
+#define PROF_MARK(ph) \
+  do {                \
+  } while (0)
+#endif
+
 enum { kModeLmlGrad = 0, kModeFactorize = 1 };
 
 struct FitParams {
@@ -39,6 +54,7 @@ struct FitParams {
   double* theta_out;        // factorize: [M][P] constrained
   double* workspace;
   long long ws_stride;  // doubles per CTA slot
+  long long* prof;      // SCAML_PROF builds only: [grid][16] cycle counters per phase
   int M, R, n_max, n_pad, d, mode;
   scaml_hyper_spec spec;
 };
@@ -512,6 +528,12 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
   int* flag = reinterpret_cast<int*>(scal + 8);
 
   double* W = p.workspace + (size_t)blockIdx.x * p.ws_stride;
+#ifdef SCAML_PROF
+  __shared__ long long profsm[16];
+  long long prof_last = clock64();
+  if (threadIdx.x < 16) profsm[threadIdx.x] = 0;
+  __syncthreads();
+#endif
   const int E = p.M * p.R;
   const scaml_hyper_spec& sp = p.spec;
 
@@ -570,6 +592,7 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
     double acc[4][4], acc2[4][4];
     double pig = 0.0;
     bool failed = false;
+    PROF_MARK(0);
 
     // ================= phase B: blocked left-looking Cholesky ========================== //
     for (int J = 0; J < NS && !failed; ++J) {
@@ -578,16 +601,19 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
         acc_zero(acc);
         CholSrc src{W, J, J};
         gemm_global<CholSrc, false>(acc, src, stage, t, skip_tile, pig, nullptr);
+        PROF_MARK(1);
         if (!skip_tile) {
           assemble_tile<KIND>(acc, J, J, t, xs, n_pad_max, d, nv, os, diag_add);
           store_tile_C(stage + (t.rb * 2 + t.cb) * kTile, acc, t, 1.0);
         }
         __syncthreads();
+        PROF_MARK(2);
         double* wd00 = W + (size_t)(tri(2 * J) + 2 * J) * kTile;
         double* wd10 = W + (size_t)(tri(2 * J + 1) + 2 * J) * kTile;
         double* wd11 = W + (size_t)(tri(2 * J + 1) + 2 * J + 1) * kTile;
         diag_factor(stage, dinvc, dinvc_g + (size_t)J * 3 * kTile, wd00, wd10, wd11, &scal[0], flag, J * kSB, t);
         __syncthreads();
+        PROF_MARK(3);
         if (*flag != 0) {
           failed = true;
           break;
@@ -598,15 +624,18 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
         acc_zero(acc);
         CholSrc src{W, I, J};
         gemm_global<CholSrc, false>(acc, src, stage, t, false, pig, nullptr);
+        PROF_MARK(1);
         assemble_tile<KIND>(acc, I, J, t, xs, n_pad_max, d, nv, os, diag_add);
         store_tile_C(stage + (t.rb * 2 + t.cb) * kTile, acc, t, 1.0);
         __syncthreads();
+        PROF_MARK(2);
         // L(I,J) = C * D^-T : A chunk kb2 = C tiles (rb,kb2); B[kk][c] = D^-1(c,kk)
         const double* const TA[2][2] = {{stage, stage + 2 * kTile}, {stage + kTile, stage + 3 * kTile}};
         acc_zero(acc2);
         gemm_smem(acc2, TA, TB, t);
         store_tile_C(W + (size_t)(tri(2 * I + t.rb) + 2 * J + t.cb) * kTile, acc2, t, 1.0);
         __syncthreads();
+        PROF_MARK(4);
       }
       __syncthreads();
     }
@@ -636,6 +665,7 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
           gemm_global<TrtriSrc, true>(acc, src, stage, t, false, pig, zv);
         else
           gemm_global<TrtriSrc, false>(acc, src, stage, t, false, pig, nullptr);
+        PROF_MARK(5);
         store_tile_R(stage + (t.rb * 2 + t.cb) * kTile, acc, t, 1.0);  // S, R-layout tiles (kb2, cb)
         __syncthreads();
         const double* const TBs[2][2] = {{stage, stage + kTile}, {stage + 2 * kTile, stage + 3 * kTile}};
@@ -646,6 +676,7 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
           store_tile_C(p.linv_out + ((size_t)m * tri(n_pad_max / kBS) + tri(2 * I + t.rb) + 2 * J + t.cb) * kTile, acc2,
                        t, -1.0);
         __syncthreads();
+        PROF_MARK(6);
       }
       // z_I = D_I^-1 (y_I - sum_{K<I} L(I,K) z_K)
       red[t.tid] = pig;
@@ -656,6 +687,7 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
       }
       __syncthreads();
       dinv_matvec(zv + I * kSB, dinvc, av, red, t);
+      PROF_MARK(7);
       if (p.mode == kModeFactorize) {
         // diagonal tiles of L^-1 in C-layout = dinvc
         double* lo = p.linv_out + (size_t)m * tri(n_pad_max / kBS) * kTile;
@@ -693,17 +725,21 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
         pig = 0.0;
         LauumSrc src{W, I, I, NS};
         gemm_global<LauumSrc, true>(acc, src, stage, t, skip_tile, pig, zv);
+        PROF_MARK(8);
         red[t.tid] = pig;
         __syncthreads();
         if (t.tid < 64) av[I * kSB + t.tid] = ((red[t.tid] + red[64 + t.tid]) + red[128 + t.tid]) + red[192 + t.tid];
         __syncthreads();
         if (!skip_tile) grad_tile<KIND>(acc, I, I, t, xs, av, n_pad_max, d, nv, gsm);
+        PROF_MARK(9);
       }
       for (int J = 0; J < I; ++J) {
         acc_zero(acc);
         LauumSrc src{W, I, J, NS};
         gemm_global<LauumSrc, false>(acc, src, stage, t, false, pig, nullptr);
+        PROF_MARK(8);
         grad_tile<KIND>(acc, I, J, t, xs, av, n_pad_max, d, nv, gsm);
+        PROF_MARK(9);
       }
     }
     __syncthreads();
@@ -735,7 +771,12 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
         p.info[e] = 0;
       }
     }
+    PROF_MARK(10);
   }
+#ifdef SCAML_PROF
+  __syncthreads();
+  if (p.prof != nullptr && threadIdx.x < 16) p.prof[(size_t)blockIdx.x * 16 + threadIdx.x] = profsm[threadIdx.x];
+#endif
 }
 
 }  // namespace scaml
