@@ -30,9 +30,10 @@ int num_sms() {
 
 inline int pad64(int n) { return ((n + 63) / 64) * 64; }
 
-// persistent grid of the fit kernels: CTAs per SM allowed by shared memory (<= 2)
+// persistent grid of the fit kernels: CTAs per SM allowed by shared memory (<= 3)
 int fit_ctas_per_sm(int n_pad, int d) {
   const size_t s = scaml::fit_smem_bytes(n_pad, d) + 1024;
+  if (3 * s <= 228 * 1024) return 3;
   return (2 * s <= 228 * 1024) ? 2 : 1;
 }
 int fit_grid_slots(int n_pad, int d) { return num_sms() * fit_ctas_per_sm(n_pad, d); }
@@ -41,13 +42,13 @@ template <int KIND>
 int launch_fit(const scaml::FitParams& p, int grid, size_t smem, void* stream) {
 #ifdef SCAML_EMU
   (void)stream;
-  cuemu::launch(dim3(grid), dim3(scaml::kThreads), smem, scaml::scaml_fit_kernel<KIND>, p);
+  cuemu::launch(dim3(grid), dim3(scaml::kFitThreads), smem, scaml::scaml_fit_kernel<KIND>, p);
   return 0;
 #else
   cudaError_t err = cudaFuncSetAttribute(scaml::scaml_fit_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
   if (err != cudaSuccess) return (int)err;
-  scaml::scaml_fit_kernel<KIND><<<grid, scaml::kThreads, smem, (cudaStream_t)stream>>>(p);
+  scaml::scaml_fit_kernel<KIND><<<grid, scaml::kFitThreads, smem, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 #endif
 }
@@ -70,7 +71,7 @@ int run_fit(scaml::FitParams p, void* workspace, size_t workspace_bytes, void* s
   if (smem > kMaxSmem) return SCAML_E_SMEM;
   if (workspace_bytes < scaml_fit_workspace_bytes(p.n_max, p.d)) return SCAML_E_WORKSPACE;
   p.workspace = static_cast<double*>(workspace);
-  p.ws_stride = scaml::fit_ws_doubles_host(p.n_pad);
+  p.ws_stride = scaml::fit_ws_doubles_host(p.n_pad, p.d);
   p.prof = g_prof;
   int grid = fit_grid_slots(p.n_pad, p.d);
   const long long E = (long long)p.M * p.R;
@@ -108,7 +109,7 @@ int scaml_fit_limits(int* n_max_limit, int* d_limit) {
 size_t scaml_fit_workspace_bytes(int n_max, int d) {
   if (n_max <= 0 || d <= 0) return 0;
   const int n_pad = pad64(n_max);
-  return (size_t)fit_grid_slots(n_pad, d) * (size_t)scaml::fit_ws_doubles_host(n_pad) * sizeof(double);
+  return (size_t)fit_grid_slots(n_pad, d) * (size_t)scaml::fit_ws_doubles_host(n_pad, d) * sizeof(double);
 }
 
 int scaml_lml_grad(const double* X, const double* y, const int32_t* n_valid, const double* theta_raw,

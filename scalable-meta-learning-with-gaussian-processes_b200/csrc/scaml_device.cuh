@@ -27,7 +27,6 @@ namespace scaml {
 constexpr int kBS = 32;           // tile edge
 constexpr int kTile = kBS * kBS;  // doubles per tile (8 KB)
 constexpr int kSB = 64;           // super-tile edge (2x2 tiles)
-constexpr int kThreads = 256;
 constexpr int kMaxP = 34;  // d <= 32
 constexpr double kLog2Pi = 1.8378770664093454835606594728112;
 
@@ -53,12 +52,6 @@ SCAML_DEVICE void cp_async_wait() {
 #ifndef SCAML_EMU
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 #endif
-}
-
-// One 32x32 tile (8 KB, contiguous) global -> shared by the whole CTA: 2 x 16 B per thread.
-SCAML_DEVICE void tile_async(double* sdst, const double* gsrc, int tid) {
-  cp_async16(sdst + 2 * tid, gsrc + 2 * tid);
-  cp_async16(sdst + 2 * (tid + kThreads), gsrc + 2 * (tid + kThreads));
 }
 
 SCAML_DEVICE double warp_sum(double v) {

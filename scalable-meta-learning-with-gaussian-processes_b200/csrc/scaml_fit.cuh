@@ -1,19 +1,21 @@
 // Fused per-task GP fit kernel: kernel-matrix assembly -> blocked Cholesky -> triangular
 // inverse -> (K^-1 contraction with dK/dtheta) for M tasks x R hyper-parameter rows.
 //
-// One persistent CTA (256 threads) owns one evaluation at a time.  The n_pad x n_pad
-// lower triangle lives in a per-CTA global workspace of 32x32 fp64 tiles (8 KB each,
-// L2-resident: 2 CTAs/SM x 148 SMs x ~0.4 MB < 126 MB), and every n^3-class step is the
-// same register-tiled micro-kernel
-//        acc[4][4] += A[kk][r] * B[kk][c]        (64x64 super-tile, 32-deep chunks)
-// fed by cp.async double-buffered 8 KB tiles.  Tile layouts are chosen per phase so that
+// One persistent 128-thread CTA owns one evaluation at a time; three CTAs share an SM
+// (<= 75 KB shared memory, 128 registers/thread) so that the latency-bound steps of one
+// evaluation (the pivot chain of the diagonal tiles, exp-heavy epilogues) overlap with
+// the DFMA-bound tile products of the other two.  The n_pad x n_pad lower triangle lives
+// in a per-CTA global workspace of 32x32 fp64 tiles (8 KB each, mostly L2 resident), and
+// every n^3-class step is the same register-tiled micro-kernel
+//        acc[8][4] += A[kk][r] * B[kk][c]        (64x64 super-tile, 16-deep sub-chunks)
+// fed by cp.async double-buffered half tiles.  Tile layouts are chosen per phase so that
 // the contraction index is always the slow index of the staged tile (no transposes):
 //   L   (Cholesky factor, off-diagonal super-tiles)  column-major tiles ("C")
 //   L^-1                                              row-major tiles    ("R")
-//   D^-1 (inverse of a 64x64 diagonal super-tile)     both (C copy in `dinvc` area)
-// K and K^-1 never reach memory: K is recomputed from the (length-scaled) inputs held in
-// shared memory in the epilogues, K^-1 super-tiles are contracted with dK/dtheta straight
-// out of the accumulator registers.
+//   D^-1 (inverse of a 64x64 diagonal super-tile)     R in the workspace, C in shared memory
+// K and K^-1 never reach memory: K is recomputed from the length-scaled inputs in the
+// epilogues, K^-1 super-tiles are contracted with dK/dtheta straight out of the
+// accumulator registers.
 //
 // Math: SURVEY.md appendix A.3-A.5; reference call sites scamlgp/utils.py:171-177,190-192
 // (objective), scamlgp/model.py:25-70 (constraints/priors), model.py:176-188 (task loop).
@@ -23,13 +25,13 @@
 namespace scaml {
 
 #ifdef SCAML_PROF
-#define PROF_MARK(ph)                                   \
-  do {                                                  \
-    if (threadIdx.x == 0) {                             \
-      const long long now_ = clock64();                 \
-      profsm[ph] += now_ - prof_last;                   \
-      prof_last = now_;                                 \
-    }                                                   \
+#define PROF_MARK(ph)                   \
+  do {                                  \
+    if (threadIdx.x == 0) {             \
+      const long long now_ = clock64(); \
+      profsm[ph] += now_ - prof_last;   \
+      prof_last = now_;                 \
+    }                                   \
   } while (0)
 #else
 #define PROF_MARK(ph) \
@@ -38,6 +40,9 @@ namespace scaml {
 #endif
 
 enum { kModeLmlGrad = 0, kModeFactorize = 1 };
+constexpr int kFitThreads = 128;
+constexpr int kFitWarps = kFitThreads / 32;
+constexpr int kHalf = kTile / 2;  // doubles in a 16-deep half tile
 
 struct FitParams {
   const double* X;          // [M][n_max][d]
@@ -59,60 +64,60 @@ struct FitParams {
   scaml_hyper_spec spec;
 };
 
-// workspace slot: [ lower tiles: tri(NB) x 1024 ][ dinvC: NS x 3 x 1024 ]
-SCAML_DEVICE long long fit_ws_doubles(int n_pad) {
-  const int NB = n_pad / kBS, NS = n_pad / kSB;
-  return (long long)tri(NB) * kTile + (long long)NS * 3 * kTile;
+// workspace slot: [ lower tiles: tri(NB) x 1024 ][ scaled inputs xs: d x n_pad ]
+inline long long fit_ws_doubles_host(int n_pad, int d) {
+  const int NB = n_pad / kBS;
+  long long v = (long long)((NB * (NB + 1)) / 2) * kTile + (long long)d * n_pad;
+  return (v + 15) & ~15LL;
 }
-inline long long fit_ws_doubles_host(int n_pad) {
-  const int NB = n_pad / kBS, NS = n_pad / kSB;
-  return (long long)((NB * (NB + 1)) / 2) * kTile + (long long)NS * 3 * kTile;
-}
-// shared memory (doubles): stage 8192 | dinvc 3072 | xs d*n_pad | y,z,alpha 3*n_pad |
-//                          red 256 | gsm 8*kMaxP | par 4*kMaxP+8 | flags
+// shared memory (doubles): stage 4096 | dinvc 3072 | y,z,alpha 3*n_pad | red 128 |
+//                          gsm 4*kMaxP | par 4*kMaxP+8 | flags 2
 inline size_t fit_smem_bytes(int n_pad, int d) {
-  return sizeof(double) * (size_t)(8192 + 3072 + (size_t)d * n_pad + 3 * (size_t)n_pad + 256 + 8 * kMaxP +
-                                   4 * kMaxP + 8 + 2);
+  (void)d;
+  return sizeof(double) * (size_t)(4096 + 3072 + 3 * (size_t)n_pad + 128 + kFitWarps * kMaxP + 4 * kMaxP + 8 + 2);
 }
 
-// per-thread coordinates inside a 64x64 super-tile (16x16 threads of 4x4 elements)
-struct Thr {
+// per-thread coordinates inside a 64x64 super-tile: warp (rb, cb) owns one 32x32 tile pair,
+// lane owns an 8x4 patch
+struct FThr {
   int tid, warp, lane;
   int rb, cb;    // tile row / col inside the super-tile (0/1) -- warp-uniform
-  int rin, cin;  // first row / col inside the tile (multiples of 4)
+  int rin, cin;  // first row (multiple of 8) / col (multiple of 4) inside the tile
 };
-SCAML_DEVICE Thr make_thr() {
-  Thr t;
+SCAML_DEVICE FThr make_fthr() {
+  FThr t;
   t.tid = threadIdx.x;
   t.warp = t.tid >> 5;
   t.lane = t.tid & 31;
-  const int tyb = t.warp >> 2, txb = t.warp & 3;
-  t.rb = tyb;
-  t.cb = txb >> 1;
-  t.rin = 4 * (t.lane >> 2);
-  t.cin = 16 * (txb & 1) + 4 * (t.lane & 3);
+  t.rb = t.warp >> 1;
+  t.cb = t.warp & 1;
+  t.rin = 8 * (t.lane >> 3);
+  t.cin = 4 * (t.lane & 7);
   return t;
 }
 
-SCAML_DEVICE void acc_zero(double (&acc)[4][4]) {
+SCAML_DEVICE void facc_zero(double (&acc)[8][4]) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 }
 
-// acc += A[kk][rin..rin+3] (x) B[kk][cin..cin+3] over one 32-deep chunk
-SCAML_DEVICE void mma_chunk(double (&acc)[4][4], const double* __restrict__ Ap, const double* __restrict__ Bp) {
-#pragma unroll 8
-  for (int kk = 0; kk < kBS; ++kk) {
+// acc += A[kk][rin..rin+7] (x) B[kk][cin..cin+3] over NK consecutive kk (row stride 32)
+template <int NK>
+SCAML_DEVICE void fmma(double (&acc)[8][4], const double* __restrict__ Ap, const double* __restrict__ Bp) {
+#pragma unroll 4
+  for (int kk = 0; kk < NK; ++kk) {
     const double2 a01 = *reinterpret_cast<const double2*>(Ap + kk * kBS);
     const double2 a23 = *reinterpret_cast<const double2*>(Ap + kk * kBS + 2);
+    const double2 a45 = *reinterpret_cast<const double2*>(Ap + kk * kBS + 4);
+    const double2 a67 = *reinterpret_cast<const double2*>(Ap + kk * kBS + 6);
     const double2 b01 = *reinterpret_cast<const double2*>(Bp + kk * kBS);
     const double2 b23 = *reinterpret_cast<const double2*>(Bp + kk * kBS + 2);
-    const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+    const double a[8] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a67.x, a67.y};
     const double b[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
   }
@@ -125,6 +130,7 @@ struct ChunkPtrs {
   int zoff;  // first global row/col index covered by this chunk (piggy-backed GEMV)
 };
 SCAML_DEVICE const double* wtile(const double* W, int bi, int bj) { return W + (size_t)(tri(bi) + bj) * kTile; }
+SCAML_DEVICE double* wtile_w(double* W, int bi, int bj) { return W + (size_t)(tri(bi) + bj) * kTile; }
 
 // Cholesky update of super-tile (I,J): sum_{kb < 2J} L(I,kb) L(J,kb)^T  (C-layout tiles)
 struct CholSrc {
@@ -178,47 +184,55 @@ struct LauumSrc {
   }
 };
 
+// half tile (16 x 32 doubles = 4 KB, contiguous) global -> shared: 2 x 16 B per thread
+SCAML_DEVICE void half_async(double* sdst, const double* gsrc, int tid) {
+  cp_async16(sdst + 2 * tid, gsrc + 2 * tid);
+  cp_async16(sdst + 2 * (tid + kFitThreads), gsrc + 2 * (tid + kFitThreads));
+}
+
+// sub-chunk s = 2*ck + h: rows [16h, 16h+16) of the four tiles of chunk ck
 template <class Src>
-SCAML_DEVICE void stage_issue(const Src& src, int ck, double* st, int tid) {
-  const ChunkPtrs c = src.get(ck);
-  if (c.a[0]) tile_async(st, c.a[0], tid);
-  if (c.a[1]) tile_async(st + kTile, c.a[1], tid);
+SCAML_DEVICE void stage_issue(const Src& src, int s, double* st, int tid) {
+  const ChunkPtrs c = src.get(s >> 1);
+  const int off = (s & 1) * kHalf;
+  if (c.a[0]) half_async(st, c.a[0] + off, tid);
+  if (c.a[1]) half_async(st + kHalf, c.a[1] + off, tid);
   if (!src.same()) {
-    if (c.b[0]) tile_async(st + 2 * kTile, c.b[0], tid);
-    if (c.b[1]) tile_async(st + 3 * kTile, c.b[1], tid);
+    if (c.b[0]) half_async(st + 2 * kHalf, c.b[0] + off, tid);
+    if (c.b[1]) half_async(st + 3 * kHalf, c.b[1] + off, tid);
   }
   cp_async_commit();
 }
 
 // acc += sum over chunks; optional piggy-backed GEMV  pig[c] += sum_kk A[kk][c] * zv[zoff+kk]
-// (c = tid & 63 over the 64 A columns of the super-tile, kk-quarter = tid >> 6).
+// (c = tid & 63 over the 64 A columns of the super-tile, kk-half = tid >> 6).
 // On return every thread has passed a __syncthreads after its last read of `stage`.
 template <class Src, bool PIGGY>
-SCAML_DEVICE void gemm_global(double (&acc)[4][4], const Src& src, double* stage, const Thr& t, bool skip_tile,
+SCAML_DEVICE void gemm_global(double (&acc)[8][4], const Src& src, double* stage, const FThr& t, bool skip_tile,
                               double& pig, const double* zv) {
-  const int n = src.count();
+  const int n = 2 * src.count();
   if (n <= 0) return;
   stage_issue(src, 0, stage, t.tid);
-  for (int ck = 0; ck < n; ++ck) {
-    double* st = stage + (ck & 1) * 4 * kTile;
-    if (ck + 1 < n) {
-      stage_issue(src, ck + 1, stage + ((ck + 1) & 1) * 4 * kTile, t.tid);
+  for (int s = 0; s < n; ++s) {
+    double* st = stage + (s & 1) * 4 * kHalf;
+    if (s + 1 < n) {
+      stage_issue(src, s + 1, stage + ((s + 1) & 1) * 4 * kHalf, t.tid);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
     __syncthreads();
-    const ChunkPtrs c = src.get(ck);
+    const ChunkPtrs c = src.get(s >> 1);
     const double* As = st;
-    const double* Bs = src.same() ? st : st + 2 * kTile;
+    const double* Bs = src.same() ? st : st + 2 * kHalf;
     const bool bvalid = src.same() ? (c.a[t.cb] != nullptr) : (c.b[t.cb] != nullptr);
     if (!skip_tile && c.a[t.rb] != nullptr && bvalid)
-      mma_chunk(acc, As + t.rb * kTile + t.rin, Bs + t.cb * kTile + t.cin);
+      fmma<16>(acc, As + t.rb * kHalf + t.rin, Bs + t.cb * kHalf + t.cin);
     if (PIGGY) {
       const int col = t.tid & 63, q = t.tid >> 6;
       if (c.a[col >> 5] != nullptr) {
-        const double* ap = As + (col >> 5) * kTile + (col & 31) + q * 8 * kBS;
-        const double* zp = zv + c.zoff + q * 8;
+        const double* ap = As + (col >> 5) * kHalf + (col & 31) + q * 8 * kBS;
+        const double* zp = zv + c.zoff + (s & 1) * 16 + q * 8;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) pig = fma(ap[kk * kBS], zp[kk], pig);
       }
@@ -227,117 +241,147 @@ SCAML_DEVICE void gemm_global(double (&acc)[4][4], const Src& src, double* stage
   }
 }
 
-// product of shared-memory resident 64x64 operands given as 2 chunks x 2 tiles each
-SCAML_DEVICE void gemm_smem(double (&acc)[4][4], const double* const (&A)[2][2], const double* const (&B)[2][2],
-                            const Thr& t) {
+// product of shared-memory resident 64x64 operands given as 2 chunks x 2 full tiles each
+SCAML_DEVICE void gemm_smem(double (&acc)[8][4], const double* const (&A)[2][2], const double* const (&B)[2][2],
+                            const FThr& t) {
 #pragma unroll
   for (int ck = 0; ck < 2; ++ck) {
     const double* a = A[ck][t.rb];
     const double* b = B[ck][t.cb];
-    if (a != nullptr && b != nullptr) mma_chunk(acc, a + t.rin, b + t.cin);
+    if (a != nullptr && b != nullptr) fmma<32>(acc, a + t.rin, b + t.cin);
   }
 }
 
-// 4x4 register tile -> one 32x32 tile, column-major ("C") or row-major ("R")
-SCAML_DEVICE void store_tile_C(double* blk, const double (&acc)[4][4], const Thr& t, double scale) {
+// 8x4 register patch -> one 32x32 tile, column-major ("C") or row-major ("R")
+SCAML_DEVICE void store_tile_C(double* blk, const double (&acc)[8][4], const FThr& t, double scale) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     double* p = blk + (t.cin + j) * kBS + t.rin;
-    *reinterpret_cast<double2*>(p) = make_double2(scale * acc[0][j], scale * acc[1][j]);
-    *reinterpret_cast<double2*>(p + 2) = make_double2(scale * acc[2][j], scale * acc[3][j]);
+#pragma unroll
+    for (int i = 0; i < 8; i += 2)
+      *reinterpret_cast<double2*>(p + i) = make_double2(scale * acc[i][j], scale * acc[i + 1][j]);
   }
 }
-SCAML_DEVICE void store_tile_R(double* blk, const double (&acc)[4][4], const Thr& t, double scale) {
+SCAML_DEVICE void store_tile_R(double* blk, const double (&acc)[8][4], const FThr& t, double scale) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 8; ++i) {
     double* p = blk + (t.rin + i) * kBS + t.cin;
     *reinterpret_cast<double2*>(p) = make_double2(scale * acc[i][0], scale * acc[i][1]);
     *reinterpret_cast<double2*>(p + 2) = make_double2(scale * acc[i][2], scale * acc[i][3]);
   }
 }
 
+// scaled inputs of rows a0..a0+7 / b0..b0+3, dimension k, from the per-CTA global scratch
+SCAML_DEVICE void load_x8(double (&x)[8], const double* xr) {
+#pragma unroll
+  for (int i = 0; i < 8; i += 2) {
+    const double2 v = __ldcg(reinterpret_cast<const double2*>(xr + i));
+    x[i] = v.x;
+    x[i + 1] = v.y;
+  }
+}
+SCAML_DEVICE void load_x4(double (&x)[4], const double* xr) {
+  const double2 v0 = __ldcg(reinterpret_cast<const double2*>(xr));
+  const double2 v1 = __ldcg(reinterpret_cast<const double2*>(xr + 2));
+  x[0] = v0.x, x[1] = v0.y, x[2] = v1.x, x[3] = v1.y;
+}
+
 // ---- epilogue 1: acc <- K_y(I,J) - acc, K recomputed from the scaled inputs ----------- //
+// (two passes of 4 rows keep r2 at 32 registers next to the 64 accumulator registers)
 template <int KIND>
-SCAML_DEVICE void assemble_tile(double (&acc)[4][4], int I, int J, const Thr& t, const double* xs, int n_pad, int d,
+SCAML_DEVICE void assemble_tile(double (&acc)[8][4], int I, int J, const FThr& t, const double* xs, int n_pad, int d,
                                 int nv, double os, double diag_add) {
-  const int a0 = I * kSB + t.rb * kBS + t.rin;
   const int b0 = J * kSB + t.cb * kBS + t.cin;
-  double r2[4][4];
-  acc_zero(r2);
-  for (int k = 0; k < d; ++k) {
-    const double* xr = xs + k * n_pad;
-    const double2 xa01 = *reinterpret_cast<const double2*>(xr + a0);
-    const double2 xa23 = *reinterpret_cast<const double2*>(xr + a0 + 2);
-    const double2 xb01 = *reinterpret_cast<const double2*>(xr + b0);
-    const double2 xb23 = *reinterpret_cast<const double2*>(xr + b0 + 2);
-    const double xa[4] = {xa01.x, xa01.y, xa23.x, xa23.y};
-    const double xb[4] = {xb01.x, xb01.y, xb23.x, xb23.y};
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int a0 = I * kSB + t.rb * kBS + t.rin + 4 * h;
+    double r2[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r2[i][j] = 0.0;
+    for (int k = 0; k < d; ++k) {
+      double xa[4], xb[4];
+      load_x4(xa, xs + k * n_pad + a0);
+      load_x4(xb, xs + k * n_pad + b0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double df = xa[i] - xb[j];
+          r2[i][j] = fma(df, df, r2[i][j]);
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const double df = xa[i] - xb[j];
-        r2[i][j] = fma(df, df, r2[i][j]);
+        const int a = a0 + i, b = b0 + j;
+        double k = os * kappa_of<KIND>(r2[i][j]);
+        if (a == b) k += diag_add;
+        if (a >= nv || b >= nv) k = (a == b) ? 1.0 : 0.0;
+        acc[4 * h + i][j] = k - acc[4 * h + i][j];
       }
   }
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int a = a0 + i, b = b0 + j;
-      double k = os * kappa_of<KIND>(r2[i][j]);
-      if (a == b) k += diag_add;
-      if (a >= nv || b >= nv) k = (a == b) ? 1.0 : 0.0;
-      acc[i][j] = k - acc[i][j];
-    }
 }
 
 // ---- epilogue 2: contract the K^-1 super-tile in `acc` with dK/dtheta ----------------- //
-// accumulates into gsm[warp][0..d-1] (lengthscales), [d] (outputscale), [d+1] (trace W)
+// accumulates into gsm[warp][0..d-1] (lengthscales), [d] (outputscale), [d+1] (trace W).
+// acc is overwritten by t_ab = wgt * W_ab * kd_ab.
 template <int KIND>
-SCAML_DEVICE void grad_tile(const double (&acc)[4][4], int I, int J, const Thr& t, const double* xs,
-                            const double* av, int n_pad, int d, int nv, double* gsm) {
-  const int a0 = I * kSB + t.rb * kBS + t.rin;
+SCAML_DEVICE void grad_tile(double (&acc)[8][4], int I, int J, const FThr& t, const double* xs, const double* av,
+                            int n_pad, int d, int nv, double* gsm) {
+  const int a00 = I * kSB + t.rb * kBS + t.rin;
   const int b0 = J * kSB + t.cb * kBS + t.cin;
-  double r2[4][4];
-  acc_zero(r2);
-  for (int k = 0; k < d; ++k) {
-    const double* xr = xs + k * n_pad;
+  double accS = 0.0, accT = 0.0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int a0 = a00 + 4 * h;
+    double r2[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r2[i][j] = 0.0;
+    for (int k = 0; k < d; ++k) {
+      double xa[4], xb[4];
+      load_x4(xa, xs + k * n_pad + a0);
+      load_x4(xb, xs + k * n_pad + b0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double df = xa[i] - xb[j];
+          r2[i][j] = fma(df, df, r2[i][j]);
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const double df = xr[a0 + i] - xr[b0 + j];
-        r2[i][j] = fma(df, df, r2[i][j]);
+        const int a = a0 + i, b = b0 + j;
+        double kap, kd;
+        kappa_pair<KIND>(r2[i][j], kap, kd);
+        const bool use = (a >= b) && (a < nv) && (b < nv);
+        const double wgt = use ? ((a == b) ? 1.0 : 2.0) : 0.0;
+        const double Wab = av[a] * av[b] - acc[4 * h + i][j];
+        const double wk = wgt * Wab;
+        accS = fma(wk, kap, accS);
+        acc[4 * h + i][j] = wk * kd;
+        if (use && a == b) accT += Wab;
       }
   }
-  double accS = 0.0, accT = 0.0;
-  double tt[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int a = a0 + i, b = b0 + j;
-      double kap, kd;
-      kappa_pair<KIND>(r2[i][j], kap, kd);
-      const bool use = (a >= b) && (a < nv) && (b < nv);
-      const double wgt = use ? ((a == b) ? 1.0 : 2.0) : 0.0;
-      const double Wab = av[a] * av[b] - acc[i][j];
-      const double wk = wgt * Wab;
-      accS = fma(wk, kap, accS);
-      tt[i][j] = wk * kd;
-      if (use && a == b) accT += Wab;
-    }
   double* g = gsm + t.warp * kMaxP;
   for (int k = 0; k < d; ++k) {
-    const double* xr = xs + k * n_pad;
+    double xa[8], xb[4];
+    load_x8(xa, xs + k * n_pad + a00);
+    load_x4(xb, xs + k * n_pad + b0);
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const double df = xr[a0 + i] - xr[b0 + j];
-        s = fma(tt[i][j], df * df, s);
+        const double df = xa[i] - xb[j];
+        s = fma(acc[i][j], df * df, s);
       }
     s = warp_sum(s);
     if (t.lane == 0) g[k] += s;
@@ -352,10 +396,11 @@ SCAML_DEVICE void grad_tile(const double (&acc)[4][4], int I, int J, const Thr& 
 
 // ---- warp-level 32x32 Cholesky + triangular inverse (row r of the tile per lane) ------ //
 // Dsm: SPD tile, C-layout (lower part valid).  Lc: 1024-double scratch (receives L, C-layout).
-// P: 32x33 scratch.  Outputs: XC (C-layout inverse, shared), XRs (R-layout, shared, optional),
-// XRg (R-layout, global, optional).  Returns 0 or the 1-based failing pivot; adds
-// sum(log L_kk^2) over the tile to *logdet (lane 0).
-SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* P, double* XC, double* XRs, double* XRg,
+// Pz: 1024-double scratch (XOR-swizzled transpose buffer).  Outputs: XC (C-layout inverse,
+// shared), XRs (R-layout, shared, optional), XRg (R-layout, global, optional).  Returns 0 or the
+// 1-based failing pivot; adds sum_k log(d_kk) (= log det of the tile) to *logdet (lane 0).
+// XRs may alias Lc (L is dead once the inverse sweep has finished).
+SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* XC, double* XRs, double* XRg,
                              double* logdet, int lane) {
   double a[kBS];
 #pragma unroll
@@ -380,7 +425,6 @@ SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* P, double* X
 #pragma unroll
     for (int j = k + 1; j < kBS; ++j) a[j] = fma(-lrk, Lc[k * kBS + j], a[j]);
   }
-  // log det contribution: sum_k log(d_kk)   (= 2 sum log L_kk)
   double ld = log(mydiag);
   ld = warp_sum(ld);
   if (lane == 0) *logdet += ld;
@@ -395,16 +439,17 @@ SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* P, double* X
 #pragma unroll
     for (int k = 0; k < j; ++k) w[k] = fma(-Lc[k * kBS + j], w[j], w[k]);
   }
+  __syncwarp();  // all lanes are done reading Lc (XRs may alias it)
 #pragma unroll
   for (int c = 0; c < kBS; ++c) {
     XC[c * kBS + lane] = w[c];
-    P[lane * 33 + c] = w[c];
+    Pz[lane * kBS + (c ^ lane)] = w[c];
   }
   __syncwarp();
   if (XRs != nullptr || XRg != nullptr) {
 #pragma unroll 4
     for (int r = 0; r < kBS; ++r) {
-      const double v = P[r * 33 + lane];
+      const double v = Pz[r * kBS + (lane ^ r)];
       if (XRs) XRs[r * kBS + lane] = v;
       if (XRg) XRg[r * kBS + lane] = v;
     }
@@ -413,88 +458,112 @@ SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* P, double* X
   return fail;
 }
 
-// 32x32x32 product by the whole CTA: out(r,c) = sum_kk A[kk][r] * B[kk][c]; thread owns a 2x2 patch
-SCAML_DEVICE void small_gemm(double (&o)[2][2], const double* A, const double* B, int tid) {
-  const int r0 = 2 * (tid & 15), c0 = 2 * (tid >> 4);
-  o[0][0] = o[0][1] = o[1][0] = o[1][1] = 0.0;
+// 32x32x32 product by the whole CTA: out(r,c) = sum_kk A[kk][r] * B[kk][c]; thread owns a 2x4 patch
+SCAML_DEVICE void small_gemm(double (&o)[2][4], const double* A, const double* B, int tid) {
+  const int r0 = 2 * (tid & 15), c0 = 4 * (tid >> 4);
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.0;
 #pragma unroll 8
   for (int kk = 0; kk < kBS; ++kk) {
     const double2 a = *reinterpret_cast<const double2*>(A + kk * kBS + r0);
-    const double2 b = *reinterpret_cast<const double2*>(B + kk * kBS + c0);
-    o[0][0] = fma(a.x, b.x, o[0][0]);
-    o[0][1] = fma(a.x, b.y, o[0][1]);
-    o[1][0] = fma(a.y, b.x, o[1][0]);
-    o[1][1] = fma(a.y, b.y, o[1][1]);
+    const double2 b01 = *reinterpret_cast<const double2*>(B + kk * kBS + c0);
+    const double2 b23 = *reinterpret_cast<const double2*>(B + kk * kBS + c0 + 2);
+    const double av[2] = {a.x, a.y};
+    const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[i][j] = fma(av[i], bv[j], o[i][j]);
   }
 }
-SCAML_DEVICE void small_store_C(double* blk, const double (&o)[2][2], int tid, double scale) {
-  const int r0 = 2 * (tid & 15), c0 = 2 * (tid >> 4);
-  *reinterpret_cast<double2*>(blk + c0 * kBS + r0) = make_double2(scale * o[0][0], scale * o[1][0]);
-  *reinterpret_cast<double2*>(blk + (c0 + 1) * kBS + r0) = make_double2(scale * o[0][1], scale * o[1][1]);
+SCAML_DEVICE void small_store_C(double* blk, const double (&o)[2][4], int tid, double scale) {
+  const int r0 = 2 * (tid & 15), c0 = 4 * (tid >> 4);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<double2*>(blk + (c0 + j) * kBS + r0) = make_double2(scale * o[0][j], scale * o[1][j]);
 }
-SCAML_DEVICE void small_store_R(double* blk, const double (&o)[2][2], int tid, double scale) {
-  const int r0 = 2 * (tid & 15), c0 = 2 * (tid >> 4);
-  *reinterpret_cast<double2*>(blk + r0 * kBS + c0) = make_double2(scale * o[0][0], scale * o[0][1]);
-  *reinterpret_cast<double2*>(blk + (r0 + 1) * kBS + c0) = make_double2(scale * o[1][0], scale * o[1][1]);
+SCAML_DEVICE void small_store_R(double* blk, const double (&o)[2][4], int tid, double scale) {
+  const int r0 = 2 * (tid & 15), c0 = 4 * (tid >> 4);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    *reinterpret_cast<double2*>(blk + (r0 + i) * kBS + c0) = make_double2(scale * o[i][0], scale * o[i][1]);
+    *reinterpret_cast<double2*>(blk + (r0 + i) * kBS + c0 + 2) = make_double2(scale * o[i][2], scale * o[i][3]);
+  }
 }
 
 // ---- factorise + invert the 64x64 diagonal super-tile held in `stage` ----------------- //
-// stage tiles (C-layout): [0]=D00  [1]=scratch (X00 R-layout)  [2]=D10  [3]=D11 ; stage[4096..] scratch.
-// Results: dinvc[0..2] = D^-1 tiles (0,0),(1,0),(1,1) C-layout (shared) + copy in `dinvc_g`;
+// stage tiles (C-layout): T0 = D00, T1 = free, T2 = D10, T3 = D11.   dinvc tiles V0..V2.
+// Results: V0, V1, V2 = D^-1 tiles (0,0), (1,0), (1,1) in C-layout (shared);
 //          R-layout tiles of D^-1 written to the workspace diagonal (wd00, wd10, wd11).
-// *logdet (shared scalar) accumulates log det; *flag receives the failing pivot (1-based, tile local + base).
-SCAML_DEVICE void diag_factor(double* stage, double* dinvc, double* dinvc_g, double* wd00, double* wd10,
-                              double* wd11, double* logdet, int* flag, int pivot_base, const Thr& t) {
-  double* D00 = stage;
-  double* XR00 = stage + kTile;
-  double* D10 = stage + 2 * kTile;
-  double* D11 = stage + 3 * kTile;
-  double* P = stage + 4 * kTile;            // 32*33
-  double* T = stage + 4 * kTile + 2 * kTile;  // R-layout temp
-  double* Lc = stage + 4 * kTile + 3 * kTile;
+// *logdet (shared scalar) accumulates log det; *flag receives the failing pivot (1-based).
+SCAML_DEVICE void diag_factor(double* stage, double* dinvc, double* wd00, double* wd10, double* wd11, double* logdet,
+                              int* flag, int pivot_base, const FThr& t) {
+  double* T0 = stage;
+  double* T1 = stage + kTile;
+  double* T2 = stage + 2 * kTile;
+  double* T3 = stage + 3 * kTile;
+  double* V0 = dinvc;
+  double* V1 = dinvc + kTile;
+  double* V2 = dinvc + 2 * kTile;
   if (t.warp == 0) {
-    const int f = chol_inv_32(D00, Lc, P, dinvc, XR00, wd00, logdet, t.lane);
+    // L scratch = V1, transpose scratch = V2, X00: C-layout -> V0, R-layout -> T1 and workspace
+    const int f = chol_inv_32(T0, V1, V2, V0, T1, wd00, logdet, t.lane);
     if (f && t.lane == 0 && *flag == 0) *flag = pivot_base + f;
   }
   __syncthreads();
-  double o[2][2];
+  double o[2][4];
   // L10 = D10 * X00^T      (A = D10 C-layout, B[kk][c] = X00(c,kk) = C-layout X00)
-  small_gemm(o, D10, dinvc, t.tid);
+  small_gemm(o, T2, V0, t.tid);
   __syncthreads();
-  small_store_C(D10, o, t.tid, 1.0);  // D10 now holds L10 (C-layout)
+  small_store_C(T2, o, t.tid, 1.0);  // T2 now holds L10 (C-layout)
   __syncthreads();
-  // D11 -= L10 L10^T ;  T = L10 * X00  (B[kk][c] = X00(kk,c) = R-layout X00)
-  small_gemm(o, D10, D10, t.tid);
+  // D11 -= L10 L10^T ;  Tm = L10 * X00  (B[kk][c] = X00(kk,c) = R-layout X00 in T1) -> V1 (R-layout)
+  small_gemm(o, T2, T2, t.tid);
   {
-    const int r0 = 2 * (t.tid & 15), c0 = 2 * (t.tid >> 4);
-    D11[c0 * kBS + r0] -= o[0][0];
-    D11[c0 * kBS + r0 + 1] -= o[1][0];
-    D11[(c0 + 1) * kBS + r0] -= o[0][1];
-    D11[(c0 + 1) * kBS + r0 + 1] -= o[1][1];
+    const int r0 = 2 * (t.tid & 15), c0 = 4 * (t.tid >> 4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      T3[(c0 + j) * kBS + r0] -= o[0][j];
+      T3[(c0 + j) * kBS + r0 + 1] -= o[1][j];
+    }
   }
-  small_gemm(o, D10, XR00, t.tid);
-  small_store_R(T, o, t.tid, 1.0);
+  small_gemm(o, T2, T1, t.tid);
+  small_store_R(V1, o, t.tid, 1.0);
   __syncthreads();
   if (t.warp == 0) {
-    const int f = chol_inv_32(D11, Lc, P, dinvc + 2 * kTile, nullptr, wd11, logdet, t.lane);
+    // L scratch = T1 (X00 R-layout is dead), transpose scratch = T0 (D00 is dead)
+    const int f = chol_inv_32(T3, T1, T0, V2, nullptr, wd11, logdet, t.lane);
     if (f && t.lane == 0 && *flag == 0) *flag = pivot_base + kBS + f;
   }
   __syncthreads();
-  // X10 = -X11 * T        (A[kk][r] = X11(r,kk) = C-layout X11, B = T R-layout)
-  small_gemm(o, dinvc + 2 * kTile, T, t.tid);
-  small_store_C(dinvc + kTile, o, t.tid, -1.0);
+  // X10 = -X11 * Tm        (A[kk][r] = X11(r,kk) = C-layout X11 in V2, B = Tm R-layout in V1)
+  small_gemm(o, V2, V1, t.tid);
+  __syncthreads();  // every thread has consumed Tm before V1 is overwritten
+  small_store_C(V1, o, t.tid, -1.0);
   small_store_R(wd10, o, t.tid, -1.0);
   __syncthreads();
-  // C-layout copy of D^-1 for the triangular-inverse phase
-  for (int i = t.tid; i < 3 * kTile / 2; i += kThreads)
-    reinterpret_cast<double2*>(dinvc_g)[i] = reinterpret_cast<const double2*>(dinvc)[i];
+}
+
+// D^-1 of diagonal super-tile I (R-layout tiles in the workspace) -> dinvc (C-layout, shared)
+SCAML_DEVICE void load_dinvc(double* dinvc, const double* W, int I, int tid) {
+  const double* src[3] = {wtile(W, 2 * I, 2 * I), wtile(W, 2 * I + 1, 2 * I), wtile(W, 2 * I + 1, 2 * I + 1)};
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+#pragma unroll 4
+    for (int idx = tid; idx < kTile; idx += kFitThreads) {
+      const int c = idx >> 5, r = idx & 31;
+      dinvc[b * kTile + c * kBS + r] = __ldcg(src[b] + r * kBS + c);
+    }
+  }
 }
 
 // out[r] = sum_kk D^-1(r,kk) v[kk] over a 64x64 lower-triangular D^-1 held as dinvc (C-layout tiles)
-SCAML_DEVICE void dinv_matvec(double* out, const double* dinvc, const double* v, double* red, const Thr& t) {
-  const int r = t.tid & 63, q = t.tid >> 6;  // q: 16-wide kk quarter
+SCAML_DEVICE void dinv_matvec(double* out, const double* dinvc, const double* v, double* red, const FThr& t) {
+  const int r = t.tid & 63, q = t.tid >> 6;  // q: 32-wide kk half
   double s = 0.0;
-  for (int kk = q * 16; kk < q * 16 + 16; ++kk) {
+  for (int kk = q * 32; kk < q * 32 + 32; ++kk) {
     if (kk > r) break;
     const int rb_ = r >> 5, kb_ = kk >> 5;
     const double* blk = dinvc + ((rb_ == 0) ? 0 : (kb_ == 0 ? kTile : 2 * kTile));
@@ -502,24 +571,23 @@ SCAML_DEVICE void dinv_matvec(double* out, const double* dinvc, const double* v,
   }
   red[q * 64 + r] = s;
   __syncthreads();
-  if (t.tid < 64) out[t.tid] = ((red[t.tid] + red[64 + t.tid]) + red[128 + t.tid]) + red[192 + t.tid];
+  if (t.tid < 64) out[t.tid] = red[t.tid] + red[64 + t.tid];
   __syncthreads();
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams p) {
+__global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitParams p) {
   SCAML_DYN_SMEM(double, sm);
-  const Thr t = make_thr();
+  const FThr t = make_fthr();
   const int d = p.d, P = p.d + 2, n_pad_max = p.n_pad;
-  double* stage = sm;
-  double* dinvc = stage + 8192;
-  double* xs = dinvc + 3072;
-  double* yv = xs + (size_t)d * n_pad_max;
+  double* stage = sm;            // 4096: 2 stages x 4 half tiles | 4 full tiles (C_in / S / diag)
+  double* dinvc = stage + 4096;  // 3 tiles
+  double* yv = dinvc + 3072;
   double* zv = yv + n_pad_max;
   double* av = zv + n_pad_max;
-  double* red = av + n_pad_max;
-  double* gsm = red + 256;
-  double* par = gsm + 8 * kMaxP;  // th | lp | dlp | chain | scalars
+  double* red = av + n_pad_max;  // 128
+  double* gsm = red + 128;       // kFitWarps * kMaxP
+  double* par = gsm + kFitWarps * kMaxP;
   double* th = par;
   double* lp = par + kMaxP;
   double* dlp = par + 2 * kMaxP;
@@ -528,6 +596,7 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
   int* flag = reinterpret_cast<int*>(scal + 8);
 
   double* W = p.workspace + (size_t)blockIdx.x * p.ws_stride;
+  double* xs = W + (size_t)tri(n_pad_max / kBS) * kTile;  // [d][n_pad_max] scaled inputs (global scratch)
 #ifdef SCAML_PROF
   __shared__ long long profsm[16];
   long long prof_last = clock64();
@@ -546,7 +615,6 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
       continue;
     }
     const int NS = (nv + kSB - 1) / kSB, n_pad = NS * kSB;
-    double* dinvc_g = W + (size_t)tri(2 * NS) * kTile;  // NS x 3 tiles
     __syncthreads();  // previous evaluation fully retired before shared state is rewritten
 
     // ---- parameters: Interval transform, priors, chain rule -------------------------- //
@@ -573,23 +641,23 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
       scal[0] = 0.0;
       *flag = 0;
     }
-    for (int i = t.tid; i < 8 * kMaxP; i += kThreads) gsm[i] = 0.0;
+    for (int i = t.tid; i < kFitWarps * kMaxP; i += kFitThreads) gsm[i] = 0.0;
     __syncthreads();
     const double os = th[d];
     const double diag_add = th[d + 1] + (p.jitter ? p.jitter[e] : 0.0);
-    // scaled inputs, dimension-major; targets
+    // scaled inputs (dimension-major, global scratch), targets
     {
       const double* Xm = p.X + (size_t)m * p.n_max * d;
-      for (int i = t.tid; i < n_pad * d; i += kThreads) {
-        const int a = i / d, k = i - a * d;
+      for (int i = t.tid; i < n_pad * d; i += kFitThreads) {
+        const int k = i / n_pad, a = i - k * n_pad;
         xs[k * n_pad_max + a] = (a < nv) ? Xm[(size_t)a * d + k] / th[k] : 0.0;
       }
       const double* ym = p.y + (size_t)m * p.n_max;
-      for (int i = t.tid; i < n_pad; i += kThreads) yv[i] = (i < nv) ? ym[i] : 0.0;
+      for (int i = t.tid; i < n_pad; i += kFitThreads) yv[i] = (i < nv) ? ym[i] : 0.0;
     }
     __syncthreads();
 
-    double acc[4][4], acc2[4][4];
+    double acc[8][4];
     double pig = 0.0;
     bool failed = false;
     PROF_MARK(0);
@@ -598,7 +666,7 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
     for (int J = 0; J < NS && !failed; ++J) {
       {  // diagonal super-tile
         const bool skip_tile = (t.rb == 0 && t.cb == 1);
-        acc_zero(acc);
+        facc_zero(acc);
         CholSrc src{W, J, J};
         gemm_global<CholSrc, false>(acc, src, stage, t, skip_tile, pig, nullptr);
         PROF_MARK(1);
@@ -608,11 +676,8 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
         }
         __syncthreads();
         PROF_MARK(2);
-        double* wd00 = W + (size_t)(tri(2 * J) + 2 * J) * kTile;
-        double* wd10 = W + (size_t)(tri(2 * J + 1) + 2 * J) * kTile;
-        double* wd11 = W + (size_t)(tri(2 * J + 1) + 2 * J + 1) * kTile;
-        diag_factor(stage, dinvc, dinvc_g + (size_t)J * 3 * kTile, wd00, wd10, wd11, &scal[0], flag, J * kSB, t);
-        __syncthreads();
+        diag_factor(stage, dinvc, wtile_w(W, 2 * J, 2 * J), wtile_w(W, 2 * J + 1, 2 * J),
+                    wtile_w(W, 2 * J + 1, 2 * J + 1), &scal[0], flag, J * kSB, t);
         PROF_MARK(3);
         if (*flag != 0) {
           failed = true;
@@ -621,7 +686,7 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
       }
       const double* const TB[2][2] = {{dinvc, dinvc + kTile}, {nullptr, dinvc + 2 * kTile}};
       for (int I = J + 1; I < NS; ++I) {
-        acc_zero(acc);
+        facc_zero(acc);
         CholSrc src{W, I, J};
         gemm_global<CholSrc, false>(acc, src, stage, t, false, pig, nullptr);
         PROF_MARK(1);
@@ -631,13 +696,12 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
         PROF_MARK(2);
         // L(I,J) = C * D^-T : A chunk kb2 = C tiles (rb,kb2); B[kk][c] = D^-1(c,kk)
         const double* const TA[2][2] = {{stage, stage + 2 * kTile}, {stage + kTile, stage + 3 * kTile}};
-        acc_zero(acc2);
-        gemm_smem(acc2, TA, TB, t);
-        store_tile_C(W + (size_t)(tri(2 * I + t.rb) + 2 * J + t.cb) * kTile, acc2, t, 1.0);
+        facc_zero(acc);
+        gemm_smem(acc, TA, TB, t);
+        store_tile_C(wtile_w(W, 2 * I + t.rb, 2 * J + t.cb), acc, t, 1.0);
         __syncthreads();
         PROF_MARK(4);
       }
-      __syncthreads();
     }
     if (failed) {
       if (t.tid == 0) {
@@ -649,17 +713,14 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
     }
 
     // ================= phase C: triangular inverse (row-wise), z = L^-1 y ============== //
-    // row 0: D^-1_0 must be re-staged (dinvc holds the last diagonal super-tile)
     for (int I = 0; I < NS; ++I) {
       __syncthreads();
-      for (int i = t.tid; i < 3 * kTile / 2; i += kThreads)
-        reinterpret_cast<double2*>(dinvc)[i] =
-            __ldcg(reinterpret_cast<const double2*>(dinvc_g + (size_t)I * 3 * kTile) + i);
+      load_dinvc(dinvc, W, I, t.tid);
       __syncthreads();
       pig = 0.0;
       const double* const TA[2][2] = {{dinvc, dinvc + kTile}, {nullptr, dinvc + 2 * kTile}};
       for (int J = 0; J < I; ++J) {
-        acc_zero(acc);
+        facc_zero(acc);
         TrtriSrc src{W, I, J};
         if (J == 0)
           gemm_global<TrtriSrc, true>(acc, src, stage, t, false, pig, zv);
@@ -669,11 +730,11 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
         store_tile_R(stage + (t.rb * 2 + t.cb) * kTile, acc, t, 1.0);  // S, R-layout tiles (kb2, cb)
         __syncthreads();
         const double* const TBs[2][2] = {{stage, stage + kTile}, {stage + 2 * kTile, stage + 3 * kTile}};
-        acc_zero(acc2);
-        gemm_smem(acc2, TA, TBs, t);
-        store_tile_R(W + (size_t)(tri(2 * I + t.rb) + 2 * J + t.cb) * kTile, acc2, t, -1.0);
+        facc_zero(acc);
+        gemm_smem(acc, TA, TBs, t);
+        store_tile_R(wtile_w(W, 2 * I + t.rb, 2 * J + t.cb), acc, t, -1.0);
         if (p.mode == kModeFactorize)
-          store_tile_C(p.linv_out + ((size_t)m * tri(n_pad_max / kBS) + tri(2 * I + t.rb) + 2 * J + t.cb) * kTile, acc2,
+          store_tile_C(p.linv_out + ((size_t)m * tri(n_pad_max / kBS) + tri(2 * I + t.rb) + 2 * J + t.cb) * kTile, acc,
                        t, -1.0);
         __syncthreads();
         PROF_MARK(6);
@@ -681,17 +742,14 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
       // z_I = D_I^-1 (y_I - sum_{K<I} L(I,K) z_K)
       red[t.tid] = pig;
       __syncthreads();
-      if (t.tid < 64) {
-        const double u = ((red[t.tid] + red[64 + t.tid]) + red[128 + t.tid]) + red[192 + t.tid];
-        av[t.tid] = yv[I * kSB + t.tid] - u;  // av used as scratch here
-      }
+      if (t.tid < 64) av[t.tid] = yv[I * kSB + t.tid] - (red[t.tid] + red[64 + t.tid]);  // av: scratch here
       __syncthreads();
       dinv_matvec(zv + I * kSB, dinvc, av, red, t);
       PROF_MARK(7);
       if (p.mode == kModeFactorize) {
         // diagonal tiles of L^-1 in C-layout = dinvc
         double* lo = p.linv_out + (size_t)m * tri(n_pad_max / kBS) * kTile;
-        for (int i = t.tid; i < kTile; i += kThreads) {
+        for (int i = t.tid; i < kTile; i += kFitThreads) {
           lo[(size_t)(tri(2 * I) + 2 * I) * kTile + i] = dinvc[i];
           lo[(size_t)(tri(2 * I + 1) + 2 * I) * kTile + i] = dinvc[kTile + i];
           lo[(size_t)(tri(2 * I + 1) + 2 * I + 1) * kTile + i] = dinvc[2 * kTile + i];
@@ -701,9 +759,9 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
     __syncthreads();
 
     if (p.mode == kModeFactorize) {
-      // alpha = L^-T z : warp w owns 32-columns bj = w, w+8, ... ; lane = column inside the tile
+      // alpha = L^-T z : warp w owns 32-columns bj = w, w+4, ... ; lane = column inside the tile
       const int NB = 2 * NS;
-      for (int bj = t.warp; bj < NB; bj += 8) {
+      for (int bj = t.warp; bj < NB; bj += kFitWarps) {
         double s = 0.0;
         for (int bi = bj; bi < NB; ++bi) {
           const double* blk = wtile(W, bi, bj);  // R-layout: (r,c) at r*32+c
@@ -712,7 +770,7 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
         }
         p.alpha_out[(size_t)m * n_pad_max + bj * kBS + t.lane] = s;
       }
-      for (int i = n_pad + t.tid; i < n_pad_max; i += kThreads) p.alpha_out[(size_t)m * n_pad_max + i] = 0.0;
+      for (int i = n_pad + t.tid; i < n_pad_max; i += kFitThreads) p.alpha_out[(size_t)m * n_pad_max + i] = 0.0;
       if (t.tid == 0) p.info[e] = 0;
       continue;
     }
@@ -721,20 +779,20 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
     for (int I = 0; I < NS; ++I) {
       {
         const bool skip_tile = (t.rb == 0 && t.cb == 1);
-        acc_zero(acc);
+        facc_zero(acc);
         pig = 0.0;
         LauumSrc src{W, I, I, NS};
         gemm_global<LauumSrc, true>(acc, src, stage, t, skip_tile, pig, zv);
         PROF_MARK(8);
         red[t.tid] = pig;
         __syncthreads();
-        if (t.tid < 64) av[I * kSB + t.tid] = ((red[t.tid] + red[64 + t.tid]) + red[128 + t.tid]) + red[192 + t.tid];
+        if (t.tid < 64) av[I * kSB + t.tid] = red[t.tid] + red[64 + t.tid];
         __syncthreads();
         if (!skip_tile) grad_tile<KIND>(acc, I, I, t, xs, av, n_pad_max, d, nv, gsm);
         PROF_MARK(9);
       }
       for (int J = 0; J < I; ++J) {
-        acc_zero(acc);
+        facc_zero(acc);
         LauumSrc src{W, I, J, NS};
         gemm_global<LauumSrc, false>(acc, src, stage, t, false, pig, nullptr);
         PROF_MARK(8);
@@ -746,25 +804,19 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit_kernel(const FitParams 
     // quad = z^T z (fixed order), final scalars
     {
       double q = 0.0;
-      for (int i = t.tid; i < n_pad; i += kThreads) q = fma(zv[i], zv[i], q);
+      for (int i = t.tid; i < n_pad; i += kFitThreads) q = fma(zv[i], zv[i], q);
       q = warp_sum(q);
       if (t.lane == 0) red[t.warp] = q;
       __syncthreads();
       if (t.tid < P) {
         double g = 0.0;
-        for (int w = 0; w < 8; ++w) g += gsm[w * kMaxP + (t.tid < d ? t.tid : t.tid)];
-        double gt;
-        if (t.tid < d)
-          gt = 0.5 * os * g / th[t.tid];
-        else if (t.tid == d)
-          gt = 0.5 * g;
-        else
-          gt = 0.5 * g;
+        for (int w = 0; w < kFitWarps; ++w) g += gsm[w * kMaxP + t.tid];
+        const double gt = (t.tid < d) ? 0.5 * os * g / th[t.tid] : 0.5 * g;
         p.grad[(size_t)e * P + t.tid] = (gt + dlp[t.tid]) * chain[t.tid] / (double)nv;
       }
       if (t.tid == 0) {
         double quad = 0.0;
-        for (int w = 0; w < 8; ++w) quad += red[w];
+        for (int w = 0; w < kFitWarps; ++w) quad += red[w];
         double prior = 0.0;
         for (int k = 0; k < P; ++k) prior += lp[k];
         p.lml[e] = (-0.5 * (quad + scal[0] + (double)nv * kLog2Pi) + prior) / (double)nv;

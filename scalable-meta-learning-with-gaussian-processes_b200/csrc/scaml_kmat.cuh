@@ -7,7 +7,7 @@
 // scamlgp/utils.py:175-177; kernels scamlgp/model.py:44-70.
 #pragma once
 #include "scaml_device.cuh"
-#include "scaml_fit.cuh"
+#include "scaml_tile256.cuh"
 
 namespace scaml {
 
@@ -21,7 +21,7 @@ struct KmatParams {
 };
 
 template <int KIND>
-__global__ void __launch_bounds__(kThreads) scaml_kmat_kernel(const KmatParams p) {
+__global__ void __launch_bounds__(256) scaml_kmat_kernel(const KmatParams p) {
   SCAML_DYN_SMEM(double, sm);
   const Thr t = make_thr();
   const int d = p.d, P = d + 2;
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(kThreads) scaml_kmat_kernel(const KmatParams p
     const double* th = p.theta + (size_t)m * P;
     const double* Xm = p.X + (size_t)m * p.n_max * d;
     __syncthreads();
-    for (int i = t.tid; i < kSB * d; i += kThreads) {
+    for (int i = t.tid; i < kSB * d; i += 256) {
       const int r = i / d, k = i - r * d;
       const int ga = ti * kSB + r, gb = tj * kSB + r;
       const double il = 1.0 / th[k];
@@ -107,10 +107,10 @@ template <int KIND>
 int launch_kmat_k(const KmatParams& p, int grid, size_t smem, void* stream) {
 #ifdef SCAML_EMU
   (void)stream;
-  cuemu::launch(dim3(grid), dim3(kThreads), smem, scaml_kmat_kernel<KIND>, p);
+  cuemu::launch(dim3(grid), dim3(256), smem, scaml_kmat_kernel<KIND>, p);
   return 0;
 #else
-  scaml_kmat_kernel<KIND><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+  scaml_kmat_kernel<KIND><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 #endif
 }

@@ -8,7 +8,7 @@
 // Reference: _compute_target_prior, scamlgp/model.py:108-135; posterior A.7 of SURVEY.md.
 #pragma once
 #include "scaml_device.cuh"
-#include "scaml_fit.cuh"
+#include "scaml_tile256.cuh"
 
 namespace scaml {
 
@@ -49,7 +49,7 @@ inline size_t predict_workspace_bytes(int M, int n_pad, int d, int B, int num_sm
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(kThreads, 1) scaml_predict_kernel(const PredParams p) {
+__global__ void __launch_bounds__(256, 1) scaml_predict_kernel(const PredParams p) {
   SCAML_DYN_SMEM(double, sm);
   const Thr t = make_thr();
   const int d = p.d, P = d + 2, n_pad = p.n_pad;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kThreads, 1) scaml_predict_kernel(const PredPa
     const int b0 = ct * kTB;
     const int m_lo = spx * mper, m_hi = (m_lo + mper < p.M) ? m_lo + mper : p.M;
     __syncthreads();
-    for (int i = t.tid; i < kTB * d; i += kThreads) {
+    for (int i = t.tid; i < kTB * d; i += 256) {
       const int c = i / d, k = i - c * d;
       xcr[k * kTB + c] = (b0 + c < p.B) ? p.Xc[(size_t)(b0 + c) * d + k] : 0.0;
     }
@@ -85,12 +85,12 @@ __global__ void __launch_bounds__(kThreads, 1) scaml_predict_kernel(const PredPa
       __syncthreads();
       {
         const double* Xm = p.X + (size_t)m * p.n_max * d;
-        for (int i = t.tid; i < npt * d; i += kThreads) {
+        for (int i = t.tid; i < npt * d; i += 256) {
           const int a = i / d, k = i - a * d;
           xst[k * n_pad + a] = (a < nv) ? Xm[(size_t)a * d + k] / th[k] : 0.0;
         }
-        for (int i = t.tid; i < npt; i += kThreads) alp[i] = p.alpha[(size_t)m * n_pad + i];
-        for (int i = t.tid; i < kTB * d; i += kThreads) {
+        for (int i = t.tid; i < npt; i += 256) alp[i] = p.alpha[(size_t)m * n_pad + i];
+        for (int i = t.tid; i < kTB * d; i += 256) {
           const int k = i / kTB;
           xcs[i] = xcr[i] / th[k];
         }
@@ -123,16 +123,16 @@ __global__ void __launch_bounds__(kThreads, 1) scaml_predict_kernel(const PredPa
         // chunk ck: A tiles (2I+rb, ck) (null above the diagonal), B = kst tiles (ck, cb)
         {
           const double* a0 = Lm + (size_t)(tri(2 * I) + 0) * kTile;
-          tile_async(ast, a0, t.tid);
-          tile_async(ast + kTile, Lm + (size_t)(tri(2 * I + 1) + 0) * kTile, t.tid);
+          tile_async256(ast, a0, t.tid);
+          tile_async256(ast + kTile, Lm + (size_t)(tri(2 * I + 1) + 0) * kTile, t.tid);
           cp_async_commit();
         }
         for (int ck = 0; ck < n; ++ck) {
           double* st = ast + (ck & 1) * 2 * kTile;
           if (ck + 1 < n) {
             double* sn = ast + ((ck + 1) & 1) * 2 * kTile;
-            if (ck + 1 <= 2 * I) tile_async(sn, Lm + (size_t)(tri(2 * I) + ck + 1) * kTile, t.tid);
-            tile_async(sn + kTile, Lm + (size_t)(tri(2 * I + 1) + ck + 1) * kTile, t.tid);
+            if (ck + 1 <= 2 * I) tile_async256(sn, Lm + (size_t)(tri(2 * I) + ck + 1) * kTile, t.tid);
+            tile_async256(sn + kTile, Lm + (size_t)(tri(2 * I + 1) + ck + 1) * kTile, t.tid);
             cp_async_commit();
             cp_async_wait<1>();
           } else {
@@ -193,13 +193,13 @@ template <int KIND>
 int launch_predict_k(const PredParams& p, int grid, size_t smem, void* stream) {
 #ifdef SCAML_EMU
   (void)stream;
-  cuemu::launch(dim3(grid), dim3(kThreads), smem, scaml_predict_kernel<KIND>, p);
+  cuemu::launch(dim3(grid), dim3(256), smem, scaml_predict_kernel<KIND>, p);
   return 0;
 #else
   cudaError_t err =
       cudaFuncSetAttribute(scaml_predict_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return (int)err;
-  scaml_predict_kernel<KIND><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+  scaml_predict_kernel<KIND><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 #endif
 }
