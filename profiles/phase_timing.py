@@ -22,7 +22,7 @@ def main():
     import ctypes as C
 
     eng = Engine(torch.device("cuda:0"), lib=lib)
-    prof = torch.zeros(148 * 2 * 16, dtype=torch.int64, device="cuda")
+    prof = torch.zeros(148 * 4 * 16, dtype=torch.int64, device="cuda")
     lib.lib.scaml_debug_set_prof.argtypes = [C.c_void_p]
     lib.lib.scaml_debug_set_prof(prof.data_ptr())
     X, Y = O.synthetic_tasks(M, n, d, seed=0)
@@ -38,7 +38,7 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     p = prof.view(-1, 16).cpu().double()
-    grid = min(M * R, 296)
+    grid = min(M * R, 444)
     p = p[:grid]
     evals_per_cta = M * R / grid
     tot = p.sum(1).mean().item()

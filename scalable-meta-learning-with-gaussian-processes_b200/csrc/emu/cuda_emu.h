@@ -81,6 +81,25 @@ inline T shfl(T v, int src) {
   return r;
 }
 
+// mma.sync.m8n8k4.f64 with the PTX fragment layout (see scaml_device.cuh)
+inline void dmma884(double (&d)[2], double a, double b) {
+  BlockCtx* c = ctx();
+  const int w = tIdx().x >> 5, l = tIdx().x & 31;
+  double ab[2] = {a, b};
+  std::memcpy(c->slot[w][l], ab, 16);
+  warp_sync();
+  const int g = l >> 2, t = l & 3;
+  for (int k = 0; k < 4; ++k) {
+    double ak[2], b0[2], b1[2];
+    std::memcpy(ak, c->slot[w][g * 4 + k], 16);
+    std::memcpy(b0, c->slot[w][(2 * t) * 4 + k], 16);
+    std::memcpy(b1, c->slot[w][(2 * t + 1) * 4 + k], 16);
+    d[0] = std::fma(ak[0], b0[1], d[0]);
+    d[1] = std::fma(ak[0], b1[1], d[1]);
+  }
+  warp_sync();
+}
+
 template <class F, class... A>
 void launch(dim3 grid, dim3 block, size_t smem_bytes, F kernel, A... args) {
   gDim() = grid;

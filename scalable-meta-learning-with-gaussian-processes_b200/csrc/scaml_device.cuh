@@ -54,6 +54,19 @@ SCAML_DEVICE void cp_async_wait() {
 #endif
 }
 
+// FP64 tensor-core MMA (DMMA): D(8x8) += A(8x4) * B(4x8).  Fragments (PTX ISA, mma.m8n8k4 .f64):
+//   a    = A[lane>>2][lane&3]        b = B[lane&3][lane>>2]
+//   d[e] = D[lane>>2][2*(lane&3)+e]
+SCAML_DEVICE void dmma884(double (&d)[2], double a, double b) {
+#ifdef SCAML_EMU
+  cuemu::dmma884(d, a, b);
+#else
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d[0]), "+d"(d[1])
+               : "d"(a), "d"(b));
+#endif
+}
+
 SCAML_DEVICE double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -2,14 +2,21 @@
 // inverse -> (K^-1 contraction with dK/dtheta) for M tasks x R hyper-parameter rows.
 //
 // One persistent 128-thread CTA owns one evaluation at a time; three CTAs share an SM
-// (<= 75 KB shared memory, 128 registers/thread) so that the latency-bound steps of one
-// evaluation (the pivot chain of the diagonal tiles, exp-heavy epilogues) overlap with
-// the DFMA-bound tile products of the other two.  The n_pad x n_pad lower triangle lives
-// in a per-CTA global workspace of 32x32 fp64 tiles (8 KB each, mostly L2 resident), and
-// every n^3-class step is the same register-tiled micro-kernel
-//        acc[8][4] += A[kk][r] * B[kk][c]        (64x64 super-tile, 16-deep sub-chunks)
-// fed by cp.async double-buffered half tiles.  Tile layouts are chosen per phase so that
-// the contraction index is always the slow index of the staged tile (no transposes):
+// (<= 75 KB shared memory) so that the latency-bound steps of one evaluation (the pivot
+// chain of the diagonal tiles, exp-heavy epilogues) overlap with the tile products of the
+// other two.  The n_pad x n_pad lower triangle lives in a per-CTA global workspace of
+// dense 32x32 fp64 tiles (8 KB each, mostly L2 resident).  Every n^3-class step is the
+// same micro-kernel: a warp owns a 32x32 output tile of the 64x64 super-tile and issues
+// FP64 tensor-core MMAs (mma.sync m8n8k4 -> SASS DMMA),
+//        C(8x8) += A[kk][r] (8x4) * B[kk][c] (4x8)
+// on operands staged by cp.async (double-buffered 16-deep half tiles) into shared memory
+// with a padded row stride of 36 doubles, which makes the DMMA fragment loads
+// bank-conflict free.  Plain DFMA register tiles are bound by shared-memory return
+// bandwidth (128 B/clk/SM) at any affordable tile size -- measured 38 % FP64-pipe
+// utilisation (profiles/r1_v1_*) -- because every lane re-reads broadcast operands;
+// DMMA fragments are distributed across the warp and need 4x fewer bytes per MAC.
+// Tile layouts are chosen per phase so that the contraction index is always the slow
+// index of the staged tile (no transposes):
 //   L   (Cholesky factor, off-diagonal super-tiles)  column-major tiles ("C")
 //   L^-1                                              row-major tiles    ("R")
 //   D^-1 (inverse of a 64x64 diagonal super-tile)     R in the workspace, C in shared memory
@@ -42,7 +49,11 @@ namespace scaml {
 enum { kModeLmlGrad = 0, kModeFactorize = 1 };
 constexpr int kFitThreads = 128;
 constexpr int kFitWarps = kFitThreads / 32;
-constexpr int kHalf = kTile / 2;  // doubles in a 16-deep half tile
+constexpr int kLd = 36;              // shared-memory row stride of a staged tile (doubles)
+constexpr int kTileS = kBS * kLd;    // padded tile in shared memory (1152 doubles)
+constexpr int kHalfS = 16 * kLd;     // padded 16-deep half tile (576 doubles)
+constexpr int kHalfG = kTile / 2;    // dense half tile in global memory (512 doubles)
+constexpr int kStage = 8 * kHalfS;   // 2 stages x 4 half tiles == 4 full padded tiles (4608)
 
 struct FitParams {
   const double* X;          // [M][n_max][d]
@@ -70,19 +81,20 @@ inline long long fit_ws_doubles_host(int n_pad, int d) {
   long long v = (long long)((NB * (NB + 1)) / 2) * kTile + (long long)d * n_pad;
   return (v + 15) & ~15LL;
 }
-// shared memory (doubles): stage 4096 | dinvc 3072 | y,z,alpha 3*n_pad | red 128 |
+// shared memory (doubles): stage 4608 | dinvc 3456 | y,z,alpha 3*n_pad | red 128 |
 //                          gsm 4*kMaxP | par 4*kMaxP+8 | flags 2
 inline size_t fit_smem_bytes(int n_pad, int d) {
   (void)d;
-  return sizeof(double) * (size_t)(4096 + 3072 + 3 * (size_t)n_pad + 128 + kFitWarps * kMaxP + 4 * kMaxP + 8 + 2);
+  return sizeof(double) *
+         (size_t)(kStage + 3 * kTileS + 3 * (size_t)n_pad + 128 + kFitWarps * kMaxP + 4 * kMaxP + 8 + 2);
 }
 
-// per-thread coordinates inside a 64x64 super-tile: warp (rb, cb) owns one 32x32 tile pair,
-// lane owns an 8x4 patch
+// per-thread coordinates: warp (rb, cb) owns one 32x32 tile of the 64x64 super-tile as a 4x4
+// grid of 8x8 DMMA tiles; lane (g, t4) owns element rows 8i+g, cols 8j+2*t4+{0,1}.
 struct FThr {
   int tid, warp, lane;
-  int rb, cb;    // tile row / col inside the super-tile (0/1) -- warp-uniform
-  int rin, cin;  // first row (multiple of 8) / col (multiple of 4) inside the tile
+  int rb, cb;  // tile row / col inside the super-tile (0/1) -- warp-uniform
+  int g, t4;   // lane >> 2, lane & 3
 };
 SCAML_DEVICE FThr make_fthr() {
   FThr t;
@@ -91,35 +103,37 @@ SCAML_DEVICE FThr make_fthr() {
   t.lane = t.tid & 31;
   t.rb = t.warp >> 1;
   t.cb = t.warp & 1;
-  t.rin = 8 * (t.lane >> 3);
-  t.cin = 4 * (t.lane & 7);
+  t.g = t.lane >> 2;
+  t.t4 = t.lane & 3;
   return t;
 }
 
-SCAML_DEVICE void facc_zero(double (&acc)[8][4]) {
+typedef double Acc[4][4][2];
+
+SCAML_DEVICE void facc_zero(Acc& acc) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 }
 
-// acc += A[kk][rin..rin+7] (x) B[kk][cin..cin+3] over NK consecutive kk (row stride 32)
-template <int NK>
-SCAML_DEVICE void fmma(double (&acc)[8][4], const double* __restrict__ Ap, const double* __restrict__ Bp) {
-#pragma unroll 4
-  for (int kk = 0; kk < NK; ++kk) {
-    const double2 a01 = *reinterpret_cast<const double2*>(Ap + kk * kBS);
-    const double2 a23 = *reinterpret_cast<const double2*>(Ap + kk * kBS + 2);
-    const double2 a45 = *reinterpret_cast<const double2*>(Ap + kk * kBS + 4);
-    const double2 a67 = *reinterpret_cast<const double2*>(Ap + kk * kBS + 6);
-    const double2 b01 = *reinterpret_cast<const double2*>(Bp + kk * kBS);
-    const double2 b23 = *reinterpret_cast<const double2*>(Bp + kk * kBS + 2);
-    const double a[8] = {a01.x, a01.y, a23.x, a23.y, a45.x, a45.y, a67.x, a67.y};
-    const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+// acc(32x32) += A[kk][r] * B[kk][c] over NK4 steps of 4 kk.  Ap/Bp: padded k-major tiles (row
+// stride kLd) at their first kk row.  LOWER: skip the strictly-upper 8x8 tiles (diagonal tiles).
+template <int NK4, bool LOWER>
+SCAML_DEVICE void fmma(Acc& acc, const double* __restrict__ Ap, const double* __restrict__ Bp, const FThr& t) {
+  const double* ar = Ap + t.t4 * kLd + t.g;
+  const double* br = Bp + t.t4 * kLd + t.g;
+#pragma unroll 2
+  for (int s = 0; s < NK4; ++s) {
+    const double a[4] = {ar[0], ar[8], ar[16], ar[24]};
+    const double b[4] = {br[0], br[8], br[16], br[24]};
+    ar += 4 * kLd;
+    br += 4 * kLd;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+      for (int j = 0; j < 4; ++j)
+        if (!LOWER || j <= i) dmma884(acc[i][j], a[i], b[j]);
   }
 }
 
@@ -184,39 +198,43 @@ struct LauumSrc {
   }
 };
 
-// half tile (16 x 32 doubles = 4 KB, contiguous) global -> shared: 2 x 16 B per thread
+// dense half tile (16 x 32 doubles, contiguous 4 KB) global -> padded shared rows: 2 x 16 B / thread
 SCAML_DEVICE void half_async(double* sdst, const double* gsrc, int tid) {
-  cp_async16(sdst + 2 * tid, gsrc + 2 * tid);
-  cp_async16(sdst + 2 * (tid + kFitThreads), gsrc + 2 * (tid + kFitThreads));
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int c2 = tid + u * kFitThreads;
+    const int row = c2 >> 4, j = c2 & 15;
+    cp_async16(sdst + row * kLd + 2 * j, gsrc + row * kBS + 2 * j);
+  }
 }
 
 // sub-chunk s = 2*ck + h: rows [16h, 16h+16) of the four tiles of chunk ck
 template <class Src>
 SCAML_DEVICE void stage_issue(const Src& src, int s, double* st, int tid) {
   const ChunkPtrs c = src.get(s >> 1);
-  const int off = (s & 1) * kHalf;
+  const int off = (s & 1) * kHalfG;
   if (c.a[0]) half_async(st, c.a[0] + off, tid);
-  if (c.a[1]) half_async(st + kHalf, c.a[1] + off, tid);
+  if (c.a[1]) half_async(st + kHalfS, c.a[1] + off, tid);
   if (!src.same()) {
-    if (c.b[0]) half_async(st + 2 * kHalf, c.b[0] + off, tid);
-    if (c.b[1]) half_async(st + 3 * kHalf, c.b[1] + off, tid);
+    if (c.b[0]) half_async(st + 2 * kHalfS, c.b[0] + off, tid);
+    if (c.b[1]) half_async(st + 3 * kHalfS, c.b[1] + off, tid);
   }
   cp_async_commit();
 }
 
 // acc += sum over chunks; optional piggy-backed GEMV  pig[c] += sum_kk A[kk][c] * zv[zoff+kk]
 // (c = tid & 63 over the 64 A columns of the super-tile, kk-half = tid >> 6).
+// DIAG: super-tile on the diagonal -> warp (0,1) idles, warps (0,0),(1,1) compute lower 8x8 tiles only.
 // On return every thread has passed a __syncthreads after its last read of `stage`.
-template <class Src, bool PIGGY>
-SCAML_DEVICE void gemm_global(double (&acc)[8][4], const Src& src, double* stage, const FThr& t, bool skip_tile,
-                              double& pig, const double* zv) {
+template <class Src, bool PIGGY, bool DIAG>
+SCAML_DEVICE void gemm_global(Acc& acc, const Src& src, double* stage, const FThr& t, double& pig, const double* zv) {
   const int n = 2 * src.count();
   if (n <= 0) return;
   stage_issue(src, 0, stage, t.tid);
   for (int s = 0; s < n; ++s) {
-    double* st = stage + (s & 1) * 4 * kHalf;
+    double* st = stage + (s & 1) * 4 * kHalfS;
     if (s + 1 < n) {
-      stage_issue(src, s + 1, stage + ((s + 1) & 1) * 4 * kHalf, t.tid);
+      stage_issue(src, s + 1, stage + ((s + 1) & 1) * 4 * kHalfS, t.tid);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
@@ -224,104 +242,115 @@ SCAML_DEVICE void gemm_global(double (&acc)[8][4], const Src& src, double* stage
     __syncthreads();
     const ChunkPtrs c = src.get(s >> 1);
     const double* As = st;
-    const double* Bs = src.same() ? st : st + 2 * kHalf;
+    const double* Bs = src.same() ? st : st + 2 * kHalfS;
     const bool bvalid = src.same() ? (c.a[t.cb] != nullptr) : (c.b[t.cb] != nullptr);
-    if (!skip_tile && c.a[t.rb] != nullptr && bvalid)
-      fmma<16>(acc, As + t.rb * kHalf + t.rin, Bs + t.cb * kHalf + t.cin);
+    if (c.a[t.rb] != nullptr && bvalid) {
+      if (DIAG) {
+        if (t.rb == t.cb)
+          fmma<4, true>(acc, As + t.rb * kHalfS, Bs + t.cb * kHalfS, t);
+        else if (t.rb > t.cb)
+          fmma<4, false>(acc, As + t.rb * kHalfS, Bs + t.cb * kHalfS, t);
+      } else {
+        fmma<4, false>(acc, As + t.rb * kHalfS, Bs + t.cb * kHalfS, t);
+      }
+    }
     if (PIGGY) {
       const int col = t.tid & 63, q = t.tid >> 6;
       if (c.a[col >> 5] != nullptr) {
-        const double* ap = As + (col >> 5) * kHalf + (col & 31) + q * 8 * kBS;
+        const double* ap = As + (col >> 5) * kHalfS + (col & 31) + q * 8 * kLd;
         const double* zp = zv + c.zoff + (s & 1) * 16 + q * 8;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) pig = fma(ap[kk * kBS], zp[kk], pig);
+        for (int kk = 0; kk < 8; ++kk) pig = fma(ap[kk * kLd], zp[kk], pig);
       }
     }
     __syncthreads();
   }
 }
 
-// product of shared-memory resident 64x64 operands given as 2 chunks x 2 full tiles each
-SCAML_DEVICE void gemm_smem(double (&acc)[8][4], const double* const (&A)[2][2], const double* const (&B)[2][2],
-                            const FThr& t) {
+// product of shared-memory resident 64x64 operands given as 2 chunks x 2 full padded tiles each
+SCAML_DEVICE void gemm_smem(Acc& acc, const double* const (&A)[2][2], const double* const (&B)[2][2], const FThr& t) {
 #pragma unroll
   for (int ck = 0; ck < 2; ++ck) {
     const double* a = A[ck][t.rb];
     const double* b = B[ck][t.cb];
-    if (a != nullptr && b != nullptr) fmma<32>(acc, a + t.rin, b + t.cin);
+    if (a != nullptr && b != nullptr) fmma<8, false>(acc, a, b, t);
   }
 }
 
-// 8x4 register patch -> one 32x32 tile, column-major ("C") or row-major ("R")
-SCAML_DEVICE void store_tile_C(double* blk, const double (&acc)[8][4], const FThr& t, double scale) {
+// warp's 32x32 accumulator -> one tile with row/col stride `ld`, column-major ("C") or row-major ("R")
+SCAML_DEVICE void store_tile_C(double* blk, int ld, const Acc& acc, const FThr& t, double scale) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      double* p = blk + (8 * j + 2 * t.t4 + e) * ld + t.g;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p[8 * i] = scale * acc[i][j][e];
+    }
+}
+SCAML_DEVICE void store_tile_R(double* blk, int ld, const Acc& acc, const FThr& t, double scale) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double* p = blk + (8 * i + t.g) * ld + 2 * t.t4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<double2*>(p + 8 * j) = make_double2(scale * acc[i][j][0], scale * acc[i][j][1]);
+  }
+}
+
+// scaled inputs of the thread's rows (a_base + 8i + g) and columns (b_base + 8j + 2*t4 + e), dimension k
+SCAML_DEVICE void load_xrows(double (&x)[4], const double* xr) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = __ldcg(xr + 8 * i);
+}
+SCAML_DEVICE void load_xcols(double (&x)[4][2], const double* xr) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    double* p = blk + (t.cin + j) * kBS + t.rin;
-#pragma unroll
-    for (int i = 0; i < 8; i += 2)
-      *reinterpret_cast<double2*>(p + i) = make_double2(scale * acc[i][j], scale * acc[i + 1][j]);
+    const double2 v = __ldcg(reinterpret_cast<const double2*>(xr + 8 * j));
+    x[j][0] = v.x;
+    x[j][1] = v.y;
   }
-}
-SCAML_DEVICE void store_tile_R(double* blk, const double (&acc)[8][4], const FThr& t, double scale) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    double* p = blk + (t.rin + i) * kBS + t.cin;
-    *reinterpret_cast<double2*>(p) = make_double2(scale * acc[i][0], scale * acc[i][1]);
-    *reinterpret_cast<double2*>(p + 2) = make_double2(scale * acc[i][2], scale * acc[i][3]);
-  }
-}
-
-// scaled inputs of rows a0..a0+7 / b0..b0+3, dimension k, from the per-CTA global scratch
-SCAML_DEVICE void load_x8(double (&x)[8], const double* xr) {
-#pragma unroll
-  for (int i = 0; i < 8; i += 2) {
-    const double2 v = __ldcg(reinterpret_cast<const double2*>(xr + i));
-    x[i] = v.x;
-    x[i + 1] = v.y;
-  }
-}
-SCAML_DEVICE void load_x4(double (&x)[4], const double* xr) {
-  const double2 v0 = __ldcg(reinterpret_cast<const double2*>(xr));
-  const double2 v1 = __ldcg(reinterpret_cast<const double2*>(xr + 2));
-  x[0] = v0.x, x[1] = v0.y, x[2] = v1.x, x[3] = v1.y;
 }
 
 // ---- epilogue 1: acc <- K_y(I,J) - acc, K recomputed from the scaled inputs ----------- //
-// (two passes of 4 rows keep r2 at 32 registers next to the 64 accumulator registers)
 template <int KIND>
-SCAML_DEVICE void assemble_tile(double (&acc)[8][4], int I, int J, const FThr& t, const double* xs, int n_pad, int d,
-                                int nv, double os, double diag_add) {
-  const int b0 = J * kSB + t.cb * kBS + t.cin;
+SCAML_DEVICE void assemble_tile(Acc& acc, int I, int J, const FThr& t, const double* xs, int n_pad, int d, int nv,
+                                double os, double diag_add) {
+  const int a0 = I * kSB + t.rb * kBS + t.g;
+  const int b0 = J * kSB + t.cb * kBS + 2 * t.t4;
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int a0 = I * kSB + t.rb * kBS + t.rin + 4 * h;
-    double r2[4][4];
+  for (int h = 0; h < 2; ++h) {  // two passes of two row-tiles keep r2 at 32 registers
+    double r2[2][4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) r2[i][j] = 0.0;
+      for (int j = 0; j < 4; ++j) r2[i][j][0] = r2[i][j][1] = 0.0;
     for (int k = 0; k < d; ++k) {
-      double xa[4], xb[4];
-      load_x4(xa, xs + k * n_pad + a0);
-      load_x4(xb, xs + k * n_pad + b0);
+      double xb[4][2];
+      load_xcols(xb, xs + k * n_pad + b0);
+      const double xa0 = __ldcg(xs + k * n_pad + a0 + 16 * h);
+      const double xa1 = __ldcg(xs + k * n_pad + a0 + 16 * h + 8);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const double df = xa[i] - xb[j];
-          r2[i][j] = fma(df, df, r2[i][j]);
+        for (int e = 0; e < 2; ++e) {
+          const double d0 = xa0 - xb[j][e], d1 = xa1 - xb[j][e];
+          r2[0][j][e] = fma(d0, d0, r2[0][j][e]);
+          r2[1][j][e] = fma(d1, d1, r2[1][j][e]);
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int a = a0 + i, b = b0 + j;
-        double k = os * kappa_of<KIND>(r2[i][j]);
-        if (a == b) k += diag_add;
-        if (a >= nv || b >= nv) k = (a == b) ? 1.0 : 0.0;
-        acc[4 * h + i][j] = k - acc[4 * h + i][j];
-      }
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int a = a0 + 8 * (2 * h + i), b = b0 + 8 * j + e;
+          double k = os * kappa_of<KIND>(r2[i][j][e]);
+          if (a == b) k += diag_add;
+          if (a >= nv || b >= nv) k = (a == b) ? 1.0 : 0.0;
+          acc[2 * h + i][j][e] = k - acc[2 * h + i][j][e];
+        }
   }
 }
 
@@ -329,82 +358,89 @@ SCAML_DEVICE void assemble_tile(double (&acc)[8][4], int I, int J, const FThr& t
 // accumulates into gsm[warp][0..d-1] (lengthscales), [d] (outputscale), [d+1] (trace W).
 // acc is overwritten by t_ab = wgt * W_ab * kd_ab.
 template <int KIND>
-SCAML_DEVICE void grad_tile(double (&acc)[8][4], int I, int J, const FThr& t, const double* xs, const double* av,
-                            int n_pad, int d, int nv, double* gsm) {
-  const int a00 = I * kSB + t.rb * kBS + t.rin;
-  const int b0 = J * kSB + t.cb * kBS + t.cin;
+SCAML_DEVICE void grad_tile(Acc& acc, int I, int J, const FThr& t, const double* xs, const double* av, int n_pad,
+                            int d, int nv, double* gsm) {
+  const int a0 = I * kSB + t.rb * kBS + t.g;
+  const int b0 = J * kSB + t.cb * kBS + 2 * t.t4;
   double accS = 0.0, accT = 0.0;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const int a0 = a00 + 4 * h;
-    double r2[4][4];
+    double r2[2][4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) r2[i][j] = 0.0;
+      for (int j = 0; j < 4; ++j) r2[i][j][0] = r2[i][j][1] = 0.0;
     for (int k = 0; k < d; ++k) {
-      double xa[4], xb[4];
-      load_x4(xa, xs + k * n_pad + a0);
-      load_x4(xb, xs + k * n_pad + b0);
+      double xb[4][2];
+      load_xcols(xb, xs + k * n_pad + b0);
+      const double xa0 = __ldcg(xs + k * n_pad + a0 + 16 * h);
+      const double xa1 = __ldcg(xs + k * n_pad + a0 + 16 * h + 8);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const double df = xa[i] - xb[j];
-          r2[i][j] = fma(df, df, r2[i][j]);
+        for (int e = 0; e < 2; ++e) {
+          const double d0 = xa0 - xb[j][e], d1 = xa1 - xb[j][e];
+          r2[0][j][e] = fma(d0, d0, r2[0][j][e]);
+          r2[1][j][e] = fma(d1, d1, r2[1][j][e]);
         }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2; ++i) {
+      const int a = a0 + 8 * (2 * h + i);
+      const double ava = av[a];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int a = a0 + i, b = b0 + j;
-        double kap, kd;
-        kappa_pair<KIND>(r2[i][j], kap, kd);
-        const bool use = (a >= b) && (a < nv) && (b < nv);
-        const double wgt = use ? ((a == b) ? 1.0 : 2.0) : 0.0;
-        const double Wab = av[a] * av[b] - acc[4 * h + i][j];
-        const double wk = wgt * Wab;
-        accS = fma(wk, kap, accS);
-        acc[4 * h + i][j] = wk * kd;
-        if (use && a == b) accT += Wab;
-      }
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int b = b0 + 8 * j + e;
+          double kap, kd;
+          kappa_pair<KIND>(r2[i][j][e], kap, kd);
+          const bool use = (a >= b) && (a < nv) && (b < nv);
+          const double wgt = use ? ((a == b) ? 1.0 : 2.0) : 0.0;
+          const double Wab = ava * av[b] - acc[2 * h + i][j][e];
+          const double wk = wgt * Wab;
+          accS = fma(wk, kap, accS);
+          acc[2 * h + i][j][e] = wk * kd;
+          if (use && a == b) accT += Wab;
+        }
+    }
   }
-  double* g = gsm + t.warp * kMaxP;
+  double* gw = gsm + t.warp * kMaxP;
   for (int k = 0; k < d; ++k) {
-    double xa[8], xb[4];
-    load_x8(xa, xs + k * n_pad + a00);
-    load_x4(xb, xs + k * n_pad + b0);
+    double xa[4], xb[4][2];
+    load_xrows(xa, xs + k * n_pad + a0);
+    load_xcols(xb, xs + k * n_pad + b0);
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const double df = xa[i] - xb[j];
-        s = fma(acc[i][j], df * df, s);
-      }
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double df = xa[i] - xb[j][e];
+          s = fma(acc[i][j][e], df * df, s);
+        }
     s = warp_sum(s);
-    if (t.lane == 0) g[k] += s;
+    if (t.lane == 0) gw[k] += s;
   }
   accS = warp_sum(accS);
   accT = warp_sum(accT);
   if (t.lane == 0) {
-    g[d] += accS;
-    g[d + 1] += accT;
+    gw[d] += accS;
+    gw[d + 1] += accT;
   }
 }
 
 // ---- warp-level 32x32 Cholesky + triangular inverse (row r of the tile per lane) ------ //
-// Dsm: SPD tile, C-layout (lower part valid).  Lc: 1024-double scratch (receives L, C-layout).
-// Pz: 1024-double scratch (XOR-swizzled transpose buffer).  Outputs: XC (C-layout inverse,
-// shared), XRs (R-layout, shared, optional), XRg (R-layout, global, optional).  Returns 0 or the
-// 1-based failing pivot; adds sum_k log(d_kk) (= log det of the tile) to *logdet (lane 0).
-// XRs may alias Lc (L is dead once the inverse sweep has finished).
+// Dsm: SPD tile, C-layout padded (lower part valid).  Lc: padded tile scratch (receives L, C-layout).
+// Pz: >= 1024-double scratch (XOR-swizzled transpose buffer).  Outputs: XC (C-layout padded inverse,
+// shared), XRs (R-layout padded, shared, optional), XRg (R-layout dense, global, optional).
+// Returns 0 or the 1-based failing pivot; adds sum_k log(d_kk) (= log det of the tile) to *logdet.
 SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* XC, double* XRs, double* XRg,
                              double* logdet, int lane) {
   double a[kBS];
 #pragma unroll
-  for (int c = 0; c < kBS; ++c) a[c] = Dsm[c * kBS + lane];
+  for (int c = 0; c < kBS; ++c) a[c] = Dsm[c * kLd + lane];
   int fail = 0;
   double mydiag = 1.0, myrs = 1.0;
 #pragma unroll
@@ -420,10 +456,10 @@ SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* 
       myrs = rs;
     }
     const double lrk = a[k] * rs;
-    Lc[k * kBS + lane] = lrk;
+    Lc[k * kLd + lane] = lrk;
     __syncwarp();
 #pragma unroll
-    for (int j = k + 1; j < kBS; ++j) a[j] = fma(-lrk, Lc[k * kBS + j], a[j]);
+    for (int j = k + 1; j < kBS; ++j) a[j] = fma(-lrk, Lc[k * kLd + j], a[j]);
   }
   double ld = log(mydiag);
   ld = warp_sum(ld);
@@ -437,12 +473,12 @@ SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* 
     const double rj = __shfl_sync(0xffffffffu, myrs, j);
     w[j] *= rj;
 #pragma unroll
-    for (int k = 0; k < j; ++k) w[k] = fma(-Lc[k * kBS + j], w[j], w[k]);
+    for (int k = 0; k < j; ++k) w[k] = fma(-Lc[k * kLd + j], w[j], w[k]);
   }
-  __syncwarp();  // all lanes are done reading Lc (XRs may alias it)
+  __syncwarp();  // all lanes are done reading Lc
 #pragma unroll
   for (int c = 0; c < kBS; ++c) {
-    XC[c * kBS + lane] = w[c];
+    XC[c * kLd + lane] = w[c];
     Pz[lane * kBS + (c ^ lane)] = w[c];
   }
   __syncwarp();
@@ -450,7 +486,7 @@ SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* 
 #pragma unroll 4
     for (int r = 0; r < kBS; ++r) {
       const double v = Pz[r * kBS + (lane ^ r)];
-      if (XRs) XRs[r * kBS + lane] = v;
+      if (XRs) XRs[r * kLd + lane] = v;
       if (XRg) XRg[r * kBS + lane] = v;
     }
   }
@@ -458,79 +494,86 @@ SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* 
   return fail;
 }
 
-// 32x32x32 product by the whole CTA: out(r,c) = sum_kk A[kk][r] * B[kk][c]; thread owns a 2x4 patch
-SCAML_DEVICE void small_gemm(double (&o)[2][4], const double* A, const double* B, int tid) {
-  const int r0 = 2 * (tid & 15), c0 = 4 * (tid >> 4);
+// 32x32x32 product by the whole CTA on padded tiles: out(r,c) = sum_kk A[kk][r] * B[kk][c];
+// warp w owns the 16x16 quadrant (w>>1, w&1) as 2x2 DMMA tiles.
+typedef double SAcc[2][2][2];
+SCAML_DEVICE void small_gemm(SAcc& o, const double* A, const double* B, const FThr& t) {
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[i][j] = 0.0;
-#pragma unroll 8
-  for (int kk = 0; kk < kBS; ++kk) {
-    const double2 a = *reinterpret_cast<const double2*>(A + kk * kBS + r0);
-    const double2 b01 = *reinterpret_cast<const double2*>(B + kk * kBS + c0);
-    const double2 b23 = *reinterpret_cast<const double2*>(B + kk * kBS + c0 + 2);
-    const double av[2] = {a.x, a.y};
-    const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) o[i][j] = fma(av[i], bv[j], o[i][j]);
+    for (int j = 0; j < 2; ++j) o[i][j][0] = o[i][j][1] = 0.0;
+  const double* ar = A + t.t4 * kLd + 16 * (t.warp >> 1) + t.g;
+  const double* br = B + t.t4 * kLd + 16 * (t.warp & 1) + t.g;
+#pragma unroll 4
+  for (int s = 0; s < 8; ++s) {
+    const double a0 = ar[0], a1 = ar[8], b0 = br[0], b1 = br[8];
+    ar += 4 * kLd;
+    br += 4 * kLd;
+    dmma884(o[0][0], a0, b0);
+    dmma884(o[0][1], a0, b1);
+    dmma884(o[1][0], a1, b0);
+    dmma884(o[1][1], a1, b1);
   }
 }
-SCAML_DEVICE void small_store_C(double* blk, const double (&o)[2][4], int tid, double scale) {
-  const int r0 = 2 * (tid & 15), c0 = 4 * (tid >> 4);
+// element (i,j,e) of the small accumulator <-> row 16*(w>>1) + 8i + g, col 16*(w&1) + 8j + 2*t4 + e
+SCAML_DEVICE void small_store_C(double* blk, int ld, const SAcc& o, const FThr& t, double scale) {
+  const int r0 = 16 * (t.warp >> 1) + t.g, c0 = 16 * (t.warp & 1) + 2 * t.t4;
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    *reinterpret_cast<double2*>(blk + (c0 + j) * kBS + r0) = make_double2(scale * o[0][j], scale * o[1][j]);
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) blk[(c0 + 8 * j + e) * ld + r0 + 8 * i] = scale * o[i][j][e];
 }
-SCAML_DEVICE void small_store_R(double* blk, const double (&o)[2][4], int tid, double scale) {
-  const int r0 = 2 * (tid & 15), c0 = 4 * (tid >> 4);
+SCAML_DEVICE void small_store_R(double* blk, int ld, const SAcc& o, const FThr& t, double scale) {
+  const int r0 = 16 * (t.warp >> 1) + t.g, c0 = 16 * (t.warp & 1) + 2 * t.t4;
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    *reinterpret_cast<double2*>(blk + (r0 + i) * kBS + c0) = make_double2(scale * o[i][0], scale * o[i][1]);
-    *reinterpret_cast<double2*>(blk + (r0 + i) * kBS + c0 + 2) = make_double2(scale * o[i][2], scale * o[i][3]);
-  }
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      *reinterpret_cast<double2*>(blk + (r0 + 8 * i) * ld + c0 + 8 * j) =
+          make_double2(scale * o[i][j][0], scale * o[i][j][1]);
 }
 
 // ---- factorise + invert the 64x64 diagonal super-tile held in `stage` ----------------- //
-// stage tiles (C-layout): T0 = D00, T1 = free, T2 = D10, T3 = D11.   dinvc tiles V0..V2.
+// stage tiles (C-layout, padded): T0 = D00, T1 = free, T2 = D10, T3 = D11.   dinvc tiles V0..V2.
 // Results: V0, V1, V2 = D^-1 tiles (0,0), (1,0), (1,1) in C-layout (shared);
-//          R-layout tiles of D^-1 written to the workspace diagonal (wd00, wd10, wd11).
+//          R-layout dense tiles of D^-1 written to the workspace diagonal (wd00, wd10, wd11).
 // *logdet (shared scalar) accumulates log det; *flag receives the failing pivot (1-based).
 SCAML_DEVICE void diag_factor(double* stage, double* dinvc, double* wd00, double* wd10, double* wd11, double* logdet,
                               int* flag, int pivot_base, const FThr& t) {
   double* T0 = stage;
-  double* T1 = stage + kTile;
-  double* T2 = stage + 2 * kTile;
-  double* T3 = stage + 3 * kTile;
+  double* T1 = stage + kTileS;
+  double* T2 = stage + 2 * kTileS;
+  double* T3 = stage + 3 * kTileS;
   double* V0 = dinvc;
-  double* V1 = dinvc + kTile;
-  double* V2 = dinvc + 2 * kTile;
+  double* V1 = dinvc + kTileS;
+  double* V2 = dinvc + 2 * kTileS;
   if (t.warp == 0) {
     // L scratch = V1, transpose scratch = V2, X00: C-layout -> V0, R-layout -> T1 and workspace
     const int f = chol_inv_32(T0, V1, V2, V0, T1, wd00, logdet, t.lane);
     if (f && t.lane == 0 && *flag == 0) *flag = pivot_base + f;
   }
   __syncthreads();
-  double o[2][4];
+  SAcc o;
   // L10 = D10 * X00^T      (A = D10 C-layout, B[kk][c] = X00(c,kk) = C-layout X00)
-  small_gemm(o, T2, V0, t.tid);
+  small_gemm(o, T2, V0, t);
   __syncthreads();
-  small_store_C(T2, o, t.tid, 1.0);  // T2 now holds L10 (C-layout)
+  small_store_C(T2, kLd, o, t, 1.0);  // T2 now holds L10 (C-layout)
   __syncthreads();
   // D11 -= L10 L10^T ;  Tm = L10 * X00  (B[kk][c] = X00(kk,c) = R-layout X00 in T1) -> V1 (R-layout)
-  small_gemm(o, T2, T2, t.tid);
+  small_gemm(o, T2, T2, t);
   {
-    const int r0 = 2 * (t.tid & 15), c0 = 4 * (t.tid >> 4);
+    const int r0 = 16 * (t.warp >> 1) + t.g, c0 = 16 * (t.warp & 1) + 2 * t.t4;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      T3[(c0 + j) * kBS + r0] -= o[0][j];
-      T3[(c0 + j) * kBS + r0 + 1] -= o[1][j];
-    }
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) T3[(c0 + 8 * j + e) * kLd + r0 + 8 * i] -= o[i][j][e];
   }
-  small_gemm(o, T2, T1, t.tid);
-  small_store_R(V1, o, t.tid, 1.0);
+  small_gemm(o, T2, T1, t);
+  small_store_R(V1, kLd, o, t, 1.0);
   __syncthreads();
   if (t.warp == 0) {
     // L scratch = T1 (X00 R-layout is dead), transpose scratch = T0 (D00 is dead)
@@ -539,14 +582,14 @@ SCAML_DEVICE void diag_factor(double* stage, double* dinvc, double* wd00, double
   }
   __syncthreads();
   // X10 = -X11 * Tm        (A[kk][r] = X11(r,kk) = C-layout X11 in V2, B = Tm R-layout in V1)
-  small_gemm(o, V2, V1, t.tid);
+  small_gemm(o, V2, V1, t);
   __syncthreads();  // every thread has consumed Tm before V1 is overwritten
-  small_store_C(V1, o, t.tid, -1.0);
-  small_store_R(wd10, o, t.tid, -1.0);
+  small_store_C(V1, kLd, o, t, -1.0);
+  small_store_R(wd10, kBS, o, t, -1.0);
   __syncthreads();
 }
 
-// D^-1 of diagonal super-tile I (R-layout tiles in the workspace) -> dinvc (C-layout, shared)
+// D^-1 of diagonal super-tile I (R-layout dense tiles in the workspace) -> dinvc (C-layout padded)
 SCAML_DEVICE void load_dinvc(double* dinvc, const double* W, int I, int tid) {
   const double* src[3] = {wtile(W, 2 * I, 2 * I), wtile(W, 2 * I + 1, 2 * I), wtile(W, 2 * I + 1, 2 * I + 1)};
 #pragma unroll
@@ -554,7 +597,7 @@ SCAML_DEVICE void load_dinvc(double* dinvc, const double* W, int I, int tid) {
 #pragma unroll 4
     for (int idx = tid; idx < kTile; idx += kFitThreads) {
       const int c = idx >> 5, r = idx & 31;
-      dinvc[b * kTile + c * kBS + r] = __ldcg(src[b] + r * kBS + c);
+      dinvc[b * kTileS + c * kLd + r] = __ldcg(src[b] + r * kBS + c);
     }
   }
 }
@@ -566,8 +609,8 @@ SCAML_DEVICE void dinv_matvec(double* out, const double* dinvc, const double* v,
   for (int kk = q * 32; kk < q * 32 + 32; ++kk) {
     if (kk > r) break;
     const int rb_ = r >> 5, kb_ = kk >> 5;
-    const double* blk = dinvc + ((rb_ == 0) ? 0 : (kb_ == 0 ? kTile : 2 * kTile));
-    s = fma(blk[(kk & 31) * kBS + (r & 31)], v[kk], s);
+    const double* blk = dinvc + ((rb_ == 0) ? 0 : (kb_ == 0 ? kTileS : 2 * kTileS));
+    s = fma(blk[(kk & 31) * kLd + (r & 31)], v[kk], s);
   }
   red[q * 64 + r] = s;
   __syncthreads();
@@ -580,9 +623,9 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
   SCAML_DYN_SMEM(double, sm);
   const FThr t = make_fthr();
   const int d = p.d, P = p.d + 2, n_pad_max = p.n_pad;
-  double* stage = sm;            // 4096: 2 stages x 4 half tiles | 4 full tiles (C_in / S / diag)
-  double* dinvc = stage + 4096;  // 3 tiles
-  double* yv = dinvc + 3072;
+  double* stage = sm;             // 2 stages x 4 padded half tiles | 4 full padded tiles (C_in / S / diag)
+  double* dinvc = stage + kStage;  // 3 padded tiles
+  double* yv = dinvc + 3 * kTileS;
   double* zv = yv + n_pad_max;
   double* av = zv + n_pad_max;
   double* red = av + n_pad_max;  // 128
@@ -657,7 +700,7 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
     }
     __syncthreads();
 
-    double acc[8][4];
+    Acc acc;
     double pig = 0.0;
     bool failed = false;
     PROF_MARK(0);
@@ -668,11 +711,11 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
         const bool skip_tile = (t.rb == 0 && t.cb == 1);
         facc_zero(acc);
         CholSrc src{W, J, J};
-        gemm_global<CholSrc, false>(acc, src, stage, t, skip_tile, pig, nullptr);
+        gemm_global<CholSrc, false, true>(acc, src, stage, t, pig, nullptr);
         PROF_MARK(1);
         if (!skip_tile) {
           assemble_tile<KIND>(acc, J, J, t, xs, n_pad_max, d, nv, os, diag_add);
-          store_tile_C(stage + (t.rb * 2 + t.cb) * kTile, acc, t, 1.0);
+          store_tile_C(stage + (t.rb * 2 + t.cb) * kTileS, kLd, acc, t, 1.0);
         }
         __syncthreads();
         PROF_MARK(2);
@@ -684,21 +727,21 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
           break;
         }
       }
-      const double* const TB[2][2] = {{dinvc, dinvc + kTile}, {nullptr, dinvc + 2 * kTile}};
+      const double* const TB[2][2] = {{dinvc, dinvc + kTileS}, {nullptr, dinvc + 2 * kTileS}};
       for (int I = J + 1; I < NS; ++I) {
         facc_zero(acc);
         CholSrc src{W, I, J};
-        gemm_global<CholSrc, false>(acc, src, stage, t, false, pig, nullptr);
+        gemm_global<CholSrc, false, false>(acc, src, stage, t, pig, nullptr);
         PROF_MARK(1);
         assemble_tile<KIND>(acc, I, J, t, xs, n_pad_max, d, nv, os, diag_add);
-        store_tile_C(stage + (t.rb * 2 + t.cb) * kTile, acc, t, 1.0);
+        store_tile_C(stage + (t.rb * 2 + t.cb) * kTileS, kLd, acc, t, 1.0);
         __syncthreads();
         PROF_MARK(2);
         // L(I,J) = C * D^-T : A chunk kb2 = C tiles (rb,kb2); B[kk][c] = D^-1(c,kk)
-        const double* const TA[2][2] = {{stage, stage + 2 * kTile}, {stage + kTile, stage + 3 * kTile}};
+        const double* const TA[2][2] = {{stage, stage + 2 * kTileS}, {stage + kTileS, stage + 3 * kTileS}};
         facc_zero(acc);
         gemm_smem(acc, TA, TB, t);
-        store_tile_C(wtile_w(W, 2 * I + t.rb, 2 * J + t.cb), acc, t, 1.0);
+        store_tile_C(wtile_w(W, 2 * I + t.rb, 2 * J + t.cb), kBS, acc, t, 1.0);
         __syncthreads();
         PROF_MARK(4);
       }
@@ -718,24 +761,24 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
       load_dinvc(dinvc, W, I, t.tid);
       __syncthreads();
       pig = 0.0;
-      const double* const TA[2][2] = {{dinvc, dinvc + kTile}, {nullptr, dinvc + 2 * kTile}};
+      const double* const TA[2][2] = {{dinvc, dinvc + kTileS}, {nullptr, dinvc + 2 * kTileS}};
       for (int J = 0; J < I; ++J) {
         facc_zero(acc);
         TrtriSrc src{W, I, J};
         if (J == 0)
-          gemm_global<TrtriSrc, true>(acc, src, stage, t, false, pig, zv);
+          gemm_global<TrtriSrc, true, false>(acc, src, stage, t, pig, zv);
         else
-          gemm_global<TrtriSrc, false>(acc, src, stage, t, false, pig, nullptr);
+          gemm_global<TrtriSrc, false, false>(acc, src, stage, t, pig, nullptr);
         PROF_MARK(5);
-        store_tile_R(stage + (t.rb * 2 + t.cb) * kTile, acc, t, 1.0);  // S, R-layout tiles (kb2, cb)
+        store_tile_R(stage + (t.rb * 2 + t.cb) * kTileS, kLd, acc, t, 1.0);  // S, R-layout tiles (kb2, cb)
         __syncthreads();
-        const double* const TBs[2][2] = {{stage, stage + kTile}, {stage + 2 * kTile, stage + 3 * kTile}};
+        const double* const TBs[2][2] = {{stage, stage + kTileS}, {stage + 2 * kTileS, stage + 3 * kTileS}};
         facc_zero(acc);
         gemm_smem(acc, TA, TBs, t);
-        store_tile_R(wtile_w(W, 2 * I + t.rb, 2 * J + t.cb), acc, t, -1.0);
+        store_tile_R(wtile_w(W, 2 * I + t.rb, 2 * J + t.cb), kBS, acc, t, -1.0);
         if (p.mode == kModeFactorize)
-          store_tile_C(p.linv_out + ((size_t)m * tri(n_pad_max / kBS) + tri(2 * I + t.rb) + 2 * J + t.cb) * kTile, acc,
-                       t, -1.0);
+          store_tile_C(p.linv_out + ((size_t)m * tri(n_pad_max / kBS) + tri(2 * I + t.rb) + 2 * J + t.cb) * kTile, kBS,
+                       acc, t, -1.0);
         __syncthreads();
         PROF_MARK(6);
       }
@@ -747,12 +790,13 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
       dinv_matvec(zv + I * kSB, dinvc, av, red, t);
       PROF_MARK(7);
       if (p.mode == kModeFactorize) {
-        // diagonal tiles of L^-1 in C-layout = dinvc
+        // diagonal tiles of L^-1 in C-layout = dinvc (padded -> dense)
         double* lo = p.linv_out + (size_t)m * tri(n_pad_max / kBS) * kTile;
         for (int i = t.tid; i < kTile; i += kFitThreads) {
-          lo[(size_t)(tri(2 * I) + 2 * I) * kTile + i] = dinvc[i];
-          lo[(size_t)(tri(2 * I + 1) + 2 * I) * kTile + i] = dinvc[kTile + i];
-          lo[(size_t)(tri(2 * I + 1) + 2 * I + 1) * kTile + i] = dinvc[2 * kTile + i];
+          const int si = (i >> 5) * kLd + (i & 31);
+          lo[(size_t)(tri(2 * I) + 2 * I) * kTile + i] = dinvc[si];
+          lo[(size_t)(tri(2 * I + 1) + 2 * I) * kTile + i] = dinvc[kTileS + si];
+          lo[(size_t)(tri(2 * I + 1) + 2 * I + 1) * kTile + i] = dinvc[2 * kTileS + si];
         }
       }
     }
@@ -782,7 +826,7 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
         facc_zero(acc);
         pig = 0.0;
         LauumSrc src{W, I, I, NS};
-        gemm_global<LauumSrc, true>(acc, src, stage, t, skip_tile, pig, zv);
+        gemm_global<LauumSrc, true, true>(acc, src, stage, t, pig, zv);
         PROF_MARK(8);
         red[t.tid] = pig;
         __syncthreads();
@@ -794,7 +838,7 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
       for (int J = 0; J < I; ++J) {
         facc_zero(acc);
         LauumSrc src{W, I, J, NS};
-        gemm_global<LauumSrc, false>(acc, src, stage, t, false, pig, nullptr);
+        gemm_global<LauumSrc, false, false>(acc, src, stage, t, pig, nullptr);
         PROF_MARK(8);
         grad_tile<KIND>(acc, I, J, t, xs, av, n_pad_max, d, nv, gsm);
         PROF_MARK(9);
