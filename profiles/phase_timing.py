@@ -13,7 +13,7 @@ from scamlgp_b200._capi import ScamlLib
 from scamlgp_b200.engine import Engine, SourceBatch
 
 NAMES = ["setup", "B gemm(update)", "B assemble(exp)+store", "B diag_factor", "B trsm+store", "C gemm1", "C gemm2+store",
-         "C z solve", "D gemm", "D grad epilogue", "final", "-", "-", "-", "-", "-"]
+         "C z solve", "D gemm", "D grad epilogue", "final", " diag: chol#1 (warp0)", " diag: L10,D11,Tm", " diag: chol#2 rest (outputs)", " chol#2: cholesky loop", " chol#2: inverse loop"]
 
 
 def main():
@@ -44,7 +44,7 @@ def main():
     tot = p.sum(1).mean().item()
     print(f"M={M} R={R} n={n} d={d}: {ms:.3f} ms, {M*R/ms*1e3:.0f} evals/s, grid={grid}, "
           f"cycles/CTA={tot:.0f} ({tot/evals_per_cta:.0f} per eval per CTA)")
-    for i, nm in enumerate(NAMES[:11]):
+    for i, nm in enumerate(NAMES[:16]):
         c = p[:, i].mean().item()
         print(f"  {nm:26s} {c/evals_per_cta:12.0f} cyc/eval  {100*c/tot:6.2f}%")
 

@@ -73,6 +73,7 @@ int run_fit(scaml::FitParams p, void* workspace, size_t workspace_bytes, void* s
   p.workspace = static_cast<double*>(workspace);
   p.ws_stride = scaml::fit_ws_doubles_host(p.n_pad, p.d);
   p.prof = g_prof;
+  p.sms = num_sms();
   int grid = fit_grid_slots(p.n_pad, p.d);
   const long long E = (long long)p.M * p.R;
   if (E < grid) grid = (int)E;

@@ -72,14 +72,15 @@ struct FitParams {
   long long ws_stride;  // doubles per CTA slot
   long long* prof;      // SCAML_PROF builds only: [grid][16] cycle counters per phase
   int M, R, n_max, n_pad, d, mode;
+  int sms;  // SM count (co-resident CTAs are blockIdx.x, blockIdx.x + sms, ...)
   scaml_hyper_spec spec;
 };
 
-// workspace slot: [ lower tiles: tri(NB) x 1024 ][ scaled inputs xs: d x n_pad ]
+// workspace slot: lower tiles, tri(NB) x 1024 doubles
 inline long long fit_ws_doubles_host(int n_pad, int d) {
+  (void)d;
   const int NB = n_pad / kBS;
-  long long v = (long long)((NB * (NB + 1)) / 2) * kTile + (long long)d * n_pad;
-  return (v + 15) & ~15LL;
+  return (long long)((NB * (NB + 1)) / 2) * kTile;
 }
 // shared memory (doubles): stage 4608 | dinvc 3456 | y,z,alpha 3*n_pad | red 128 |
 //                          gsm 4*kMaxP | par 4*kMaxP+8 | flags 2
@@ -119,8 +120,9 @@ SCAML_DEVICE void facc_zero(Acc& acc) {
 
 // acc(32x32) += A[kk][r] * B[kk][c] over NK4 steps of 4 kk.  Ap/Bp: padded k-major tiles (row
 // stride kLd) at their first kk row.  LOWER: skip the strictly-upper 8x8 tiles (diagonal tiles).
-template <int NK4, bool LOWER>
-SCAML_DEVICE void fmma(Acc& acc, const double* __restrict__ Ap, const double* __restrict__ Bp, const FThr& t) {
+template <int NK4>
+SCAML_DEVICE void fmma(Acc& acc, const double* __restrict__ Ap, const double* __restrict__ Bp, const FThr& t,
+                       bool lower) {
   const double* ar = Ap + t.t4 * kLd + t.g;
   const double* br = Bp + t.t4 * kLd + t.g;
 #pragma unroll 2
@@ -133,7 +135,7 @@ SCAML_DEVICE void fmma(Acc& acc, const double* __restrict__ Ap, const double* __
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (!LOWER || j <= i) dmma884(acc[i][j], a[i], b[j]);
+        if (j <= i || !lower) dmma884(acc[i][j], a[i], b[j]);
   }
 }
 
@@ -226,10 +228,13 @@ SCAML_DEVICE void stage_issue(const Src& src, int s, double* st, int tid) {
 // (c = tid & 63 over the 64 A columns of the super-tile, kk-half = tid >> 6).
 // DIAG: super-tile on the diagonal -> warp (0,1) idles, warps (0,0),(1,1) compute lower 8x8 tiles only.
 // On return every thread has passed a __syncthreads after its last read of `stage`.
-template <class Src, bool PIGGY, bool DIAG>
-SCAML_DEVICE void gemm_global(Acc& acc, const Src& src, double* stage, const FThr& t, double& pig, const double* zv) {
+template <class Src>
+SCAML_DEVICE void gemm_global(Acc& acc, const Src& src, double* stage, const FThr& t, bool diag, bool piggy,
+                              double& pig, const double* zv) {
   const int n = 2 * src.count();
   if (n <= 0) return;
+  const bool active = !(diag && t.rb < t.cb);
+  const bool lower = diag && (t.rb == t.cb);
   stage_issue(src, 0, stage, t.tid);
   for (int s = 0; s < n; ++s) {
     double* st = stage + (s & 1) * 4 * kHalfS;
@@ -244,17 +249,8 @@ SCAML_DEVICE void gemm_global(Acc& acc, const Src& src, double* stage, const FTh
     const double* As = st;
     const double* Bs = src.same() ? st : st + 2 * kHalfS;
     const bool bvalid = src.same() ? (c.a[t.cb] != nullptr) : (c.b[t.cb] != nullptr);
-    if (c.a[t.rb] != nullptr && bvalid) {
-      if (DIAG) {
-        if (t.rb == t.cb)
-          fmma<4, true>(acc, As + t.rb * kHalfS, Bs + t.cb * kHalfS, t);
-        else if (t.rb > t.cb)
-          fmma<4, false>(acc, As + t.rb * kHalfS, Bs + t.cb * kHalfS, t);
-      } else {
-        fmma<4, false>(acc, As + t.rb * kHalfS, Bs + t.cb * kHalfS, t);
-      }
-    }
-    if (PIGGY) {
+    if (active && c.a[t.rb] != nullptr && bvalid) fmma<4>(acc, As + t.rb * kHalfS, Bs + t.cb * kHalfS, t, lower);
+    if (piggy) {
       const int col = t.tid & 63, q = t.tid >> 6;
       if (c.a[col >> 5] != nullptr) {
         const double* ap = As + (col >> 5) * kHalfS + (col & 31) + q * 8 * kLd;
@@ -273,7 +269,7 @@ SCAML_DEVICE void gemm_smem(Acc& acc, const double* const (&A)[2][2], const doub
   for (int ck = 0; ck < 2; ++ck) {
     const double* a = A[ck][t.rb];
     const double* b = B[ck][t.cb];
-    if (a != nullptr && b != nullptr) fmma<8, false>(acc, a, b, t);
+    if (a != nullptr && b != nullptr) fmma<8>(acc, a, b, t, false);
   }
 }
 
@@ -298,47 +294,59 @@ SCAML_DEVICE void store_tile_R(double* blk, int ld, const Acc& acc, const FThr& 
   }
 }
 
-// scaled inputs of the thread's rows (a_base + 8i + g) and columns (b_base + 8j + 2*t4 + e), dimension k
-SCAML_DEVICE void load_xrows(double (&x)[4], const double* xr) {
+// ---- x-block: length-scaled inputs of the 64 row points (super-tile I) and the 64 column points
+// (super-tile J) of one epilogue, xblk[k * 128 + p] (p < 64: rows, p >= 64: columns).  Thread `tid`
+// owns point p = tid in every dimension; the first kXpre dimensions are fetched into registers
+// BEFORE the tile product so that their latency is hidden behind it.
+constexpr int kXpre = 8;
+SCAML_DEVICE void xpre_load(double (&xp)[kXpre], const double* Xm, int I, int J, int nv, int d, int tid) {
+  const int a = (tid < kSB) ? I * kSB + tid : J * kSB + (tid - kSB);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) x[i] = __ldcg(xr + 8 * i);
+  for (int k = 0; k < kXpre; ++k) xp[k] = (k < d && a < nv) ? __ldg(Xm + (size_t)a * d + k) : 0.0;
 }
-SCAML_DEVICE void load_xcols(double (&x)[4][2], const double* xr) {
+SCAML_DEVICE void xblk_store(double* xblk, const double (&xp)[kXpre], const double* Xm, const double* th, int I,
+                             int J, int nv, int d, int tid) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const double2 v = __ldcg(reinterpret_cast<const double2*>(xr + 8 * j));
-    x[j][0] = v.x;
-    x[j][1] = v.y;
+  for (int k = 0; k < kXpre; ++k)
+    if (k < d) xblk[k * 128 + tid] = xp[k] / th[k];
+  if (d > kXpre) {
+    const int a = (tid < kSB) ? I * kSB + tid : J * kSB + (tid - kSB);
+    for (int k = kXpre; k < d; ++k) xblk[k * 128 + tid] = (a < nv) ? __ldg(Xm + (size_t)a * d + k) / th[k] : 0.0;
+  }
+}
+
+// squared scaled distances between the thread's row points ra, ra + 8 and its 8 column points
+SCAML_DEVICE void pair_r2(double (&r2)[2][4][2], const double* xblk, int d, int ra, int cb0) {
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r2[i][j][0] = r2[i][j][1] = 0.0;
+#pragma unroll 2
+  for (int k = 0; k < d; ++k) {
+    const double* xr = xblk + k * 128;
+    const double xa0 = xr[ra], xa1 = xr[ra + 8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double2 xb = *reinterpret_cast<const double2*>(xr + cb0 + 8 * j);
+      const double d00 = xa0 - xb.x, d01 = xa0 - xb.y, d10 = xa1 - xb.x, d11 = xa1 - xb.y;
+      r2[0][j][0] = fma(d00, d00, r2[0][j][0]);
+      r2[0][j][1] = fma(d01, d01, r2[0][j][1]);
+      r2[1][j][0] = fma(d10, d10, r2[1][j][0]);
+      r2[1][j][1] = fma(d11, d11, r2[1][j][1]);
+    }
   }
 }
 
 // ---- epilogue 1: acc <- K_y(I,J) - acc, K recomputed from the scaled inputs ----------- //
 template <int KIND>
-SCAML_DEVICE void assemble_tile(Acc& acc, int I, int J, const FThr& t, const double* xs, int n_pad, int d, int nv,
-                                double os, double diag_add) {
-  const int a0 = I * kSB + t.rb * kBS + t.g;
-  const int b0 = J * kSB + t.cb * kBS + 2 * t.t4;
+SCAML_DEVICE void assemble_tile(Acc& acc, int I, int J, const FThr& t, const double* xblk, int d, int nv, double os,
+                                double diag_add) {
+  const int ra = t.rb * kBS + t.g, cb0 = kSB + t.cb * kBS + 2 * t.t4;
+  const int a0 = I * kSB + ra, b0 = J * kSB + t.cb * kBS + 2 * t.t4;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {  // two passes of two row-tiles keep r2 at 32 registers
     double r2[2][4][2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) r2[i][j][0] = r2[i][j][1] = 0.0;
-    for (int k = 0; k < d; ++k) {
-      double xb[4][2];
-      load_xcols(xb, xs + k * n_pad + b0);
-      const double xa0 = __ldcg(xs + k * n_pad + a0 + 16 * h);
-      const double xa1 = __ldcg(xs + k * n_pad + a0 + 16 * h + 8);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const double d0 = xa0 - xb[j][e], d1 = xa1 - xb[j][e];
-          r2[0][j][e] = fma(d0, d0, r2[0][j][e]);
-          r2[1][j][e] = fma(d1, d1, r2[1][j][e]);
-        }
-    }
+    pair_r2(r2, xblk, d, ra + 16 * h, cb0);
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -358,32 +366,15 @@ SCAML_DEVICE void assemble_tile(Acc& acc, int I, int J, const FThr& t, const dou
 // accumulates into gsm[warp][0..d-1] (lengthscales), [d] (outputscale), [d+1] (trace W).
 // acc is overwritten by t_ab = wgt * W_ab * kd_ab.
 template <int KIND>
-SCAML_DEVICE void grad_tile(Acc& acc, int I, int J, const FThr& t, const double* xs, const double* av, int n_pad,
-                            int d, int nv, double* gsm) {
-  const int a0 = I * kSB + t.rb * kBS + t.g;
-  const int b0 = J * kSB + t.cb * kBS + 2 * t.t4;
+SCAML_DEVICE void grad_tile(Acc& acc, int I, int J, const FThr& t, const double* xblk, const double* av, int d,
+                            int nv, double* gsm) {
+  const int ra = t.rb * kBS + t.g, cb0 = kSB + t.cb * kBS + 2 * t.t4;
+  const int a0 = I * kSB + ra, b0 = J * kSB + t.cb * kBS + 2 * t.t4;
   double accS = 0.0, accT = 0.0;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     double r2[2][4][2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) r2[i][j][0] = r2[i][j][1] = 0.0;
-    for (int k = 0; k < d; ++k) {
-      double xb[4][2];
-      load_xcols(xb, xs + k * n_pad + b0);
-      const double xa0 = __ldcg(xs + k * n_pad + a0 + 16 * h);
-      const double xa1 = __ldcg(xs + k * n_pad + a0 + 16 * h + 8);
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const double d0 = xa0 - xb[j][e], d1 = xa1 - xb[j][e];
-          r2[0][j][e] = fma(d0, d0, r2[0][j][e]);
-          r2[1][j][e] = fma(d1, d1, r2[1][j][e]);
-        }
-    }
+    pair_r2(r2, xblk, d, ra + 16 * h, cb0);
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int a = a0 + 8 * (2 * h + i);
@@ -407,19 +398,21 @@ SCAML_DEVICE void grad_tile(Acc& acc, int I, int J, const FThr& t, const double*
   }
   double* gw = gsm + t.warp * kMaxP;
   for (int k = 0; k < d; ++k) {
-    double xa[4], xb[4][2];
-    load_xrows(xa, xs + k * n_pad + a0);
-    load_xcols(xb, xs + k * n_pad + b0);
+    const double* xr = xblk + k * 128;
+    double xa[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xa[i] = xr[ra + 8 * i];
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      const double2 xb = *reinterpret_cast<const double2*>(xr + cb0 + 8 * j);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const double df = xa[i] - xb[j][e];
-          s = fma(acc[i][j][e], df * df, s);
-        }
+      for (int i = 0; i < 4; ++i) {
+        const double d0 = xa[i] - xb.x, d1 = xa[i] - xb.y;
+        s = fma(acc[i][j][0], d0 * d0, s);
+        s = fma(acc[i][j][1], d1 * d1, s);
+      }
+    }
     s = warp_sum(s);
     if (t.lane == 0) gw[k] += s;
   }
@@ -436,16 +429,17 @@ SCAML_DEVICE void grad_tile(Acc& acc, int I, int J, const FThr& t, const double*
 // Pz: >= 1024-double scratch (XOR-swizzled transpose buffer).  Outputs: XC (C-layout padded inverse,
 // shared), XRs (R-layout padded, shared, optional), XRg (R-layout dense, global, optional).
 // Returns 0 or the 1-based failing pivot; adds sum_k log(d_kk) (= log det of the tile) to *logdet.
-SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* XC, double* XRs, double* XRg,
-                             double* logdet, int lane) {
-  double a[kBS];
-#pragma unroll
-  for (int c = 0; c < kBS; ++c) a[c] = Dsm[c * kLd + lane];
-  int fail = 0;
-  double mydiag = 1.0, myrs = 1.0;
-#pragma unroll
-  for (int k = 0; k < kBS; ++k) {
-    double dkk = __shfl_sync(0xffffffffu, a[k], k);
+// Both sweeps are ROLLED loops over the pivot with a rotating register window (slot 0 is always the
+// current column) so the body stays ~100 instructions (a fully unrolled version was a 50 KB
+// instruction stream: 10 % of the v3 stall samples were no_instruction).  The window shrinks every 8
+// pivots (32, 24, 16, 8 slots).  Slots that have rotated past the tile edge read a few doubles beyond
+// Lc's rows (still inside this CTA's shared memory) and only ever feed other dead slots.
+template <int W>
+SCAML_DEVICE void chol_steps(double (&a)[kBS], int k0, double* Lc, int lane, int& fail, double& mydiag, double& myrs,
+                             double& dnext) {
+#pragma unroll 1
+  for (int k = k0; k < k0 + 8; ++k) {
+    double dkk = dnext;  // A(k,k) of the current Schur complement
     if (!(dkk > 0.0) || !(dkk < 1e300)) {
       if (fail == 0) fail = k + 1;
       dkk = 1.0;
@@ -455,32 +449,52 @@ SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* 
       mydiag = dkk;
       myrs = rs;
     }
-    const double lrk = a[k] * rs;
+    const double lrk = a[0] * rs;  // a[i] = A(lane, k + i)
     Lc[k * kLd + lane] = lrk;
+    // next pivot without the shared-memory round trip: lane k+1 needs only its own L(k+1,k)
+    dnext = __shfl_sync(0xffffffffu, fma(-lrk, lrk, a[1]), (k + 1) & 31);
     __syncwarp();
+    const double* lk = Lc + k * kLd + k;  // lk[j] = L(k + j, k)
 #pragma unroll
-    for (int j = k + 1; j < kBS; ++j) a[j] = fma(-lrk, Lc[k * kLd + j], a[j]);
+    for (int j = 1; j < W; ++j) a[j - 1] = fma(-lrk, lk[j], a[j]);
   }
+}
+template <int W>
+SCAML_DEVICE void inv_steps(double (&b)[kBS], int j0, const double* Lc, double* XC, double* Pz, int lane, double myrs) {
+#pragma unroll 1
+  for (int j = j0; j > j0 - 8; --j) {
+    const double rj = __shfl_sync(0xffffffffu, myrs, j);
+    const double b0 = b[0] * rj;  // X(lane, j);  b[i] = w(j - i)
+    XC[j * kLd + lane] = b0;
+    Pz[lane * kBS + (j ^ lane)] = b0;
+    const double* lj = Lc + j * kLd + j;  // lj[-i * kLd] = L(j, j - i)
+#pragma unroll
+    for (int i = 1; i < W; ++i) b[i - 1] = fma(-lj[-i * kLd], b0, b[i]);
+  }
+}
+SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* XC, double* XRs, double* XRg,
+                             double* logdet, int lane) {
+  double a[kBS];
+#pragma unroll
+  for (int c = 0; c < kBS; ++c) a[c] = Dsm[c * kLd + lane];
+  int fail = 0;
+  double mydiag = 1.0, myrs = 1.0;
+  double dnext = __shfl_sync(0xffffffffu, a[0], 0);
+  chol_steps<32>(a, 0, Lc, lane, fail, mydiag, myrs, dnext);
+  chol_steps<24>(a, 8, Lc, lane, fail, mydiag, myrs, dnext);
+  chol_steps<16>(a, 16, Lc, lane, fail, mydiag, myrs, dnext);
+  chol_steps<8>(a, 24, Lc, lane, fail, mydiag, myrs, dnext);
   double ld = log(mydiag);
   ld = warp_sum(ld);
   if (lane == 0) *logdet += ld;
   // inverse, row `lane` of X = L^-1 by a backward column sweep on L^T
-  double w[kBS];
+  double b[kBS];
 #pragma unroll
-  for (int c = 0; c < kBS; ++c) w[c] = (c == lane) ? 1.0 : 0.0;
-#pragma unroll
-  for (int j = kBS - 1; j >= 0; --j) {
-    const double rj = __shfl_sync(0xffffffffu, myrs, j);
-    w[j] *= rj;
-#pragma unroll
-    for (int k = 0; k < j; ++k) w[k] = fma(-Lc[k * kLd + j], w[j], w[k]);
-  }
-  __syncwarp();  // all lanes are done reading Lc
-#pragma unroll
-  for (int c = 0; c < kBS; ++c) {
-    XC[c * kLd + lane] = w[c];
-    Pz[lane * kBS + (c ^ lane)] = w[c];
-  }
+  for (int i = 0; i < kBS; ++i) b[i] = (i == kBS - 1 - lane) ? 1.0 : 0.0;
+  inv_steps<32>(b, 31, Lc, XC, Pz, lane, myrs);
+  inv_steps<24>(b, 23, Lc, XC, Pz, lane, myrs);
+  inv_steps<16>(b, 15, Lc, XC, Pz, lane, myrs);
+  inv_steps<8>(b, 7, Lc, XC, Pz, lane, myrs);
   __syncwarp();
   if (XRs != nullptr || XRg != nullptr) {
 #pragma unroll 4
@@ -540,8 +554,15 @@ SCAML_DEVICE void small_store_R(double* blk, int ld, const SAcc& o, const FThr& 
 // Results: V0, V1, V2 = D^-1 tiles (0,0), (1,0), (1,1) in C-layout (shared);
 //          R-layout dense tiles of D^-1 written to the workspace diagonal (wd00, wd10, wd11).
 // *logdet (shared scalar) accumulates log det; *flag receives the failing pivot (1-based).
+#ifdef SCAML_PROF
+#define DIAG_PROF_ARGS , long long* profsm, long long& prof_last
+#define DIAG_PROF_PASS , profsm, prof_last
+#else
+#define DIAG_PROF_ARGS
+#define DIAG_PROF_PASS
+#endif
 SCAML_DEVICE void diag_factor(double* stage, double* dinvc, double* wd00, double* wd10, double* wd11, double* logdet,
-                              int* flag, int pivot_base, const FThr& t) {
+                              int* flag, int pivot_base, const FThr& t, int chain_warp DIAG_PROF_ARGS) {
   double* T0 = stage;
   double* T1 = stage + kTileS;
   double* T2 = stage + 2 * kTileS;
@@ -549,11 +570,12 @@ SCAML_DEVICE void diag_factor(double* stage, double* dinvc, double* wd00, double
   double* V0 = dinvc;
   double* V1 = dinvc + kTileS;
   double* V2 = dinvc + 2 * kTileS;
-  if (t.warp == 0) {
+  if (t.warp == chain_warp) {
     // L scratch = V1, transpose scratch = V2, X00: C-layout -> V0, R-layout -> T1 and workspace
     const int f = chol_inv_32(T0, V1, V2, V0, T1, wd00, logdet, t.lane);
     if (f && t.lane == 0 && *flag == 0) *flag = pivot_base + f;
   }
+  PROF_MARK(11);
   __syncthreads();
   SAcc o;
   // L10 = D10 * X00^T      (A = D10 C-layout, B[kk][c] = X00(c,kk) = C-layout X00)
@@ -575,11 +597,13 @@ SCAML_DEVICE void diag_factor(double* stage, double* dinvc, double* wd00, double
   small_gemm(o, T2, T1, t);
   small_store_R(V1, kLd, o, t, 1.0);
   __syncthreads();
-  if (t.warp == 0) {
+  PROF_MARK(12);
+  if (t.warp == chain_warp) {
     // L scratch = T1 (X00 R-layout is dead), transpose scratch = T0 (D00 is dead)
     const int f = chol_inv_32(T3, T1, T0, V2, nullptr, wd11, logdet, t.lane);
     if (f && t.lane == 0 && *flag == 0) *flag = pivot_base + kBS + f;
   }
+  PROF_MARK(13);
   __syncthreads();
   // X10 = -X11 * Tm        (A[kk][r] = X11(r,kk) = C-layout X11 in V2, B = Tm R-layout in V1)
   small_gemm(o, V2, V1, t);
@@ -590,16 +614,27 @@ SCAML_DEVICE void diag_factor(double* stage, double* dinvc, double* wd00, double
 }
 
 // D^-1 of diagonal super-tile I (R-layout dense tiles in the workspace) -> dinvc (C-layout padded)
-SCAML_DEVICE void load_dinvc(double* dinvc, const double* W, int I, int tid) {
+// Coalesced cp.async into `stage` (which must be idle), then a shared->shared transpose; ends with
+// a __syncthreads.
+SCAML_DEVICE void load_dinvc(double* dinvc, double* stage, const double* W, int I, int tid) {
   const double* src[3] = {wtile(W, 2 * I, 2 * I), wtile(W, 2 * I + 1, 2 * I), wtile(W, 2 * I + 1, 2 * I + 1)};
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    half_async(stage + b * kTileS, src[b], tid);
+    half_async(stage + b * kTileS + kHalfS, src[b] + kHalfG, tid);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
 #pragma unroll
   for (int b = 0; b < 3; ++b) {
 #pragma unroll 4
     for (int idx = tid; idx < kTile; idx += kFitThreads) {
-      const int c = idx >> 5, r = idx & 31;
-      dinvc[b * kTileS + c * kLd + r] = __ldcg(src[b] + r * kBS + c);
+      const int r = idx >> 5, c = idx & 31;
+      dinvc[b * kTileS + c * kLd + r] = stage[b * kTileS + r * kLd + c];
     }
   }
+  __syncthreads();
 }
 
 // out[r] = sum_kk D^-1(r,kk) v[kk] over a 64x64 lower-triangular D^-1 held as dinvc (C-layout tiles)
@@ -639,7 +674,6 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
   int* flag = reinterpret_cast<int*>(scal + 8);
 
   double* W = p.workspace + (size_t)blockIdx.x * p.ws_stride;
-  double* xs = W + (size_t)tri(n_pad_max / kBS) * kTile;  // [d][n_pad_max] scaled inputs (global scratch)
 #ifdef SCAML_PROF
   __shared__ long long profsm[16];
   long long prof_last = clock64();
@@ -648,6 +682,8 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
 #endif
   const int E = p.M * p.R;
   const scaml_hyper_spec& sp = p.spec;
+  // the pivot chains of the CTAs sharing an SM should sit on different sub-partitions (warp w -> SMSP w%4)
+  const int chain_warp = (p.sms > 0 ? (int)(blockIdx.x / p.sms) : 0) & (kFitWarps - 1);
 
   for (int e = blockIdx.x; e < E; e += gridDim.x) {
     if (p.skip != nullptr && p.skip[e] != 0) continue;
@@ -688,13 +724,8 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
     __syncthreads();
     const double os = th[d];
     const double diag_add = th[d + 1] + (p.jitter ? p.jitter[e] : 0.0);
-    // scaled inputs (dimension-major, global scratch), targets
+    const double* Xm = p.X + (size_t)m * p.n_max * d;
     {
-      const double* Xm = p.X + (size_t)m * p.n_max * d;
-      for (int i = t.tid; i < n_pad * d; i += kFitThreads) {
-        const int k = i / n_pad, a = i - k * n_pad;
-        xs[k * n_pad_max + a] = (a < nv) ? Xm[(size_t)a * d + k] / th[k] : 0.0;
-      }
       const double* ym = p.y + (size_t)m * p.n_max;
       for (int i = t.tid; i < n_pad; i += kFitThreads) yv[i] = (i < nv) ? ym[i] : 0.0;
     }
@@ -706,44 +737,41 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
     PROF_MARK(0);
 
     // ================= phase B: blocked left-looking Cholesky ========================== //
+    const bool upper_warp = (t.rb == 0 && t.cb == 1);  // idle on diagonal super-tiles
     for (int J = 0; J < NS && !failed; ++J) {
-      {  // diagonal super-tile
-        const bool skip_tile = (t.rb == 0 && t.cb == 1);
-        facc_zero(acc);
-        CholSrc src{W, J, J};
-        gemm_global<CholSrc, false, true>(acc, src, stage, t, pig, nullptr);
-        PROF_MARK(1);
-        if (!skip_tile) {
-          assemble_tile<KIND>(acc, J, J, t, xs, n_pad_max, d, nv, os, diag_add);
-          store_tile_C(stage + (t.rb * 2 + t.cb) * kTileS, kLd, acc, t, 1.0);
-        }
-        __syncthreads();
-        PROF_MARK(2);
-        diag_factor(stage, dinvc, wtile_w(W, 2 * J, 2 * J), wtile_w(W, 2 * J + 1, 2 * J),
-                    wtile_w(W, 2 * J + 1, 2 * J + 1), &scal[0], flag, J * kSB, t);
-        PROF_MARK(3);
-        if (*flag != 0) {
-          failed = true;
-          break;
-        }
-      }
       const double* const TB[2][2] = {{dinvc, dinvc + kTileS}, {nullptr, dinvc + 2 * kTileS}};
-      for (int I = J + 1; I < NS; ++I) {
+      for (int I = J; I < NS; ++I) {
+        const bool diag = (I == J);
         facc_zero(acc);
+        double xp[kXpre];
+        xpre_load(xp, Xm, I, J, nv, d, t.tid);
         CholSrc src{W, I, J};
-        gemm_global<CholSrc, false, false>(acc, src, stage, t, pig, nullptr);
+        gemm_global(acc, src, stage, t, diag, false, pig, nullptr);
         PROF_MARK(1);
-        assemble_tile<KIND>(acc, I, J, t, xs, n_pad_max, d, nv, os, diag_add);
-        store_tile_C(stage + (t.rb * 2 + t.cb) * kTileS, kLd, acc, t, 1.0);
+        xblk_store(stage, xp, Xm, th, I, J, nv, d, t.tid);  // stage is idle: x-block lives there
+        __syncthreads();
+        if (!(diag && upper_warp)) assemble_tile<KIND>(acc, I, J, t, stage, d, nv, os, diag_add);
+        __syncthreads();  // x-block consumed before C_in overwrites it
+        if (!(diag && upper_warp)) store_tile_C(stage + (t.rb * 2 + t.cb) * kTileS, kLd, acc, t, 1.0);
         __syncthreads();
         PROF_MARK(2);
-        // L(I,J) = C * D^-T : A chunk kb2 = C tiles (rb,kb2); B[kk][c] = D^-1(c,kk)
-        const double* const TA[2][2] = {{stage, stage + 2 * kTileS}, {stage + kTileS, stage + 3 * kTileS}};
-        facc_zero(acc);
-        gemm_smem(acc, TA, TB, t);
-        store_tile_C(wtile_w(W, 2 * I + t.rb, 2 * J + t.cb), kBS, acc, t, 1.0);
-        __syncthreads();
-        PROF_MARK(4);
+        if (diag) {
+          diag_factor(stage, dinvc, wtile_w(W, 2 * J, 2 * J), wtile_w(W, 2 * J + 1, 2 * J),
+                      wtile_w(W, 2 * J + 1, 2 * J + 1), &scal[0], flag, J * kSB, t, chain_warp DIAG_PROF_PASS);
+          PROF_MARK(3);
+          if (*flag != 0) {
+            failed = true;
+            break;
+          }
+        } else {
+          // L(I,J) = C * D^-T : A chunk kb2 = C tiles (rb,kb2); B[kk][c] = D^-1(c,kk)
+          const double* const TA[2][2] = {{stage, stage + 2 * kTileS}, {stage + kTileS, stage + 3 * kTileS}};
+          facc_zero(acc);
+          gemm_smem(acc, TA, TB, t);
+          store_tile_C(wtile_w(W, 2 * I + t.rb, 2 * J + t.cb), kBS, acc, t, 1.0);
+          __syncthreads();
+          PROF_MARK(4);
+        }
       }
     }
     if (failed) {
@@ -758,17 +786,13 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
     // ================= phase C: triangular inverse (row-wise), z = L^-1 y ============== //
     for (int I = 0; I < NS; ++I) {
       __syncthreads();
-      load_dinvc(dinvc, W, I, t.tid);
-      __syncthreads();
+      load_dinvc(dinvc, stage, W, I, t.tid);
       pig = 0.0;
       const double* const TA[2][2] = {{dinvc, dinvc + kTileS}, {nullptr, dinvc + 2 * kTileS}};
       for (int J = 0; J < I; ++J) {
         facc_zero(acc);
         TrtriSrc src{W, I, J};
-        if (J == 0)
-          gemm_global<TrtriSrc, true, false>(acc, src, stage, t, pig, zv);
-        else
-          gemm_global<TrtriSrc, false, false>(acc, src, stage, t, pig, nullptr);
+        gemm_global(acc, src, stage, t, false, J == 0, pig, zv);
         PROF_MARK(5);
         store_tile_R(stage + (t.rb * 2 + t.cb) * kTileS, kLd, acc, t, 1.0);  // S, R-layout tiles (kb2, cb)
         __syncthreads();
@@ -821,26 +845,25 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
 
     // ================= phase D: K^-1 super-tiles, fused gradient contraction ========== //
     for (int I = 0; I < NS; ++I) {
-      {
-        const bool skip_tile = (t.rb == 0 && t.cb == 1);
+      for (int jj = 0; jj <= I; ++jj) {  // diagonal super-tile first: it completes alpha_I
+        const bool diag = (jj == 0);
+        const int J = diag ? I : jj - 1;
         facc_zero(acc);
         pig = 0.0;
-        LauumSrc src{W, I, I, NS};
-        gemm_global<LauumSrc, true, true>(acc, src, stage, t, pig, zv);
-        PROF_MARK(8);
-        red[t.tid] = pig;
-        __syncthreads();
-        if (t.tid < 64) av[I * kSB + t.tid] = red[t.tid] + red[64 + t.tid];
-        __syncthreads();
-        if (!skip_tile) grad_tile<KIND>(acc, I, I, t, xs, av, n_pad_max, d, nv, gsm);
-        PROF_MARK(9);
-      }
-      for (int J = 0; J < I; ++J) {
-        facc_zero(acc);
+        double xp[kXpre];
+        xpre_load(xp, Xm, I, J, nv, d, t.tid);
         LauumSrc src{W, I, J, NS};
-        gemm_global<LauumSrc, false, false>(acc, src, stage, t, pig, nullptr);
+        gemm_global(acc, src, stage, t, diag, diag, pig, zv);
         PROF_MARK(8);
-        grad_tile<KIND>(acc, I, J, t, xs, av, n_pad_max, d, nv, gsm);
+        xblk_store(stage, xp, Xm, th, I, J, nv, d, t.tid);
+        if (diag) red[t.tid] = pig;
+        __syncthreads();
+        if (diag) {
+          if (t.tid < 64) av[I * kSB + t.tid] = red[t.tid] + red[64 + t.tid];
+          __syncthreads();
+        }
+        if (!(diag && upper_warp)) grad_tile<KIND>(acc, I, J, t, stage, av, d, nv, gsm);
+        __syncthreads();  // x-block consumed before the next product stages tiles over it
         PROF_MARK(9);
       }
     }
