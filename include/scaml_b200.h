@@ -125,14 +125,37 @@ int scaml_predict_weighted(const double* X, const int32_t* n_valid, const double
                            size_t workspace_bytes, int M, int n_max, int d, int B,
                            int kernel, void* stream);
 
-/* Per-task (un-reduced) source posteriors at n_t target inputs: mean [n_t][M] and dense
- * covariance [n_t][n_t][M] in raw-Y units -- the `source_means` / `source_covs` caches of
- * `ScaMLGP.__init__` (reference scamlgp/model.py:278-289).  n_t <= 64 per call tile. */
+/* K6/K7 with q > 1: source posteriors at two point sets A (nA) and B (nB),
+ *   mean_m(A),  Sigma_m(A,B) = ystd_m^2 (K_m(A,B) - V_m(A)^T V_m(B)),  V_m(.) = L_m^-1 K_m(X_m, .)
+ * reduce = 0: per task, mean [nA][M] and cov [nA][nB][M] in raw-Y units -- the `source_means` /
+ *             `source_covs` caches of `ScaMLGP.__init__` (reference scamlgp/model.py:278-289);
+ * reduce = 1: mean [nA] = sum_m w_m mean_m, cov [nA][nB] = sum_m w_m^2 Sigma_m in a fixed order --
+ *             the joint prior blocks `ScaMLGP.forward` builds in eval mode
+ *             (reference scamlgp/model.py:364-375 via _compute_target_prior :108-135).
+ * n_max <= 256 in this release (k(X,A), k(X,B) are held in shared memory). */
+size_t scaml_predict_cross_workspace_bytes(int M, int nA, int nB, int reduce);
 int scaml_predict_cross(const double* X, const int32_t* n_valid, const double* theta,
                         const double* linv_packed, const double* alpha, const double* ybar,
-                        const double* ystd, const double* Xt, double* source_means,
-                        double* source_covs, int M, int n_max, int d, int n_t, int kernel,
-                        void* stream);
+                        const double* ystd, const double* w, const double* XA, const double* XB,
+                        double* mean, double* cov, void* workspace, size_t workspace_bytes, int M,
+                        int n_max, int d, int nA, int nB, int kernel, int reduce, void* stream);
+
+/* a7: ScaML-GP target objective in training mode, R rows (restarts) per call:
+ *   mean = (S w - mu_all)/s_all,  K = (sum_i w_i^2 C_i)/s_all^2 + s k(X_t) + (noise + jitter) I
+ *   lml[r] = ( log N(y_t | mean, K) + log p(theta_t) + sum_i log p(w_i) ) / n_t
+ * and its gradient w.r.t. the weights (grad_w [R][M]) and the RAW kernel parameters
+ * (grad_theta [R][P]).  S = source_means [n_t][M], C = source_covs [n_t][n_t][M] (outputs of
+ * scaml_predict_cross, reduce = 0), y_t standardised with the frozen all-data transform.
+ * Replaces `mll(model(X_t), y_t)` + backward on the `ScaMLGP.forward` training branch
+ * (reference scamlgp/model.py:359-363,376-383; weights prior :325-330).  n_t <= 116. */
+size_t scaml_target_workspace_bytes(int n_t, int R);
+int scaml_target_lml_grad(const double* source_means, const double* source_covs, const double* Xt,
+                          const double* yt, const double* w, const double* theta_raw,
+                          const double* jitter, double mu_all, double s_all, double* lml,
+                          double* grad_w, double* grad_theta, int32_t* info, void* workspace,
+                          size_t workspace_bytes, int M, int n_t, int d, int R,
+                          const scaml_hyper_spec* spec, int w_prior, double w_p1, double w_p2,
+                          void* stream);
 
 #ifdef __cplusplus
 }

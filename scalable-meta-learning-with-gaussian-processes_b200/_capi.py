@@ -95,7 +95,10 @@ EXPORTED_SYMBOLS = (
     "scaml_factorize",
     "scaml_predict_workspace_bytes",
     "scaml_predict_weighted",
+    "scaml_predict_cross_workspace_bytes",
     "scaml_predict_cross",
+    "scaml_target_workspace_bytes",
+    "scaml_target_lml_grad",
 )
 
 
@@ -136,7 +139,14 @@ class ScamlLib:
         L.scaml_predict_workspace_bytes.restype = sz
         L.scaml_predict_workspace_bytes.argtypes = [i32, i32, i32, i32]
         L.scaml_predict_weighted.argtypes = [vp] * 12 + [sz, i32, i32, i32, i32, i32, vp]
-        L.scaml_predict_cross.argtypes = [vp] * 10 + [i32, i32, i32, i32, i32, vp]
+        L.scaml_predict_cross_workspace_bytes.restype = sz
+        L.scaml_predict_cross_workspace_bytes.argtypes = [i32, i32, i32, i32]
+        L.scaml_predict_cross.argtypes = [vp] * 13 + [sz, i32, i32, i32, i32, i32, i32, i32, vp]
+        L.scaml_target_workspace_bytes.restype = sz
+        L.scaml_target_workspace_bytes.argtypes = [i32, i32]
+        L.scaml_target_lml_grad.argtypes = ([vp] * 7 + [C.c_double, C.c_double] + [vp] * 5 +
+                                            [sz, i32, i32, i32, i32, C.POINTER(CHyperSpec), i32, C.c_double,
+                                             C.c_double, vp])
 
     # ---- thin, address-based wrappers ------------------------------------------------ #
     def version(self) -> str:
@@ -174,10 +184,26 @@ class ScamlLib:
                                                ws, ws_bytes, M, n_max, d, B, kernel, stream),
                "scaml_predict_weighted")
 
-    def predict_cross(self, X, n_valid, theta, linv, alpha, ybar, ystd, Xt, means, covs, M, n_max, d, n_t,
-                      kernel, stream=0):
-        _check(self.lib.scaml_predict_cross(X, n_valid, theta, linv, alpha, ybar, ystd, Xt, means, covs,
-                                            M, n_max, d, n_t, kernel, stream), "scaml_predict_cross")
+    def predict_cross_workspace_bytes(self, M: int, nA: int, nB: int, reduce: int) -> int:
+        return int(self.lib.scaml_predict_cross_workspace_bytes(M, nA, nB, reduce))
+
+    def predict_cross(self, X, n_valid, theta, linv, alpha, ybar, ystd, w, XA, XB, mean, cov, ws, ws_bytes,
+                      M, n_max, d, nA, nB, kernel, reduce, stream=0):
+        _check(self.lib.scaml_predict_cross(X, n_valid, theta, linv, alpha, ybar, ystd, w, XA, XB, mean, cov,
+                                            ws, ws_bytes, M, n_max, d, nA, nB, kernel, reduce, stream),
+               "scaml_predict_cross")
+
+
+    def target_workspace_bytes(self, n_t: int, R: int) -> int:
+        return int(self.lib.scaml_target_workspace_bytes(n_t, R))
+
+    def target_lml_grad(self, smeans, scovs, Xt, yt, w, theta_raw, jitter, mu_all, s_all, lml, grad_w, grad_theta,
+                        info, ws, ws_bytes, M, n_t, d, R, spec: HyperSpec, w_prior=(PRIOR_GAMMA, 1.0, 1.0), stream=0):
+        cs = spec.to_c()
+        _check(self.lib.scaml_target_lml_grad(smeans, scovs, Xt, yt, w, theta_raw, jitter, float(mu_all), float(s_all),
+                                              lml, grad_w, grad_theta, info, ws, ws_bytes, M, n_t, d, R, C.byref(cs),
+                                              int(w_prior[0]), float(w_prior[1]), float(w_prior[2]), stream),
+               "scaml_target_lml_grad")
 
 
 _cuda_lib: Optional[ScamlLib] = None

@@ -3,6 +3,8 @@
 #include "scaml_fit.cuh"
 #include "scaml_kmat.cuh"
 #include "scaml_predict.cuh"
+#include "scaml_cross.cuh"
+#include "scaml_target.cuh"
 
 #ifndef SCAML_EMU
 #include <cuda_runtime.h>
@@ -165,16 +167,53 @@ int scaml_predict_weighted(const double* X, const int32_t* n_valid, const double
                                         num_sms(), stream);
 }
 
+size_t scaml_predict_cross_workspace_bytes(int M, int nA, int nB, int reduce) {
+  return scaml::cross_workspace_bytes(M, nA, nB, reduce, num_sms());
+}
+
 int scaml_predict_cross(const double* X, const int32_t* n_valid, const double* theta, const double* linv_packed,
-                        const double* alpha, const double* ybar, const double* ystd, const double* Xt,
-                        double* source_means, double* source_covs, int M, int n_max, int d, int n_t, int kernel,
-                        void* stream) {
-  if (!X || !theta || !linv_packed || !alpha || !ybar || !ystd || !Xt || !source_means || !source_covs)
-    return SCAML_E_ARG;
-  if (M <= 0 || n_max <= 0 || d <= 0 || n_t <= 0 || kernel < 0 || kernel > 3) return SCAML_E_ARG;
+                        const double* alpha, const double* ybar, const double* ystd, const double* w, const double* XA,
+                        const double* XB, double* mean, double* cov, void* workspace, size_t workspace_bytes, int M,
+                        int n_max, int d, int nA, int nB, int kernel, int reduce, void* stream) {
+  if (!X || !theta || !linv_packed || !alpha || !ybar || !ystd || !XA || !XB || !mean || !cov) return SCAML_E_ARG;
+  if (reduce && !w) return SCAML_E_ARG;
+  if (M <= 0 || n_max <= 0 || d <= 0 || nA <= 0 || nB <= 0 || kernel < 0 || kernel > 3) return SCAML_E_ARG;
   if (d > scaml::kMaxP - 2) return SCAML_E_UNSUPPORTED;
-  return scaml::launch_predict_cross(X, n_valid, theta, linv_packed, alpha, ybar, ystd, Xt, source_means,
-                                     source_covs, M, n_max, pad64(n_max), d, n_t, kernel, stream);
+  const size_t need = scaml_predict_cross_workspace_bytes(M, nA, nB, reduce);
+  if (workspace_bytes < need || (need && !workspace)) return SCAML_E_WORKSPACE;
+  return scaml::launch_predict_cross(X, n_valid, theta, linv_packed, alpha, ybar, ystd, w, XA, XB, mean, cov,
+                                     static_cast<double*>(workspace), M, n_max, pad64(n_max), d, nA, nB, kernel,
+                                     reduce, num_sms(), stream);
+}
+
+size_t scaml_target_workspace_bytes(int n_t, int R) {
+  if (n_t <= 0 || R <= 0) return 0;
+  return scaml::target_workspace_doubles(n_t, R) * sizeof(double);
+}
+
+int scaml_target_lml_grad(const double* source_means, const double* source_covs, const double* Xt, const double* yt,
+                          const double* w, const double* theta_raw, const double* jitter, double mu_all, double s_all,
+                          double* lml, double* grad_w, double* grad_theta, int32_t* info, void* workspace,
+                          size_t workspace_bytes, int M, int n_t, int d, int R, const scaml_hyper_spec* spec,
+                          int w_prior, double w_p1, double w_p2, void* stream) {
+  if (!source_means || !source_covs || !Xt || !yt || !w || !theta_raw || !lml || !grad_w || !grad_theta || !info ||
+      !workspace || !spec)
+    return SCAML_E_ARG;
+  if (M <= 0 || n_t <= 0 || d <= 0 || R <= 0 || !(s_all > 0.0)) return SCAML_E_ARG;
+  if (d > scaml::kMaxP - 2) return SCAML_E_UNSUPPORTED;
+  if (workspace_bytes < scaml_target_workspace_bytes(n_t, R)) return SCAML_E_WORKSPACE;
+  scaml::TargetParams p{};
+  p.smeans = source_means, p.scovs = source_covs, p.Xt = Xt, p.yt = yt, p.w = w, p.theta_raw = theta_raw;
+  p.jitter = jitter, p.lml = lml, p.grad_w = grad_w, p.grad_theta = grad_theta, p.info = info;
+  double* ws = static_cast<double*>(workspace);
+  p.covw = ws;
+  p.Wmat = ws + (size_t)R * n_t * n_t;
+  p.meanw = ws + 2 * (size_t)R * n_t * n_t;
+  p.alpha = p.meanw + (size_t)R * n_t;
+  p.mu_all = mu_all, p.s_all = s_all;
+  p.M = M, p.nt = n_t, p.d = d, p.R = R, p.w_prior = w_prior, p.w_p1 = w_p1, p.w_p2 = w_p2;
+  p.spec = *spec;
+  return scaml::launch_target(p, num_sms(), stream);
 }
 
 }  // extern "C"

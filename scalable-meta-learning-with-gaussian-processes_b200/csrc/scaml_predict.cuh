@@ -237,10 +237,4 @@ inline int launch_predict_weighted(const double* X, const int32_t* n_valid, cons
 #endif
 }
 
-inline int launch_predict_cross(const double*, const int32_t*, const double*, const double*, const double*,
-                                const double*, const double*, const double*, double*, double*, int, int, int, int, int,
-                                int, void*) {
-  return SCAML_E_UNSUPPORTED;  // implemented in a later milestone
-}
-
 }  // namespace scaml

@@ -128,6 +128,7 @@ class Engine:
         self.lib = lib if lib is not None else load_cuda_library()
         self._ws: Optional[torch.Tensor] = None
         self._pws: Optional[torch.Tensor] = None
+        self._cws: Optional[torch.Tensor] = None
         self.launches = 0  # kernels launched through this engine (bench.py reports it)
 
     # ---- workspaces ------------------------------------------------------------------ #
@@ -240,18 +241,37 @@ class Engine:
         self.launches += 2 if need else 1
         return mean, var
 
-    def predict_cross(self, fs: FittedSources, Xt: torch.Tensor):
-        """source_means [n_t, M] and source_covs [n_t, n_t, M] (reference model.py:278-289)."""
+    def predict_cross(self, fs: FittedSources, XA: torch.Tensor, XB: Optional[torch.Tensor] = None,
+                      w: Optional[torch.Tensor] = None):
+        """Source posteriors at point sets A, B (B defaults to A), raw-Y units.
+
+        w is None : per task -> mean [nA, M], cov [nA, nB, M]  (`source_means` / `source_covs`,
+                    reference model.py:278-289)
+        w given   : reduced  -> mean [nA] = sum_m w_m mean_m, cov [nA, nB] = sum_m w_m^2 Sigma_m
+        """
         b = fs.batch
-        Xt = Xt.to(torch.float64).contiguous()
-        nt = Xt.shape[0]
-        means = torch.empty(nt, b.M, dtype=torch.float64, device=self.device)
-        covs = torch.empty(nt, nt, b.M, dtype=torch.float64, device=self.device)
+        XA = XA.to(torch.float64).contiguous()
+        XB = XA if XB is None else XB.to(torch.float64).contiguous()
+        nA, nB = XA.shape[0], XB.shape[0]
+        reduce = 0 if w is None else 1
+        if reduce:
+            w = w.to(torch.float64).contiguous()
+            mean = torch.empty(nA, dtype=torch.float64, device=self.device)
+            cov = torch.empty(nA, nB, dtype=torch.float64, device=self.device)
+        else:
+            mean = torch.empty(nA, b.M, dtype=torch.float64, device=self.device)
+            cov = torch.empty(nA, nB, b.M, dtype=torch.float64, device=self.device)
+        need = self.lib.predict_cross_workspace_bytes(b.M, nA, nB, reduce)
+        ws = None
+        if need:
+            if self._cws is None or self._cws.numel() * 8 < need:
+                self._cws = torch.empty((need + 7) // 8, dtype=torch.float64, device=self.device)
+            ws = self._cws
         self.lib.predict_cross(_ptr(b.X), _ptr(b.n_valid), _ptr(fs.theta), _ptr(fs.linv), _ptr(fs.alpha),
-                               _ptr(b.ybar), _ptr(b.ystd), _ptr(Xt), _ptr(means), _ptr(covs), b.M, b.n_max, b.d, nt,
-                               fs.spec.kernel, self._stream())
-        self.launches += 1
-        return means, covs
+                               _ptr(b.ybar), _ptr(b.ystd), _ptr(w), _ptr(XA), _ptr(XB), _ptr(mean), _ptr(cov),
+                               _ptr(ws), need, b.M, b.n_max, b.d, nA, nB, fs.spec.kernel, reduce, self._stream())
+        self.launches += 2 if need else 1
+        return mean, cov
 
 
 _default_engine: Optional[Engine] = None

@@ -126,3 +126,93 @@ def test_emu_kernel_matrix(emu_lib):
             if nv < n:
                 assert np.array_equal(K[m, nv:, nv:], np.eye(n - nv))
                 assert (K[m, :nv, nv:] == 0).all() and (K[m, nv:, :nv] == 0).all()
+
+
+def test_emu_predict_cross_per_task_and_reduced(emu_lib):
+    """source_means / source_covs caches (per task) and the weighted joint prior blocks (reduced)."""
+    lib = emu_lib
+    M, n, d = 3, 128, 3
+    pb = make_problem(M, 2, n, d, seed=7, n_valid=[128, 70, 9])
+    th = pb["th"][:, 1].contiguous()
+    X = np.ascontiguousarray(pb["X"].numpy())
+    y = np.ascontiguousarray(pb["yt"].numpy())
+    thn = np.ascontiguousarray(th.numpy())
+    linv = np.zeros((M, packed_tiles(n), 1024))
+    alpha = np.zeros((M, pad64(n)))
+    theta = np.zeros((M, d + 2))
+    info = np.zeros(M, dtype=np.int32)
+    wsb = lib.fit_workspace_bytes(n, d)
+    ws = np.zeros(wsb // 8 + 8)
+    lib.factorize(P(X), P(y), P(pb["nv"]), P(thn), None, P(linv), P(alpha), P(theta), P(info), P(ws), wsb, M, n, d,
+                  pb["cspec"])
+    states = [O.factorize(pb["X"][m, : pb["nv"][m]], pb["Y"][m, : pb["nv"][m]], th[m], pb["ospec"]) for m in range(M)]
+    g = torch.Generator().manual_seed(11)
+    XA = torch.rand(37, d, dtype=torch.float64, generator=g)
+    XB = torch.rand(33, d, dtype=torch.float64, generator=g)
+    XAn, XBn = np.ascontiguousarray(XA.numpy()), np.ascontiguousarray(XB.numpy())
+    nA, nB = XA.shape[0], XB.shape[0]
+    # per task
+    mean = np.full((nA, M), np.nan)
+    cov = np.full((nA, nB, M), np.nan)
+    lib.predict_cross(P(X), P(pb["nv"]), P(theta), P(linv), P(alpha), P(pb["ybar"]), P(pb["ystd"]), None, P(XAn),
+                      P(XBn), P(mean), P(cov), None, 0, M, n, d, nA, nB, 0, 0)
+    ref_cov = []
+    for m in range(M):
+        mu, c = O.posterior(states[m], torch.cat([XA, XB]), full_cov=True)
+        assert rel_err(mean[:, m], mu[:nA].numpy()) < TOL_MEAN_VAR
+        rc = c[:nA, nA:].numpy()
+        ref_cov.append(rc)
+        assert np.abs(cov[:, :, m] - rc).max() < TOL_MEAN_VAR * float(states[m].os) * states[m].ystd ** 2
+    # reduced with weights (one task pruned)
+    w = np.array([0.7, 0.0, 0.2])
+    wb = lib.predict_cross_workspace_bytes(M, nA, nB, 1)
+    wsr = np.zeros(wb // 8 + 8)
+    mean_r = np.full(nA, np.nan)
+    cov_r = np.full((nA, nB), np.nan)
+    lib.predict_cross(P(X), P(pb["nv"]), P(theta), P(linv), P(alpha), P(pb["ybar"]), P(pb["ystd"]), P(w), P(XAn),
+                      P(XBn), P(mean_r), P(cov_r), P(wsr), wb, M, n, d, nA, nB, 0, 1)
+    assert rel_err(mean_r, (mean * w[None, :]).sum(1)) < 1e-12
+    assert np.abs(cov_r - sum(w[m] ** 2 * ref_cov[m] for m in range(M))).max() < 1e-9
+
+
+def _oracle_target_value_and_grads(cache, w, th, ospec):
+    w = w.clone().requires_grad_(True)
+    th = th.clone().requires_grad_(True)
+    v = O.target_objective(cache, w, th, ospec)
+    gw, gt = torch.autograd.grad(v, [w, th])
+    return float(v.detach()), gw.numpy(), gt.numpy()
+
+
+@pytest.mark.parametrize("kernel,nt", [(0, 9), (3, 17), (1, 1)])
+def test_emu_target_lml_grad_matches_oracle(emu_lib, kernel, nt):
+    """a7: target objective on the ScaMLGP training branch + gradient wrt weights and raw kernel params."""
+    lib = emu_lib
+    M, n, d, R = 5, 64, 3, 2
+    pb = make_problem(M, 1, n, d, seed=9, n_valid=[64, 40, 64, 7, 33])
+    states = [O.factorize(pb["X"][m, : pb["nv"][m]], pb["Y"][m, : pb["nv"][m]], pb["th"][m, 0], pb["ospec"])
+              for m in range(M)]
+    g = torch.Generator().manual_seed(21)
+    Xt = torch.rand(nt, d, dtype=torch.float64, generator=g)
+    Yt = torch.randn(nt, dtype=torch.float64, generator=g)
+    cache = O.build_target_cache(states, Xt, Yt)
+    ospec, cspec = O.HyperSpec.target(kernel), HyperSpec.target(kernel)
+    W = torch.rand(R, M, dtype=torch.float64, generator=g) + 0.05
+    TH = O.sample_theta_raw(1, R, d, ospec, seed=4)[0]
+    sm = np.ascontiguousarray(cache.source_means.numpy())
+    sc = np.ascontiguousarray(cache.source_covs.numpy())
+    Xtn, ytn = np.ascontiguousarray(Xt.numpy()), np.ascontiguousarray(cache.yt_std.numpy())
+    Wn, THn = np.ascontiguousarray(W.numpy()), np.ascontiguousarray(TH.numpy())
+    lml = np.full(R, np.nan)
+    gw = np.full((R, M), np.nan)
+    gt = np.full((R, d + 2), np.nan)
+    info = np.full(R, -9, dtype=np.int32)
+    wsb = lib.target_workspace_bytes(nt, R)
+    ws = np.zeros(wsb // 8 + 8)
+    lib.target_lml_grad(P(sm), P(sc), P(Xtn), P(ytn), P(Wn), P(THn), None, cache.mu_all, cache.s_all, P(lml), P(gw),
+                        P(gt), P(info), P(ws), wsb, M, nt, d, R, cspec)
+    assert (info == 0).all()
+    for r in range(R):
+        v, ogw, ogt = _oracle_target_value_and_grads(cache, W[r], TH[r], ospec)
+        assert abs(lml[r] - v) < TOL_LML * abs(v)
+        assert np.abs(gw[r] - ogw).max() < TOL_GRAD * np.abs(ogw).max()
+        assert np.abs(gt[r] - ogt).max() < TOL_GRAD * max(np.abs(ogt).max(), np.abs(ogw).max())
