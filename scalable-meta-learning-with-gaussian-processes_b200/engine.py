@@ -19,7 +19,7 @@ from typing import List, Optional, Sequence, Tuple
 
 import torch
 
-from ._capi import HyperSpec, ScamlError, ScamlLib, load_cuda_library, pad64, packed_tiles
+from ._capi import PRIOR_GAMMA, HyperSpec, ScamlError, ScamlLib, load_cuda_library, pad64, packed_tiles
 
 JITTER_LADDER = (1e-8, 1e-7, 1e-6)  # linear_operator psd_safe_cholesky (fp64), SURVEY A.5
 
@@ -129,6 +129,7 @@ class Engine:
         self._ws: Optional[torch.Tensor] = None
         self._pws: Optional[torch.Tensor] = None
         self._cws: Optional[torch.Tensor] = None
+        self._tws: Optional[torch.Tensor] = None
         self.launches = 0  # kernels launched through this engine (bench.py reports it)
 
     # ---- workspaces ------------------------------------------------------------------ #
@@ -272,6 +273,51 @@ class Engine:
                                _ptr(ws), need, b.M, b.n_max, b.d, nA, nB, fs.spec.kernel, reduce, self._stream())
         self.launches += 2 if need else 1
         return mean, cov
+
+    # ---- a7: target objective ------------------------------------------------------------ #
+    def target_lml_grad(self, source_means: torch.Tensor, source_covs: torch.Tensor, Xt: torch.Tensor,
+                        yt: torch.Tensor, w: torch.Tensor, theta_raw: torch.Tensor, mu_all: float, s_all: float,
+                        spec: HyperSpec, w_prior=(PRIOR_GAMMA, 1.0, 1.0), jitter: Optional[torch.Tensor] = None):
+        """ScaML-GP target objective (training branch) for R rows: w [R, M], theta_raw [R, P].
+
+        source_means [n_t, M], source_covs [n_t, n_t, M] are the per-task caches of `predict_cross`
+        (reference model.py:278-289), yt the targets standardised with the frozen all-data transform.
+        Returns lml [R], grad_w [R, M], grad_theta [R, P], info [R] (no jitter ladder: see
+        `target_lml_grad_safe`)."""
+        R, M = w.shape
+        nt, d = Xt.shape
+        P = d + 2
+        assert source_means.shape == (nt, M) and source_covs.shape == (nt, nt, M) and theta_raw.shape == (R, P)
+        for t in (source_means, source_covs, Xt, yt, w, theta_raw):
+            assert t.is_contiguous() and t.dtype == torch.float64
+        lml = torch.empty(R, dtype=torch.float64, device=self.device)
+        gw = torch.empty(R, M, dtype=torch.float64, device=self.device)
+        gt = torch.empty(R, P, dtype=torch.float64, device=self.device)
+        info = torch.empty(R, dtype=torch.int32, device=self.device)
+        need = self.lib.target_workspace_bytes(nt, R)
+        if self._tws is None or self._tws.numel() * 8 < need:
+            self._tws = torch.empty((need + 7) // 8, dtype=torch.float64, device=self.device)
+        self.lib.target_lml_grad(_ptr(source_means), _ptr(source_covs), _ptr(Xt), _ptr(yt), _ptr(w), _ptr(theta_raw),
+                                 _ptr(jitter), mu_all, s_all, _ptr(lml), _ptr(gw), _ptr(gt), _ptr(info),
+                                 _ptr(self._tws), need, M, nt, d, R, spec, w_prior, self._stream())
+        self.launches += 3
+        return lml, gw, gt, info
+
+    def target_lml_grad_safe(self, source_means, source_covs, Xt, yt, w, theta_raw, mu_all, s_all, spec,
+                             w_prior=(PRIOR_GAMMA, 1.0, 1.0)):
+        """target_lml_grad with the psd_safe_cholesky jitter ladder on failed rows."""
+        out = self.target_lml_grad(source_means, source_covs, Xt, yt, w, theta_raw, mu_all, s_all, spec, w_prior)
+        lml, gw, gt, info = out
+        for jit in JITTER_LADDER:
+            bad = info > 0
+            if not bool(bad.any()):
+                break
+            idx = bad.nonzero().flatten()
+            jitter = torch.full((idx.numel(),), jit, dtype=torch.float64, device=self.device)
+            l2, gw2, gt2, i2 = self.target_lml_grad(source_means, source_covs, Xt, yt, w[idx].contiguous(),
+                                                    theta_raw[idx].contiguous(), mu_all, s_all, spec, w_prior, jitter)
+            lml[idx], gw[idx], gt[idx], info[idx] = l2, gw2, gt2, i2
+        return lml, gw, gt, info
 
 
 _default_engine: Optional[Engine] = None

@@ -168,3 +168,76 @@ def test_full_size_properties_config3(engine):
     fd = (lp - lm) / (2 * eps)
     an = (grad * dirn).sum(-1)
     assert float(((fd - an).abs() / (an.abs() + 1e-2)).max()) < 1e-4
+
+
+def _states(pb, col=0):
+    M = pb["M"]
+    return [O.factorize(pb["X"][m, : pb["nv"][m]], pb["Y"][m, : pb["nv"][m]], pb["th"][m, col], pb["ospec"])
+            for m in range(M)]
+
+
+@pytest.mark.parametrize("kernel,nA,nB", [(0, 100, 80), (3, 33, 31), (0, 1, 1)])
+def test_predict_cross_per_task_and_reduced(engine, kernel, nA, nB):
+    """source_means / source_covs caches (reference model.py:278-289) and the weighted joint blocks."""
+    M, n, d = 7, 256, 6
+    pb = make_problem(M, 1, n, d, seed=13, n_valid=[256, 200, 64, 65, 1, 130, 256], kernel=kernel)
+    batch = _batch(pb)
+    fs = engine.factorize(batch, pb["th"][:, 0].contiguous().cuda(), pb["cspec"])
+    states = _states(pb)
+    g = torch.Generator().manual_seed(3)
+    XA = torch.rand(nA, d, dtype=torch.float64, generator=g)
+    XB = torch.rand(nB, d, dtype=torch.float64, generator=g)
+    mean, cov = engine.predict_cross(fs, XA.cuda(), XB.cuda())
+    mean, cov = mean.cpu().numpy(), cov.cpu().numpy()
+    ref = []
+    for m in range(M):
+        mu, c = O.posterior(states[m], torch.cat([XA, XB]), full_cov=True)
+        rc = c[:nA, nA:].numpy()
+        ref.append(rc)
+        assert np.abs(mean[:, m] - mu[:nA].numpy()).max() < TOL_MEAN_VAR * max(1.0, float(mu.abs().max()))
+        assert np.abs(cov[:, :, m] - rc).max() < TOL_MEAN_VAR * float(states[m].os) * states[m].ystd ** 2
+    w = torch.rand(M, dtype=torch.float64, generator=g)
+    w[2] = 0.0
+    mr, cr = engine.predict_cross(fs, XA.cuda(), XB.cuda(), w=w.cuda())
+    wn = w.numpy()
+    scale = max(float(states[m].os) * states[m].ystd ** 2 for m in range(M))
+    assert np.abs(mr.cpu().numpy() - (mean * wn[None, :]).sum(1)).max() < 1e-11 * max(1.0, np.abs(mean).max())
+    assert np.abs(cr.cpu().numpy() - sum(wn[m] ** 2 * ref[m] for m in range(M))).max() < TOL_MEAN_VAR * scale
+    # symmetric call: Sigma(A, A) is symmetric and its diagonal equals the q = 1 variance
+    _, caa = engine.predict_cross(fs, XA.cuda(), None, w=w.cuda())
+    _, var = engine.predict_weighted(fs, w.cuda(), XA.cuda())
+    assert float((caa - caa.T).abs().max()) < 1e-12 * scale
+    assert float((caa.diagonal() - var).abs().max()) < TOL_MEAN_VAR * scale
+
+
+@pytest.mark.parametrize("kernel,nt,M", [(0, 40, 64), (3, 80, 33), (0, 116, 8), (2, 1, 5)])
+def test_target_lml_grad_matches_oracle(engine, kernel, nt, M):
+    """a7: ScaMLGP.forward training branch + priors (reference model.py:319-338,359-383)."""
+    n, d, R = 64, 4, 3
+    pb = make_problem(M, 1, n, d, seed=17)
+    batch = _batch(pb)
+    fs = engine.factorize(batch, pb["th"][:, 0].contiguous().cuda(), pb["cspec"])
+    states = _states(pb)
+    g = torch.Generator().manual_seed(5)
+    Xt = torch.rand(nt, d, dtype=torch.float64, generator=g)
+    Yt = torch.sin(3.0 * Xt.sum(1)) + 0.1 * torch.randn(nt, dtype=torch.float64, generator=g)
+    cache = O.build_target_cache(states, Xt, Yt)
+    sm, sc = engine.predict_cross(fs, Xt.cuda())
+    scale = max(float(s.os) * s.ystd ** 2 for s in states)
+    assert float((sm.cpu() - cache.source_means).abs().max()) < TOL_MEAN_VAR * max(1.0, float(cache.source_means.abs().max()))
+    assert float((sc.cpu() - cache.source_covs).abs().max()) < TOL_MEAN_VAR * scale
+    ospec, cspec = O.HyperSpec.target(kernel), HyperSpec.target(kernel)
+    W = torch.rand(R, M, dtype=torch.float64, generator=g) / M + 1e-3
+    TH = O.sample_theta_raw(1, R, d, ospec, seed=4)[0].contiguous()
+    lml, gw, gt, info = engine.target_lml_grad(sm, sc, Xt.cuda(), cache.yt_std.cuda().contiguous(), W.cuda(), TH.cuda(),
+                                               cache.mu_all, cache.s_all, cspec)
+    assert int(info.abs().max()) == 0
+    for r in range(R):
+        w = W[r].clone().requires_grad_(True)
+        th = TH[r].clone().requires_grad_(True)
+        v = O.target_objective(cache, w, th, ospec)
+        ogw, ogt = torch.autograd.grad(v, [w, th])
+        assert abs(float(lml[r]) - float(v)) < TOL_LML * abs(float(v))
+        gmax = max(float(ogw.abs().max()), float(ogt.abs().max()))
+        assert float((gw[r].cpu() - ogw).abs().max()) < TOL_GRAD * gmax
+        assert float((gt[r].cpu() - ogt).abs().max()) < TOL_GRAD * gmax
