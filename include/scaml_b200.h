@@ -157,6 +157,32 @@ int scaml_target_lml_grad(const double* source_means, const double* source_covs,
                           const scaml_hyper_spec* spec, int w_prior, double w_p1, double w_p2,
                           void* stream);
 
+/* Target-GP prediction state at the fitted parameters (R = 1): row-major L_t^-1 [n_t][n_t] of
+ * K = (sum_i w_i^2 C_i)/s_all^2 + s k(X_t) + (noise + jitter) I, alpha_t = K^-1 (y_t - mean) [n_t], the
+ * constrained kernel parameters theta [P] and the objective value lml[1].  Replaces the prediction
+ * strategy gpytorch builds on the first `ScaMLGP.posterior` call in eval mode (exact_prediction over the
+ * training-branch prior, reference scamlgp/model.py:359-363,376-383).  Workspace:
+ * scaml_target_workspace_bytes(n_t, 1) + 8 * (d + 3) bytes. */
+int scaml_target_factorize(const double* source_means, const double* source_covs, const double* Xt,
+                           const double* yt, const double* w, const double* theta_raw,
+                           double jitter_value, double mu_all, double s_all, double* linv_t,
+                           double* alpha_t, double* theta, double* lml, int32_t* info,
+                           void* workspace, size_t workspace_bytes, int M, int n_t, int d,
+                           const scaml_hyper_spec* spec, void* stream);
+
+/* ScaML-GP posterior at B candidates (q = 1) conditioned on the n_t target points:
+ *   k_s[j]  = cross[b][j]/s_all^2 + s k(x_b, X_t[j])
+ *   mean[b] = mu_all + s_all ((prior_mean[b] - mu_all)/s_all + k_s . alpha_t)
+ *   var[b]  = s_all^2 (prior_var[b]/s_all^2 + s - ||L_t^-1 k_s||^2)
+ * prior_mean / prior_var [B] come from scaml_predict_weighted and cross [B][n_t] from
+ * scaml_predict_cross (reduce = 1, A = candidates, B = X_t), all with the pruned weights.  Replaces the
+ * eval branch of `ScaMLGP.forward` + gpytorch exact prediction + un-standardisation
+ * (reference scamlgp/model.py:364-383); consumer: UpperConfidenceBound, scamlgp/utils.py:215-224. */
+int scaml_target_posterior(const double* prior_mean, const double* prior_var, const double* cross,
+                           const double* Xc, const double* Xt, const double* theta,
+                           const double* linv_t, const double* alpha_t, double mu_all, double s_all,
+                           double* mean, double* var, int B, int n_t, int d, int kernel, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

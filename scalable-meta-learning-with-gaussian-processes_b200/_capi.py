@@ -99,6 +99,8 @@ EXPORTED_SYMBOLS = (
     "scaml_predict_cross",
     "scaml_target_workspace_bytes",
     "scaml_target_lml_grad",
+    "scaml_target_factorize",
+    "scaml_target_posterior",
 )
 
 
@@ -142,6 +144,10 @@ class ScamlLib:
         L.scaml_predict_cross_workspace_bytes.restype = sz
         L.scaml_predict_cross_workspace_bytes.argtypes = [i32, i32, i32, i32]
         L.scaml_predict_cross.argtypes = [vp] * 13 + [sz, i32, i32, i32, i32, i32, i32, i32, vp]
+        dbl = C.c_double
+        L.scaml_target_factorize.argtypes = ([vp] * 6 + [dbl, dbl, dbl] + [vp] * 6 +
+                                             [sz, i32, i32, i32, C.POINTER(CHyperSpec), vp])
+        L.scaml_target_posterior.argtypes = [vp] * 8 + [dbl, dbl, vp, vp, i32, i32, i32, i32, vp]
         L.scaml_target_workspace_bytes.restype = sz
         L.scaml_target_workspace_bytes.argtypes = [i32, i32]
         L.scaml_target_lml_grad.argtypes = ([vp] * 7 + [C.c_double, C.c_double] + [vp] * 5 +
@@ -193,6 +199,19 @@ class ScamlLib:
                                             ws, ws_bytes, M, n_max, d, nA, nB, kernel, reduce, stream),
                "scaml_predict_cross")
 
+
+    def target_factorize(self, smeans, scovs, Xt, yt, w, theta_raw, jitter_value, mu_all, s_all, linv_t, alpha_t, theta,
+                         lml, info, ws, ws_bytes, M, n_t, d, spec: HyperSpec, stream=0):
+        cs = spec.to_c()
+        _check(self.lib.scaml_target_factorize(smeans, scovs, Xt, yt, w, theta_raw, float(jitter_value), float(mu_all),
+                                               float(s_all), linv_t, alpha_t, theta, lml, info, ws, ws_bytes, M, n_t, d,
+                                               C.byref(cs), stream), "scaml_target_factorize")
+
+    def target_posterior(self, pm, pv, cross, Xc, Xt, theta, linv_t, alpha_t, mu_all, s_all, mean, var, B, n_t, d,
+                         kernel, stream=0):
+        _check(self.lib.scaml_target_posterior(pm, pv, cross, Xc, Xt, theta, linv_t, alpha_t, float(mu_all),
+                                               float(s_all), mean, var, B, n_t, d, kernel, stream),
+               "scaml_target_posterior")
 
     def target_workspace_bytes(self, n_t: int, R: int) -> int:
         return int(self.lib.scaml_target_workspace_bytes(n_t, R))

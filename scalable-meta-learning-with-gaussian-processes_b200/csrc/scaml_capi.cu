@@ -216,4 +216,48 @@ int scaml_target_lml_grad(const double* source_means, const double* source_covs,
   return scaml::launch_target(p, num_sms(), stream);
 }
 
+int scaml_target_factorize(const double* source_means, const double* source_covs, const double* Xt, const double* yt,
+                           const double* w, const double* theta_raw, double jitter_value, double mu_all, double s_all,
+                           double* linv_t, double* alpha_t, double* theta, double* lml, int32_t* info, void* workspace,
+                           size_t workspace_bytes, int M, int n_t, int d, const scaml_hyper_spec* spec, void* stream) {
+  if (!source_means || !source_covs || !Xt || !yt || !w || !theta_raw || !linv_t || !alpha_t || !theta || !lml ||
+      !info || !workspace || !spec)
+    return SCAML_E_ARG;
+  if (M <= 0 || n_t <= 0 || d <= 0 || !(s_all > 0.0)) return SCAML_E_ARG;
+  if (d > scaml::kMaxP - 2) return SCAML_E_UNSUPPORTED;
+  if (workspace_bytes < scaml_target_workspace_bytes(n_t, 1) + sizeof(double) * (size_t)(d + 2 + 1))
+    return SCAML_E_WORKSPACE;
+  scaml::TargetParams p{};
+  p.smeans = source_means, p.scovs = source_covs, p.Xt = Xt, p.yt = yt, p.w = w, p.theta_raw = theta_raw;
+  double* ws = static_cast<double*>(workspace);
+  p.covw = ws;
+  p.Wmat = ws + (size_t)n_t * n_t;
+  p.meanw = ws + 2 * (size_t)n_t * n_t;
+  p.alpha = alpha_t;
+  p.grad_theta = p.meanw + n_t + n_t;  // scratch: the gradient is not part of this call's contract
+  p.jitter = nullptr;
+  p.lml = lml, p.grad_w = nullptr, p.info = info;
+  p.linv_out = linv_t, p.theta_out = theta;
+  p.mu_all = mu_all, p.s_all = s_all;
+  p.M = M, p.nt = n_t, p.d = d, p.R = 1, p.w_prior = 0, p.w_p1 = 0, p.w_p2 = 0;
+  p.spec = *spec;
+  p.jitter_value = jitter_value;
+  return scaml::launch_target(p, num_sms(), stream);
+}
+
+int scaml_target_posterior(const double* prior_mean, const double* prior_var, const double* cross, const double* Xc,
+                           const double* Xt, const double* theta, const double* linv_t, const double* alpha_t,
+                           double mu_all, double s_all, double* mean, double* var, int B, int n_t, int d, int kernel,
+                           void* stream) {
+  if (!prior_mean || !prior_var || !cross || !Xc || !Xt || !theta || !linv_t || !alpha_t || !mean || !var)
+    return SCAML_E_ARG;
+  if (B <= 0 || n_t <= 0 || d <= 0 || kernel < 0 || kernel > 3 || !(s_all > 0.0)) return SCAML_E_ARG;
+  if (d > scaml::kMaxP - 2) return SCAML_E_UNSUPPORTED;
+  scaml::TargetPostParams p{};
+  p.pm = prior_mean, p.pv = prior_var, p.cross = cross, p.Xc = Xc, p.Xt = Xt, p.theta = theta, p.linv = linv_t;
+  p.alpha = alpha_t, p.mean = mean, p.var = var, p.mu_all = mu_all, p.s_all = s_all;
+  p.B = B, p.nt = n_t, p.d = d, p.kernel = kernel;
+  return scaml::launch_target_posterior(p, num_sms(), stream);
+}
+
 }  // extern "C"

@@ -34,7 +34,10 @@ struct TargetParams {
   double* meanw;            // ws [R][nt]
   double* Wmat;             // ws [R][nt][nt]
   double* alpha;            // ws [R][nt]
+  double* linv_out;         // factorize: [nt][nt] row-major L^-1 (lower), or null
+  double* theta_out;        // factorize: [P] constrained, or null
   double mu_all, s_all;
+  double jitter_value;      // used when `jitter` is null
   int M, nt, d, R, w_prior;
   double w_p1, w_p2;
   scaml_hyper_spec spec;
@@ -118,10 +121,11 @@ __global__ void __launch_bounds__(kTgtThreads) scaml_target_factor_kernel(const 
     lp[tid] = log_prior(pk, p1, p2, v);
     dlp[tid] = dlog_prior(pk, p1, p2, v);
     chain[tid] = (hi - lo) * sg * (1.0 - sg);
+    if (p.theta_out != nullptr) p.theta_out[(size_t)r * P + tid] = v;
   }
   if (tid == 0) *flag = 0;
   __syncthreads();
-  const double os = th[d], diag_add = th[d + 1] + (p.jitter ? p.jitter[r] : 0.0);
+  const double os = th[d], diag_add = th[d + 1] + (p.jitter ? p.jitter[r] : p.jitter_value);
   for (int i = tid; i < nt * d; i += kTgtThreads) {
     const int a = i / d, k = i - a * d;
     xs[k * nt + a] = p.Xt[i] / th[k];
@@ -183,6 +187,8 @@ __global__ void __launch_bounds__(kTgtThreads) scaml_target_factor_kernel(const 
     }
   }
   __syncthreads();
+  if (p.linv_out != nullptr)
+    for (int i = tid; i < nt * nt; i += kTgtThreads) p.linv_out[(size_t)r * nt * nt + i] = Li[(i / nt) * ld + (i % nt)];
   // z = L^-1 r ; alpha = L^-T z
   for (int a = tid; a < nt; a += kTgtThreads) {
     double s = 0.0;
@@ -270,6 +276,98 @@ __global__ void __launch_bounds__(kTgtThreads) scaml_target_wgrad_kernel(const T
   }
 }
 
+// ---- conditioning on the target data at B candidates (q = 1) --------------------------------- //
+//   k_s[j]  = cross[b][j] / s_all^2 + s k(x_b, X_t[j])
+//   mean[b] = mu_all + s_all ( (pm[b] - mu_all)/s_all + k_s . alpha_t )
+//   var[b]  = s_all^2 ( pv[b]/s_all^2 + s - || L_t^-1 k_s ||^2 )
+// exact-GP conditioning of ExactGP.__call__ in eval mode on top of ScaMLGP.forward
+// (reference scamlgp/model.py:364-383); one warp per candidate, L_t^-1 staged in shared memory.
+struct TargetPostParams {
+  const double* pm;     // [B] weighted source posterior mean (raw-Y units)
+  const double* pv;     // [B] weighted source posterior variance
+  const double* cross;  // [B][nt] weighted source cross-covariance with the target inputs
+  const double* Xc;     // [B][d]
+  const double* Xt;     // [nt][d]
+  const double* theta;  // [P] constrained target-kernel parameters
+  const double* linv;   // [nt][nt] row-major L_t^-1
+  const double* alpha;  // [nt]
+  double* mean;         // [B]
+  double* var;          // [B]
+  double mu_all, s_all;
+  int B, nt, d, kernel;
+};
+constexpr int kPostThreads = 256;
+inline size_t target_post_smem_bytes(int nt, int d) {
+  const int ld = nt | 1;
+  return sizeof(double) * ((size_t)nt * ld + (size_t)nt * d + nt + (kPostThreads / 32) * (size_t)(nt + d) + kMaxP);
+}
+__global__ void __launch_bounds__(kPostThreads) scaml_target_posterior_kernel(const TargetPostParams p) {
+  SCAML_DYN_SMEM(double, sm);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nt = p.nt, d = p.d, ld = nt | 1;
+  double* Li = sm;                        // nt x ld
+  double* xt = Li + (size_t)nt * ld;      // [nt][d] scaled
+  double* al = xt + (size_t)nt * d;       // nt
+  double* wk = al + nt;                   // per warp: k_s [nt] | x_b scaled [d]
+  double* th = wk + (kPostThreads / 32) * (size_t)(nt + d);
+  if (tid < d + 2) th[tid] = p.theta[tid];
+  __syncthreads();
+  for (int i = tid; i < nt * nt; i += kPostThreads) Li[(i / nt) * ld + (i % nt)] = p.linv[i];
+  for (int i = tid; i < nt * d; i += kPostThreads) xt[i] = p.Xt[i] / th[i % d];
+  for (int i = tid; i < nt; i += kPostThreads) al[i] = p.alpha[i];
+  __syncthreads();
+  const double os = th[d], s2 = p.s_all * p.s_all;
+  double* ks = wk + warp * (size_t)(nt + d);
+  double* xb = ks + nt;
+  const int wpg = kPostThreads / 32;
+  for (long long b = (long long)blockIdx.x * wpg + warp; b < p.B; b += (long long)gridDim.x * wpg) {
+    __syncwarp();
+    for (int k = lane; k < d; k += 32) xb[k] = p.Xc[(size_t)b * d + k] / th[k];
+    __syncwarp();
+    double dot = 0.0;
+    for (int j = lane; j < nt; j += 32) {
+      double r2 = 0.0;
+      for (int k = 0; k < d; ++k) {
+        const double df = xb[k] - xt[j * d + k];
+        r2 = fma(df, df, r2);
+      }
+      const double v = p.cross[(size_t)b * nt + j] / s2 + os * kappa_rt(p.kernel, r2);
+      ks[j] = v;
+      dot = fma(v, al[j], dot);
+    }
+    __syncwarp();
+    double ssq = 0.0;
+    for (int i = lane; i < nt; i += 32) {
+      double s = 0.0;
+      const double* row = Li + (size_t)i * ld;
+      for (int j = 0; j <= i; ++j) s = fma(row[j], ks[j], s);
+      ssq = fma(s, s, ssq);
+    }
+    dot = warp_sum(dot);
+    ssq = warp_sum(ssq);
+    if (lane == 0) {
+      p.mean[b] = p.mu_all + p.s_all * ((p.pm[b] - p.mu_all) / p.s_all + dot);
+      p.var[b] = s2 * (p.pv[b] / s2 + os - ssq);
+    }
+  }
+}
+inline int launch_target_posterior(const TargetPostParams& p, int num_sms, void* stream) {
+  const size_t smem = target_post_smem_bytes(p.nt, p.d);
+  if (smem > 227 * 1024) return SCAML_E_SMEM;
+  long long gx = ((long long)p.B + kPostThreads / 32 - 1) / (kPostThreads / 32);
+  if (gx > 2LL * num_sms) gx = 2LL * num_sms;
+#ifdef SCAML_EMU
+  (void)stream;
+  cuemu::launch(dim3(gx < 2 ? (unsigned)gx : 2u), dim3(kPostThreads), smem, scaml_target_posterior_kernel, p);
+  return 0;
+#else
+  cudaError_t err =
+      cudaFuncSetAttribute(scaml_target_posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return (int)err;
+  scaml_target_posterior_kernel<<<(unsigned)gx, kPostThreads, smem, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
+#endif
+}
+
 template <int KIND>
 int launch_target_factor(const TargetParams& p, size_t smem, void* stream) {
 #ifdef SCAML_EMU
@@ -298,7 +396,8 @@ inline int launch_target(const TargetParams& p, int num_sms, void* stream) {
     TargetParams q = p;
     q.R = 1;
     q.w += (size_t)r * p.M, q.theta_raw += (size_t)r * (p.d + 2), q.jitter = p.jitter ? p.jitter + r : nullptr;
-    q.lml += r, q.grad_w += (size_t)r * p.M, q.grad_theta += (size_t)r * (p.d + 2), q.info += r;
+    q.lml += r, q.grad_theta += (size_t)r * (p.d + 2), q.info += r;
+    if (p.grad_w) q.grad_w += (size_t)r * p.M;
     q.covw += (size_t)r * p.nt * p.nt, q.meanw += (size_t)r * p.nt, q.Wmat += (size_t)r * p.nt * p.nt,
         q.alpha += (size_t)r * p.nt;
     cuemu::launch(dim3(2), dim3(kTgtThreads), 0, scaml_target_reduce_kernel, q);
@@ -310,7 +409,7 @@ inline int launch_target(const TargetParams& p, int num_sms, void* stream) {
       default: rc = launch_target_factor<SCAML_KERNEL_MATERN52>(q, smem, stream); break;
     }
     if (rc) return rc;
-    cuemu::launch(dim3(gw < 2 ? gw : 2), dim3(kTgtThreads), 0, scaml_target_wgrad_kernel, q);
+    if (p.grad_w != nullptr) cuemu::launch(dim3(gw < 2 ? gw : 2), dim3(kTgtThreads), 0, scaml_target_wgrad_kernel, q);
   }
   return 0;
 #else
@@ -323,7 +422,7 @@ inline int launch_target(const TargetParams& p, int num_sms, void* stream) {
     case SCAML_KERNEL_MATERN32: rc = launch_target_factor<SCAML_KERNEL_MATERN32>(p, smem, stream); break;
     default: rc = launch_target_factor<SCAML_KERNEL_MATERN52>(p, smem, stream); break;
   }
-  if (rc) return rc;
+  if (rc || p.grad_w == nullptr) return rc;
   if (gw > 4 * num_sms) gw = 4 * num_sms;
   scaml_target_wgrad_kernel<<<dim3(gw, p.R), kTgtThreads, 0, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();

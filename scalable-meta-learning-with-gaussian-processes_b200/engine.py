@@ -85,11 +85,12 @@ class SourceBatch:
         return SourceBatch(X, y.contiguous(), n_valid, ybar.contiguous(), ystd.contiguous(), Y)
 
     @staticmethod
-    def from_ragged(tasks: Sequence[Tuple[torch.Tensor, torch.Tensor]], device) -> "SourceBatch":
+    def from_ragged(tasks: Sequence[Tuple[torch.Tensor, torch.Tensor]], device,
+                    n_max: Optional[int] = None) -> "SourceBatch":
         """tasks: sequence of (X_i [n_i, d], Y_i [n_i] or [n_i, 1]) host or device tensors."""
         M = len(tasks)
         d = tasks[0][0].shape[-1]
-        n_max = max(int(t[0].shape[-2]) for t in tasks)
+        n_max = max([int(t[0].shape[-2]) for t in tasks] + [int(n_max or 0)])
         X = torch.zeros(M, n_max, d, dtype=torch.float64)
         Y = torch.zeros(M, n_max, dtype=torch.float64)
         nv = torch.zeros(M, dtype=torch.int32)
@@ -116,6 +117,23 @@ class FittedSources:
     alpha: torch.Tensor  # [M, n_pad]
     info: torch.Tensor  # [M] int32
     spec: HyperSpec
+
+    def select(self, idx: torch.Tensor) -> "FittedSources":
+        """Sub-batch of the tasks `idx` (copies; used when a caller re-orders or subsets the source GPs)."""
+        b = self.batch
+        nb = SourceBatch(b.X[idx].contiguous(), b.y[idx].contiguous(), b.n_valid[idx].contiguous(),
+                         b.ybar[idx].contiguous(), b.ystd[idx].contiguous(), b.Y_raw[idx].contiguous())
+        return FittedSources(nb, self.theta_raw[idx].contiguous(), self.theta[idx].contiguous(),
+                             self.linv[idx].contiguous(), self.alpha[idx].contiguous(), self.info[idx].contiguous(),
+                             self.spec)
+
+    def task_slice(self, i: int) -> "FittedSources":
+        """Zero-copy view of the single task i."""
+        b = self.batch
+        nb = SourceBatch(b.X[i:i + 1], b.y[i:i + 1], b.n_valid[i:i + 1], b.ybar[i:i + 1], b.ystd[i:i + 1],
+                         b.Y_raw[i:i + 1])
+        return FittedSources(nb, self.theta_raw[i:i + 1], self.theta[i:i + 1], self.linv[i:i + 1],
+                             self.alpha[i:i + 1], self.info[i:i + 1], self.spec)
 
 
 class Engine:
@@ -180,20 +198,28 @@ class Engine:
         self.launches += 1
         return lml, grad, info
 
-    def lml_grad(self, batch: SourceBatch, theta_raw: torch.Tensor, spec: HyperSpec):
+    def lml_grad(self, batch: SourceBatch, theta_raw: torch.Tensor, spec: HyperSpec,
+                 skip: Optional[torch.Tensor] = None):
         """LML+grad with the psd_safe_cholesky jitter ladder (only failed rows are re-run).
 
-        Rows that still fail keep info > 0 and NaN outputs -- the reference hands NaN to
-        scipy in that case."""
-        lml, grad, info = self.lml_grad_raw(batch, theta_raw, spec)
+        skip [M, R] int32 (optional): non-zero rows are neither evaluated nor written (their outputs
+        are NaN / info 0).  Rows that still fail keep info > 0 and NaN outputs -- the reference hands
+        NaN to scipy in that case."""
+        out = None
+        if skip is not None:
+            M, R, P = theta_raw.shape
+            out = (torch.full((M, R), float("nan"), dtype=torch.float64, device=self.device),
+                   torch.full((M, R, P), float("nan"), dtype=torch.float64, device=self.device),
+                   torch.zeros(M, R, dtype=torch.int32, device=self.device))
+        lml, grad, info = self.lml_grad_raw(batch, theta_raw, spec, skip=skip, out=out)
         if bool((info > 0).any()):
             for jit in JITTER_LADDER:
                 bad = info > 0
                 if not bool(bad.any()):
                     break
-                skip = (~bad).to(torch.int32).contiguous()
+                skip_j = (~bad).to(torch.int32).contiguous()
                 jitter = torch.where(bad, torch.full_like(lml, jit), torch.zeros_like(lml)).contiguous()
-                self.lml_grad_raw(batch, theta_raw, spec, jitter=jitter, skip=skip, out=(lml, grad, info))
+                self.lml_grad_raw(batch, theta_raw, spec, jitter=jitter, skip=skip_j, out=(lml, grad, info))
         return lml, grad, info
 
     # ---- K1-K3 for prediction ------------------------------------------------------------ #
@@ -318,6 +344,57 @@ class Engine:
                                                     theta_raw[idx].contiguous(), mu_all, s_all, spec, w_prior, jitter)
             lml[idx], gw[idx], gt[idx], info[idx] = l2, gw2, gt2, i2
         return lml, gw, gt, info
+
+    # ---- target prediction state + conditioning ---------------------------------------- #
+    def target_factorize(self, source_means, source_covs, Xt, yt, w, theta_raw, mu_all, s_all, spec) -> "TargetState":
+        """L_t^-1, alpha_t and constrained kernel parameters of the target GP at (w [M], theta_raw [P]);
+        psd_safe_cholesky jitter ladder on failure."""
+        nt, d = Xt.shape
+        M, P = w.numel(), d + 2
+        linv = torch.empty(nt, nt, dtype=torch.float64, device=self.device)
+        alpha = torch.empty(nt, dtype=torch.float64, device=self.device)
+        theta = torch.empty(P, dtype=torch.float64, device=self.device)
+        lml = torch.empty(1, dtype=torch.float64, device=self.device)
+        info = torch.empty(1, dtype=torch.int32, device=self.device)
+        need = self.lib.target_workspace_bytes(nt, 1) + 8 * (d + 3)
+        if self._tws is None or self._tws.numel() * 8 < need:
+            self._tws = torch.empty((need + 7) // 8, dtype=torch.float64, device=self.device)
+        for jit in (0.0,) + JITTER_LADDER:
+            self.lib.target_factorize(_ptr(source_means), _ptr(source_covs), _ptr(Xt), _ptr(yt), _ptr(w),
+                                      _ptr(theta_raw), jit, mu_all, s_all, _ptr(linv), _ptr(alpha), _ptr(theta),
+                                      _ptr(lml), _ptr(info), _ptr(self._tws), need, M, nt, d, spec, self._stream())
+            self.launches += 2
+            if int(info.item()) == 0:
+                break
+        return TargetState(Xt, linv, alpha, theta, float(mu_all), float(s_all), int(info.item()), float(lml.item()),
+                           spec.kernel)
+
+    def target_posterior(self, ts: "TargetState", prior_mean, prior_var, cross, Xc):
+        """Condition the weighted source prior at candidates Xc [B, d] on the target data (q = 1)."""
+        B, d = Xc.shape
+        nt = ts.Xt.shape[0]
+        mean = torch.empty(B, dtype=torch.float64, device=self.device)
+        var = torch.empty(B, dtype=torch.float64, device=self.device)
+        self.lib.target_posterior(_ptr(prior_mean), _ptr(prior_var), _ptr(cross), _ptr(Xc), _ptr(ts.Xt), _ptr(ts.theta),
+                                  _ptr(ts.linv), _ptr(ts.alpha), ts.mu_all, ts.s_all, _ptr(mean), _ptr(var), B, nt, d,
+                                  ts.kernel, self._stream())
+        self.launches += 1
+        return mean, var
+
+
+@dataclass
+class TargetState:
+    """Prediction state of the fitted target GP (output of Engine.target_factorize)."""
+
+    Xt: torch.Tensor  # [n_t, d]
+    linv: torch.Tensor  # [n_t, n_t] row-major L_t^-1
+    alpha: torch.Tensor  # [n_t]
+    theta: torch.Tensor  # [P] constrained
+    mu_all: float
+    s_all: float
+    info: int
+    lml: float
+    kernel: int
 
 
 _default_engine: Optional[Engine] = None

@@ -1,0 +1,344 @@
+"""ScaML-GP model API -- mirror of the reference's scamlgp/model.py on the B200 engine.
+
+Same names, arguments and error behaviour as the reference:
+  meta_fit_scamlgp            scamlgp/model.py:138-189
+  ScaMLGP                     scamlgp/model.py:218-384
+  significant_weights_mask    scamlgp/model.py:192-215
+  _compute_target_prior       scamlgp/model.py:108-135
+  _get_default_likelihood / _get_kernel_source_gp / _get_default_kernel   model.py:25-105
+What changes is where the arithmetic runs: the per-task Python loops (model.py:128,176,281) become
+single batched kernel launches through `engine.Engine` (C ABI: include/scaml_b200.h).
+"""
+from __future__ import annotations
+
+import copy
+from typing import Dict, Hashable, List, Optional, Tuple
+
+import torch
+
+from ._capi import PRIOR_GAMMA, HyperSpec
+from .engine import Engine, FittedSources, SourceBatch, TargetState, default_engine
+from .fit import fit_sources, sample_theta_raw
+from .modules import (DT, GammaPrior, GaussianLikelihood, GreaterThan, Interval, LogNormalPrior, MaternKernel,
+                      MultivariateNormal, Posterior, RBFKernel, ScaleKernel, Standardize, SupervisedDataset,
+                      hyper_spec_of, set_theta_raw, theta_raw_of)
+from .utils import validate_meta_data
+
+
+# ---- defaults (reference model.py:25-105) ---------------------------------------------------- #
+def _get_default_likelihood(batch_shape: torch.Size = torch.Size()) -> GaussianLikelihood:
+    return GaussianLikelihood(noise_prior=LogNormalPrior(-8.0, 2.0), noise_constraint=Interval(1e-8, 1e-2, 1e-3),
+                              batch_shape=batch_shape)
+
+
+def _get_kernel_source_gp(base_kernel=RBFKernel, ard_num_dims: Optional[int] = None,
+                          batch_shape: torch.Size = torch.Size()) -> ScaleKernel:
+    return ScaleKernel(
+        base_kernel=base_kernel(ard_num_dims=ard_num_dims, batch_shape=batch_shape,
+                                lengthscale_prior=GammaPrior(3.0, 6.0),
+                                lengthscale_constraint=Interval(1e-4, 1e2, 0.5)),
+        batch_shape=batch_shape, outputscale_prior=GammaPrior(2.0, 0.15),
+        outputscale_constraint=Interval(1e-4, 1e2, 1.0))
+
+
+def _get_default_kernel(base_kernel=RBFKernel, ard_num_dims: Optional[int] = None,
+                        batch_shape: torch.Size = torch.Size()) -> ScaleKernel:
+    return ScaleKernel(
+        base_kernel=base_kernel(ard_num_dims=ard_num_dims, batch_shape=batch_shape,
+                                lengthscale_prior=LogNormalPrior(0.5, 1.5),
+                                lengthscale_constraint=Interval(1e-4, 1e2, 1.0)),
+        batch_shape=batch_shape, outputscale_prior=LogNormalPrior(-2.0, 3.0),
+        outputscale_constraint=Interval(1e-4, 1e2, 0.1))
+
+
+# ---- fitted source GP (stand-in for the botorch SingleTaskGP the reference returns) ---------- #
+class SourceGP:
+    """One fitted source task.  Holds its data, fitted modules and Standardize state; predictions go
+    through the shared device batch (`owner.fitted`, index `index`)."""
+
+    def __init__(self, train_X, train_Y, likelihood, covar_module, outcome_transform, owner: "SourceGPDict",
+                 index: int):
+        self.train_inputs = (train_X,)
+        self.train_targets = ((train_Y.reshape(-1) - outcome_transform.means.reshape(())) /
+                              outcome_transform.stdvs.reshape(()))
+        self.likelihood = likelihood
+        self.covar_module = covar_module
+        self.outcome_transform = outcome_transform
+        self._raw_Y = train_Y
+        self._owner = owner
+        self._index = index
+
+    def posterior(self, X: torch.Tensor) -> Posterior:
+        """Posterior of this source GP at X [n, d] (un-standardised, noise-free), full covariance."""
+        fs = self._owner.fitted.task_slice(self._index)
+        eng = self._owner.engine
+        Xd = X.reshape(-1, X.shape[-1]).to(eng.device, DT).contiguous()
+        mean, cov = eng.predict_cross(fs, Xd)
+        mean, cov = mean[:, 0].to(X.device), cov[:, :, 0].to(X.device)
+        return Posterior(mean, cov.diagonal(), cov)
+
+
+class SourceGPDict(dict):
+    """Dict[task_id, SourceGP] that also carries the device-resident batch of all fitted tasks."""
+
+    engine: Engine
+    fitted: FittedSources
+
+
+def _batch_from_sources(source_gps: Dict[Hashable, SourceGP], engine: Engine) -> FittedSources:
+    """Re-assemble (and re-factorise) a device batch from individual SourceGP objects, in dict order."""
+    gps = list(source_gps.values())
+    d = gps[0].train_inputs[0].shape[-1]
+    batch = SourceBatch.from_ragged([(g.train_inputs[0], g._raw_Y) for g in gps], engine.device)
+    spec = hyper_spec_of(gps[0].likelihood, gps[0].covar_module)
+    theta = torch.stack([theta_raw_of(g.likelihood, g.covar_module, d) for g in gps]).to(engine.device).contiguous()
+    return engine.factorize(batch, theta, spec)
+
+
+def fitted_sources_of(source_gps: Dict[Hashable, SourceGP], engine: Optional[Engine] = None) -> FittedSources:
+    """The device batch behind a dict of source GPs, in the dict's iteration order."""
+    if isinstance(source_gps, SourceGPDict) and [g._index for g in source_gps.values()] == list(range(len(source_gps))):
+        return source_gps.fitted
+    eng = engine or (source_gps.engine if isinstance(source_gps, SourceGPDict) else default_engine())
+    owner = next(iter(source_gps.values()))._owner
+    idx = [g._index for g in source_gps.values()]
+    if all(g._owner is owner for g in source_gps.values()):
+        return owner.fitted.select(torch.tensor(idx, device=owner.fitted.theta.device))
+    return _batch_from_sources(source_gps, eng)
+
+
+def meta_fit_scamlgp(meta_data: Dict[Hashable, SupervisedDataset], likelihood: Optional[GaussianLikelihood] = None,
+                     covar_module: Optional[ScaleKernel] = None, num_restarts_log_likelihood: int = 5,
+                     seed: Optional[int] = None, *, engine: Optional[Engine] = None,
+                     fit_options: Optional[dict] = None) -> Dict[Hashable, SourceGP]:
+    """Train the source GPs on the given meta-data (reference scamlgp/model.py:138-189).
+
+    All tasks and all restarts are optimised together on the GPU; returns {task_id: SourceGP} in the
+    order of `meta_data` (a SourceGPDict, which also owns the packed device state used for prediction)."""
+    generator = None
+    if seed is not None:
+        torch.manual_seed(seed)
+        generator = torch.Generator().manual_seed(seed)
+    validate_meta_data(meta_data)
+    first = list(meta_data.values())[0]
+    d = first.X.shape[-1]
+    batch_shape = first.X.shape[:-2]
+    if len(batch_shape) != 0:
+        raise NotImplementedError("batched meta-data (batch_shape != ()) is not supported; the reference optimizer "
+                                  "always uses torch.Size() (scamlgp/optimizer.py:121)")
+    if likelihood is None:
+        likelihood = _get_default_likelihood(batch_shape=batch_shape)
+    if covar_module is None:
+        covar_module = _get_kernel_source_gp(base_kernel=RBFKernel, ard_num_dims=d, batch_shape=batch_shape)
+    eng = engine or default_engine()
+    spec = hyper_spec_of(likelihood, covar_module)
+    theta0 = theta_raw_of(likelihood, covar_module, d)
+    tasks = [(ds.X(), ds.Y()) for ds in meta_data.values()]
+    batch = SourceBatch.from_ragged(tasks, eng.device)
+    M, R = len(tasks), 1 + int(num_restarts_log_likelihood)
+    rows = [theta0.reshape(1, 1, -1).expand(M, 1, -1)]
+    if R > 1:
+        rows.append(sample_theta_raw(spec, theta0, M, R - 1, generator))
+    fit = fit_sources(eng, batch, spec, torch.cat(rows, dim=1), fit_options)
+    fitted = eng.factorize(batch, fit.theta_raw, spec)
+    out = SourceGPDict()
+    out.engine, out.fitted, out.fit = eng, fitted, fit
+    theta_host = fit.theta_raw.cpu()
+    ybar, ystd = batch.ybar.cpu(), batch.ystd.cpu()
+    for i, (task_id, (X, Y)) in enumerate(zip(meta_data.keys(), tasks)):
+        lk, cm = copy.deepcopy(likelihood), copy.deepcopy(covar_module)
+        set_theta_raw(lk, cm, theta_host[i])
+        tf = Standardize(1)
+        tf.means, tf.stdvs, tf._is_trained = ybar[i].reshape(1, 1), ystd[i].reshape(1, 1), True
+        tf.eval()
+        out[task_id] = SourceGP(X, Y, lk, cm, tf, out, i)
+    return out
+
+
+def significant_weights_mask(weights: torch.Tensor, std_Y_vals: torch.Tensor, threshold: float) -> torch.Tensor:
+    r"""Mask of weights with w_i sigma_i n_w / sum_j w_j sigma_j >= threshold (reference model.py:192-215)."""
+    num_weights = len(weights)
+    w_times_sigma = weights * std_Y_vals
+    norm_weights = w_times_sigma * num_weights / w_times_sigma.sum()
+    return norm_weights >= threshold
+
+
+def _compute_target_prior(x: torch.Tensor, source_gps: List[SourceGP], weights: torch.Tensor,
+                          engine: Optional[Engine] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Prior of the target GP at x [n, d]: mean [n, 1] = sum_i w_i mu_i(x), cov [n, n] = sum_i w_i^2 Sigma_i(x, x)
+    (reference model.py:108-135) -- one launch reduced over the tasks instead of a Python loop."""
+    if len(source_gps) != len(weights):
+        raise ValueError(f"The number of source GPs, {len(source_gps)}, does not equal the number of weights, "
+                         f"{len(weights)}")
+    fs = fitted_sources_of(dict(enumerate(source_gps)), engine)
+    eng = engine or source_gps[0]._owner.engine
+    mean, cov = eng.predict_cross(fs, x.to(eng.device, DT).contiguous(), None, w=weights.to(eng.device, DT))
+    return mean.unsqueeze(-1), cov
+
+
+class ScaMLGP:
+    """Scalable and Modular Kernel for Transfer Learning with Gaussian Processes (reference model.py:218-384)."""
+
+    def __init__(self, train_X: torch.Tensor, train_Y: torch.Tensor, source_gps: Dict[Hashable, SourceGP],
+                 likelihood: Optional[GaussianLikelihood] = None, covar_module: Optional[ScaleKernel] = None,
+                 weight_pruning_threshold: float = 1e-3, *, engine: Optional[Engine] = None) -> None:
+        self._weight_pruning_threshold = weight_pruning_threshold
+        if len(train_Y.shape[:-2]) != 0:
+            raise NotImplementedError("batch_shape must be ()")
+        n_source_tasks = len(source_gps)
+        gps = list(source_gps.values())
+        self.engine = engine or (source_gps.engine if isinstance(source_gps, SourceGPDict) else gps[0]._owner.engine)
+        dev = self.engine.device
+        self._fitted = fitted_sources_of(source_gps, self.engine)
+        d = train_X.shape[-1]
+        # all-data normaliser (model.py:264-276): every source task's raw Y + the target Y, frozen
+        b = self._fitted.batch
+        mask = torch.arange(b.n_max, device=dev).unsqueeze(0) < b.n_valid.unsqueeze(1)
+        Y_all = torch.cat([b.Y_raw[mask], train_Y.reshape(-1).to(dev, DT)])
+        outcome_transform = Standardize(1)
+        outcome_transform(Y_all.cpu())
+        outcome_transform.eval()
+        self.train_inputs = (train_X,)
+        self._train_Y = train_Y
+        n_t = train_Y.shape[-2]
+        self._Xt = train_X.reshape(n_t, d).to(dev, DT).contiguous()
+        # cache the source posteriors at the target inputs (model.py:278-289): one launch for all tasks
+        if n_t > 0:
+            self.source_means, self.source_covs = self.engine.predict_cross(self._fitted, self._Xt)
+        if covar_module is None:
+            covar_module = _get_default_kernel(base_kernel=RBFKernel, ard_num_dims=d)
+        self.source_gps = source_gps
+        if likelihood is None:
+            likelihood = _get_default_likelihood()
+        self.likelihood, self.covar_module = likelihood, covar_module
+        if train_Y.nelement() == 0:  # empty input: do not standardise (model.py:307-308)
+            self.outcome_transform = None
+            self.train_targets = train_Y.reshape(-1).to(DT)
+        else:
+            self.outcome_transform = outcome_transform
+            self.train_targets = outcome_transform(train_Y.to(DT))[0].reshape(-1)
+        self.raw_weights = torch.full((n_source_tasks,), 1.0 / n_source_tasks, dtype=DT)
+        self.weights_prior = GammaPrior(1.0, 1.0)
+        self.raw_weights_constraint = GreaterThan(1e-10, transform=None)
+        self.training = True
+        self._tstate: Optional[TargetState] = None
+
+    # ---- parameters ------------------------------------------------------------------------- #
+    @property
+    def weights(self) -> torch.Tensor:
+        return self.raw_weights_constraint.transform(self.raw_weights)
+
+    @weights.setter
+    def weights(self, value):
+        self._set_weights(value)
+
+    def _set_weights(self, value):
+        if not torch.is_tensor(value):
+            value = torch.as_tensor(value)
+        self.raw_weights = self.raw_weights_constraint.inverse_transform(value.detach().to("cpu", DT)).clone()
+        self._tstate = None
+
+    def train(self, mode: bool = True):
+        self.training = mode
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        sd = {"raw_weights": self.raw_weights.clone()}
+        sd.update(self.likelihood.state_dict("likelihood.noise_covar."))
+        sd.update(self.covar_module.state_dict("covar_module."))
+        return sd
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        self.raw_weights = sd["raw_weights"].clone()
+        self.likelihood.load_state_dict(sd, "likelihood.noise_covar.")
+        self.covar_module.load_state_dict(sd, "covar_module.")
+        self._tstate = None
+
+    def named_priors(self):
+        """(name, module, prior, closure, setting_closure) like gpytorch's Module.named_priors."""
+        bk = self.covar_module.base_kernel
+        yield ("covar_module.base_kernel.lengthscale_prior", bk, bk.lengthscale_prior, lambda m: m.lengthscale,
+               lambda m, v: setattr(m, "lengthscale", v))
+        yield ("covar_module.outputscale_prior", self.covar_module, self.covar_module.outputscale_prior,
+               lambda m: m.outputscale, lambda m, v: setattr(m, "outputscale", v))
+        yield ("likelihood.noise_covar.noise_prior", self.likelihood, self.likelihood.noise_prior,
+               lambda m: m.noise, lambda m, v: setattr(m, "noise", v))
+        yield ("weights_prior", self, self.weights_prior, lambda m: m.weights, lambda m, v: m._set_weights(v))
+
+    # ---- internals ---------------------------------------------------------------------------- #
+    @property
+    def num_train(self) -> int:
+        return self._Xt.shape[0]
+
+    def hyper_spec(self) -> HyperSpec:
+        return hyper_spec_of(self.likelihood, self.covar_module)
+
+    def theta_raw(self) -> torch.Tensor:
+        return theta_raw_of(self.likelihood, self.covar_module, self._Xt.shape[1])
+
+    def _std_Y_vals(self) -> torch.Tensor:
+        return self._fitted.batch.ystd
+
+    def pruned_weights(self) -> torch.Tensor:
+        """Device weights with the insignificant ones zeroed (the kernels skip w == 0), model.py:365-372."""
+        w = self.weights.to(self.engine.device, DT)
+        mask = significant_weights_mask(w, self._std_Y_vals(), self._weight_pruning_threshold)
+        return torch.where(mask, w, torch.zeros_like(w)).contiguous()
+
+    def _target_state(self) -> TargetState:
+        if self._tstate is None:
+            dev = self.engine.device
+            ot = self.outcome_transform
+            # conditioning uses the CACHED train-branch prior (all weights), exactly as gpytorch's prediction
+            # strategy is built from forward(train_X) in ... eval mode -> pruned weights (model.py:364-375)
+            w = self.pruned_weights()
+            self._tstate = self.engine.target_factorize(
+                self.source_means, self.source_covs, self._Xt, self.train_targets.to(dev, DT).contiguous(), w,
+                self.theta_raw().to(dev).contiguous(), float(ot.means), float(ot.stdvs), self.hyper_spec())
+        return self._tstate
+
+    # ---- forward / posterior ------------------------------------------------------------------ #
+    def forward(self, x: torch.Tensor) -> MultivariateNormal:
+        """Prior of the target process at x [n, d] in the (all-data) standardised space (model.py:359-384)."""
+        eng, dev = self.engine, self.engine.device
+        xd = x.reshape(-1, x.shape[-1]).to(dev, DT).contiguous()
+        if self.training:
+            w = self.weights.to(dev, DT)
+            mean = self.source_means @ w
+            cov = self.source_covs @ w ** 2
+        else:
+            mean, cov = eng.predict_cross(self._fitted, xd, None, w=self.pruned_weights())
+        if self.outcome_transform is not None:
+            mu, sd = float(self.outcome_transform.means), float(self.outcome_transform.stdvs)
+            mean = (mean - mu) / sd
+            cov = cov / sd ** 2
+        spec = self.hyper_spec()
+        ls = self.covar_module.base_kernel.lengthscale.reshape(-1).to(dev)
+        if ls.numel() == 1:
+            ls = ls.expand(xd.shape[1])
+        theta = torch.cat([ls, self.covar_module.outputscale.reshape(1).to(dev), torch.zeros(1, dtype=DT, device=dev)])
+        kt = eng.kernel_matrix(xd.unsqueeze(0), theta.reshape(1, -1).contiguous(), spec.kernel)[0]
+        return MultivariateNormal(mean, cov + kt)
+
+    def posterior(self, X: torch.Tensor, observation_noise: bool = False) -> Posterior:
+        """Posterior at candidates X [B, d] or [B, 1, d] (q = 1), un-standardised: mean/variance [B, 1]."""
+        if observation_noise:
+            raise NotImplementedError("observation_noise=True is not used on the reference path")
+        eng, dev = self.engine, self.engine.device
+        if X.dim() == 3:
+            if X.shape[-2] != 1:
+                raise NotImplementedError("only q = 1 candidate batches (the acquisition path) are supported")
+            X = X[:, 0, :]
+        Xc = X.to(dev, DT).contiguous()
+        w = self.pruned_weights()
+        pm, pv = eng.predict_weighted(self._fitted, w, Xc)
+        if self.num_train == 0:
+            # prior-only model (optimizer.py:135-141): no outcome transform, var + s_t
+            mean, var = pm, pv + float(self.covar_module.outputscale)
+        else:
+            _, cross = eng.predict_cross(self._fitted, Xc, self._Xt, w=w)
+            mean, var = eng.target_posterior(self._target_state(), pm, pv, cross, Xc)
+        return Posterior(mean.to(X.device), var.to(X.device))

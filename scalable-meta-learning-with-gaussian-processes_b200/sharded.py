@@ -1,0 +1,149 @@
+"""Task sharding over the GPUs of one box: one process per GPU, torch.distributed for plumbing.
+
+The source GPs factor independently (reference scamlgp/model.py:176-188 fits them one by one and
+model.py:128 queries them one by one), so the M tasks are cut into contiguous blocks, one per rank:
+
+  * fit       -- no collective on the data path: every rank optimises its own tasks x restarts; afterwards one
+                 `all_gather` of the fitted rows [M/G, P+1] so that every rank knows every task's parameters;
+  * predict   -- every rank reduces its own tasks inside the prediction kernel (weighted mean / variance /
+                 cross-covariance partials for the replicated candidates), then ONE `all_reduce(sum)` over the
+                 stacked partials ([2, B] for q = 1);
+  * target    -- the per-task caches `source_means` [n_t, M] / `source_covs` [n_t, n_t, M] (model.py:278-289) are
+                 computed for the local tasks and `all_gather`ed along the task axis; the small target-GP fit
+                 (n_t <= 116) then runs replicated and bit-identically on every rank.
+
+Traffic is tiny next to the compute (16 MB per all-reduce at B = 1 Mi against ~1 s of FP64 work), so plain
+NCCL collectives are used; there is nothing to fuse.  The same code runs on the `gloo` backend with CPU
+tensors -- that is how tests/test_sharded.py covers it at world_size 2 without GPUs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+from ._capi import HyperSpec
+from .engine import Engine, FittedSources, SourceBatch, TargetState
+from .fit import SourceFit, fit_sources
+
+DT = torch.float64
+
+
+def task_partition(M: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous blocks of ceil(M / world) tasks; trailing ranks may own fewer (or zero) tasks."""
+    per = (M + world - 1) // world
+    return [(min(r * per, M), min((r + 1) * per, M)) for r in range(world)]
+
+
+def _world(group) -> Tuple[int, int]:
+    if not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(group), dist.get_world_size(group)
+
+
+def _all_gather_rows(local: torch.Tensor, counts: Sequence[int], group) -> torch.Tensor:
+    """Concatenate per-rank row blocks of different heights along dim 0 (padded all_gather)."""
+    rank, world = _world(group)
+    if world == 1:
+        return local
+    per = max(max(counts), 1)
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad.contiguous(), group=group)
+    return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
+
+
+@dataclass
+class ShardedFit:
+    local: SourceFit  # this rank's tasks
+    theta_raw: torch.Tensor  # [M, P] all tasks (gathered)
+    lml: torch.Tensor  # [M]
+
+
+class ShardedSources:
+    """This rank's block of the source GPs plus the collectives that make it look like all M of them."""
+
+    def __init__(self, engine: Engine, tasks: Sequence[Tuple[torch.Tensor, torch.Tensor]], group=None):
+        """tasks: ALL M tasks as (X_i [n_i, d], Y_i [n_i]) host tensors, identical on every rank (meta-data are
+        a few MB); only this rank's block is moved to its GPU."""
+        self.engine, self.group = engine, group
+        self.rank, self.world = _world(group)
+        self.M = len(tasks)
+        self.parts = task_partition(self.M, self.world)
+        self.counts = [hi - lo for lo, hi in self.parts]
+        self.lo, self.hi = self.parts[self.rank]
+        if self.hi <= self.lo:
+            raise ValueError(f"rank {self.rank} owns no task: use at most M = {self.M} ranks")
+        n_max = max(int(t[0].shape[-2]) for t in tasks)  # common padding: identical kernels on every rank
+        local = list(tasks[self.lo:self.hi])
+        self.batch = SourceBatch.from_ragged(local, engine.device, n_max=n_max)
+        # the all-data Standardize of the target model needs every raw Y (model.py:264-276): cheap, host side
+        self.all_Y = torch.cat([t[1].reshape(-1).to(DT) for t in tasks])
+        self.ystd_all: Optional[torch.Tensor] = None
+        self.fitted: Optional[FittedSources] = None
+
+    # ---- fit: no collective on the data path ----------------------------------------------------------- #
+    def fit(self, spec: HyperSpec, theta_init: torch.Tensor, fit_options: Optional[dict] = None) -> ShardedFit:
+        """theta_init [M, R, P] for ALL tasks (identical on every rank: restart draws are positional)."""
+        local = fit_sources(self.engine, self.batch, spec, theta_init[self.lo:self.hi].contiguous(), fit_options)
+        self.fitted = self.engine.factorize(self.batch, local.theta_raw, spec)
+        rows = torch.cat([local.theta_raw, local.lml.unsqueeze(1), self.batch.ystd.unsqueeze(1)], dim=1)
+        rows = _all_gather_rows(rows, self.counts, self.group)
+        P = local.theta_raw.shape[1]
+        self.ystd_all = rows[:, P + 1].contiguous()
+        return ShardedFit(local, rows[:, :P].contiguous(), rows[:, P].contiguous())
+
+    def set_parameters(self, spec: HyperSpec, theta_raw_all: torch.Tensor) -> None:
+        """Factorise this rank's block at given parameters [M, P] (e.g. restored from a previous fit)."""
+        th = theta_raw_all[self.lo:self.hi].to(self.engine.device, DT).contiguous()
+        self.fitted = self.engine.factorize(self.batch, th, spec)
+        self.ystd_all = _all_gather_rows(self.batch.ystd.unsqueeze(1), self.counts, self.group).squeeze(1).contiguous()
+
+    def _local_w(self, w: torch.Tensor) -> torch.Tensor:
+        return w.to(self.engine.device, DT)[self.lo:self.hi].contiguous()
+
+    # ---- predict: partials reduced in-kernel over local tasks, one all_reduce over ranks ---------------- #
+    def predict_weighted(self, w: torch.Tensor, Xc: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """sum_m w_m mu_m(x), sum_m w_m^2 var_m(x) over ALL tasks; w [M], Xc [B, d] replicated."""
+        B = Xc.shape[0]
+        part = torch.empty(2, B, dtype=DT, device=self.engine.device)
+        self.engine.predict_weighted(self.fitted, self._local_w(w), Xc.to(self.engine.device, DT),
+                                     out=(part[0], part[1]))
+        if self.world > 1:
+            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
+        return part[0], part[1]
+
+    def predict_cross(self, w: torch.Tensor, XA: torch.Tensor, XB: Optional[torch.Tensor] = None):
+        """Weighted joint prior blocks over ALL tasks: mean [nA], cov [nA, nB]."""
+        mean, cov = self.engine.predict_cross(self.fitted, XA, XB, w=self._local_w(w))
+        if self.world > 1:
+            flat = torch.cat([mean.reshape(-1), cov.reshape(-1)])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            mean, cov = flat[: mean.numel()].reshape(mean.shape), flat[mean.numel():].reshape(cov.shape)
+        return mean, cov
+
+    def target_caches(self, Xt: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """`source_means` [n_t, M], `source_covs` [n_t, n_t, M] for ALL tasks, gathered along the task axis."""
+        sm, sc = self.engine.predict_cross(self.fitted, Xt)
+        if self.world == 1:
+            return sm, sc
+        nt = Xt.shape[0]
+        rows = torch.cat([sm.t().reshape(-1, nt), sc.permute(2, 0, 1).reshape(-1, nt * nt)], dim=1)  # [M_loc, ...]
+        rows = _all_gather_rows(rows.contiguous(), self.counts, self.group)
+        sm_all = rows[:, :nt].t().contiguous()
+        sc_all = rows[:, nt:].reshape(self.M, nt, nt).permute(1, 2, 0).contiguous()
+        return sm_all, sc_all
+
+    def posterior(self, w: torch.Tensor, Xc: torch.Tensor, tstate: Optional[TargetState] = None,
+                  prior_outputscale: float = 0.0):
+        """ScaML-GP posterior mean / variance at Xc [B, d] (q = 1).  `w` are the (already pruned) weights of
+        all M tasks.  tstate None -> prior-only model (n_t = 0, optimizer.py:135-141): var + s_t."""
+        Xc = Xc.to(self.engine.device, DT).contiguous()
+        pm, pv = self.predict_weighted(w, Xc)
+        if tstate is None:
+            return pm, pv + prior_outputscale
+        _, cross = self.predict_cross(w, Xc, tstate.Xt)
+        return self.engine.target_posterior(tstate, pm.contiguous(), pv.contiguous(), cross.contiguous(), Xc)

@@ -1,0 +1,135 @@
+"""Mirror of the reference's scamlgp/utils.py: restart driver, prior sampling, meta-data
+conversion/validation and the UCB acquisition, on the B200 engine.
+
+  sample_all_priors              scamlgp/utils.py:31-69
+  metadata_to_numerical          scamlgp/utils.py:72-109
+  validate_meta_data             scamlgp/utils.py:112-136
+  optimize_marginal_likelihood   scamlgp/utils.py:139-212
+  UpperConfidenceBound           scamlgp/utils.py:215-224
+"""
+from __future__ import annotations
+
+import logging
+import warnings
+from typing import Dict, Hashable, Iterable, Optional, Union
+
+import torch
+
+from .modules import DT, ModelFittingError, SupervisedDataset
+
+logger = logging.getLogger("scamlgp_b200")
+
+
+def sample_all_priors(model, num_retries: int = 5, generator: Optional[torch.Generator] = None) -> None:
+    r"""Sample every registered prior in place (reference utils.py:31-69): a draw is rejected when the
+    constraint's inverse transform is not finite; more than `num_retries` rejections raise RuntimeError."""
+    for prior_name, module, prior, closure, setting_closure in model.named_priors():
+        if prior is None:
+            continue
+        if setting_closure is None:
+            raise RuntimeError("Must provide inverse transform to be able to sample from prior.")
+        parameter_name = "_".join(prior_name.split(".")[-1].split("_")[:-1])
+        constraint = getattr(module, "raw_" + parameter_name + "_constraint")
+        for i in range(num_retries + 1):
+            sample = prior.sample(closure(module).shape, generator=generator)
+            if bool(constraint.inverse_transform(sample).isfinite().all()):
+                setting_closure(module, sample)
+                break
+        else:
+            raise RuntimeError(f"Sampling of {prior_name} failed {num_retries} times. Please check the compatibility "
+                               "between prior support and the constraint.")
+        if i > 0:
+            logger.warning(f"Sampling from {prior_name} failed {i} times in a row.")
+
+
+def metadata_to_numerical(meta_data: Dict[Hashable, Iterable], search_space, objective,
+                          batch_shape: torch.Size = torch.Size(), torch_dtype: torch.dtype = torch.float32
+                          ) -> Dict[Hashable, SupervisedDataset]:
+    """Meta evaluations -> tensors; evaluations are sorted first so runs do not depend on their order, NaNs of
+    inactive (conditional) parameters are imputed (reference utils.py:72-109)."""
+    from .space import impute_nans_with_constant, sort_evaluations, to_numerical
+
+    out = {}
+    for task_id, task_data in meta_data.items():
+        X_raw, Y = to_numerical(sort_evaluations(task_data), search_space, [objective], batch_shape=batch_shape,
+                                torch_dtype=torch_dtype)
+        out[task_id] = SupervisedDataset(impute_nans_with_constant(X_raw), Y)
+    return out
+
+
+def validate_meta_data(meta_data: Dict[Hashable, SupervisedDataset]):
+    """Shape checks of the meta-data (reference utils.py:112-136; same messages)."""
+    if len(meta_data) == 0:
+        raise ValueError("Empty meta data. Needs at least one source task.")
+    task_id_source_0, data_source_0 = list(meta_data.items())[0]
+    X_shape = data_source_0.X.shape
+    Y_shape = data_source_0.Y.shape
+    if X_shape[:-2] != Y_shape[:-2]:
+        raise ValueError(f"The X and Y batch sizes of task {task_id_source_0} are not equal.")
+    for task_id, task_data in meta_data.items():
+        if (task_data.X.shape[:-2] != X_shape[:-2] or task_data.Y.shape[:-2] != Y_shape[:-2]
+                or task_data.X.shape[-1] != X_shape[-1]):
+            raise ValueError(f"Dimensions of tasks {task_id_source_0} and {task_id} do not match.")
+        if task_data.Y.shape[-1] != 1:
+            raise ValueError(f"The output dimension of task {task_id} is {task_data.Y.shape[-1]} but must be one")
+
+
+def optimize_marginal_likelihood(model, num_restarts: int = 0, generator: Optional[torch.Generator] = None,
+                                 **fit_options):
+    """Refit the ScaML-GP target model by maximising (LML + log priors)/n_t (reference utils.py:139-212).
+
+    1 warm start from the current parameters + `num_restarts` prior-sampled starts, all optimised together
+    (one batched objective launch per L-BFGS round); the best final value wins, failed rows are skipped
+    with a warning, all failed -> ModelFittingError."""
+    from .fit import fit_target
+    from .model import ScaMLGP
+    from .modules import set_theta_raw
+
+    if not isinstance(model, ScaMLGP):
+        raise TypeError("optimize_marginal_likelihood expects a ScaMLGP (source GPs are fitted by meta_fit_scamlgp)")
+    if model.num_train == 0:
+        raise ValueError("cannot optimise the marginal likelihood of a model without training data")
+    fit_options.pop("max_attempts", None)
+    fit_options.pop("caught_exception_types", None)
+    state0 = model.state_dict()
+    rows_w, rows_t = [model.weights.clone()], [model.theta_raw()]
+    for _ in range(num_restarts):
+        sample_all_priors(model, generator=generator)
+        rows_w.append(model.weights.clone())
+        rows_t.append(model.theta_raw())
+    model.load_state_dict(state0)
+    eng, dev = model.engine, model.engine.device
+    ot = model.outcome_transform
+    fit = fit_target(eng, model.source_means, model.source_covs, model._Xt,
+                     model.train_targets.to(dev, DT).contiguous(), float(ot.means), float(ot.stdvs), model.hyper_spec(),
+                     torch.stack(rows_w), torch.stack(rows_t), w_prior=model.weights_prior.spec(),
+                     w_lower=model.raw_weights_constraint.lower_bound, fit_options=fit_options or None)
+    nfail = int(torch.isinf(fit.all_lml).sum())
+    if nfail:
+        logger.warning(f"Error occurred while optimizing the model hyperparameters: {nfail} restart(s) skipped.")
+    model.raw_weights = fit.weights.detach().cpu().clone()
+    set_theta_raw(model.likelihood, model.covar_module, fit.theta_raw)
+    model._tstate = None
+    model.last_fit = fit
+    return fit
+
+
+class UpperConfidenceBound:
+    """UCB with default beta = 9.0, always minimising (reference utils.py:215-224): botorch's UCB with
+    maximize=False returns -mu + sqrt(beta * sigma^2), to be maximised."""
+
+    def __init__(self, model, beta: Union[float, torch.Tensor] = 9.0, posterior_transform=None, **kwargs):
+        if kwargs.get("maximize", False):
+            raise ValueError("Only acquisition functions to be minimized are supported")
+        self.model = model
+        self.beta = float(beta)
+        self.maximize = False
+
+    def __call__(self, X: torch.Tensor) -> torch.Tensor:
+        return self.forward(X)
+
+    def forward(self, X: torch.Tensor) -> torch.Tensor:
+        post = self.model.posterior(X)
+        mean = post.mean.reshape(-1)
+        var = post.variance.reshape(-1).clamp_min(1e-9)  # botorch: sigma = variance.clamp_min(1e-9).sqrt()
+        return -mean + torch.sqrt(self.beta * var)

@@ -1,0 +1,185 @@
+"""Host layer (model.py / utils.py / fit.py mirrors of the reference API) driven end to end.
+
+The same checks run twice:
+  * not-gpu: through `EmuEngine` (CPU logic emulation of the kernel sources, tests only) at tiny sizes,
+  * gpu:     through the product `Engine` (libscaml_b200.so) at the reference's experiment sizes.
+The oracle is the checker: at the hyper-parameters the fit returns, every quantity the model exposes
+(source posteriors, caches, target objective, conditioned posterior, UCB) must match the oracle's
+restatement of scamlgp/model.py within the north-star tolerances.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import scaml_oracle as O
+from tests.helpers import TOL_GRAD, TOL_LML, TOL_MEAN_VAR, rel_err
+
+DT = torch.float64
+
+
+@pytest.fixture(scope="module")
+def emu_engine(emu_lib):
+    from tests.emu_engine import EmuEngine
+
+    return EmuEngine(emu_lib)
+
+
+def _meta_data(M, n, d, seed, ragged=False):
+    from scamlgp_b200.modules import SupervisedDataset
+
+    X, Y = O.synthetic_tasks(M, n, d, seed=seed)
+    out = {}
+    for i in range(M):
+        ni = n if not ragged else max(1, n - 3 * i)
+        out[f"task{i}"] = SupervisedDataset(X[i, :ni], Y[i, :ni].reshape(-1, 1))
+    return out
+
+
+def _oracle_states(gps):
+    spec = O.HyperSpec.source()
+    states = []
+    for gp in gps.values():
+        from scamlgp_b200.modules import theta_raw_of
+
+        X = gp.train_inputs[0]
+        th = theta_raw_of(gp.likelihood, gp.covar_module, X.shape[-1])
+        states.append(O.factorize(X, gp._raw_Y.reshape(-1), th, spec))
+    return states
+
+
+def _pipeline(eng, M, n, d, n_t, B, restarts, fit_options, ragged=False):
+    from scamlgp_b200.model import ScaMLGP, meta_fit_scamlgp
+    from scamlgp_b200.modules import theta_raw_of
+    from scamlgp_b200.utils import UpperConfidenceBound, optimize_marginal_likelihood
+
+    md = _meta_data(M, n, d, seed=11, ragged=ragged)
+    gps = meta_fit_scamlgp(md, num_restarts_log_likelihood=restarts, seed=0, engine=eng, fit_options=fit_options)
+    assert list(gps.keys()) == list(md.keys())
+    fit = gps.fit
+    # ---- (1) the fit only ever improves on the warm start, and reports the oracle's objective ---------- #
+    ospec = O.HyperSpec.source()
+    th0 = O.initial_theta_raw(d, ospec)
+    for i, (tid, gp) in enumerate(gps.items()):
+        X, Y = md[tid].X(), md[tid].Y().reshape(-1)
+        yt, ybar, ystd = O.standardize(Y)
+        v0, _ = O.lml_and_grad_autograd(X, yt, th0, ospec)
+        th = theta_raw_of(gp.likelihood, gp.covar_module, d)
+        v1, g1 = O.lml_and_grad_autograd(X, yt, th, ospec)
+        assert float(v1) >= float(v0) - 1e-12
+        assert abs(float(fit.lml[i]) - float(v1)) <= TOL_LML * abs(float(v1))
+        assert abs(float(gp.outcome_transform.means) - ybar) < 1e-12 * max(1.0, abs(ybar))
+        assert abs(float(gp.outcome_transform.stdvs) - ystd) < 1e-12 * ystd
+    states = _oracle_states(gps)
+    g = torch.Generator().manual_seed(5)
+    # ---- (2) a single source GP's posterior (model.py:128-134) ------------------------------------------- #
+    Xq = torch.rand(9, d, dtype=DT, generator=g)
+    first = next(iter(gps.values()))
+    p = first.posterior(Xq)
+    om, oc = O.posterior(states[0], Xq, full_cov=True)
+    scale = float(states[0].os) * states[0].ystd ** 2
+    assert rel_err(p.mean.reshape(-1).numpy(), om.numpy()) < TOL_MEAN_VAR
+    assert float((p.mvn.covariance_matrix - oc).abs().max()) < TOL_MEAN_VAR * scale
+    # ---- (3) prior-only model (n_t = 0, optimizer.py:135-141) ---------------------------------------------- #
+    Xc = torch.rand(B, d, dtype=DT, generator=g)
+    prior_model = ScaMLGP(torch.empty(0, d, dtype=DT), torch.empty(0, 1, dtype=DT), gps, engine=eng).eval()
+    w0 = torch.full((M,), 1.0 / M, dtype=DT)
+    tspec = O.HyperSpec.target()
+    pp = prior_model.posterior(Xc.unsqueeze(1))
+    om, ov = O.scaml_posterior(states, w0, None, O.initial_theta_raw(d, tspec), tspec, Xc)
+    assert pp.mean.shape == (B, 1) and pp.variance.shape == (B, 1)
+    assert rel_err(pp.mean.reshape(-1).numpy(), om.numpy()) < TOL_MEAN_VAR
+    assert rel_err(pp.variance.reshape(-1).numpy(), ov.numpy()) < TOL_MEAN_VAR
+    # ---- (4) target model: caches, training-branch prior, fit, conditioned posterior ----------------------- #
+    Xt = torch.rand(n_t, d, dtype=DT, generator=g)
+    Yt = (torch.sin(3.0 * Xt).sum(1, keepdim=True) + 0.05 * torch.randn(n_t, 1, dtype=DT, generator=g))
+    model = ScaMLGP(Xt, Yt, gps, engine=eng)
+    cache = O.build_target_cache(states, Xt, Yt)
+    cscale = float(max(float(s.os) * s.ystd ** 2 for s in states))
+    assert rel_err(model.source_means.cpu().numpy(), cache.source_means.numpy()) < TOL_MEAN_VAR
+    assert float((model.source_covs.cpu() - cache.source_covs).abs().max()) < TOL_MEAN_VAR * cscale
+    assert abs(float(model.outcome_transform.means) - cache.mu_all) < 1e-12 * max(1.0, abs(cache.mu_all))
+    assert abs(float(model.outcome_transform.stdvs) - cache.s_all) < 1e-12 * cache.s_all
+    assert rel_err(model.train_targets.numpy(), cache.yt_std.numpy()) < 1e-12
+    mvn = model.forward(Xt)  # training branch (model.py:360-363,376-383)
+    ls, os_, noise = O.split_theta(O.initial_theta_raw(d, tspec), tspec)
+    o_mean = (cache.source_means @ w0 - cache.mu_all) / cache.s_all
+    o_cov = (cache.source_covs @ w0 ** 2) / cache.s_all ** 2 + O.kernel_matrix(Xt, Xt, ls, os_, tspec.kernel)
+    assert rel_err(mvn.mean.cpu().numpy(), o_mean.numpy()) < TOL_MEAN_VAR
+    assert float((mvn.covariance_matrix.cpu() - o_cov).abs().max()) < TOL_MEAN_VAR * float(o_cov.abs().max())
+    v_start = float(O.target_objective(cache, w0, O.initial_theta_raw(d, tspec), tspec))
+    tfit = optimize_marginal_likelihood(model, restarts, generator=torch.Generator().manual_seed(1),
+                                        **(fit_options or {}))
+    w = model.weights
+    th = model.theta_raw()
+    assert bool((w >= 1e-10).all())
+    v_end = float(O.target_objective(cache, w, th, tspec))
+    assert v_end >= v_start - 1e-12
+    assert abs(tfit.lml - v_end) <= 1e-8 * abs(v_end)
+    model.eval()
+    post = model.posterior(Xc)
+    om, ov = O.scaml_posterior(states, w, cache, th, tspec, Xc)
+    vscale = float(ov.abs().max())
+    assert rel_err(post.mean.reshape(-1).numpy(), om.numpy()) < 1e-8
+    assert float((post.variance.reshape(-1) - ov).abs().max()) < 1e-8 * vscale
+    # ---- (5) acquisition value (utils.py:215-224) ----------------------------------------------------------- #
+    af = UpperConfidenceBound(model)
+    assert rel_err(af(Xc.unsqueeze(1)).numpy(), O.ucb(om, ov).numpy()) < 1e-7
+    # ---- (6) state_dict round trip (utils.py:169,205) ------------------------------------------------------ #
+    sd = model.state_dict()
+    model.weights = torch.full((M,), 0.5, dtype=DT)
+    model.load_state_dict(sd)
+    assert torch.equal(model.weights, w)
+    return gps, model
+
+
+def test_pipeline_on_emulator(emu_engine):
+    _pipeline(emu_engine, M=2, n=14, d=2, n_t=4, B=5, restarts=1, fit_options=dict(maxiter=6), ragged=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,n,d,n_t,ragged", [(8, 32, 2, 10, False), (16, 64, 6, 24, True)])
+def test_pipeline_on_gpu(engine, M, n, d, n_t, ragged):
+    _pipeline(engine, M=M, n=n, d=d, n_t=n_t, B=300, restarts=5, fit_options=None, ragged=ragged)
+
+
+@pytest.mark.gpu
+def test_batched_lbfgs_reaches_scipy_lbfgsb_optimum(engine):
+    """The reference optimises with scipy L-BFGS-B (botorch fit_gpytorch_mll, utils.py:175); from the same
+    start our lock-step L-BFGS must end at an objective at least as good (up to the ftol both use)."""
+    from scipy.optimize import minimize
+
+    from scamlgp_b200._capi import HyperSpec
+    from scamlgp_b200.engine import SourceBatch
+    from scamlgp_b200.fit import fit_sources
+
+    M, n, d = 12, 64, 6
+    X, Y = O.synthetic_tasks(M, n, d, seed=4)
+    ospec = O.HyperSpec.source()
+    th0 = O.initial_theta_raw(d, ospec)
+    batch = SourceBatch.from_padded(X.cuda(), Y.cuda())
+    fit = fit_sources(engine, batch, HyperSpec.source(), th0.reshape(1, 1, -1).expand(M, 1, -1).contiguous())
+    for m in range(M):
+        yt, _, _ = O.standardize(Y[m])
+
+        def f(x):
+            v, g = O.lml_and_grad_autograd(X[m], yt, torch.tensor(x, dtype=DT), ospec)
+            return -float(v), -g.numpy()
+
+        res = minimize(f, th0.numpy(), jac=True, method="L-BFGS-B")
+        assert float(fit.lml[m]) >= -res.fun - 5e-6 * max(1.0, abs(res.fun)), (m, float(fit.lml[m]), -res.fun)
+
+
+@pytest.mark.gpu
+def test_meta_fit_is_deterministic_and_order_invariant(engine):
+    """scamlgp/testing.py:50-100: shuffling the meta-data must not change what is learnt per task."""
+    from scamlgp_b200.model import meta_fit_scamlgp
+
+    md = _meta_data(6, 32, 3, seed=2)
+    a = meta_fit_scamlgp(md, seed=3, engine=engine)
+    b = meta_fit_scamlgp(md, seed=3, engine=engine)
+    assert torch.equal(a.fit.theta_raw, b.fit.theta_raw)
+    # warm-start row only (restart draws are positional): same optimum whatever the neighbours in the batch
+    rev = dict(reversed(list(md.items())))
+    c = meta_fit_scamlgp(md, num_restarts_log_likelihood=0, seed=3, engine=engine)
+    e = meta_fit_scamlgp(rev, num_restarts_log_likelihood=0, seed=3, engine=engine)
+    assert torch.equal(c.fit.theta_raw, e.fit.theta_raw.flip(0))

@@ -1,0 +1,274 @@
+"""Behavioural contract of `ScaMLGPBO`, restating the reference's acceptance tests on our stand-in types:
+
+  tests/optimizer_test.py:25-53   blackboxopt ALL_REFERENCE_TESTS (sequential optimisation, determinism with a
+                                  fixed seed, determinism under shuffled reporting, list reporting, unknown
+                                  objective, fixed parameter, conditional space)
+  tests/optimizer_test.py:56-97   evaluations with a missing objective are kept but not used for the model
+  scamlgp/testing.py:50-100       shuffled meta-data -> identical proposals; other meta-data -> different ones
+
+The not-gpu variants drive the host logic through the CPU emulation engine (tests only) with tiny budgets;
+the gpu variants run the same scenarios on the product engine with the reference's settings.
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from scamlgp_b200.optimizer import ScaMLGPBO
+from scamlgp_b200.space import (CategoricalParameter, ContinuousParameter, Evaluation, EvaluationsError,
+                                IntegerParameter, Objective, OptimizerNotReady, ParameterSpace)
+from scamlgp_b200.utils import UpperConfidenceBound
+
+LOSS = Objective("loss", greater_is_better=False)
+TINY = dict(af_optimizer_kwargs=dict(raw_samples=12, num_restarts=2, rounds=1, perturbations=3, num_random_choices=6),
+            fit_options=dict(maxiter=3))
+
+
+@pytest.fixture(scope="module")
+def emu_engine(emu_lib):
+    from tests.emu_engine import EmuEngine
+
+    return EmuEngine(emu_lib)
+
+
+def E(configuration, loss):
+    return Evaluation(configuration=configuration, objectives={"loss": loss})
+
+
+# meta-data in the spirit of the reference fixtures (tests/meta_data_examples.py:8-138): tiny tasks of 1-2 points
+def meta_1d():
+    return {"task1": [E({"p1": 0.01}, 0.6), E({"p1": 0.5}, 0.5)]}
+
+
+def meta_fixed():
+    return {"task1": [E({"x": -1.0, "my_fixed_param": 1.0}, 2.0), E({"x": 1.5, "my_fixed_param": 1.0}, 3.25)],
+            "task2": [E({"x": 1.0, "my_fixed_param": 1.0}, 0.5), E({"x": -1.5, "my_fixed_param": 1.0}, 1.125)]}
+
+
+def meta_conditional():
+    return {"task1": [E({"optimizer": "adam", "lr": 0.01}, 0.6),
+                      E({"optimizer": "sgd", "lr": 0.01, "momentum": 0.5}, 0.5)]}
+
+
+def meta_mixed():
+    return {"task1": [E({"p1": 2, "p2": -0.1, "p3": 0.5, "p4": False, "p5": "small"}, 1.0),
+                      E({"p1": 3, "p2": -0.2, "p3": 0.3, "p4": False, "p5": "medium"}, 0.0)],
+            "task2": [E({"p1": 10, "p2": -0.3, "p3": 0.5, "p4": True, "p5": "medium"}, 1.0),
+                      E({"p1": 12, "p2": -0.2, "p3": 0.3, "p4": False, "p5": "medium"}, 1.0)]}
+
+
+def space_1d(name="p1", bounds=(0.0, 1.0)):
+    s = ParameterSpace()
+    s.add(ContinuousParameter(name, bounds))
+    return s
+
+
+def space_mixed():
+    s = ParameterSpace()
+    s.add(IntegerParameter("p1", (-10, 10)))
+    s.add(ContinuousParameter("p2", (-0.5, 0.5)))
+    s.add(ContinuousParameter("p3", (1e-5, 1.0)))
+    s.add(CategoricalParameter("p4", [True, False]))
+    s.add(CategoricalParameter("p5", ["small", "medium", "large"]))
+    return s
+
+
+def space_fixed():
+    s = ParameterSpace()
+    s.add(ContinuousParameter("x", (-2.0, 2.0)))
+    s.add(ContinuousParameter("my_fixed_param", (-10.0, 200.0)))
+    s.fix(my_fixed_param=1.0)
+    return s
+
+
+def space_conditional():
+    s = ParameterSpace()
+    s.add(CategoricalParameter("optimizer", ["adam", "sgd"]))
+    s.add(ContinuousParameter("lr", (1e-4, 1e-1)))
+    s.add(ContinuousParameter("momentum", (0.0, 1.0)), condition=lambda c: c.get("optimizer") == "sgd")
+    return s
+
+
+def _loop(opt, f, steps):
+    evs = []
+    for _ in range(steps):
+        es = opt.generate_evaluation_specification()
+        ev = es.create_evaluation(objectives={"loss": f(es.configuration)})
+        opt.report(ev)
+        evs.append(ev)
+    return evs
+
+
+def _quartic(x0):
+    return float(np.polyval(np.array([0.75, 0.0, -10.0, 0.0, 0.0]), x0))
+
+
+META_1D_POLY = [(0.8, -6.07), (1.49, -18.6), (1.56, -19.9), (2.5, -33.2), (3.0, -29.2), (1.2, -31.1), (2.7, -30.2)]
+
+
+def _shuffled_meta_data_scenario(eng, seed, steps, extra):
+    """scamlgp/testing.py:50-100."""
+    runs = []
+    rnd = random.Random(seed)
+    for _ in range(2):
+        pts = list(META_1D_POLY)
+        rnd.shuffle(pts)
+        md = {"task_1": [E({"x0": x}, y) for x, y in pts]}
+        opt = ScaMLGPBO(space_1d("x0", (0.5, 3.0)), LOSS, md, seed=seed, num_initial_random_samples=1,
+                        max_pending_evaluations=5, engine=eng, **extra)
+        runs.append([e.configuration["x0"] for e in _loop(opt, lambda c: _quartic(c["x0"]), steps)])
+    other = {"task_1": [E({"x0": 0.55}, -4.07)]}
+    opt = ScaMLGPBO(space_1d("x0", (0.5, 3.0)), LOSS, other, seed=seed, num_initial_random_samples=1,
+                    max_pending_evaluations=5, engine=eng, **extra)
+    third = [e.configuration["x0"] for e in _loop(opt, lambda c: _quartic(c["x0"]), steps)]
+    assert set(runs[0]) == set(runs[1])
+    assert set(third) != set(runs[1])
+
+
+def _missing_objective_scenario(eng, extra, n_source=32):
+    """tests/optimizer_test.py:56-97 with a Forrester-family source task (meta_data_examples.py:141-175)."""
+    space = space_1d("x")
+    xs = np.linspace(0.0, 1.0, n_source)
+    a, b, c = 0.95, 0.02, 1.0
+    ys = a * (6 * xs - 2) ** 2 * np.sin(12 * xs - 4) + b * (xs - 0.5) - c
+    md = {0: [E({"x": float(x)}, float(y)) for x, y in zip(xs, ys)]}
+    opt = ScaMLGPBO(space, LOSS, md, acquisition_function_factory=UpperConfidenceBound,
+                    num_initial_random_samples=1, num_restarts_log_likelihood=2, max_pending_evaluations=5,
+                    engine=eng, **extra)
+    n = 5
+    evaluations = []
+    for i in range(n):
+        spec = opt.generate_evaluation_specification()
+        evaluations.append(spec.create_evaluation(objectives={"loss": 0.42 + 0.1 * i}))
+    with pytest.raises(OptimizerNotReady):
+        opt.generate_evaluation_specification()
+    evaluations[-2].objectives["loss"] = None
+    opt.report(evaluations)
+    opt.generate_evaluation_specification()
+    assert len(opt.pending_specifications) == 1
+    assert opt.X.numel() == n and opt.losses.numel() == n
+    assert opt.model.train_inputs[0].numel() == n - 1
+    assert opt.model.train_targets.numel() == n - 1
+    assert len(opt.source_gps) == 1
+
+
+def _spaces_scenario(eng, extra, steps):
+    # sequential optimisation of a single parameter
+    opt = ScaMLGPBO(space_1d(), LOSS, meta_1d(), seed=1, num_initial_random_samples=1, max_pending_evaluations=5,
+                    engine=eng, **extra)
+    evs = _loop(opt, lambda c: (c["p1"] - 0.3) ** 2, steps)
+    assert len(evs) == steps and all(0.0 <= e.configuration["p1"] <= 1.0 for e in evs)
+    # unknown objective
+    with pytest.raises(EvaluationsError):
+        opt.report(Evaluation(configuration={"p1": 0.2}, objectives={"unknown": 1.0}))
+    # fixed parameter is respected
+    opt = ScaMLGPBO(space_fixed(), LOSS, meta_fixed(), seed=1, num_initial_random_samples=1,
+                    max_pending_evaluations=5, engine=eng, **extra)
+    for e in _loop(opt, lambda c: c["x"] ** 2, steps):
+        assert e.configuration["my_fixed_param"] == 1.0
+    # conditional space: inactive parameters never appear, active ones always do
+    opt = ScaMLGPBO(space_conditional(), LOSS, meta_conditional(), seed=1, num_initial_random_samples=1,
+                    max_pending_evaluations=5, engine=eng, **extra)
+    for e in _loop(opt, lambda c: c["lr"], 2):
+        assert ("momentum" in e.configuration) == (e.configuration["optimizer"] == "sgd")
+    # mixed space, list reporting
+    opt = ScaMLGPBO(space_mixed(), LOSS, meta_mixed(), seed=1, num_initial_random_samples=1,
+                    max_pending_evaluations=5, engine=eng, **extra)
+    specs = [opt.generate_evaluation_specification() for _ in range(3)]
+    opt.report([s.create_evaluation(objectives={"loss": float(i)}) for i, s in enumerate(specs)])
+    assert len(opt.pending_specifications) == 0 and opt.X.shape == (3, 5)
+    nxt = opt.generate_evaluation_specification()
+    assert set(nxt.configuration) == {"p1", "p2", "p3", "p4", "p5"}
+
+
+def _determinism_scenario(eng, extra, steps):
+    """fixed seed -> same proposals; reporting the same evaluations shuffled -> same next proposal."""
+    runs = []
+    for _ in range(2):
+        opt = ScaMLGPBO(space_1d(), LOSS, meta_1d(), seed=7, num_initial_random_samples=1, max_pending_evaluations=5,
+                        engine=eng, **extra)
+        runs.append([e.configuration["p1"] for e in _loop(opt, lambda c: (c["p1"] - 0.3) ** 2, steps)])
+    assert runs[0] == runs[1]
+    evs = [E({"p1": 0.1 + 0.2 * i}, (0.1 + 0.2 * i - 0.3) ** 2) for i in range(4)]
+    proposals = []
+    for order in (evs, list(reversed(evs))):
+        opt = ScaMLGPBO(space_1d(), LOSS, meta_1d(), seed=7, num_initial_random_samples=1, max_pending_evaluations=5,
+                        engine=eng, **extra)
+        opt.report(list(order))
+        proposals.append(opt.generate_evaluation_specification().configuration["p1"])
+    assert abs(proposals[0] - proposals[1]) < 1e-6
+
+
+# ---- CPU (emulation engine, tiny budgets) --------------------------------------------------------------- #
+def test_missing_objective_emulated(emu_engine):
+    _missing_objective_scenario(emu_engine, TINY, n_source=10)
+
+
+def test_spaces_emulated(emu_engine):
+    _spaces_scenario(emu_engine, TINY, steps=2)
+
+
+def test_greater_is_better_flips_sign_and_maximizing_acquisition_is_rejected(emu_engine):
+    obj = Objective("score", greater_is_better=True)
+    md = {"t": [Evaluation(configuration={"p1": 0.2}, objectives={"score": 1.0}),
+                Evaluation(configuration={"p1": 0.7}, objectives={"score": 3.0})]}
+    opt = ScaMLGPBO(space_1d(), obj, md, seed=0, engine=emu_engine, **TINY)
+    gp = opt.source_gps["t"]
+    assert sorted(gp._raw_Y.reshape(-1).tolist()) == [-3.0, -1.0]
+    with pytest.raises(ValueError):
+        UpperConfidenceBound(opt.model, maximize=True)
+
+
+# ---- GPU (product engine, reference settings) ------------------------------------------------------------ #
+@pytest.mark.gpu
+def test_missing_objective_gpu(engine):
+    _missing_objective_scenario(engine, {})
+
+
+@pytest.mark.gpu
+def test_spaces_gpu(engine):
+    _spaces_scenario(engine, {}, steps=6)
+
+
+@pytest.mark.gpu
+def test_determinism_gpu(engine):
+    _determinism_scenario(engine, {}, steps=4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [0, 12345])
+def test_shuffled_meta_data_gpu(engine, seed):
+    _shuffled_meta_data_scenario(engine, seed, steps=5, extra={})
+
+
+@pytest.mark.gpu
+def test_branin_regret_improves_with_meta_data(engine):
+    """Config 1 in miniature (configurations/branin.py:47-75): M = 8 Branin tasks x 32 points, sigma = 1;
+    after 12 BO steps ScaML-GP's best value is within reach of the optimum and beats its first proposal."""
+    rng = np.random.default_rng(0)
+
+    def branin(x1, x2, a, b, c, r, s, t):
+        return a * (x2 - b * x1 ** 2 + c * x1 - r) ** 2 + s * (1 - t) * np.cos(x1) + s
+
+    def task():
+        return dict(a=rng.uniform(0.5, 1.5), b=rng.uniform(0.1, 0.15), c=rng.uniform(1.0, 2.0), r=rng.uniform(5.0, 7.0),
+                    s=rng.uniform(8.0, 12.0), t=rng.uniform(0.03, 0.05))
+
+    space = ParameterSpace()
+    space.add(ContinuousParameter("x1", (-5.0, 10.0)))
+    space.add(ContinuousParameter("x2", (0.0, 15.0)))
+    md = {}
+    for k in range(8):
+        p = task()
+        x1, x2 = rng.uniform(-5, 10, 32), rng.uniform(0, 15, 32)
+        y = branin(x1, x2, **p) + rng.normal(0, 1.0, 32)
+        md[k] = [E({"x1": float(a), "x2": float(b)}, float(v)) for a, b, v in zip(x1, x2, y)]
+    target = task()
+    opt = ScaMLGPBO(space, LOSS, md, seed=0, engine=engine)
+    evs = _loop(opt, lambda c: float(branin(c["x1"], c["x2"], **target)), 12)
+    losses = [e.objectives["loss"] for e in evs]
+    g1, g2 = np.meshgrid(np.linspace(-5, 10, 400), np.linspace(0, 15, 400))
+    fmin = float(branin(g1, g2, **target).min())
+    assert min(losses) - fmin < 3.0, (min(losses), fmin)
+    assert min(losses) <= losses[0]

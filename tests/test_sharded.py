@@ -1,0 +1,96 @@
+"""Task sharding over ranks (scamlgp_b200/sharded.py): world_size-2 `gloo` processes on CPU, each driving the
+emulation engine (tests only), must reproduce the single-process result over all tasks -- fitted rows,
+weighted prior prediction, per-task caches and the conditioned posterior."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DT = torch.float64
+M, N, D, NT, B = 3, 12, 2, 3, 4  # 3 tasks over 2 ranks: blocks of 2 and 1 (uneven on purpose)
+
+
+def _free_port() -> int:
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _tasks():
+    from oracle import scaml_oracle as O
+
+    X, Y = O.synthetic_tasks(M, N, D, seed=21)
+    return [(X[i, : N - 2 * i], Y[i, : N - 2 * i]) for i in range(M)]  # ragged
+
+
+def _run(engine, group):
+    from oracle import scaml_oracle as O
+    from scamlgp_b200._capi import HyperSpec
+    from scamlgp_b200.sharded import ShardedSources
+
+    g = torch.Generator().manual_seed(9)
+    spec, tspec = HyperSpec.source(), HyperSpec.target()
+    th0 = O.sample_theta_raw(M, 2, D, O.HyperSpec.source(), seed=2)
+    src = ShardedSources(engine, _tasks(), group=group)
+    fit = src.fit(spec, th0, fit_options=dict(maxiter=4))
+    w = torch.tensor([0.5, 0.3, 0.2], dtype=DT)
+    Xc = torch.rand(B, D, dtype=DT, generator=g)
+    Xt = torch.rand(NT, D, dtype=DT, generator=g)
+    yt = torch.randn(NT, dtype=DT, generator=g)
+    pm, pv = src.predict_weighted(w, Xc)
+    sm, sc = src.target_caches(Xt)
+    ts = engine.target_factorize(sm, sc, Xt, yt, w, O.initial_theta_raw(D, O.HyperSpec.target()), 0.1, 1.3, tspec)
+    mean, var = src.posterior(w, Xc, ts)
+    return dict(theta=fit.theta_raw, lml=fit.lml, ystd=src.ystd_all, pm=pm.clone(), pv=pv.clone(), sm=sm, sc=sc,
+                mean=mean, var=var)
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    from scamlgp_b200 import build
+    from scamlgp_b200._capi import ScamlLib
+    from tests.emu_engine import EmuEngine
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        res = _run(EmuEngine(ScamlLib(build.build_emu())), None)
+        torch.save(res, os.path.join(out_dir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_task_partition():
+    from scamlgp_b200.sharded import task_partition
+
+    assert task_partition(4096, 8) == [(i * 512, (i + 1) * 512) for i in range(8)]
+    assert task_partition(3, 2) == [(0, 2), (2, 3)]
+    assert task_partition(5, 4) == [(0, 2), (2, 4), (4, 5), (5, 5)]
+
+
+def test_two_rank_gloo_matches_single_process(emu_lib, tmp_path):
+    from tests.emu_engine import EmuEngine
+
+    single = _run(EmuEngine(emu_lib), None)
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = torch.load(os.path.join(tmp_path, "rank0.pt"))
+    r1 = torch.load(os.path.join(tmp_path, "rank1.pt"))
+    for k in single:
+        # every rank ends with the same replicated result ...
+        assert torch.equal(r0[k], r1[k]), k
+        # ... equal to the single-process one: bit-identical where nothing is re-associated across ranks
+        if k in ("theta", "lml", "ystd", "sm", "sc"):
+            assert torch.equal(r0[k], single[k]), k
+        else:
+            scale = float(single[k].abs().max())
+            assert float((r0[k] - single[k]).abs().max()) <= 1e-13 * scale, k
