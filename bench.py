@@ -311,6 +311,55 @@ def run_ours(args) -> None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), eng.launches - launches0
 
+    # ---- second half of BASELINE.json's metric: posterior points/s over all tasks (config 5 shape) ------ #
+    def posterior_bench():
+        """Weighted ScaML-GP prior prediction (mean + variance, reduced over the rank's 4096 fitted base GPs
+        inside the kernel) at B candidates; one "point" = one (task, candidate) pair.  Config 5 asks for
+        B = 1 Mi; a step here is a bounded slice of it (B_STEP candidates = 2 waves of 148 x 64-candidate
+        tiles) so the default run stays short -- points/s does not depend on B beyond one wave."""
+        B_STEP = 2 * 148 * 64
+        fs = eng.factorize(batch, thd[:, 0].contiguous(), spec)
+        w = torch.full((M,), 1.0 / M, dtype=torch.float64, device=device)
+        g = torch.Generator().manual_seed(100 + rank)
+        hXc = torch.rand(B_STEP, d, dtype=torch.float64, generator=g).pin_memory()
+        Xc = hXc.to(device)
+        pm = torch.empty(B_STEP, dtype=torch.float64, device=device)
+        pv = torch.empty(B_STEP, dtype=torch.float64, device=device)
+        part = torch.empty(2, B_STEP, dtype=torch.float64, device=device)
+        h_out = torch.empty(2, B_STEP, dtype=torch.float64).pin_memory()
+
+        def step_res():
+            eng.predict_weighted(fs, w, Xc, out=(pm, pv))
+
+        def step_e2e():
+            xc = hXc.to(device, non_blocking=True)
+            eng.predict_weighted(fs, w, xc, out=(part[0], part[1]))
+            if world > 1:  # sum of weighted predictions over the task shards (north_star item 5)
+                dist.all_reduce(part, op=dist.ReduceOp.SUM)
+            h_out.copy_(part, non_blocking=True)
+            torch.cuda.current_stream(device).synchronize()
+
+        psteps = max(2, min(args.steps, 4))
+        ms_r, nl = timed(step_res, psteps, 3)
+        ms_e, _ = timed(step_e2e, psteps, 1)
+        ok_info = int((fs.info == 0).all())
+        finite = bool(torch.isfinite(pm).all() and torch.isfinite(pv).all() and (pv > 0).all())
+        del fs
+        pts = float(M) * B_STEP * world
+        Fp = float(n) ** 2 + float(n) * (3.0 * d + 12.0)  # SURVEY 8d: flop per (task, candidate) point
+        ach = float(M) * B_STEP * Fp / (ms_r / psteps * 1e-3) / 1e12
+        return {"metric": "posterior points/s over all tasks", "value": pts * psteps / (ms_r * 1e-3),
+                "unit": "points/s", "ms_per_step": ms_r / psteps, "steps": psteps,
+                "config": {"workload": f"config5 slice: {M} fitted base GPs (n={n}, d={d}) per GPU x {B_STEP} "
+                                       "candidates per step, weighted mean+variance (q=1)",
+                           "candidates_per_step": B_STEP, "factor_info_zero": bool(ok_info), "finite": finite},
+                "e2e": {"value": pts * psteps / (ms_e * 1e-3), "unit": "points/s",
+                        "h2d_bytes_per_step": int(hXc.numel()) * 8, "d2h_bytes_per_step": int(h_out.numel()) * 8,
+                        "collective": "all_reduce(sum) [2,B] fp64 over ranks" if world > 1 else None},
+                "gpu_launches": nl,
+                "roofline": {"bound": "fp64", "achieved": ach, "unit": "TFLOP/s", "flops_per_point": Fp,
+                             "kernel": "scaml_predict_kernel<RBF>"}}
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -319,6 +368,7 @@ def run_ours(args) -> None:
     ms_e2e, _ = timed(step_e2e, max(2, min(args.steps, 5)), 2)
     e2e_steps = max(2, min(args.steps, 5))
     ok = int((info == 0).all())
+    posterior = None if args.no_posterior else posterior_bench()
     if world > 1:
         okt = torch.tensor([ok], device=device)
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
@@ -351,6 +401,11 @@ def run_ours(args) -> None:
                          "fp64_peaks_tflops": peaks},
             "clocks": clocks,
         }
+        if posterior is not None:
+            pk = peak
+            posterior["roofline"]["peak"] = pk
+            posterior["roofline"]["frac"] = (posterior["roofline"]["achieved"] / pk) if pk else None
+            line["posterior"] = posterior
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
@@ -365,6 +420,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-posterior", action="store_true", help="skip the posterior points/s measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
