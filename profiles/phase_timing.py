@@ -13,7 +13,7 @@ from scamlgp_b200._capi import ScamlLib
 from scamlgp_b200.engine import Engine, SourceBatch
 
 NAMES = ["setup", "B gemm(update)", "B assemble(exp)+store", "B diag_factor", "B trsm+store", "C gemm1", "C gemm2+store",
-         "C z solve", "D gemm", "D grad epilogue", "final", " diag: chol#1 (warp0)", " diag: L10,D11,Tm", " diag: chol#2 rest (outputs)", " chol#2: cholesky loop", " chol#2: inverse loop"]
+         "C z solve", "D gemm", "D grad epilogue", "final", " diag: chol#1 (warp0)", " diag: L10,D11,Tm", " diag: chol#2 rest (outputs)", " gemm_global: wait+bar+issue (thread 0)", " gemm_global: compute (thread 0)"]
 
 
 def main():
@@ -38,7 +38,7 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     p = prof.view(-1, 16).cpu().double()
-    grid = min(M * R, 444)
+    grid = min(M * R, 148 * int(os.environ.get('SCAML_FIT_CTAS_PER_SM', '3')))
     p = p[:grid]
     evals_per_cta = M * R / grid
     tot = p.sum(1).mean().item()

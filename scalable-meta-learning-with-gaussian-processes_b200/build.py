@@ -67,6 +67,19 @@ def build_prof(force: bool = False) -> str:
     return out
 
 
+def build_ablate(force: bool = False) -> str:
+    """Timing-only ablation variant (-DSCAML_ABLATE, wrong results by design); experiments only."""
+    out = os.path.join(CSRC, "libscaml_b200_abl.so")
+    deps = [os.path.join(CSRC, s) for s in CUDA_SOURCES + HEADERS]
+    if not force and _newer(out, deps):
+        return out
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-DSCAML_ABLATE", "-o", out] + CUDA_SOURCES
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc (ablation build) failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 def build_emu(force: bool = False) -> str:
     deps = [os.path.join(CSRC, s) for s in ["scaml_capi.cu"] + HEADERS]
     if not force and _newer(EMU_LIB, deps):

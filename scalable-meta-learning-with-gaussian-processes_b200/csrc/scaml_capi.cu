@@ -9,6 +9,8 @@
 #ifndef SCAML_EMU
 #include <cuda_runtime.h>
 #endif
+#include <cmath>
+#include <cstdlib>
 
 namespace {
 
@@ -38,7 +40,14 @@ int fit_ctas_per_sm(int n_pad, int d) {
   if (3 * s <= 228 * 1024) return 3;
   return (2 * s <= 228 * 1024) ? 2 : 1;
 }
-int fit_grid_slots(int n_pad, int d) { return num_sms() * fit_ctas_per_sm(n_pad, d); }
+int fit_grid_slots(int n_pad, int d) {
+  int c = fit_ctas_per_sm(n_pad, d);
+  if (const char* env = getenv("SCAML_FIT_CTAS_PER_SM")) {  // experiment knob: fewer co-resident CTAs
+    const int v = atoi(env);
+    if (v >= 1 && v < c) c = v;
+  }
+  return num_sms() * c;
+}
 
 template <int KIND>
 int launch_fit(const scaml::FitParams& p, int grid, size_t smem, void* stream) {
@@ -79,6 +88,14 @@ int run_fit(scaml::FitParams p, void* workspace, size_t workspace_bytes, void* s
   int grid = fit_grid_slots(p.n_pad, p.d);
   const long long E = (long long)p.M * p.R;
   if (E < grid) grid = (int)E;
+  // start offset of the co-resident CTAs: ~1/3 of one evaluation (measured 0.67 ms at n_pad = 256, ~n^1.8),
+  // only when every CTA has several evaluations to amortise it over
+  p.stagger_ns = 0;
+  if (E >= 4ll * grid && grid > p.sms) {
+    double ns = 0.0;  // measured: no effect on B200 (sweep 0..450 us, profiles/r1_stagger_sweep.txt)
+    if (const char* env = getenv("SCAML_FIT_STAGGER_NS")) ns = atof(env);
+    p.stagger_ns = (unsigned)(ns < 0 ? 0 : (ns > 4e6 ? 4e6 : ns));
+  }
   return dispatch_fit(p, grid, smem, stream);
 }
 
@@ -86,6 +103,9 @@ int run_fit(scaml::FitParams p, void* workspace, size_t workspace_bytes, void* s
 
 extern "C" {
 
+#ifdef SCAML_ABLATE
+void scaml_debug_set_ablate(int bits) { cudaMemcpyToSymbol(scaml::g_ablate, &bits, sizeof(int)); }
+#endif
 #ifdef SCAML_PROF
 // diagnostics build only: device buffer of [grid][16] long long phase counters
 void scaml_debug_set_prof(void* buf) { g_prof = static_cast<long long*>(buf); }

@@ -32,6 +32,7 @@
 namespace scaml {
 
 #ifdef SCAML_PROF
+__shared__ long long profsm[16];  // per-CTA phase cycle counters (diagnostics build only)
 #define PROF_MARK(ph)                   \
   do {                                  \
     if (threadIdx.x == 0) {             \
@@ -47,6 +48,13 @@ namespace scaml {
 #endif
 
 enum { kModeLmlGrad = 0, kModeFactorize = 1 };
+#ifdef SCAML_ABLATE
+// timing-only ablation build (WRONG results by design): which phase is on the critical path?
+__device__ int g_ablate = 0;
+#define ABL(bit) ((g_ablate & (bit)) != 0)
+#else
+#define ABL(bit) false
+#endif
 constexpr int kFitThreads = 128;
 constexpr int kFitWarps = kFitThreads / 32;
 constexpr int kLd = 36;              // shared-memory row stride of a staged tile (doubles)
@@ -73,6 +81,7 @@ struct FitParams {
   long long* prof;      // SCAML_PROF builds only: [grid][16] cycle counters per phase
   int M, R, n_max, n_pad, d, mode;
   int sms;  // SM count (co-resident CTAs are blockIdx.x, blockIdx.x + sms, ...)
+  unsigned stagger_ns;  // start offset between the co-resident CTAs of an SM (0 = none)
   scaml_hyper_spec spec;
 };
 
@@ -215,6 +224,7 @@ template <class Src>
 SCAML_DEVICE void stage_issue(const Src& src, int s, double* st, int tid) {
   const ChunkPtrs c = src.get(s >> 1);
   const int off = (s & 1) * kHalfG;
+  if (ABL(16)) return;
   if (c.a[0]) half_async(st, c.a[0] + off, tid);
   if (c.a[1]) half_async(st + kHalfS, c.a[1] + off, tid);
   if (!src.same()) {
@@ -238,18 +248,23 @@ SCAML_DEVICE void gemm_global(Acc& acc, const Src& src, double* stage, const FTh
   stage_issue(src, 0, stage, t.tid);
   for (int s = 0; s < n; ++s) {
     double* st = stage + (s & 1) * 4 * kHalfS;
-    if (s + 1 < n) {
-      stage_issue(src, s + 1, stage + ((s + 1) & 1) * 4 * kHalfS, t.tid);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+#ifdef SCAML_PROF
+    const long long pc0 = clock64();
+#endif
+    // ONE barrier per step: after it sub-chunk s is visible to everyone and everyone has finished reading
+    // sub-chunk s-1, whose buffer the prefetch of s+1 may therefore overwrite.
+    cp_async_wait<0>();
     __syncthreads();
+    if (s + 1 < n) stage_issue(src, s + 1, stage + ((s + 1) & 1) * 4 * kHalfS, t.tid);
+#ifdef SCAML_PROF
+    const long long pc1 = clock64();
+#endif
     const ChunkPtrs c = src.get(s >> 1);
     const double* As = st;
     const double* Bs = src.same() ? st : st + 2 * kHalfS;
     const bool bvalid = src.same() ? (c.a[t.cb] != nullptr) : (c.b[t.cb] != nullptr);
-    if (active && c.a[t.rb] != nullptr && bvalid) fmma<4>(acc, As + t.rb * kHalfS, Bs + t.cb * kHalfS, t, lower);
+    if (active && c.a[t.rb] != nullptr && bvalid && !ABL(8))
+      fmma<4>(acc, As + t.rb * kHalfS, Bs + t.cb * kHalfS, t, lower);
     if (piggy) {
       const int col = t.tid & 63, q = t.tid >> 6;
       if (c.a[col >> 5] != nullptr) {
@@ -259,8 +274,14 @@ SCAML_DEVICE void gemm_global(Acc& acc, const Src& src, double* stage, const FTh
         for (int kk = 0; kk < 8; ++kk) pig = fma(ap[kk * kLd], zp[kk], pig);
       }
     }
-    __syncthreads();
+#ifdef SCAML_PROF
+    if (threadIdx.x == 0) {
+      profsm[14] += pc1 - pc0;          // wait + barrier + issue next
+      profsm[15] += clock64() - pc1;    // compute
+    }
+#endif
   }
+  __syncthreads();
 }
 
 // product of shared-memory resident 64x64 operands given as 2 chunks x 2 full padded tiles each
@@ -269,12 +290,13 @@ SCAML_DEVICE void gemm_smem(Acc& acc, const double* const (&A)[2][2], const doub
   for (int ck = 0; ck < 2; ++ck) {
     const double* a = A[ck][t.rb];
     const double* b = B[ck][t.cb];
-    if (a != nullptr && b != nullptr) fmma<8>(acc, a, b, t, false);
+    if (a != nullptr && b != nullptr && !ABL(128)) fmma<8>(acc, a, b, t, false);
   }
 }
 
 // warp's 32x32 accumulator -> one tile with row/col stride `ld`, column-major ("C") or row-major ("R")
 SCAML_DEVICE void store_tile_C(double* blk, int ld, const Acc& acc, const FThr& t, double scale) {
+  if (ABL(4096) && ld == kBS) return;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -285,6 +307,7 @@ SCAML_DEVICE void store_tile_C(double* blk, int ld, const Acc& acc, const FThr& 
     }
 }
 SCAML_DEVICE void store_tile_R(double* blk, int ld, const Acc& acc, const FThr& t, double scale) {
+  if (ABL(4096) && ld == kBS) return;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     double* p = blk + (8 * i + t.g) * ld + 2 * t.t4;
@@ -308,7 +331,7 @@ SCAML_DEVICE void xblk_store(double* xblk, const double (&xp)[kXpre], const doub
                              int J, int nv, int d, int tid) {
 #pragma unroll
   for (int k = 0; k < kXpre; ++k)
-    if (k < d) xblk[k * 128 + tid] = xp[k] / th[k];
+    if (k < d) xblk[k * 128 + tid] = ABL(2048) ? xp[k] * th[k] : xp[k] / th[k];
   if (d > kXpre) {
     const int a = (tid < kSB) ? I * kSB + tid : J * kSB + (tid - kSB);
     for (int k = kXpre; k < d; ++k) xblk[k * 128 + tid] = (a < nv) ? __ldg(Xm + (size_t)a * d + k) / th[k] : 0.0;
@@ -321,6 +344,7 @@ SCAML_DEVICE void pair_r2(double (&r2)[2][4][2], const double* xblk, int d, int 
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) r2[i][j][0] = r2[i][j][1] = 0.0;
+  if (ABL(512)) return;
 #pragma unroll 2
   for (int k = 0; k < d; ++k) {
     const double* xr = xblk + k * 128;
@@ -354,7 +378,7 @@ SCAML_DEVICE void assemble_tile(Acc& acc, int I, int J, const FThr& t, const dou
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int a = a0 + 8 * (2 * h + i), b = b0 + 8 * j + e;
-          double k = os * kappa_of<KIND>(r2[i][j][e]);
+          double k = ABL(2) ? os * (1.0 - 1e-3 * r2[i][j][e]) : os * kappa_of<KIND>(r2[i][j][e]);
           if (a == b) k += diag_add;
           if (a >= nv || b >= nv) k = (a == b) ? 1.0 : 0.0;
           acc[2 * h + i][j][e] = k - acc[2 * h + i][j][e];
@@ -385,7 +409,11 @@ SCAML_DEVICE void grad_tile(Acc& acc, int I, int J, const FThr& t, const double*
         for (int e = 0; e < 2; ++e) {
           const int b = b0 + 8 * j + e;
           double kap, kd;
-          kappa_pair<KIND>(r2[i][j][e], kap, kd);
+          if (ABL(4)) {
+            kap = kd = 1.0 - 1e-3 * r2[i][j][e];
+          } else {
+            kappa_pair<KIND>(r2[i][j][e], kap, kd);
+          }
           const bool use = (a >= b) && (a < nv) && (b < nv);
           const double wgt = use ? ((a == b) ? 1.0 : 2.0) : 0.0;
           const double Wab = ava * av[b] - acc[2 * h + i][j][e];
@@ -397,7 +425,7 @@ SCAML_DEVICE void grad_tile(Acc& acc, int I, int J, const FThr& t, const double*
     }
   }
   double* gw = gsm + t.warp * kMaxP;
-  for (int k = 0; k < d; ++k) {
+  for (int k = 0; k < (ABL(1024) ? 0 : d); ++k) {
     const double* xr = xblk + k * 128;
     double xa[4];
 #pragma unroll
@@ -434,17 +462,22 @@ SCAML_DEVICE void grad_tile(Acc& acc, int I, int J, const FThr& t, const double*
 // instruction stream: 10 % of the v3 stall samples were no_instruction).  The window shrinks every 8
 // pivots (32, 24, 16, 8 slots).  Slots that have rotated past the tile edge read a few doubles beyond
 // Lc's rows (still inside this CTA's shared memory) and only ever feed other dead slots.
+// pivot check shared by the chain: non-positive / non-finite pivot -> remember the first failure, continue with 1
+SCAML_DEVICE double checked_pivot(double dkk, int k, int& fail) {
+  if (!(dkk > 0.0) || !(dkk < 1e300)) {
+    if (fail == 0) fail = k + 1;
+    dkk = 1.0;
+  }
+  return dkk;
+}
+// dnext / rsnext: the current pivot A(k,k) of the Schur complement and its rsqrt, produced one step ahead so
+// that the (software, ~20 dependent instructions) rsqrt of pivot k+1 overlaps the trailing update of step k.
 template <int W>
 SCAML_DEVICE void chol_steps(double (&a)[kBS], int k0, double* Lc, int lane, int& fail, double& mydiag, double& myrs,
-                             double& dnext) {
+                             double& dnext, double& rsnext) {
 #pragma unroll 1
   for (int k = k0; k < k0 + 8; ++k) {
-    double dkk = dnext;  // A(k,k) of the current Schur complement
-    if (!(dkk > 0.0) || !(dkk < 1e300)) {
-      if (fail == 0) fail = k + 1;
-      dkk = 1.0;
-    }
-    const double rs = rsqrt(dkk);
+    const double dkk = dnext, rs = rsnext;
     if (lane == k) {
       mydiag = dkk;
       myrs = rs;
@@ -452,7 +485,10 @@ SCAML_DEVICE void chol_steps(double (&a)[kBS], int k0, double* Lc, int lane, int
     const double lrk = a[0] * rs;  // a[i] = A(lane, k + i)
     Lc[k * kLd + lane] = lrk;
     // next pivot without the shared-memory round trip: lane k+1 needs only its own L(k+1,k)
-    dnext = __shfl_sync(0xffffffffu, fma(-lrk, lrk, a[1]), (k + 1) & 31);
+    double dn = __shfl_sync(0xffffffffu, fma(-lrk, lrk, a[1]), (k + 1) & 31);
+    if (k + 1 < kBS) dn = checked_pivot(dn, k + 1, fail);
+    dnext = dn;
+    rsnext = rsqrt(dn);
     __syncwarp();
     const double* lk = Lc + k * kLd + k;  // lk[j] = L(k + j, k)
 #pragma unroll
@@ -479,11 +515,14 @@ SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* 
   for (int c = 0; c < kBS; ++c) a[c] = Dsm[c * kLd + lane];
   int fail = 0;
   double mydiag = 1.0, myrs = 1.0;
-  double dnext = __shfl_sync(0xffffffffu, a[0], 0);
-  chol_steps<32>(a, 0, Lc, lane, fail, mydiag, myrs, dnext);
-  chol_steps<24>(a, 8, Lc, lane, fail, mydiag, myrs, dnext);
-  chol_steps<16>(a, 16, Lc, lane, fail, mydiag, myrs, dnext);
-  chol_steps<8>(a, 24, Lc, lane, fail, mydiag, myrs, dnext);
+  double dnext = checked_pivot(__shfl_sync(0xffffffffu, a[0], 0), 0, fail);
+  double rsnext = rsqrt(dnext);
+  if (!ABL(32)) {
+    chol_steps<32>(a, 0, Lc, lane, fail, mydiag, myrs, dnext, rsnext);
+    chol_steps<24>(a, 8, Lc, lane, fail, mydiag, myrs, dnext, rsnext);
+    chol_steps<16>(a, 16, Lc, lane, fail, mydiag, myrs, dnext, rsnext);
+    chol_steps<8>(a, 24, Lc, lane, fail, mydiag, myrs, dnext, rsnext);
+  }
   double ld = log(mydiag);
   ld = warp_sum(ld);
   if (lane == 0) *logdet += ld;
@@ -491,10 +530,12 @@ SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* 
   double b[kBS];
 #pragma unroll
   for (int i = 0; i < kBS; ++i) b[i] = (i == kBS - 1 - lane) ? 1.0 : 0.0;
-  inv_steps<32>(b, 31, Lc, XC, Pz, lane, myrs);
-  inv_steps<24>(b, 23, Lc, XC, Pz, lane, myrs);
-  inv_steps<16>(b, 15, Lc, XC, Pz, lane, myrs);
-  inv_steps<8>(b, 7, Lc, XC, Pz, lane, myrs);
+  if (!ABL(1)) {
+    inv_steps<32>(b, 31, Lc, XC, Pz, lane, myrs);
+    inv_steps<24>(b, 23, Lc, XC, Pz, lane, myrs);
+    inv_steps<16>(b, 15, Lc, XC, Pz, lane, myrs);
+    inv_steps<8>(b, 7, Lc, XC, Pz, lane, myrs);
+  }
   __syncwarp();
   if (XRs != nullptr || XRg != nullptr) {
 #pragma unroll 4
@@ -518,6 +559,7 @@ SCAML_DEVICE void small_gemm(SAcc& o, const double* A, const double* B, const FT
     for (int j = 0; j < 2; ++j) o[i][j][0] = o[i][j][1] = 0.0;
   const double* ar = A + t.t4 * kLd + 16 * (t.warp >> 1) + t.g;
   const double* br = B + t.t4 * kLd + 16 * (t.warp & 1) + t.g;
+  if (ABL(256)) return;
 #pragma unroll 4
   for (int s = 0; s < 8; ++s) {
     const double a0 = ar[0], a1 = ar[8], b0 = br[0], b1 = br[8];
@@ -555,8 +597,8 @@ SCAML_DEVICE void small_store_R(double* blk, int ld, const SAcc& o, const FThr& 
 //          R-layout dense tiles of D^-1 written to the workspace diagonal (wd00, wd10, wd11).
 // *logdet (shared scalar) accumulates log det; *flag receives the failing pivot (1-based).
 #ifdef SCAML_PROF
-#define DIAG_PROF_ARGS , long long* profsm, long long& prof_last
-#define DIAG_PROF_PASS , profsm, prof_last
+#define DIAG_PROF_ARGS , long long& prof_last
+#define DIAG_PROF_PASS , prof_last
 #else
 #define DIAG_PROF_ARGS
 #define DIAG_PROF_PASS
@@ -675,13 +717,25 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
 
   double* W = p.workspace + (size_t)blockIdx.x * p.ws_stride;
 #ifdef SCAML_PROF
-  __shared__ long long profsm[16];
   long long prof_last = clock64();
   if (threadIdx.x < 16) profsm[threadIdx.x] = 0;
   __syncthreads();
 #endif
   const int E = p.M * p.R;
   const scaml_hyper_spec& sp = p.spec;
+#ifndef SCAML_EMU
+  // Co-resident CTAs run identical work: started together they stay in phase (all in the latency-bound pivot
+  // chains, then all on the tensor pipe).  Offsetting their start by a fraction of one evaluation keeps one
+  // CTA's chains / exp epilogues under the other CTAs' tile products.
+  if (p.stagger_ns != 0 && p.sms > 0) {
+    const unsigned slot = blockIdx.x / (unsigned)p.sms;
+    for (unsigned long long left = (unsigned long long)slot * p.stagger_ns; left > 0;) {
+      const unsigned step = left > 500000ull ? 500000u : (unsigned)left;
+      __nanosleep(step);
+      left -= step;
+    }
+  }
+#endif
   // the pivot chains of the CTAs sharing an SM should sit on different sub-partitions (warp w -> SMSP w%4)
   const int chain_warp = (p.sms > 0 ? (int)(blockIdx.x / p.sms) : 0) & (kFitWarps - 1);
 
@@ -759,7 +813,7 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
           diag_factor(stage, dinvc, wtile_w(W, 2 * J, 2 * J), wtile_w(W, 2 * J + 1, 2 * J),
                       wtile_w(W, 2 * J + 1, 2 * J + 1), &scal[0], flag, J * kSB, t, chain_warp DIAG_PROF_PASS);
           PROF_MARK(3);
-          if (*flag != 0) {
+          if (*flag != 0 && !ABL(0x7fffffff)) {
             failed = true;
             break;
           }

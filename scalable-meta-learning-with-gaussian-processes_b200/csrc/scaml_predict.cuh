@@ -1,18 +1,22 @@
-// Weighted ScaML-GP prediction (K6-K9): for a tile of 64 candidates a CTA walks over the
-// tasks of its split, builds k*(X_m, candidates) once in shared memory, streams the packed
-// L_m^-1 tiles (cp.async, double buffered) through the same 4x4 register-tiled micro-kernel
-// as the fit, and folds  w_m (ybar_m + ystd_m k*^T alpha_m)  and
-// w_m^2 ystd_m^2 (s_m - ||L_m^-1 k*||^2)  into per-candidate accumulators that stay in
-// registers for the whole task loop -> the reduction over tasks happens inside the kernel
-// in a fixed order (deterministic, no atomics).
+// Weighted ScaML-GP prediction (K6-K9): for a tile of CT (64 or 32) candidates a CTA walks over the
+// tasks of its split.  Per task it (1) builds k*(X_m, candidates) once in shared memory (padded
+// k-major 32x32 tiles) together with the mean partials k*^T alpha, (2) streams the packed L_m^-1
+// tiles through a 3-stage cp.async pipeline (one barrier per 32-deep chunk, the pipeline does not
+// drain between the super-rows of a task) and forms V = L^-1 k* on the FP64 tensor cores
+// (mma.sync m8n8k4 -> DMMA; 8 warps, warp tile 32 x CT/4; the zero half of the diagonal tiles is
+// skipped), (3) folds  w_m (ybar_m + ystd_m k*^T alpha_m)  and  w_m^2 ystd_m^2 (s_m - ||V||^2)  into
+// per-candidate accumulators that stay in registers for the whole task loop -> the reduction over
+// tasks happens inside the kernel in a fixed order (deterministic, no atomics).
 // Reference: _compute_target_prior, scamlgp/model.py:108-135; posterior A.7 of SURVEY.md.
 #pragma once
 #include "scaml_device.cuh"
-#include "scaml_tile256.cuh"
 
 namespace scaml {
 
-constexpr int kTB = 64;  // candidates per tile
+constexpr int kPLd = 36;               // padded row stride of a staged tile (conflict-free DMMA fragment loads)
+constexpr int kPTile = kBS * kPLd;     // 1152 doubles
+constexpr int kPStages = 3;
+constexpr int kPredThreads = 256;
 
 struct PredParams {
   const double* X;
@@ -27,52 +31,104 @@ struct PredParams {
   double* mean;
   double* var;
   double* part;  // [nsplit][2][B] when nsplit > 1
-  int M, n_max, n_pad, d, B, nsplit, ntile;
+  int M, n_max, n_pad, d, B, nsplit, ntile, ct, alias;
 };
 
-inline size_t predict_smem_bytes(int n_pad, int d) {
-  return sizeof(double) *
-         ((size_t)n_pad * kTB + 4096 + (size_t)d * n_pad + (size_t)n_pad + 2 * (size_t)d * kTB + 256 + 128 + 8);
+// shared memory (doubles): kst | stage | [xst | alp | xcs] (aliased onto stage when alias) | xcr | red | vsq
+#ifdef SCAML_EMU
+inline
+#else
+__host__ __device__ inline
+#endif
+size_t predict_aux_doubles(int n_pad, int d, int ct) { return (size_t)d * n_pad + n_pad + (size_t)d * ct; }
+inline size_t predict_smem_bytes(int n_pad, int d, int ct, int alias) {
+  const size_t kst = (size_t)(n_pad / kBS) * (ct / kBS) * kPTile;
+  const size_t stage = (size_t)kPStages * 2 * kPTile;
+  const size_t aux = predict_aux_doubles(n_pad, d, ct);
+  return sizeof(double) * (kst + stage + (alias ? 0 : aux) + (size_t)d * ct + 4 * ct + 2 * ct + 2 * kMaxP + 8);
 }
-inline int predict_nsplit(int M, int B, int num_sms) {
-  const int ntile = (B + kTB - 1) / kTB;
+// candidate tile width / layout for (n_pad, d): widest tile that fits 227 KB, un-aliased if possible
+inline bool predict_config(int n_pad, int d, int* ct, int* alias) {
+  for (int c = 64; c >= 32; c -= 32)
+    for (int a = 0; a <= 1; ++a) {
+      if (a && predict_aux_doubles(n_pad, d, c) > (size_t)kPStages * 2 * kPTile) continue;
+      if (predict_smem_bytes(n_pad, d, c, a) <= 227 * 1024) {
+        *ct = c, *alias = a;
+        return true;
+      }
+    }
+  return false;
+}
+inline int predict_nsplit(int M, int B, int num_sms, int ct) {
+  const int ntile = (B + ct - 1) / ct;
   int ns = (2 * num_sms + ntile - 1) / ntile;
   if (ns < 1) ns = 1;
   if (ns > M) ns = M;
   return ns;
 }
 inline size_t predict_workspace_bytes(int M, int n_pad, int d, int B, int num_sms) {
-  (void)n_pad;
-  (void)d;
-  const int ns = predict_nsplit(M, B, num_sms);
+  int ct = 64, alias = 0;
+  if (!predict_config(n_pad, d, &ct, &alias)) return 0;
+  const int ns = predict_nsplit(M, B, num_sms, ct);
   return ns > 1 ? sizeof(double) * 2 * (size_t)ns * (size_t)B : 0;
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(256, 1) scaml_predict_kernel(const PredParams p) {
+// one dense 32x32 tile (8 KB, contiguous) global -> padded shared rows: 2 x 16 B per thread (256 threads)
+SCAML_DEVICE void ptile_async(double* sdst, const double* gsrc, int tid) {
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int c2 = tid + u * kPredThreads;
+    const int row = c2 >> 4, j = c2 & 15;
+    cp_async16(sdst + row * kPLd + 2 * j, gsrc + row * kBS + 2 * j);
+  }
+}
+
+// flat chunk q of a task: super-row I, 32-wide column block ck (0 .. 2I+1)
+struct PChunk {
+  int I, ck;
+  SCAML_DEVICE void next() {
+    if (++ck > 2 * I + 1) {
+      ++I;
+      ck = 0;
+    }
+  }
+};
+SCAML_DEVICE void pred_issue(const double* Lm, const PChunk& c, double* st, int tid) {
+  if (c.ck <= 2 * c.I) ptile_async(st, Lm + (size_t)(tri(2 * c.I) + c.ck) * kTile, tid);
+  ptile_async(st + kPTile, Lm + (size_t)(tri(2 * c.I + 1) + c.ck) * kTile, tid);
+}
+
+template <int KIND, int CT>
+__global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const PredParams p) {
+  constexpr int NJ = CT / 32;  // 8-column DMMA tiles per warp (warp tile: 32 rows x 8*NJ candidates)
+  constexpr int CBT = CT / 32;  // kst tile columns
   SCAML_DYN_SMEM(double, sm);
-  const Thr t = make_thr();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  const int rb = warp >> 2, col0 = (warp & 3) * 8 * NJ, cb = col0 >> 5, cin = col0 & 31;
   const int d = p.d, P = d + 2, n_pad = p.n_pad;
-  double* kst = sm;                           // n_pad x 64 as 32x32 tiles (ab*2+cb), [a][c]
-  double* ast = kst + (size_t)n_pad * kTB;    // 2 stages x 2 tiles
-  double* xst = ast + 4096;                   // [d][n_pad]
-  double* alp = xst + (size_t)d * n_pad;      // [n_pad]
-  double* xcr = alp + n_pad;                  // [d][64] raw candidates
-  double* xcs = xcr + d * kTB;                // [d][64] scaled for the current task
-  double* red = xcs + d * kTB;                // 256
-  double* vsq = red + 256;                    // 128
+  double* kst = sm;                                                // (n_pad/32) x CBT padded tiles [a][c]
+  double* stage = kst + (size_t)(n_pad / kBS) * CBT * kPTile;      // kPStages x 2 padded tiles
+  double* aux = stage + (p.alias ? 0 : kPStages * 2 * kPTile);
+  double* xst = aux;                                               // [d][n_pad] scaled inputs of the task
+  double* alp = xst + (size_t)d * n_pad;                           // [n_pad]
+  double* xcs = alp + n_pad;                                       // [d][CT] scaled candidates
+  double* xcr = stage + kPStages * 2 * kPTile + (p.alias ? 0 : predict_aux_doubles(n_pad, d, CT));  // [d][CT] raw
+  double* red = xcr + d * CT;                                      // 4 x CT mean partials
+  double* vsq = red + 4 * CT;                                      // 2 x CT
+  double* invl2 = vsq + 2 * CT;                                    // 2 x kMaxP reciprocal lengthscales (task parity)
+  int tcount = 0;
   const long long lstride = (long long)tri(n_pad / kBS) * kTile;
   const int items = p.ntile * p.nsplit;
   const int mper = (p.M + p.nsplit - 1) / p.nsplit;
 
   for (int it = blockIdx.x; it < items; it += gridDim.x) {
     const int ct = it % p.ntile, spx = it / p.ntile;
-    const int b0 = ct * kTB;
+    const int b0 = ct * CT;
     const int m_lo = spx * mper, m_hi = (m_lo + mper < p.M) ? m_lo + mper : p.M;
     __syncthreads();
-    for (int i = t.tid; i < kTB * d; i += 256) {
+    for (int i = tid; i < CT * d; i += kPredThreads) {
       const int c = i / d, k = i - c * d;
-      xcr[k * kTB + c] = (b0 + c < p.B) ? p.Xc[(size_t)(b0 + c) * d + k] : 0.0;
+      xcr[k * CT + c] = (b0 + c < p.B) ? p.Xc[(size_t)(b0 + c) * d + k] : 0.0;
     }
     double macc = 0.0, vacc = 0.0;
     for (int m = m_lo; m < m_hi; ++m) {
@@ -80,98 +136,156 @@ __global__ void __launch_bounds__(256, 1) scaml_predict_kernel(const PredParams 
       if (wm == 0.0) continue;
       const int nv = p.n_valid ? p.n_valid[m] : p.n_max;
       const int NS = (nv + kSB - 1) / kSB, npt = NS * kSB;
+      const int L = NS * (NS + 1);  // flat chunks of this task
       const double* th = p.theta + (size_t)m * P;
       const double os = th[d];
-      __syncthreads();
+      const double* Lm = p.linv + (size_t)m * lstride;
+      // x * (1/l) instead of x / l: an FP64 division is ~30 instructions per staged coordinate (<= 1 ulp apart)
+      double* invl = invl2 + (tcount & 1) * kMaxP;
+      ++tcount;
+      if (tid < d) invl[tid] = 1.0 / th[tid];
+      __syncthreads();  // previous task fully consumed (kst, stage, aux); invl visible
+      PChunk qi{0, 0};
+      int issued = 0;
+      if (!p.alias) {  // start streaming L^-1 under the exp-heavy assembly below
+        for (; issued < 2 && issued < L; ++issued, qi.next()) {
+          pred_issue(Lm, qi, stage + (issued % kPStages) * 2 * kPTile, tid);
+          cp_async_commit();
+        }
+      }
       {
         const double* Xm = p.X + (size_t)m * p.n_max * d;
-        for (int i = t.tid; i < npt * d; i += 256) {
+        for (int i = tid; i < npt * d; i += kPredThreads) {
           const int a = i / d, k = i - a * d;
-          xst[k * n_pad + a] = (a < nv) ? Xm[(size_t)a * d + k] / th[k] : 0.0;
+          xst[k * n_pad + a] = (a < nv) ? Xm[(size_t)a * d + k] * invl[k] : 0.0;
         }
-        for (int i = t.tid; i < npt; i += 256) alp[i] = p.alpha[(size_t)m * n_pad + i];
-        for (int i = t.tid; i < kTB * d; i += 256) {
-          const int k = i / kTB;
-          xcs[i] = xcr[i] / th[k];
-        }
+        for (int i = tid; i < npt; i += kPredThreads) alp[i] = p.alpha[(size_t)m * n_pad + i];
+        for (int i = tid; i < CT * d; i += kPredThreads) xcs[i] = xcr[i] * invl[i / CT];
       }
       __syncthreads();
       // ---- k*(X_m, candidates) and the mean partials -------------------------------- //
+      // a thread owns one candidate and walks the task's points 8 at a time: 8 independent distance / exp
+      // chains per thread keep the FP64 pipe busy (a single chain per thread is latency bound).
       {
-        const int c = t.tid & 63, q = t.tid >> 6;
+        constexpr int QN = kPredThreads / CT;  // row phases (4 for CT = 64, 8 for CT = 32)
+        constexpr int U = 8;
+        const int c = tid % CT, q = tid / CT;
         double mu = 0.0;
-        for (int a = q; a < npt; a += 4) {
-          double r2 = 0.0;
+        for (int a0 = q; a0 < npt; a0 += QN * U) {
+          double r2[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) r2[u] = 0.0;
           for (int k = 0; k < d; ++k) {
-            const double df = xst[k * n_pad + a] - xcs[k * kTB + c];
-            r2 = fma(df, df, r2);
+            const double xc = xcs[k * CT + c];
+            const double* xr = xst + k * n_pad + a0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const double df = xr[u * QN] - xc;
+              r2[u] = fma(df, df, r2[u]);
+            }
           }
-          const double kv = (a < nv) ? os * kappa_of<KIND>(r2) : 0.0;
-          kst[((a >> 5) * 2 + (c >> 5)) * kTile + (a & 31) * kBS + (c & 31)] = kv;
-          mu = fma(kv, alp[a], mu);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int a = a0 + u * QN;
+            const double kv = (a < nv) ? os * kappa_of<KIND>(r2[u]) : 0.0;
+            kst[((a >> 5) * CBT + (c >> 5)) * kPTile + (a & 31) * kPLd + (c & 31)] = kv;
+            mu = fma(kv, alp[a], mu);
+          }
         }
-        red[q * 64 + c] = mu;
+        if (q < 4) red[q * CT + c] = mu;
+        if (QN > 4) {  // CT = 32: fold phases 4..7 onto 0..3 in a fixed order
+          __syncthreads();
+          if (q >= 4) red[(q - 4) * CT + c] += mu;
+        }
       }
       __syncthreads();
-      // ---- V = L^-1 k*  super-tile by super-tile, column sums of squares ------------- //
-      const double* Lm = p.linv + (size_t)m * lstride;
-      double vs[4] = {0.0, 0.0, 0.0, 0.0};
-      for (int I = 0; I < NS; ++I) {
-        double acc[4][4];
-        acc_zero(acc);
-        const int n = 2 * I + 2;
-        // chunk ck: A tiles (2I+rb, ck) (null above the diagonal), B = kst tiles (ck, cb)
-        {
-          const double* a0 = Lm + (size_t)(tri(2 * I) + 0) * kTile;
-          tile_async256(ast, a0, t.tid);
-          tile_async256(ast + kTile, Lm + (size_t)(tri(2 * I + 1) + 0) * kTile, t.tid);
+      if (p.alias) {
+        for (; issued < 2 && issued < L; ++issued, qi.next()) {
+          pred_issue(Lm, qi, stage + (issued % kPStages) * 2 * kPTile, tid);
           cp_async_commit();
         }
-        for (int ck = 0; ck < n; ++ck) {
-          double* st = ast + (ck & 1) * 2 * kTile;
-          if (ck + 1 < n) {
-            double* sn = ast + ((ck + 1) & 1) * 2 * kTile;
-            if (ck + 1 <= 2 * I) tile_async256(sn, Lm + (size_t)(tri(2 * I) + ck + 1) * kTile, t.tid);
-            tile_async256(sn + kTile, Lm + (size_t)(tri(2 * I + 1) + ck + 1) * kTile, t.tid);
-            cp_async_commit();
-            cp_async_wait<1>();
-          } else {
-            cp_async_wait<0>();
-          }
-          __syncthreads();
-          if (ck <= 2 * I + t.rb)
-            mma_chunk(acc, st + t.rb * kTile + t.rin, kst + (ck * 2 + t.cb) * kTile + t.cin);
-          __syncthreads();
+      }
+      // ---- V = L^-1 k*  on the FP64 tensor cores, column sums of squares ------------- //
+      double acc[4][NJ][2];
+      double vs[NJ][2];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) vs[j][0] = vs[j][1] = 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      PChunk qc{0, 0};
+      for (int q = 0; q < L; ++q) {
+        cp_async_wait<1>();
+        __syncthreads();  // chunk q visible to everyone; everyone has finished reading chunk q-1
+        if (issued < L) {
+          pred_issue(Lm, qi, stage + (issued % kPStages) * 2 * kPTile, tid);
+          ++issued;
+          qi.next();
         }
+        cp_async_commit();  // always commit (possibly empty): keeps the wait<1> accounting uniform
+        const int brow = 2 * qc.I + rb;  // 32-row block of L^-1 this warp multiplies
+        if (qc.ck <= brow) {
+          const bool dg = (qc.ck == brow);  // diagonal tile: L^-1(r, kk) = 0 for kk > r
+          const double* ar = stage + ((q % kPStages) * 2 + rb) * kPTile + t4 * kPLd + g;
+          const double* br = kst + (qc.ck * CBT + cb) * kPTile + t4 * kPLd + cin + g;
+#pragma unroll 2
+          for (int s = 0; s < 8; ++s) {
+            const double a[4] = {ar[0], ar[8], ar[16], ar[24]};
+            double b[NJ];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < NJ; ++j) b[j] = br[8 * j];
+            ar += 4 * kPLd;
+            br += 4 * kPLd;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) vs[j] = fma(acc[i][j], acc[i][j], vs[j]);
+            for (int i = 0; i < 4; ++i)
+              if (!dg || s < 2 * i + 2) {
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j], a[i], b[j]);
+              }
+          }
+        }
+        if (qc.ck == 2 * qc.I + 1) {  // super-row complete: ||V_I||^2 per candidate column
+#pragma unroll
+          for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                vs[j][e] = fma(acc[i][j][e], acc[i][j][e], vs[j][e]);
+                acc[i][j][e] = 0.0;
+              }
+            }
+        }
+        qc.next();
       }
+      cp_async_wait<0>();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        double s = vs[j];
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        s += __shfl_xor_sync(0xffffffffu, s, 8);
-        s += __shfl_xor_sync(0xffffffffu, s, 16);
-        if ((t.lane >> 2) == 0) vsq[t.rb * 64 + t.cb * kBS + t.cin + j] = s;
-      }
+      for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          double s = vs[j][e];
+          s += __shfl_xor_sync(0xffffffffu, s, 4);
+          s += __shfl_xor_sync(0xffffffffu, s, 8);
+          s += __shfl_xor_sync(0xffffffffu, s, 16);
+          if (g == 0) vsq[rb * CT + col0 + 8 * j + 2 * t4 + e] = s;
+        }
       __syncthreads();
-      if (t.tid < kTB) {
-        const double mu = ((red[t.tid] + red[64 + t.tid]) + red[128 + t.tid]) + red[192 + t.tid];
-        const double ssq = vsq[t.tid] + vsq[64 + t.tid];
+      if (tid < CT) {
+        const double mu = ((red[tid] + red[CT + tid]) + red[2 * CT + tid]) + red[3 * CT + tid];
+        const double ssq = vsq[tid] + vsq[CT + tid];
         const double ys = p.ystd[m];
         macc = fma(wm, p.ybar[m] + ys * mu, macc);
         vacc = fma(wm * wm * ys * ys, os - ssq, vacc);
       }
     }
-    if (t.tid < kTB && b0 + t.tid < p.B) {
+    if (tid < CT && b0 + tid < p.B) {
       if (p.nsplit == 1) {
-        p.mean[b0 + t.tid] = macc;
-        p.var[b0 + t.tid] = vacc;
+        p.mean[b0 + tid] = macc;
+        p.var[b0 + tid] = vacc;
       } else {
-        p.part[((size_t)spx * 2 + 0) * p.B + b0 + t.tid] = macc;
-        p.part[((size_t)spx * 2 + 1) * p.B + b0 + t.tid] = vacc;
+        p.part[((size_t)spx * 2 + 0) * p.B + b0 + tid] = macc;
+        p.part[((size_t)spx * 2 + 1) * p.B + b0 + tid] = vacc;
       }
     }
   }
@@ -189,19 +303,24 @@ __global__ void scaml_predict_reduce_kernel(const double* part, double* mean, do
   }
 }
 
-template <int KIND>
-int launch_predict_k(const PredParams& p, int grid, size_t smem, void* stream) {
+template <int KIND, int CT>
+int launch_predict_kc(const PredParams& p, int grid, size_t smem, void* stream) {
 #ifdef SCAML_EMU
   (void)stream;
-  cuemu::launch(dim3(grid), dim3(256), smem, scaml_predict_kernel<KIND>, p);
+  cuemu::launch(dim3(grid), dim3(kPredThreads), smem, scaml_predict_kernel<KIND, CT>, p);
   return 0;
 #else
   cudaError_t err =
-      cudaFuncSetAttribute(scaml_predict_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(scaml_predict_kernel<KIND, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return (int)err;
-  scaml_predict_kernel<KIND><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+  scaml_predict_kernel<KIND, CT><<<grid, kPredThreads, smem, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 #endif
+}
+template <int KIND>
+int launch_predict_k(const PredParams& p, int grid, size_t smem, void* stream) {
+  return p.ct == 64 ? launch_predict_kc<KIND, 64>(p, grid, smem, stream)
+                    : launch_predict_kc<KIND, 32>(p, grid, smem, stream);
 }
 
 inline int launch_predict_weighted(const double* X, const int32_t* n_valid, const double* theta, const double* linv,
@@ -212,10 +331,10 @@ inline int launch_predict_weighted(const double* X, const int32_t* n_valid, cons
   p.X = X, p.n_valid = n_valid, p.theta = theta, p.linv = linv, p.alpha = alpha, p.ybar = ybar, p.ystd = ystd;
   p.w = w, p.Xc = Xc, p.mean = mean, p.var = var, p.part = workspace;
   p.M = M, p.n_max = n_max, p.n_pad = n_pad, p.d = d, p.B = B;
-  p.ntile = (B + kTB - 1) / kTB;
-  p.nsplit = predict_nsplit(M, B, num_sms);
-  const size_t smem = predict_smem_bytes(n_pad, d);
-  if (smem > 227 * 1024) return SCAML_E_SMEM;
+  if (!predict_config(n_pad, d, &p.ct, &p.alias)) return SCAML_E_SMEM;
+  p.ntile = (B + p.ct - 1) / p.ct;
+  p.nsplit = predict_nsplit(M, B, num_sms, p.ct);
+  const size_t smem = predict_smem_bytes(n_pad, d, p.ct, p.alias);
   long long items = (long long)p.ntile * p.nsplit;
   int grid = (int)(items < num_sms ? items : num_sms);
   int rc;

@@ -115,6 +115,30 @@ def test_factorize_and_weighted_prediction(engine):
     assert torch.equal(m1, m2) and torch.equal(v1, v2)
 
 
+@pytest.mark.parametrize("n,d,kernel,nvs", [
+    (320, 6, 0, [320, 257, 100]),    # 32-candidate tiles (k* of 64 candidates no longer fits shared memory)
+    (512, 10, 3, [512, 400, 1]),     # config-4 shape: 32-candidate tiles, task staging aliased onto the L^-1 stages
+    (256, 20, 2, [256, 130, 64]),    # 64-candidate tiles, aliased staging (large d)
+])
+def test_weighted_prediction_other_layouts(engine, n, d, kernel, nvs):
+    M, B = len(nvs), 150
+    pb = make_problem(M, 2, n, d, seed=8, n_valid=nvs, kernel=kernel)
+    batch = _batch(pb)
+    th = pb["th"][:, 1].contiguous()
+    fs = engine.factorize(batch, th.cuda(), pb["cspec"])
+    assert int(fs.info.abs().max()) == 0
+    states = [O.factorize(pb["X"][m, : pb["nv"][m]], pb["Y"][m, : pb["nv"][m]], th[m], pb["ospec"]) for m in range(M)]
+    g = torch.Generator().manual_seed(6)
+    Xc = torch.rand(B, d, dtype=torch.float64, generator=g)
+    w = torch.rand(M, dtype=torch.float64, generator=g)
+    mean, var = engine.predict_weighted(fs, w.cuda(), Xc.cuda())
+    om, ov = O.scaml_prior_predict(states, w, Xc)
+    assert rel_err(mean.cpu().numpy(), om.numpy()) < TOL_MEAN_VAR
+    # variances are differences s - ||v||^2: compare relative to the prior scale
+    scale = float(sum(float(wi) ** 2 * float(st.os) * st.ystd ** 2 for wi, st in zip(w, states)))
+    assert float((var.cpu() - ov).abs().max()) < TOL_MEAN_VAR * scale
+
+
 def test_kernel_matrix(engine):
     M, n, d = 5, 200, 6
     pb = make_problem(M, 1, n, d, seed=2, n_valid=[200, 33, 64, 199, 128])
