@@ -103,6 +103,12 @@ int run_fit(scaml::FitParams p, void* workspace, size_t workspace_bytes, void* s
 
 extern "C" {
 
+#ifdef SCAML_EMU
+// tests only: the device exponential evaluated on the host (same source, same FMA semantics)
+void scaml_debug_exp_nonpos(const double* x, double* out, int n) {
+  for (int i = 0; i < n; ++i) out[i] = scaml::exp_nonpos(x[i]);
+}
+#endif
 #ifdef SCAML_ABLATE
 void scaml_debug_set_ablate(int bits) { cudaMemcpyToSymbol(scaml::g_ablate, &bits, sizeof(int)); }
 #endif

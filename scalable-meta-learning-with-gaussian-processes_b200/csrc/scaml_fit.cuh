@@ -339,11 +339,9 @@ SCAML_DEVICE void xblk_store(double* xblk, const double (&xp)[kXpre], const doub
 }
 
 // squared scaled distances between the thread's row points ra, ra + 8 and its 8 column points
-SCAML_DEVICE void pair_r2(double (&r2)[2][4][2], const double* xblk, int d, int ra, int cb0) {
+SCAML_DEVICE void pair_r2(double (&r2)[16], const double* xblk, int d, int ra, int cb0) {
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) r2[i][j][0] = r2[i][j][1] = 0.0;
+  for (int u = 0; u < 16; ++u) r2[u] = 0.0;
   if (ABL(512)) return;
 #pragma unroll 2
   for (int k = 0; k < d; ++k) {
@@ -353,10 +351,10 @@ SCAML_DEVICE void pair_r2(double (&r2)[2][4][2], const double* xblk, int d, int 
     for (int j = 0; j < 4; ++j) {
       const double2 xb = *reinterpret_cast<const double2*>(xr + cb0 + 8 * j);
       const double d00 = xa0 - xb.x, d01 = xa0 - xb.y, d10 = xa1 - xb.x, d11 = xa1 - xb.y;
-      r2[0][j][0] = fma(d00, d00, r2[0][j][0]);
-      r2[0][j][1] = fma(d01, d01, r2[0][j][1]);
-      r2[1][j][0] = fma(d10, d10, r2[1][j][0]);
-      r2[1][j][1] = fma(d11, d11, r2[1][j][1]);
+      r2[2 * j] = fma(d00, d00, r2[2 * j]);
+      r2[2 * j + 1] = fma(d01, d01, r2[2 * j + 1]);
+      r2[8 + 2 * j] = fma(d10, d10, r2[8 + 2 * j]);
+      r2[8 + 2 * j + 1] = fma(d11, d11, r2[8 + 2 * j + 1]);
     }
   }
 }
@@ -369,8 +367,9 @@ SCAML_DEVICE void assemble_tile(Acc& acc, int I, int J, const FThr& t, const dou
   const int a0 = I * kSB + ra, b0 = J * kSB + t.cb * kBS + 2 * t.t4;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {  // two passes of two row-tiles keep r2 at 32 registers
-    double r2[2][4][2];
+    double r2[16];  // [i][j][e] -> 8 i + 2 j + e
     pair_r2(r2, xblk, d, ra + 16 * h, cb0);
+    if (!ABL(2)) kappa_n<KIND, 16, false>(r2, r2, r2);  // 16 independent exponentials, interleaved
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -378,7 +377,7 @@ SCAML_DEVICE void assemble_tile(Acc& acc, int I, int J, const FThr& t, const dou
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int a = a0 + 8 * (2 * h + i), b = b0 + 8 * j + e;
-          double k = ABL(2) ? os * (1.0 - 1e-3 * r2[i][j][e]) : os * kappa_of<KIND>(r2[i][j][e]);
+          double k = os * r2[8 * i + 2 * j + e];
           if (a == b) k += diag_add;
           if (a >= nv || b >= nv) k = (a == b) ? 1.0 : 0.0;
           acc[2 * h + i][j][e] = k - acc[2 * h + i][j][e];
@@ -397,8 +396,13 @@ SCAML_DEVICE void grad_tile(Acc& acc, int I, int J, const FThr& t, const double*
   double accS = 0.0, accT = 0.0;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    double r2[2][4][2];
+    double r2[16], kdv[16];  // [i][j][e] -> 8 i + 2 j + e
     pair_r2(r2, xblk, d, ra + 16 * h, cb0);
+    if (KIND == SCAML_KERNEL_RBF) {
+      if (!ABL(4)) kappa_n<KIND, 16, false>(r2, r2, r2);  // kd == kappa for the RBF kernel (kdv unused)
+    } else {
+      kappa_n<KIND, 16, true>(r2, r2, kdv);
+    }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int a = a0 + 8 * (2 * h + i);
@@ -408,12 +412,8 @@ SCAML_DEVICE void grad_tile(Acc& acc, int I, int J, const FThr& t, const double*
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int b = b0 + 8 * j + e;
-          double kap, kd;
-          if (ABL(4)) {
-            kap = kd = 1.0 - 1e-3 * r2[i][j][e];
-          } else {
-            kappa_pair<KIND>(r2[i][j][e], kap, kd);
-          }
+          const double kap = r2[8 * i + 2 * j + e];
+          const double kd = (KIND == SCAML_KERNEL_RBF) ? kap : kdv[8 * i + 2 * j + e];
           const bool use = (a >= b) && (a < nv) && (b < nv);
           const double wgt = use ? ((a == b) ? 1.0 : 2.0) : 0.0;
           const double Wab = ava * av[b] - acc[2 * h + i][j][e];

@@ -155,10 +155,8 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
       }
       {
         const double* Xm = p.X + (size_t)m * p.n_max * d;
-        for (int i = tid; i < npt * d; i += kPredThreads) {
-          const int a = i / d, k = i - a * d;
-          xst[k * n_pad + a] = (a < nv) ? Xm[(size_t)a * d + k] * invl[k] : 0.0;
-        }
+        for (int a = tid; a < npt; a += kPredThreads)  // one point per thread: no runtime integer division
+          for (int k = 0; k < d; ++k) xst[k * n_pad + a] = (a < nv) ? Xm[(size_t)a * d + k] * invl[k] : 0.0;
         for (int i = tid; i < npt; i += kPredThreads) alp[i] = p.alpha[(size_t)m * n_pad + i];
         for (int i = tid; i < CT * d; i += kPredThreads) xcs[i] = xcr[i] * invl[i / CT];
       }
@@ -184,10 +182,12 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
               r2[u] = fma(df, df, r2[u]);
             }
           }
+          double kap[U];
+          kappa_n<KIND, U, false>(r2, kap, kap);
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const int a = a0 + u * QN;
-            const double kv = (a < nv) ? os * kappa_of<KIND>(r2[u]) : 0.0;
+            const double kv = ((a < nv) ? os : 0.0) * kap[u];
             kst[((a >> 5) * CBT + (c >> 5)) * kPTile + (a & 31) * kPLd + (c & 31)] = kv;
             mu = fma(kv, alp[a], mu);
           }
