@@ -149,10 +149,16 @@ SCAML_DEVICE void fmma(Acc& acc, const double* __restrict__ Ap, const double* __
 }
 
 // ---- chunk sources: which global tiles feed chunk `ck` of a super-tile product ------- //
+// Scalar fields only: arrays indexed by the (runtime) warp coordinates would be placed in local memory
+// and put LDL/STL round trips on the critical path of every pipeline step.
 struct ChunkPtrs {
-  const double* a[2];
-  const double* b[2];
+  const double* a0;
+  const double* a1;
+  const double* b0;
+  const double* b1;
   int zoff;  // first global row/col index covered by this chunk (piggy-backed GEMV)
+  SCAML_DEVICE bool a_ok(int rb) const { return rb == 0 ? a0 != nullptr : a1 != nullptr; }
+  SCAML_DEVICE bool b_ok(int cb) const { return cb == 0 ? b0 != nullptr : b1 != nullptr; }
 };
 SCAML_DEVICE const double* wtile(const double* W, int bi, int bj) { return W + (size_t)(tri(bi) + bj) * kTile; }
 SCAML_DEVICE double* wtile_w(double* W, int bi, int bj) { return W + (size_t)(tri(bi) + bj) * kTile; }
@@ -165,10 +171,10 @@ struct CholSrc {
   SCAML_DEVICE bool same() const { return I == J; }
   SCAML_DEVICE ChunkPtrs get(int ck) const {
     ChunkPtrs c;
-    c.a[0] = wtile(W, 2 * I, ck);
-    c.a[1] = wtile(W, 2 * I + 1, ck);
-    c.b[0] = wtile(W, 2 * J, ck);
-    c.b[1] = wtile(W, 2 * J + 1, ck);
+    c.a0 = wtile(W, 2 * I, ck);
+    c.a1 = wtile(W, 2 * I + 1, ck);
+    c.b0 = wtile(W, 2 * J, ck);
+    c.b1 = wtile(W, 2 * J + 1, ck);
     c.zoff = ck * kBS;
     return c;
   }
@@ -183,10 +189,10 @@ struct TrtriSrc {
   SCAML_DEVICE ChunkPtrs get(int ck) const {
     ChunkPtrs c;
     const int kcol = 2 * J + ck;
-    c.a[0] = wtile(W, 2 * I, kcol);
-    c.a[1] = wtile(W, 2 * I + 1, kcol);
-    c.b[0] = wtile(W, kcol, 2 * J);
-    c.b[1] = (kcol >= 2 * J + 1) ? wtile(W, kcol, 2 * J + 1) : nullptr;
+    c.a0 = wtile(W, 2 * I, kcol);
+    c.a1 = wtile(W, 2 * I + 1, kcol);
+    c.b0 = wtile(W, kcol, 2 * J);
+    c.b1 = (kcol >= 2 * J + 1) ? wtile(W, kcol, 2 * J + 1) : nullptr;
     c.zoff = kcol * kBS;
     return c;
   }
@@ -200,10 +206,10 @@ struct LauumSrc {
   SCAML_DEVICE ChunkPtrs get(int ck) const {
     ChunkPtrs c;
     const int krow = 2 * I + ck;
-    c.a[0] = wtile(W, krow, 2 * I);
-    c.a[1] = (krow >= 2 * I + 1) ? wtile(W, krow, 2 * I + 1) : nullptr;
-    c.b[0] = wtile(W, krow, 2 * J);
-    c.b[1] = (krow >= 2 * J + 1) ? wtile(W, krow, 2 * J + 1) : nullptr;
+    c.a0 = wtile(W, krow, 2 * I);
+    c.a1 = (krow >= 2 * I + 1) ? wtile(W, krow, 2 * I + 1) : nullptr;
+    c.b0 = wtile(W, krow, 2 * J);
+    c.b1 = (krow >= 2 * J + 1) ? wtile(W, krow, 2 * J + 1) : nullptr;
     c.zoff = krow * kBS;
     return c;
   }
@@ -225,11 +231,11 @@ SCAML_DEVICE void stage_issue(const Src& src, int s, double* st, int tid) {
   const ChunkPtrs c = src.get(s >> 1);
   const int off = (s & 1) * kHalfG;
   if (ABL(16)) return;
-  if (c.a[0]) half_async(st, c.a[0] + off, tid);
-  if (c.a[1]) half_async(st + kHalfS, c.a[1] + off, tid);
+  if (c.a0) half_async(st, c.a0 + off, tid);
+  if (c.a1) half_async(st + kHalfS, c.a1 + off, tid);
   if (!src.same()) {
-    if (c.b[0]) half_async(st + 2 * kHalfS, c.b[0] + off, tid);
-    if (c.b[1]) half_async(st + 3 * kHalfS, c.b[1] + off, tid);
+    if (c.b0) half_async(st + 2 * kHalfS, c.b0 + off, tid);
+    if (c.b1) half_async(st + 3 * kHalfS, c.b1 + off, tid);
   }
   cp_async_commit();
 }
@@ -262,12 +268,12 @@ SCAML_DEVICE void gemm_global(Acc& acc, const Src& src, double* stage, const FTh
     const ChunkPtrs c = src.get(s >> 1);
     const double* As = st;
     const double* Bs = src.same() ? st : st + 2 * kHalfS;
-    const bool bvalid = src.same() ? (c.a[t.cb] != nullptr) : (c.b[t.cb] != nullptr);
-    if (active && c.a[t.rb] != nullptr && bvalid && !ABL(8))
+    const bool bvalid = src.same() ? c.a_ok(t.cb) : c.b_ok(t.cb);
+    if (active && c.a_ok(t.rb) && bvalid && !ABL(8))
       fmma<4>(acc, As + t.rb * kHalfS, Bs + t.cb * kHalfS, t, lower);
     if (piggy) {
       const int col = t.tid & 63, q = t.tid >> 6;
-      if (c.a[col >> 5] != nullptr) {
+      if (c.a_ok(col >> 5)) {
         const double* ap = As + (col >> 5) * kHalfS + (col & 31) + q * 8 * kLd;
         const double* zp = zv + c.zoff + (s & 1) * 16 + q * 8;
 #pragma unroll
@@ -284,13 +290,28 @@ SCAML_DEVICE void gemm_global(Acc& acc, const Src& src, double* stage, const FTh
   __syncthreads();
 }
 
-// product of shared-memory resident 64x64 operands given as 2 chunks x 2 full padded tiles each
-SCAML_DEVICE void gemm_smem(Acc& acc, const double* const (&A)[2][2], const double* const (&B)[2][2], const FThr& t) {
+// products of shared-memory resident 64x64 operands (2 chunks of full padded tiles); tile addresses are
+// computed arithmetically from the warp coordinates (no pointer tables -> no local memory).
+//   full 2x2 operand `F` : tile (r, c) at F + (2 r + c) * kTileS   (or (2 c + r) when stored chunk-major)
+//   lower-triangular `D`: tiles (0,0), (1,0), (1,1) at D, D + kTileS, D + 2 kTileS; (0,1) is null
+// trsm  (phase B): acc = C_in * D^-T ; A chunk ck = C_in tile (rb, ck) at stage + (2 rb + ck) kTileS,
+//                  B[kk][c] = D^-1(c, kk): chunk ck, col-tile cb -> D tile (cb, ck), null for cb < ck
+SCAML_DEVICE void gemm_smem_trsm(Acc& acc, const double* cin, const double* dinvc, const FThr& t) {
+  if (ABL(128)) return;
 #pragma unroll
   for (int ck = 0; ck < 2; ++ck) {
-    const double* a = A[ck][t.rb];
-    const double* b = B[ck][t.cb];
-    if (a != nullptr && b != nullptr && !ABL(128)) fmma<8>(acc, a, b, t, false);
+    if (t.cb < ck) continue;
+    fmma<8>(acc, cin + (2 * t.rb + ck) * kTileS, dinvc + (t.cb + ck) * kTileS, t, false);
+  }
+}
+// trtri (phase C): acc = D^-1 * S ; A[kk][r] = D^-1(r, kk): chunk ck, row-tile rb -> D tile (rb, ck), null for
+//                  rb < ck ; B chunk ck = S tile (ck, cb) at stage + (2 ck + cb) kTileS
+SCAML_DEVICE void gemm_smem_trtri(Acc& acc, const double* dinvc, const double* sst, const FThr& t) {
+  if (ABL(128)) return;
+#pragma unroll
+  for (int ck = 0; ck < 2; ++ck) {
+    if (t.rb < ck) continue;
+    fmma<8>(acc, dinvc + (t.rb + ck) * kTileS, sst + (2 * ck + t.cb) * kTileS, t, false);
   }
 }
 
@@ -793,7 +814,6 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
     // ================= phase B: blocked left-looking Cholesky ========================== //
     const bool upper_warp = (t.rb == 0 && t.cb == 1);  // idle on diagonal super-tiles
     for (int J = 0; J < NS && !failed; ++J) {
-      const double* const TB[2][2] = {{dinvc, dinvc + kTileS}, {nullptr, dinvc + 2 * kTileS}};
       for (int I = J; I < NS; ++I) {
         const bool diag = (I == J);
         facc_zero(acc);
@@ -819,9 +839,8 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
           }
         } else {
           // L(I,J) = C * D^-T : A chunk kb2 = C tiles (rb,kb2); B[kk][c] = D^-1(c,kk)
-          const double* const TA[2][2] = {{stage, stage + 2 * kTileS}, {stage + kTileS, stage + 3 * kTileS}};
           facc_zero(acc);
-          gemm_smem(acc, TA, TB, t);
+          gemm_smem_trsm(acc, stage, dinvc, t);
           store_tile_C(wtile_w(W, 2 * I + t.rb, 2 * J + t.cb), kBS, acc, t, 1.0);
           __syncthreads();
           PROF_MARK(4);
@@ -842,7 +861,6 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
       __syncthreads();
       load_dinvc(dinvc, stage, W, I, t.tid);
       pig = 0.0;
-      const double* const TA[2][2] = {{dinvc, dinvc + kTileS}, {nullptr, dinvc + 2 * kTileS}};
       for (int J = 0; J < I; ++J) {
         facc_zero(acc);
         TrtriSrc src{W, I, J};
@@ -850,9 +868,8 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
         PROF_MARK(5);
         store_tile_R(stage + (t.rb * 2 + t.cb) * kTileS, kLd, acc, t, 1.0);  // S, R-layout tiles (kb2, cb)
         __syncthreads();
-        const double* const TBs[2][2] = {{stage, stage + kTileS}, {stage + 2 * kTileS, stage + 3 * kTileS}};
         facc_zero(acc);
-        gemm_smem(acc, TA, TBs, t);
+        gemm_smem_trtri(acc, dinvc, stage, t);
         store_tile_R(wtile_w(W, 2 * I + t.rb, 2 * J + t.cb), kBS, acc, t, -1.0);
         if (p.mode == kModeFactorize)
           store_tile_C(p.linv_out + ((size_t)m * tri(n_pad_max / kBS) + tri(2 * I + t.rb) + 2 * J + t.cb) * kTile, kBS,
