@@ -103,7 +103,8 @@ inline size_t fit_smem_bytes(int n_pad, int d) {
 // grid of 8x8 DMMA tiles; lane (g, t4) owns element rows 8i+g, cols 8j+2*t4+{0,1}.
 struct FThr {
   int tid, warp, lane;
-  int rb, cb;  // tile row / col inside the super-tile (0/1) -- warp-uniform
+  int role;    // which 32x32 tile of the 64x64 super-tile this warp owns for the current evaluation
+  int rb, cb;  // = role >> 1, role & 1 (0/1) -- warp-uniform
   int g, t4;   // lane >> 2, lane & 3
 };
 SCAML_DEVICE FThr make_fthr() {
@@ -111,8 +112,9 @@ SCAML_DEVICE FThr make_fthr() {
   t.tid = threadIdx.x;
   t.warp = t.tid >> 5;
   t.lane = t.tid & 31;
-  t.rb = t.warp >> 1;
-  t.cb = t.warp & 1;
+  t.role = t.warp;
+  t.rb = t.role >> 1;
+  t.cb = t.role & 1;
   t.g = t.lane >> 2;
   t.t4 = t.lane & 3;
   return t;
@@ -445,7 +447,7 @@ SCAML_DEVICE void grad_tile(Acc& acc, int I, int J, const FThr& t, const double*
         }
     }
   }
-  double* gw = gsm + t.warp * kMaxP;
+  double* gw = gsm + t.role * kMaxP;  // per ROLE: the reduction order does not depend on the warp rotation
   for (int k = 0; k < (ABL(1024) ? 0 : d); ++k) {
     const double* xr = xblk + k * 128;
     double xa[4];
@@ -719,7 +721,7 @@ SCAML_DEVICE void dinv_matvec(double* out, const double* dinvc, const double* v,
 template <int KIND>
 __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitParams p) {
   SCAML_DYN_SMEM(double, sm);
-  const FThr t = make_fthr();
+  FThr t = make_fthr();
   const int d = p.d, P = p.d + 2, n_pad_max = p.n_pad;
   double* stage = sm;             // 2 stages x 4 padded half tiles | 4 full padded tiles (C_in / S / diag)
   double* dinvc = stage + kStage;  // 3 padded tiles
@@ -757,8 +759,12 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
     }
   }
 #endif
-  // the pivot chains of the CTAs sharing an SM should sit on different sub-partitions (warp w -> SMSP w%4)
-  const int chain_warp = (p.sms > 0 ? (int)(blockIdx.x / p.sms) : 0) & (kFitWarps - 1);
+  // The four tile roles of a super-tile carry unequal work (on diagonal super-tiles role (1,0) multiplies a
+  // full tile, (0,0)/(1,1) the lower 8x8 blocks only and (0,1) nothing, epilogues included), and warp w of
+  // every co-resident CTA sits on sub-partition w % 4.  Rotating the warp -> role map by the CTA's slot on
+  // its SM and by the evaluation index spreads the heavy role over the four tensor pipes; the pivot chains run
+  // on the warp that holds the lightest role.  Results do not depend on the rotation (role-indexed reductions).
+  const int slot = p.sms > 0 ? (int)(blockIdx.x / p.sms) : 0;
 
   for (int e = blockIdx.x; e < E; e += gridDim.x) {
     if (p.skip != nullptr && p.skip[e] != 0) continue;
@@ -769,6 +775,11 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
       continue;
     }
     const int NS = (nv + kSB - 1) / kSB, n_pad = NS * kSB;
+    const int rot = slot + e / (int)gridDim.x;
+    t.role = (t.warp + rot) & (kFitWarps - 1);
+    t.rb = t.role >> 1;
+    t.cb = t.role & 1;
+    const int chain_warp = (1 - rot) & (kFitWarps - 1);  // the warp whose role is (0,1)
     __syncthreads();  // previous evaluation fully retired before shared state is rewritten
 
     // ---- parameters: Interval transform, priors, chain rule -------------------------- //
