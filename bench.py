@@ -64,6 +64,24 @@ def _cpu_worker(args):
     return hi - lo, time.perf_counter() - t0, acc
 
 
+def _cpu_post_worker(args):
+    """Reference-style posterior of the source GPs: Python loop over tasks (scamlgp/model.py:128-134), each a
+    kernel row block, an alpha dot and a triangular solve for the variance."""
+    lo, hi = args
+    import torch
+
+    from oracle import scaml_oracle as O
+
+    torch.set_num_threads(1)
+    states, Xc = _CPU_JOB["states"], _CPU_JOB["Xc"]
+    t0 = time.perf_counter()
+    acc = 0.0
+    for m in range(lo, hi):
+        mu, var = O.posterior(states[m], Xc)
+        acc += float(mu[0]) + float(var[0])
+    return (hi - lo) * Xc.shape[0], time.perf_counter() - t0, acc
+
+
 class CpuReference:
     """Reference-style CPU evaluation of LML+grad on a bounded sample of the workload."""
 
@@ -78,7 +96,11 @@ class CpuReference:
         X, Y = O.synthetic_tasks(tasks, N_PTS, DIM, seed=0)
         spec = O.HyperSpec.source()
         Yt = torch.stack([O.standardize(Y[m])[0] for m in range(tasks)])
-        _CPU_JOB.update(X=X, Yt=Yt, th=O.sample_theta_raw(tasks, R_ROWS, DIM, spec, seed=0), spec=spec)
+        th = O.sample_theta_raw(tasks, R_ROWS, DIM, spec, seed=0)
+        g = torch.Generator().manual_seed(5)
+        _CPU_JOB.update(X=X, Yt=Yt, th=th, spec=spec,
+                        states=[O.factorize(X[m], Y[m], th[m, 0], spec) for m in range(tasks)],
+                        Xc=torch.rand(2048, DIM, dtype=torch.float64, generator=g))
         import multiprocessing as mp
 
         self.pool = mp.get_context("fork").Pool(cores)
@@ -91,6 +113,19 @@ class CpuReference:
         t0 = time.perf_counter()
         self.pool.map(_cpu_worker, chunks)
         return time.perf_counter() - t0
+
+    def posterior_points_per_s(self, candidates: int = 2048, passes: int = 2) -> dict:
+        """points/s of the per-task posterior (mean + variance) on the same sample of tasks."""
+        per = (self.tasks + self.cores - 1) // self.cores
+        chunks = [(i, min(i + per, self.tasks)) for i in range(0, self.tasks, per)]
+        self.pool.map(_cpu_post_worker, chunks)  # warm-up
+        t0 = time.perf_counter()
+        for _ in range(passes):
+            self.pool.map(_cpu_post_worker, chunks)
+        dt = time.perf_counter() - t0
+        return {"value": self.tasks * candidates * passes / dt, "unit": "points/s", "cores": self.cores, "kind": "port",
+                "sample": f"{self.tasks} fitted tasks (n={N_PTS}, d={DIM}) x {candidates} candidates, oracle posterior "
+                          f"mean+variance per task, {self.cores} single-threaded processes, {passes} timed passes"}
 
     def close(self):
         self.pool.close()
@@ -229,12 +264,13 @@ def run_ours(args) -> None:
     cores = host_cores()
 
     # CPU baseline first (fork-based pool must be created before CUDA is initialised)
-    cpu_baseline = None
+    cpu_baseline = cpu_posterior = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         tasks = cpu_sample_tasks(cores)
         ref = CpuReference(tasks, cores)
         ref.step()  # warm-up
         ts = [ref.step() for _ in range(3)]
+        cpu_posterior = None if args.no_posterior else ref.posterior_points_per_s()
         ref.close()
         cpu_baseline = {
             "value": ref.evals * len(ts) / sum(ts), "unit": "evals/s", "cores": cores, "kind": "port",
@@ -405,6 +441,8 @@ def run_ours(args) -> None:
             pk = peak
             posterior["roofline"]["peak"] = pk
             posterior["roofline"]["frac"] = (posterior["roofline"]["achieved"] / pk) if pk else None
+            if cpu_posterior is not None:
+                posterior["cpu_baseline"] = cpu_posterior
             line["posterior"] = posterior
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline

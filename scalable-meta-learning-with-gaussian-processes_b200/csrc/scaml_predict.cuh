@@ -131,6 +131,13 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
       xcr[k * CT + c] = (b0 + c < p.B) ? p.Xc[(size_t)(b0 + c) * d + k] : 0.0;
     }
     double macc = 0.0, vacc = 0.0;
+    // inputs of the NEXT task (point `tid`, first kPreD dimensions, alpha) are fetched into registers while the
+    // tensor-core phase of the current task runs, so that the staging below does not wait on global memory
+    constexpr int kPreD = 8;
+    int pre_m = -1;
+    double xpre[kPreD], apre = 0.0;
+#pragma unroll
+    for (int k = 0; k < kPreD; ++k) xpre[k] = 0.0;
     for (int m = m_lo; m < m_hi; ++m) {
       const double wm = p.w[m];
       if (wm == 0.0) continue;
@@ -155,9 +162,21 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
       }
       {
         const double* Xm = p.X + (size_t)m * p.n_max * d;
-        for (int a = tid; a < npt; a += kPredThreads)  // one point per thread: no runtime integer division
+        const bool have = (pre_m == m);
+        if (tid < npt) {  // one point per thread: no runtime integer division
+#pragma unroll
+          for (int k = 0; k < kPreD; ++k)
+            if (k < d) {
+              const double v = have ? xpre[k] : ((tid < nv) ? Xm[(size_t)tid * d + k] : 0.0);
+              xst[k * n_pad + tid] = (tid < nv) ? v * invl[k] : 0.0;
+            }
+          for (int k = kPreD; k < d; ++k) xst[k * n_pad + tid] = (tid < nv) ? Xm[(size_t)tid * d + k] * invl[k] : 0.0;
+          alp[tid] = have ? apre : p.alpha[(size_t)m * n_pad + tid];
+        }
+        for (int a = tid + kPredThreads; a < npt; a += kPredThreads) {
           for (int k = 0; k < d; ++k) xst[k * n_pad + a] = (a < nv) ? Xm[(size_t)a * d + k] * invl[k] : 0.0;
-        for (int i = tid; i < npt; i += kPredThreads) alp[i] = p.alpha[(size_t)m * n_pad + i];
+          alp[a] = p.alpha[(size_t)m * n_pad + a];
+        }
         for (int i = tid; i < CT * d; i += kPredThreads) xcs[i] = xcr[i] * invl[i / CT];
       }
       __syncthreads();
@@ -204,6 +223,14 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
           pred_issue(Lm, qi, stage + (issued % kPStages) * 2 * kPTile, tid);
           cp_async_commit();
         }
+      }
+      if (m + 1 < m_hi) {  // prefetch for the next task (lands during the product below)
+        pre_m = m + 1;
+        const int nv1 = p.n_valid ? p.n_valid[m + 1] : p.n_max;
+        const double* X1 = p.X + (size_t)(m + 1) * p.n_max * d;
+#pragma unroll
+        for (int k = 0; k < kPreD; ++k) xpre[k] = (k < d && tid < nv1) ? X1[(size_t)tid * d + k] : 0.0;
+        apre = (tid < n_pad) ? p.alpha[(size_t)(m + 1) * n_pad + tid] : 0.0;
       }
       // ---- V = L^-1 k*  on the FP64 tensor cores, column sums of squares ------------- //
       double acc[4][NJ][2];
