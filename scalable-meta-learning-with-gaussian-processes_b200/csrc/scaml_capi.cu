@@ -1,6 +1,7 @@
 // extern "C" entry points of libscaml_b200.so (see include/scaml_b200.h).
 // No torch types, no allocation: raw device pointers + sizes + stream.
 #include "scaml_fit.cuh"
+#include "scaml_fit8.cuh"
 #include "scaml_kmat.cuh"
 #include "scaml_predict.cuh"
 #include "scaml_cross.cuh"
@@ -64,6 +65,45 @@ int launch_fit(const scaml::FitParams& p, int grid, size_t smem, void* stream) {
 #endif
 }
 
+template <int KIND>
+int launch_fit8(const scaml::FitParams& p, int grid, size_t smem, void* stream) {
+#ifdef SCAML_EMU
+  (void)stream;
+  cuemu::launch(dim3(grid), dim3(scaml::f8::kThreads), smem, scaml::f8::scaml_fit8_kernel<KIND>, p);
+  return 0;
+#else
+  cudaError_t err = cudaFuncSetAttribute(scaml::f8::scaml_fit8_kernel<KIND>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return (int)err;
+  scaml::f8::scaml_fit8_kernel<KIND><<<grid, scaml::f8::kThreads, smem, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
+#endif
+}
+
+int dispatch_fit8(const scaml::FitParams& p, int grid, size_t smem, void* stream) {
+  switch (p.spec.kernel) {
+    case SCAML_KERNEL_RBF: return launch_fit8<SCAML_KERNEL_RBF>(p, grid, smem, stream);
+    case SCAML_KERNEL_MATERN12: return launch_fit8<SCAML_KERNEL_MATERN12>(p, grid, smem, stream);
+    case SCAML_KERNEL_MATERN32: return launch_fit8<SCAML_KERNEL_MATERN32>(p, grid, smem, stream);
+    case SCAML_KERNEL_MATERN52: return launch_fit8<SCAML_KERNEL_MATERN52>(p, grid, smem, stream);
+    default: return SCAML_E_ARG;
+  }
+}
+
+// Two variants of the fit kernel (same algorithm, same results): 4-warp CTAs, three per SM (scaml_fit.cuh), and
+// 8-warp CTAs, two per SM (scaml_fit8.cuh).  Measured on B200 (profiles/r1_fit_variants.txt): the 4-warp
+// kernel wins for the RBF kernel up to n = 320 (661k vs 631k evals/s at n = 256), the 8-warp kernel for larger
+// tasks (115k vs 110k at n = 512, d = 10) and for the Matern family, whose epilogues are heavier (580k vs 509k).
+// SCAML_FIT_IMPL=4|8 forces one (A/B runs).
+bool use_fit8(int n_pad, int kernel) {
+  if (const char* env = getenv("SCAML_FIT_IMPL")) {
+    const int v = atoi(env);
+    if (v == 4) return false;
+    if (v == 8) return true;
+  }
+  return kernel != SCAML_KERNEL_RBF || n_pad >= 384;
+}
+
 int dispatch_fit(const scaml::FitParams& p, int grid, size_t smem, void* stream) {
   switch (p.spec.kernel) {
     case SCAML_KERNEL_RBF: return launch_fit<SCAML_KERNEL_RBF>(p, grid, smem, stream);
@@ -78,7 +118,8 @@ int run_fit(scaml::FitParams p, void* workspace, size_t workspace_bytes, void* s
   if (p.M <= 0 || p.R <= 0 || p.n_max <= 0 || p.d <= 0) return SCAML_E_ARG;
   if (p.d > scaml::kMaxP - 2) return SCAML_E_UNSUPPORTED;
   p.n_pad = pad64(p.n_max);
-  const size_t smem = scaml::fit_smem_bytes(p.n_pad, p.d);
+  const bool f8 = use_fit8(p.n_pad, p.spec.kernel);
+  const size_t smem = f8 ? scaml::f8::smem_bytes(p.n_pad, p.d) : scaml::fit_smem_bytes(p.n_pad, p.d);
   if (smem > kMaxSmem) return SCAML_E_SMEM;
   if (workspace_bytes < scaml_fit_workspace_bytes(p.n_max, p.d)) return SCAML_E_WORKSPACE;
   p.workspace = static_cast<double*>(workspace);
@@ -86,6 +127,10 @@ int run_fit(scaml::FitParams p, void* workspace, size_t workspace_bytes, void* s
   p.prof = g_prof;
   p.sms = num_sms();
   int grid = fit_grid_slots(p.n_pad, p.d);
+  if (f8) {  // register-limited to two 256-thread CTAs per SM
+    const int per_sm = (2 * (smem + 1024) <= 228 * 1024) ? 2 : 1;
+    if (grid > per_sm * p.sms) grid = per_sm * p.sms;
+  }
   const long long E = (long long)p.M * p.R;
   if (E < grid) grid = (int)E;
   // start offset of the co-resident CTAs: ~1/3 of one evaluation (measured 0.67 ms at n_pad = 256, ~n^1.8),
@@ -96,7 +141,7 @@ int run_fit(scaml::FitParams p, void* workspace, size_t workspace_bytes, void* s
     if (const char* env = getenv("SCAML_FIT_STAGGER_NS")) ns = atof(env);
     p.stagger_ns = (unsigned)(ns < 0 ? 0 : (ns > 4e6 ? 4e6 : ns));
   }
-  return dispatch_fit(p, grid, smem, stream);
+  return f8 ? dispatch_fit8(p, grid, smem, stream) : dispatch_fit(p, grid, smem, stream);
 }
 
 }  // namespace

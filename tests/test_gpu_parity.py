@@ -45,6 +45,30 @@ def test_lml_grad_matches_oracle(engine, M, R, n, d, nv, kernel):
     assert grad_rel_err(grad.cpu().numpy(), g) < TOL_GRAD
 
 
+@pytest.mark.parametrize("impl", ["4", "8"])
+@pytest.mark.parametrize("M,R,n,d,nv,kernel", [
+    (6, 2, 192, 6, [130, 1, 64, 2, 192, 65], 0),
+    (3, 2, 256, 6, None, 3),
+    (2, 1, 512, 10, None, 0),
+])
+def test_both_fit_kernel_variants_match_oracle_and_each_other(engine, monkeypatch, impl, M, R, n, d, nv, kernel):
+    """SCAML_FIT_IMPL forces the 4-warp (3 CTAs/SM) or the 8-warp (2 CTAs/SM) fit kernel; the default picks by
+    shape.  Both must meet the oracle tolerances whatever the heuristic would choose."""
+    monkeypatch.setenv("SCAML_FIT_IMPL", impl)
+    pb = make_problem(M, R, n, d, seed=13, n_valid=nv, kernel=kernel)
+    batch = _batch(pb)
+    lml, grad, info = engine.lml_grad(batch, pb["th"].cuda().contiguous(), pb["cspec"])
+    v, g = oracle_lml_grad(pb)
+    assert int(info.abs().max()) == 0
+    assert lml_rel_err(lml.cpu().numpy(), v) < TOL_LML
+    assert grad_rel_err(grad.cpu().numpy(), g) < TOL_GRAD
+    fs = engine.factorize(batch, pb["th"][:, 0].contiguous().cuda(), pb["cspec"])
+    for m in range(M):
+        k = int(pb["nv"][m])
+        st = O.factorize(pb["X"][m, :k], pb["Y"][m, :k], pb["th"][m, 0], pb["ospec"])
+        assert rel_err(fs.alpha[m, :k].cpu().numpy(), st.alpha.numpy()) < 1e-8
+
+
 def test_golden_fixtures(engine):
     from scamlgp_b200.engine import SourceBatch
 
