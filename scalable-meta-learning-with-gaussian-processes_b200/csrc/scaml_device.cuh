@@ -136,12 +136,11 @@ SCAML_DEVICE void exp_nonpos_n(const double (&in)[U], double (&out)[U]) {
   for (int u = 0; u < U; ++u) {
     const double q = fma(p[u], r[u], 1.0);
     int hi = dbl_hi(q) + n[u] * 1048576, lo = dbl_lo(q);
-    // |x| >= 707 (incl. inf / NaN): 0, or NaN for NaN -- integer selects only, no branch, no FP64-pipe work
-    const unsigned hx = (unsigned)xh[u] & 0x7fffffffu;
-    const bool big = hx >= 0x40861800u;
-    const bool isnan_ = hx > 0x7ff00000u || (hx == 0x7ff00000u && xl[u] != 0);
-    hi = big ? (isnan_ ? xh[u] : 0) : hi;
-    lo = big ? (isnan_ ? xl[u] : 0) : lo;
+    // |x| >= 707 (incl. -inf / NaN): 0, or NaN for NaN -- selects only, no branch
+    const bool big = ((unsigned)xh[u] & 0x7fffffffu) >= 0x40861800u;
+    const bool neg = in[u] < 0.0;  // false for NaN
+    hi = big ? (neg ? 0 : xh[u]) : hi;
+    lo = big ? (neg ? 0 : xl[u]) : lo;
     out[u] = dbl_make(hi, lo);
   }
 }
