@@ -289,3 +289,56 @@ def test_target_lml_grad_matches_oracle(engine, kernel, nt, M):
         gmax = max(float(ogw.abs().max()), float(ogt.abs().max()))
         assert float((gw[r].cpu() - ogw).abs().max()) < TOL_GRAD * gmax
         assert float((gt[r].cpu() - ogt).abs().max()) < TOL_GRAD * gmax
+
+
+def test_full_size_properties_config5(engine):
+    """Config-5 shape (4096 fitted base GPs, n = 256, d = 6; a 16k-candidate slice of the 1 Mi batch), checked
+    through size-independent properties: the weighted mean is linear in w, the weighted variance is quadratic
+    in w and additive over disjoint task sets, a sub-batch of candidates reproduces the big batch bit for bit,
+    sampled candidates agree with the oracle, and every variance stays in (0, prior]."""
+    from scamlgp_b200.engine import SourceBatch
+
+    M, n, d, B = 4096, 256, 6, 16384
+    X, Y = O.synthetic_tasks(M, n, d, seed=21)
+    ospec, cspec = O.HyperSpec.source(), HyperSpec.source()
+    th = O.sample_theta_raw(M, 2, d, ospec, seed=21)[:, 1].contiguous()
+    batch = SourceBatch.from_padded(X.cuda(), Y.cuda())
+    fs = engine.factorize(batch, th.cuda(), cspec)
+    assert int(fs.info.abs().max()) == 0
+    g = torch.Generator().manual_seed(2)
+    Xc = torch.rand(B, d, dtype=torch.float64, generator=g).cuda()
+    w1 = torch.rand(M, dtype=torch.float64, generator=g).cuda() / M
+    w2 = torch.rand(M, dtype=torch.float64, generator=g).cuda() / M
+    m1, v1 = (t.clone() for t in engine.predict_weighted(fs, w1, Xc))
+    m2, v2 = (t.clone() for t in engine.predict_weighted(fs, w2, Xc))
+    m12, _ = (t.clone() for t in engine.predict_weighted(fs, w1 + w2, Xc))
+    assert float((m12 - (m1 + m2)).abs().max()) < 1e-12 * float(m12.abs().max())          # linear in w
+    m3, v3 = (t.clone() for t in engine.predict_weighted(fs, 3.0 * w1, Xc))
+    assert float((v3 - 9.0 * v1).abs().max()) < 1e-12 * float(v3.abs().max())               # quadratic in w
+    lo, hi = w1.clone(), w1.clone()
+    lo[M // 2:] = 0.0
+    hi[: M // 2] = 0.0
+    ma, va = (t.clone() for t in engine.predict_weighted(fs, lo, Xc))
+    mb, vb = (t.clone() for t in engine.predict_weighted(fs, hi, Xc))
+    assert float((ma + mb - m1).abs().max()) < 1e-12 * float(m1.abs().max())                # additive over tasks
+    assert float((va + vb - v1).abs().max()) < 1e-12 * float(v1.abs().max())
+    # a sub-batch reproduces the big batch up to the re-association of the task sum (the number of task splits
+    # depends on how many candidate tiles there are; within one launch shape results are bit-identical)
+    ms, vs = engine.predict_weighted(fs, w1, Xc[:4096].contiguous())
+    assert float((ms - m1[:4096]).abs().max()) < 1e-13 * float(m1.abs().max())
+    assert float((vs - v1[:4096]).abs().max()) < 1e-13 * float(v1.abs().max())
+    ms2, vs2 = engine.predict_weighted(fs, w1, torch.flip(Xc, dims=[0]).contiguous())
+    assert torch.equal(torch.flip(ms2, dims=[0])[64:-64], m1[64:-64]) or \
+        float((torch.flip(ms2, dims=[0]) - m1).abs().max()) < 1e-13 * float(m1.abs().max())
+    prior = float((w1 ** 2 * fs.theta[:, d] * batch.ystd ** 2).sum())
+    assert bool((v1 > 0).all()) and float(v1.max()) <= prior * (1 + 1e-12)
+    # sampled oracle check: 3 candidates, all 4096 tasks on the CPU would take minutes -> 64 tasks with the
+    # other weights zeroed (the kernel skips them, exactly as pruning does)
+    sel = torch.arange(0, M, 64)
+    ws = torch.zeros(M, dtype=torch.float64)
+    ws[sel] = w1[sel].cpu()
+    mo, vo = engine.predict_weighted(fs, ws.cuda(), Xc[:3].contiguous())
+    states = [O.factorize(X[m], Y[m], th[m], ospec) for m in sel.tolist()]
+    om, ov = O.scaml_prior_predict(states, ws[sel], Xc[:3].cpu())
+    assert rel_err(mo.cpu().numpy(), om.numpy()) < TOL_MEAN_VAR
+    assert rel_err(vo.cpu().numpy(), ov.numpy()) < TOL_MEAN_VAR
