@@ -229,6 +229,16 @@ def run_reference(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes (read + write) per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)[kernel]
+        return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def measure_fp64_peak(torch, lib_path: str, device) -> dict:
     """Live FP64 denominators: register-resident DFMA chains and DMMA chains."""
     import ctypes as C
@@ -394,6 +404,9 @@ def run_ours(args) -> None:
                         "collective": "all_reduce(sum) [2,B] fp64 over ranks" if world > 1 else None},
                 "gpu_launches": nl,
                 "roofline": {"bound": "fp64", "achieved": ach, "unit": "TFLOP/s", "flops_per_point": Fp,
+                             "traffic": ncu_traffic("scaml_predict_kernel<RBF>"),
+                             "traffic_unit": "DRAM bytes per launch (ncu)",
+                             "algorithmic_bytes": 8.0 * (M * (n * n / 2 + n * d + n) * 2 + B_STEP * (d + 2)),
                              "kernel": "scaml_predict_kernel<RBF>"}}
 
     sampler = ClockSampler(local_rank)
@@ -430,7 +443,9 @@ def run_ours(args) -> None:
                     "d2h_bytes_per_step": int(h_lml.numel() + h_grad.numel()) * 8, "steps": e2e_steps},
             "gpu_launches": launches,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if peak else None, "traffic": None,
+                         "frac": (achieved / peak) if peak else None,
+                         "traffic": ncu_traffic("scaml_fit_kernel<RBF>"), "traffic_unit": "DRAM bytes per launch (ncu)",
+                         "algorithmic_bytes": 8.0 * M * (n * d + n + R * (2 * (d + 2) + 1)),
                          "kernel": "scaml_fit_kernel<RBF>", "flops_per_eval": F,
                          "peak_source": "live register-resident DFMA microbench in this run "
                                         "(MEASURED_PEAKS.json has no FP64 entry)",
