@@ -403,7 +403,7 @@ def run_ours(args) -> None:
                         "h2d_bytes_per_step": int(hXc.numel()) * 8, "d2h_bytes_per_step": int(h_out.numel()) * 8,
                         "collective": "all_reduce(sum) [2,B] fp64 over ranks" if world > 1 else None},
                 "gpu_launches": nl,
-                "roofline": {"bound": "fp64", "achieved": ach, "unit": "TFLOP/s", "flops_per_point": Fp,
+                "roofline": {"bound": "tensor", "pipe": "FP64 tensor cores (DMMA)", "achieved": ach, "unit": "TFLOP/s", "flops_per_point": Fp,
                              "traffic": ncu_traffic("scaml_predict_kernel<RBF>"),
                              "traffic_unit": "DRAM bytes per launch (ncu)",
                              "algorithmic_bytes": 8.0 * (M * (n * n / 2 + n * d + n) * 2 + B_STEP * (d + 2)),
@@ -442,7 +442,7 @@ def run_ours(args) -> None:
                     "h2d_bytes_per_step": int(hX.numel() + hY.numel() + hT.numel()) * 8,
                     "d2h_bytes_per_step": int(h_lml.numel() + h_grad.numel()) * 8, "steps": e2e_steps},
             "gpu_launches": launches,
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "pipe": "FP64 tensor cores (mma.sync f64 -> DMMA; shares its pipe with DFMA)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if peak else None,
                          "traffic": ncu_traffic("scaml_fit_kernel<RBF>"), "traffic_unit": "DRAM bytes per launch (ncu)",
                          "algorithmic_bytes": 8.0 * M * (n * d + n + R * (2 * (d + 2) + 1)),

@@ -183,6 +183,33 @@ int scaml_target_posterior(const double* prior_mean, const double* prior_var, co
                            const double* linv_t, const double* alpha_t, double mu_all, double s_all,
                            double* mean, double* var, int B, int n_t, int d, int kernel, void* stream);
 
+/* Device-side batched projected L-BFGS (m = history, E independent rows of dimension D, one warp per row).
+ * One call consumes the objective values ft [E] / gradients gt [E][D] at the trial points xt [E][D] and
+ * overwrites xt with the next trial points of the rows that are still active; flags [E]: bit 0 active, bit 1
+ * converged (gtol / ftol / line search at the resolution of the objective), bit 2 failed (objective not finite
+ * at the start).  init != 0: xt holds the starting points (already clamped to `lower`), state is initialised.
+ * `lower` [D] or NULL (-inf = free variable).  The caller owns every buffer; state buffers must persist between
+ * calls.  Replaces the scipy L-BFGS-B loop behind `fit_gpytorch_mll` (reference scamlgp/utils.py:175,190), for
+ * all tasks x restarts at once. */
+typedef struct scaml_lbfgs_state {
+  double* x;         /* [E][D] accepted iterates            */
+  double* f;         /* [E]    objective at x               */
+  double* g;         /* [E][D] gradient at x                */
+  double* d;         /* [E][D] search directions            */
+  double* t;         /* [E]    step lengths                 */
+  double* S;         /* [E][m][D] iterate differences       */
+  double* Y;         /* [E][m][D] gradient differences      */
+  double* rho;       /* [E][m]                              */
+  int32_t* count;    /* [E] stored pairs                    */
+  int32_t* head;     /* [E] next history slot               */
+  int32_t* iters;    /* [E] accepted steps                  */
+  int32_t* ls_count; /* [E] consecutive rejected trials     */
+  int32_t* flags;    /* [E]                                 */
+} scaml_lbfgs_state;
+int scaml_lbfgs_step(const scaml_lbfgs_state* state, double* xt, const double* ft, const double* gt,
+                     const double* lower, int E, int D, int m, int init, double gtol, double ftol,
+                     int maxiter, int max_ls, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

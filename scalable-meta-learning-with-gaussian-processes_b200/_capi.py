@@ -86,6 +86,11 @@ class HyperSpec:
         )
 
 
+class CLbfgsState(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("x", "f", "g", "d", "t", "S", "Y", "rho", "count", "head", "iters",
+                                          "ls_count", "flags")]
+
+
 EXPORTED_SYMBOLS = (
     "scaml_version",
     "scaml_fit_limits",
@@ -101,6 +106,7 @@ EXPORTED_SYMBOLS = (
     "scaml_target_lml_grad",
     "scaml_target_factorize",
     "scaml_target_posterior",
+    "scaml_lbfgs_step",
 )
 
 
@@ -148,6 +154,7 @@ class ScamlLib:
         L.scaml_target_factorize.argtypes = ([vp] * 6 + [dbl, dbl, dbl] + [vp] * 6 +
                                              [sz, i32, i32, i32, C.POINTER(CHyperSpec), vp])
         L.scaml_target_posterior.argtypes = [vp] * 8 + [dbl, dbl, vp, vp, i32, i32, i32, i32, vp]
+        L.scaml_lbfgs_step.argtypes = [C.POINTER(CLbfgsState), vp, vp, vp, vp, i32, i32, i32, i32, dbl, dbl, i32, i32, vp]
         L.scaml_target_workspace_bytes.restype = sz
         L.scaml_target_workspace_bytes.argtypes = [i32, i32]
         L.scaml_target_lml_grad.argtypes = ([vp] * 7 + [C.c_double, C.c_double] + [vp] * 5 +
@@ -212,6 +219,10 @@ class ScamlLib:
         _check(self.lib.scaml_target_posterior(pm, pv, cross, Xc, Xt, theta, linv_t, alpha_t, float(mu_all),
                                                float(s_all), mean, var, B, n_t, d, kernel, stream),
                "scaml_target_posterior")
+
+    def lbfgs_step(self, state: "CLbfgsState", xt, ft, gt, lower, E, D, m, init, gtol, ftol, maxiter, max_ls, stream=0):
+        _check(self.lib.scaml_lbfgs_step(C.byref(state), xt, ft, gt, lower, E, D, m, int(init), float(gtol),
+                                         float(ftol), int(maxiter), int(max_ls), stream), "scaml_lbfgs_step")
 
     def target_workspace_bytes(self, n_t: int, R: int) -> int:
         return int(self.lib.scaml_target_workspace_bytes(n_t, R))

@@ -156,6 +156,11 @@ inline T __shfl_down_sync(unsigned, T v, int d) {
   int l = threadIdx.x & 31;
   return cuemu::shfl(v, l + d < 32 ? l + d : l);
 }
+inline int __any_sync(unsigned, int pred) {
+  int v = pred ? 1 : 0;
+  for (int o = 16; o > 0; o >>= 1) v |= cuemu::shfl(v, (int)((threadIdx.x & 31) ^ o));
+  return v;
+}
 template <class T>
 inline T __ldcg(const T* p) {
   return *p;

@@ -6,6 +6,7 @@
 #include "scaml_predict.cuh"
 #include "scaml_cross.cuh"
 #include "scaml_target.cuh"
+#include "scaml_lbfgs.cuh"
 
 #ifndef SCAML_EMU
 #include <cuda_runtime.h>
@@ -329,6 +330,19 @@ int scaml_target_posterior(const double* prior_mean, const double* prior_var, co
   p.alpha = alpha_t, p.mean = mean, p.var = var, p.mu_all = mu_all, p.s_all = s_all;
   p.B = B, p.nt = n_t, p.d = d, p.kernel = kernel;
   return scaml::launch_target_posterior(p, num_sms(), stream);
+}
+
+int scaml_lbfgs_step(const scaml_lbfgs_state* st, double* xt, const double* ft, const double* gt, const double* lower,
+                     int E, int D, int m, int init, double gtol, double ftol, int maxiter, int max_ls, void* stream) {
+  if (!st || !xt || !ft || !gt || !st->x || !st->f || !st->g || !st->d || !st->t || !st->S || !st->Y || !st->rho ||
+      !st->count || !st->head || !st->iters || !st->ls_count || !st->flags)
+    return SCAML_E_ARG;
+  scaml::LbfgsParams p;
+  p.x = st->x, p.f = st->f, p.g = st->g, p.d = st->d, p.t = st->t, p.S = st->S, p.Y = st->Y, p.rho = st->rho;
+  p.count = st->count, p.head = st->head, p.iters = st->iters, p.ls_count = st->ls_count, p.flags = st->flags;
+  p.xt = xt, p.ft = ft, p.gt = gt, p.lower = lower;
+  p.E = E, p.D = D, p.m = m, p.init = init, p.maxiter = maxiter, p.max_ls = max_ls, p.gtol = gtol, p.ftol = ftol;
+  return scaml::launch_lbfgs_step(p, stream);
 }
 
 }  // extern "C"

@@ -3,7 +3,8 @@
 The reference fits M source GPs one after another, each with 1 warm start + `num_restarts`
 prior-sampled restarts of scipy L-BFGS-B (scamlgp/model.py:176-188, utils.py:139-212).  Here
 all M x (1 + num_restarts) optimisations advance in lock-step on the GPU: one fused
-`scaml_lml_grad` launch per L-BFGS round over the rows that are still active.
+`scaml_lml_grad` launch plus one `scaml_lbfgs_step` launch (device-side update, one warp per row) per L-BFGS
+round over the rows that are still active.
 
 Semantics kept (scamlgp/utils.py:139-212):
   * row 0 of every task is the warm start (the parameters the caller's modules hold), rows 1..R-1
@@ -26,7 +27,7 @@ import torch
 
 from ._capi import PRIOR_GAMMA, PRIOR_LOGNORMAL, PRIOR_NONE, HyperSpec
 from .engine import Engine, SourceBatch
-from .lbfgs import LbfgsResult, lbfgs_minimize
+from .lbfgs import LbfgsResult, lbfgs_minimize_device
 from .modules import ModelFittingError
 
 DT = torch.float64
@@ -106,7 +107,7 @@ def fit_sources(engine: Engine, batch: SourceBatch, spec: HyperSpec, theta_init:
         lml, grad, _ = engine.lml_grad(batch, x.reshape(M, R, P).contiguous(), spec, skip=skip)
         return -lml.reshape(-1), -grad.reshape(M * R, P)
 
-    res = lbfgs_minimize(fun, x0, **opts)
+    res = lbfgs_minimize_device(engine, fun, x0, **opts)
     lml = torch.where(res.failed | ~torch.isfinite(res.f), torch.full_like(res.f, float("-inf")), -res.f).reshape(M, R)
     best = torch.argmax(lml, dim=1)  # first maximum wins ties: the warm start is row 0
     best_lml = lml.gather(1, best.unsqueeze(1)).squeeze(1)
@@ -146,18 +147,13 @@ def fit_target(engine: Engine, source_means: torch.Tensor, source_covs: torch.Te
     lower = torch.cat([torch.full((M,), w_lower, dtype=DT), torch.full((P,), float("-inf"), dtype=DT)]).to(dev)
 
     def fun(x, active):
-        idx = torch.nonzero(active).flatten()
-        f = torch.full((R,), float("nan"), dtype=DT, device=dev)
-        g = torch.full((R, M + P), float("nan"), dtype=DT, device=dev)
-        if idx.numel():
-            xa = x[idx]
-            lml, gw, gt, _ = engine.target_lml_grad_safe(source_means, source_covs, Xt, yt, xa[:, :M].contiguous(),
-                                                         xa[:, M:].contiguous(), mu_all, s_all, spec, w_prior)
-            f[idx] = -lml
-            g[idx] = -torch.cat([gw, gt], dim=1)
-        return f, g
+        # all R rows are evaluated every round (R is small): no data-dependent shapes, no host sync; the update
+        # kernel ignores the rows that are no longer active
+        lml, gw, gt, _ = engine.target_lml_grad_safe(source_means, source_covs, Xt, yt, x[:, :M].contiguous(),
+                                                     x[:, M:].contiguous(), mu_all, s_all, spec, w_prior)
+        return -lml, -torch.cat([gw, gt], dim=1)
 
-    res = lbfgs_minimize(fun, x0, lower=lower, **opts)
+    res = lbfgs_minimize_device(engine, fun, x0, lower=lower, **opts)
     lml = torch.where(res.failed | ~torch.isfinite(res.f), torch.full_like(res.f, float("-inf")), -res.f)
     best = int(torch.argmax(lml))
     if not bool(torch.isfinite(lml[best])):

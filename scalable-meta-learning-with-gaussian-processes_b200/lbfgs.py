@@ -179,3 +179,59 @@ def lbfgs_minimize(fun: Callable[[torch.Tensor, torch.Tensor], Tuple[torch.Tenso
 
     f_out = torch.where(failed, torch.full_like(f, float("nan")), f)
     return LbfgsResult(x=x, f=f_out, converged=converged, failed=failed, iterations=iters, evaluations=evals)
+
+
+# ------------------------------------------------------------------------------------------------ #
+# device-side driver: the same algorithm with the whole update in ONE kernel (csrc/scaml_lbfgs.cuh)
+# ------------------------------------------------------------------------------------------------ #
+FLAG_ACTIVE, FLAG_CONVERGED, FLAG_FAILED = 1, 2, 4
+
+
+def lbfgs_minimize_device(engine, fun: Callable[[torch.Tensor, torch.Tensor], Tuple[torch.Tensor, torch.Tensor]],
+                          x0: torch.Tensor, lower: Optional[torch.Tensor] = None, maxiter: int = 200,
+                          gtol: float = 1e-5, ftol: float = 2.2e-9, history: int = 10, max_ls: int = 20,
+                          max_evals: Optional[int] = None, poll_every: int = 4) -> LbfgsResult:
+    """`lbfgs_minimize` with the per-round update done by `scaml_lbfgs_step` (one warp per row).
+
+    Every round is the objective launch(es) + one update launch; the host reads back only the number of
+    active rows, every `poll_every` rounds.  `lower` must be a [D] tensor (or None)."""
+    from ._capi import CLbfgsState
+
+    E, D = x0.shape
+    dev, dt = x0.device, torch.float64
+    m = int(history)
+    xt = x0.to(dt).clone().contiguous()
+    low = None
+    if lower is not None:
+        low = lower.to(device=dev, dtype=dt).reshape(-1).contiguous()
+        assert low.numel() == D, "device L-BFGS takes one lower bound per variable"
+        xt = torch.maximum(xt, low)
+
+    def buf(*shape, dtype=dt):
+        return torch.zeros(*shape, dtype=dtype, device=dev)
+
+    st = dict(x=buf(E, D), f=buf(E), g=buf(E, D), d=buf(E, D), t=buf(E), S=buf(E, m, D), Y=buf(E, m, D), rho=buf(E, m),
+              count=buf(E, dtype=torch.int32), head=buf(E, dtype=torch.int32), iters=buf(E, dtype=torch.int32),
+              ls_count=buf(E, dtype=torch.int32), flags=buf(E, dtype=torch.int32))
+    cst = CLbfgsState(**{k: v.data_ptr() for k, v in st.items()})
+    flags = st["flags"]
+    active = torch.ones(E, dtype=torch.bool, device=dev)
+    budget = max_evals if max_evals is not None else maxiter * 3 + max_ls
+    evals = 0
+    init = True
+    while evals < budget:
+        ft, gt = fun(xt, active)
+        ft, gt = ft.contiguous(), gt.contiguous()
+        evals += 1
+        engine.lib.lbfgs_step(cst, xt.data_ptr(), ft.data_ptr(), gt.data_ptr(), None if low is None else low.data_ptr(),
+                              E, D, m, init, gtol, ftol, maxiter, max_ls, engine._stream())
+        engine.launches += 1
+        init = False
+        active = (flags & FLAG_ACTIVE) != 0
+        if evals % poll_every == 0 and not bool(active.any()):
+            break
+    failed = (flags & FLAG_FAILED) != 0
+    converged = (flags & FLAG_CONVERGED) != 0
+    f_out = torch.where(failed, torch.full_like(st["f"], float("nan")), st["f"])
+    return LbfgsResult(x=st["x"], f=f_out, converged=converged, failed=failed, iterations=st["iters"].to(torch.int64),
+                       evaluations=evals)
