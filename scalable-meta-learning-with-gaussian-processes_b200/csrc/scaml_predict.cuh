@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
       // chains per thread keep the FP64 pipe busy (a single chain per thread is latency bound).
       {
         constexpr int QN = kPredThreads / CT;  // row phases (4 for CT = 64, 8 for CT = 32)
-        constexpr int U = 8;
+        constexpr int U = 16;
         const int c = tid % CT, q = tid / CT;
         double mu = 0.0;
         for (int a0 = q; a0 < npt; a0 += QN * U) {
