@@ -166,6 +166,14 @@ class ParameterSpace:
                 out[i] = p.to_num(config[p.name])
         return out
 
+    def to_numerical_batch(self, configs: Sequence[Dict[str, Any]]) -> np.ndarray:
+        """[n, d] numerical representation of many configurations (column-wise: one pass per parameter)."""
+        out = np.full((len(configs), len(self._params)), np.nan)
+        for i, p in enumerate(self._params):
+            name, conv = p.name, p.to_num
+            out[:, i] = [conv(v) if (v := c.get(name)) is not None else np.nan for c in configs]
+        return out
+
     def from_numerical(self, vec) -> Dict[str, Any]:
         config: Dict[str, Any] = {}
         for p, u in zip(self._params, np.asarray(vec, dtype=float)):
@@ -202,12 +210,29 @@ def to_numerical(evaluations: Iterable[Evaluation], search_space: ParameterSpace
     for e in evaluations:
         if obj.name not in e.objectives:
             raise EvaluationsError(f"Evaluation does not report the objective '{obj.name}'")
-    X = np.stack([search_space.to_numerical(e.configuration) for e in evaluations]) if evaluations else \
-        np.zeros((0, len(search_space)))
+    X = search_space.to_numerical_batch([e.configuration for e in evaluations])
     sign = -1.0 if obj.greater_is_better else 1.0
-    Y = np.array([[np.nan if e.objectives[obj.name] is None else sign * float(e.objectives[obj.name])]
-                  for e in evaluations]).reshape(-1, 1)
+    Y = np.array([np.nan if e.objectives[obj.name] is None else sign * float(e.objectives[obj.name])
+                  for e in evaluations], dtype=float).reshape(-1, 1)
     return torch.tensor(X, dtype=torch_dtype), torch.tensor(Y, dtype=torch_dtype)
+
+
+def sort_numerical(X: torch.Tensor, Y: torch.Tensor):
+    """Rows of [X | Y] in lexicographic order (NaN last): the same deterministic, report-order independent
+    arrangement `sort_evaluations` gives, obtained on the numerical representation (one numpy lexsort instead of
+    one JSON key per evaluation -- the meta-data of 4096 tasks x 256 points are a million evaluations)."""
+    if X.shape[0] <= 1:
+        return X, Y
+    A = np.concatenate([X.numpy().astype(float), Y.numpy().astype(float)], axis=1)
+    keys = []
+    for j in range(A.shape[1] - 1, -1, -1):  # lexsort: last key is the primary one
+        col = A[:, j]
+        keys.append(np.where(np.isnan(col), np.inf, col))
+        keys.append(np.isnan(col))
+    # primary: column 0 value (NaN flag first so that NaN rows sort last within a column)
+    order = np.lexsort(tuple(keys))
+    idx = torch.as_tensor(order.copy())
+    return X[idx], Y[idx]
 
 
 def impute_nans_with_constant(X: torch.Tensor, c: float = -1.0) -> torch.Tensor:

@@ -47,12 +47,14 @@ def metadata_to_numerical(meta_data: Dict[Hashable, Iterable], search_space, obj
                           ) -> Dict[Hashable, SupervisedDataset]:
     """Meta evaluations -> tensors; evaluations are sorted first so runs do not depend on their order, NaNs of
     inactive (conditional) parameters are imputed (reference utils.py:72-109)."""
-    from .space import impute_nans_with_constant, sort_evaluations, to_numerical
+    from .space import impute_nans_with_constant, sort_numerical, to_numerical
 
     out = {}
     for task_id, task_data in meta_data.items():
-        X_raw, Y = to_numerical(sort_evaluations(task_data), search_space, [objective], batch_shape=batch_shape,
-                                torch_dtype=torch_dtype)
+        # the reference sorts the evaluations first (utils.py:99) so that runs do not depend on their order; the
+        # same order independence is obtained by sorting the numerical rows (see space.sort_numerical)
+        X_raw, Y = to_numerical(task_data, search_space, [objective], batch_shape=batch_shape, torch_dtype=torch_dtype)
+        X_raw, Y = sort_numerical(X_raw, Y)
         out[task_id] = SupervisedDataset(impute_nans_with_constant(X_raw), Y)
     return out
 
