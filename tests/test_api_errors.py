@@ -1,0 +1,108 @@
+"""Error behaviour of the public API at the same points as the reference (no GPU needed: the checks run before
+any kernel is launched, or through the emulation engine)."""
+import pytest
+import torch
+
+from scamlgp_b200._capi import ScamlError, load_cuda_library
+from scamlgp_b200.model import ScaMLGP, _compute_target_prior, meta_fit_scamlgp, significant_weights_mask
+from scamlgp_b200.modules import (GammaPrior, GaussianLikelihood, Interval, MaternKernel, ModelFittingError, RBFKernel,
+                                  ScaleKernel, SupervisedDataset)
+from scamlgp_b200.utils import UpperConfidenceBound, sample_all_priors, validate_meta_data
+
+DT = torch.float64
+
+
+@pytest.fixture(scope="module")
+def emu_engine(emu_lib):
+    from tests.emu_engine import EmuEngine
+
+    return EmuEngine(emu_lib)
+
+
+def _ds(n, d, ydim=1):
+    g = torch.Generator().manual_seed(n + d)
+    return SupervisedDataset(torch.rand(n, d, dtype=DT, generator=g), torch.rand(n, ydim, dtype=DT, generator=g))
+
+
+def test_validate_meta_data_messages_match_reference():
+    """scamlgp/utils.py:112-136."""
+    with pytest.raises(ValueError, match="Empty meta data"):
+        validate_meta_data({})
+    with pytest.raises(ValueError, match="Dimensions of tasks a and b do not match"):
+        validate_meta_data({"a": _ds(4, 2), "b": _ds(4, 3)})
+    with pytest.raises(ValueError, match="output dimension of task b is 2 but must be one"):
+        validate_meta_data({"a": _ds(4, 2), "b": _ds(4, 2, ydim=2)})
+    validate_meta_data({"a": _ds(4, 2), "b": _ds(7, 2)})  # ragged n is fine
+
+
+def test_significant_weights_mask_matches_reference_formula():
+    """scamlgp/model.py:192-215: w_i sigma_i M / sum_j w_j sigma_j >= tau."""
+    w = torch.tensor([0.5, 1e-6, 0.2, 0.0], dtype=DT)
+    s = torch.tensor([1.0, 2.0, 0.5, 3.0], dtype=DT)
+    m = significant_weights_mask(w, s, 1e-3)
+    assert m.tolist() == [True, False, True, False]
+    assert significant_weights_mask(torch.ones(3, dtype=DT), torch.ones(3, dtype=DT), 1e-3).all()
+
+
+def test_engine_refuses_to_run_without_cuda_and_library_must_exist(tmp_path):
+    from scamlgp_b200._capi import ScamlLib
+    from scamlgp_b200.engine import Engine
+
+    if not torch.cuda.is_available():
+        with pytest.raises(ScamlError, match="no CPU fallback"):
+            Engine()
+    with pytest.raises(ScamlError, match="not found"):
+        ScamlLib(str(tmp_path / "libmissing.so"))
+    assert load_cuda_library().version().endswith("sm_100a")  # the product library is built in-tree
+
+
+def test_kernel_family_checks():
+    with pytest.raises(ValueError):
+        MaternKernel(nu=1.0, ard_num_dims=2)
+    with pytest.raises(TypeError):
+        from scamlgp_b200.modules import hyper_spec_of
+
+        hyper_spec_of(GaussianLikelihood(), RBFKernel(ard_num_dims=2))  # must be ScaleKernel(base)
+    k = ScaleKernel(MaternKernel(nu=2.5, ard_num_dims=3, lengthscale_constraint=Interval(1e-3, 10.0, 0.7)))
+    assert abs(float(k.base_kernel.lengthscale[0, 0]) - 0.7) < 1e-12
+    k.base_kernel.lengthscale = 0.3
+    assert torch.allclose(k.base_kernel.lengthscale, torch.full((1, 3), 0.3, dtype=DT))
+
+
+def test_sample_all_priors_rejects_incompatible_prior_and_constraint():
+    """utils.py:47-69: a prior whose support misses the constraint interval fails after num_retries."""
+
+    class M:
+        def __init__(self):
+            self.likelihood = GaussianLikelihood(noise_prior=GammaPrior(400.0, 1.0),  # mass around 400 >> 1e-2
+                                                 noise_constraint=Interval(1e-8, 1e-2, 1e-3))
+
+        def named_priors(self):
+            yield ("likelihood.noise_covar.noise_prior", self.likelihood, self.likelihood.noise_prior,
+                   lambda m: m.noise, lambda m, v: setattr(m, "noise", v))
+
+    with pytest.raises(RuntimeError, match="failed 5 times"):
+        sample_all_priors(M(), generator=torch.Generator().manual_seed(0))
+
+
+def test_model_errors_through_emulation(emu_engine):
+    md = {"a": _ds(6, 2), "b": _ds(5, 2)}
+    gps = meta_fit_scamlgp(md, num_restarts_log_likelihood=0, seed=0, engine=emu_engine, fit_options=dict(maxiter=2))
+    # number of weights must equal the number of source GPs (model.py:123-127)
+    with pytest.raises(ValueError, match="does not equal the number of weights"):
+        _compute_target_prior(torch.rand(3, 2, dtype=DT), list(gps.values()), torch.ones(3, dtype=DT), emu_engine)
+    # batched meta-data are not supported (the reference optimizer never produces them)
+    with pytest.raises(NotImplementedError):
+        meta_fit_scamlgp({"a": SupervisedDataset(torch.rand(2, 4, 2, dtype=DT), torch.rand(2, 4, 1, dtype=DT))},
+                         engine=emu_engine)
+    model = ScaMLGP(torch.empty(0, 2, dtype=DT), torch.empty(0, 1, dtype=DT), gps, engine=emu_engine)
+    assert model.outcome_transform is None and model.num_train == 0  # empty input: no standardisation (model.py:307-308)
+    assert torch.allclose(model.weights, torch.full((2,), 0.5, dtype=DT))
+    with pytest.raises(NotImplementedError):
+        model.posterior(torch.rand(4, 2, 2, dtype=DT))  # q > 1
+    with pytest.raises(ValueError):
+        UpperConfidenceBound(model, maximize=True)
+    # all restarts failing -> ModelFittingError (utils.py:207-212): NaN targets poison every row
+    bad = {"a": SupervisedDataset(torch.rand(5, 2, dtype=DT), torch.full((5, 1), float("nan"), dtype=DT))}
+    with pytest.raises(ModelFittingError, match="failed for all attempts"):
+        meta_fit_scamlgp(bad, num_restarts_log_likelihood=1, seed=0, engine=emu_engine, fit_options=dict(maxiter=2))
