@@ -183,6 +183,26 @@ int scaml_target_posterior(const double* prior_mean, const double* prior_var, co
                            const double* linv_t, const double* alpha_t, double mu_all, double s_all,
                            double* mean, double* var, int B, int n_t, int d, int kernel, void* stream);
 
+/* Conditioning at scale.  scaml_cond_prepare: A_m = K_m^-1 K_m(X_m, X_t) for every source task, A [M][n_pad][n_tp]
+ * with n_pad = 64*ceil(n_max/64), n_tp = 8*ceil(n_t/8) (rows >= n_valid and columns >= n_t are zero; the caller
+ * zero-initialises A).  It depends only on the fitted source GPs and the target inputs: once per
+ * `ScaMLGPBO.report`.  scaml_predict_conditioned: weighted prior mean / variance at B candidates as
+ * scaml_predict_weighted PLUS the weighted prior cross-covariance with the target inputs
+ *   cross[b][j] = sum_m w_m^2 ystd_m^2 ( K_m(x_b, x_tj) - k*_m(x_b)^T A_m[:, j] )          [B][n_t]
+ * with the k*^T A contraction fused into the prediction kernel (the k* tile is already in shared memory).
+ * Together with scaml_target_posterior this replaces the eval branch of `ScaMLGP.forward` for q = 1 candidate
+ * batches (reference scamlgp/model.py:364-375 evaluates every source posterior at [X_t; x] jointly).
+ * n_max <= 256 (64-candidate tiles must fit shared memory), n_t <= 128. */
+int scaml_cond_prepare(const double* X, const int32_t* n_valid, const double* theta, const double* linv_packed,
+                       const double* Xt, double* A, int M, int n_max, int d, int n_t, int kernel, void* stream);
+size_t scaml_predict_conditioned_workspace_bytes(int M, int n_max, int d, int B, int n_t);
+int scaml_predict_conditioned(const double* X, const int32_t* n_valid, const double* theta,
+                              const double* linv_packed, const double* alpha, const double* ybar,
+                              const double* ystd, const double* w, const double* Xc, const double* Xt,
+                              const double* A, double* mean, double* var, double* cross, void* workspace,
+                              size_t workspace_bytes, int M, int n_max, int d, int B, int n_t, int kernel,
+                              void* stream);
+
 /* Device-side batched projected L-BFGS (m = history, E independent rows of dimension D, one warp per row).
  * One call consumes the objective values ft [E] / gradients gt [E][D] at the trial points xt [E][D] and
  * overwrites xt with the next trial points of the rows that are still active; flags [E]: bit 0 active, bit 1

@@ -107,6 +107,9 @@ EXPORTED_SYMBOLS = (
     "scaml_target_factorize",
     "scaml_target_posterior",
     "scaml_lbfgs_step",
+    "scaml_cond_prepare",
+    "scaml_predict_conditioned_workspace_bytes",
+    "scaml_predict_conditioned",
 )
 
 
@@ -155,6 +158,10 @@ class ScamlLib:
                                              [sz, i32, i32, i32, C.POINTER(CHyperSpec), vp])
         L.scaml_target_posterior.argtypes = [vp] * 8 + [dbl, dbl, vp, vp, i32, i32, i32, i32, vp]
         L.scaml_lbfgs_step.argtypes = [C.POINTER(CLbfgsState), vp, vp, vp, vp, i32, i32, i32, i32, dbl, dbl, i32, i32, vp]
+        L.scaml_cond_prepare.argtypes = [vp] * 6 + [i32] * 5 + [vp]
+        L.scaml_predict_conditioned_workspace_bytes.restype = sz
+        L.scaml_predict_conditioned_workspace_bytes.argtypes = [i32] * 5
+        L.scaml_predict_conditioned.argtypes = [vp] * 15 + [sz] + [i32] * 6 + [vp]
         L.scaml_target_workspace_bytes.restype = sz
         L.scaml_target_workspace_bytes.argtypes = [i32, i32]
         L.scaml_target_lml_grad.argtypes = ([vp] * 7 + [C.c_double, C.c_double] + [vp] * 5 +
@@ -223,6 +230,19 @@ class ScamlLib:
     def lbfgs_step(self, state: "CLbfgsState", xt, ft, gt, lower, E, D, m, init, gtol, ftol, maxiter, max_ls, stream=0):
         _check(self.lib.scaml_lbfgs_step(C.byref(state), xt, ft, gt, lower, E, D, m, int(init), float(gtol),
                                          float(ftol), int(maxiter), int(max_ls), stream), "scaml_lbfgs_step")
+
+    def cond_prepare(self, X, n_valid, theta, linv, Xt, A, M, n_max, d, n_t, kernel, stream=0):
+        _check(self.lib.scaml_cond_prepare(X, n_valid, theta, linv, Xt, A, M, n_max, d, n_t, kernel, stream),
+               "scaml_cond_prepare")
+
+    def predict_conditioned_workspace_bytes(self, M, n_max, d, B, n_t) -> int:
+        return int(self.lib.scaml_predict_conditioned_workspace_bytes(M, n_max, d, B, n_t))
+
+    def predict_conditioned(self, X, n_valid, theta, linv, alpha, ybar, ystd, w, Xc, Xt, A, mean, var, cross, ws,
+                            ws_bytes, M, n_max, d, B, n_t, kernel, stream=0):
+        _check(self.lib.scaml_predict_conditioned(X, n_valid, theta, linv, alpha, ybar, ystd, w, Xc, Xt, A, mean, var,
+                                                  cross, ws, ws_bytes, M, n_max, d, B, n_t, kernel, stream),
+               "scaml_predict_conditioned")
 
     def target_workspace_bytes(self, n_t: int, R: int) -> int:
         return int(self.lib.scaml_target_workspace_bytes(n_t, R))

@@ -4,6 +4,7 @@
 #include "scaml_fit8.cuh"
 #include "scaml_kmat.cuh"
 #include "scaml_predict.cuh"
+#include "scaml_cond.cuh"
 #include "scaml_cross.cuh"
 #include "scaml_target.cuh"
 #include "scaml_lbfgs.cuh"
@@ -343,6 +344,48 @@ int scaml_lbfgs_step(const scaml_lbfgs_state* st, double* xt, const double* ft, 
   p.xt = xt, p.ft = ft, p.gt = gt, p.lower = lower;
   p.E = E, p.D = D, p.m = m, p.init = init, p.maxiter = maxiter, p.max_ls = max_ls, p.gtol = gtol, p.ftol = ftol;
   return scaml::launch_lbfgs_step(p, stream);
+}
+
+int scaml_cond_prepare(const double* X, const int32_t* n_valid, const double* theta, const double* linv_packed,
+                       const double* Xt, double* A, int M, int n_max, int d, int n_t, int kernel, void* stream) {
+  if (!X || !theta || !linv_packed || !Xt || !A) return SCAML_E_ARG;
+  if (M <= 0 || n_max <= 0 || d <= 0 || n_t <= 0 || kernel < 0 || kernel > 3) return SCAML_E_ARG;
+  if (d > scaml::kMaxP - 2 || n_t > 128) return SCAML_E_UNSUPPORTED;
+  scaml::CondPrepParams p{};
+  p.X = X, p.n_valid = n_valid, p.theta = theta, p.linv = linv_packed, p.Xt = Xt, p.A = A;
+  p.M = M, p.n_max = n_max, p.n_pad = pad64(n_max), p.d = d, p.n_t = n_t;
+  return scaml::launch_cond_prepare(p, kernel, num_sms(), stream);
+}
+
+size_t scaml_predict_conditioned_workspace_bytes(int M, int n_max, int d, int B, int n_t) {
+  if (M <= 0 || n_max <= 0 || d <= 0 || B <= 0 || n_t <= 0) return 0;
+  const int ns = scaml::predict_nsplit(M, B, num_sms(), 64);
+  const size_t pv = ns > 1 ? sizeof(double) * 2 * (size_t)ns * (size_t)B : 0;
+  return pv + sizeof(double) * (size_t)ns * (size_t)B * (size_t)scaml::cond_ntp(n_t);
+}
+
+int scaml_predict_conditioned(const double* X, const int32_t* n_valid, const double* theta, const double* linv_packed,
+                              const double* alpha, const double* ybar, const double* ystd, const double* w,
+                              const double* Xc, const double* Xt, const double* A, double* mean, double* var,
+                              double* cross, void* workspace, size_t workspace_bytes, int M, int n_max, int d, int B,
+                              int n_t, int kernel, void* stream) {
+  if (!X || !theta || !linv_packed || !alpha || !ybar || !ystd || !w || !Xc || !Xt || !A || !mean || !var || !cross ||
+      !workspace)
+    return SCAML_E_ARG;
+  if (M <= 0 || n_max <= 0 || d <= 0 || B <= 0 || n_t <= 0 || kernel < 0 || kernel > 3) return SCAML_E_ARG;
+  if (d > scaml::kMaxP - 2 || n_t > 128) return SCAML_E_UNSUPPORTED;
+  if (workspace_bytes < scaml_predict_conditioned_workspace_bytes(M, n_max, d, B, n_t)) return SCAML_E_WORKSPACE;
+  const int n_tp = scaml::cond_ntp(n_t);
+  const int ns = scaml::predict_nsplit(M, B, num_sms(), 64);
+  double* part = static_cast<double*>(workspace);
+  double* cxp = part + (ns > 1 ? 2 * (size_t)ns * (size_t)B : 0);
+  int rc = scaml::launch_predict_weighted(X, n_valid, theta, linv_packed, alpha, ybar, ystd, w, Xc, mean, var, part, M,
+                                          n_max, pad64(n_max), d, B, kernel, num_sms(), stream, A, cxp, n_tp);
+  if (rc != 0) return rc;
+  scaml::CondCombineParams c{};
+  c.theta = theta, c.ystd = ystd, c.w = w, c.Xc = Xc, c.Xt = Xt, c.cxp = cxp, c.cross = cross;
+  c.M = M, c.d = d, c.B = B, c.n_t = n_t, c.n_tp = n_tp, c.nsplit = ns;
+  return scaml::launch_cond_combine(c, kernel, stream);
 }
 
 }  // extern "C"

@@ -273,7 +273,7 @@ SCAML_DEVICE void gemm_global(Acc& acc, const Src& src, double* stage, const FTh
     const bool bvalid = src.same() ? c.a_ok(t.cb) : c.b_ok(t.cb);
     if (active && c.a_ok(t.rb) && bvalid && !ABL(8))
       fmma<4>(acc, As + t.rb * kHalfS, Bs + t.cb * kHalfS, t, lower);
-    if (piggy) {
+    if (piggy && !ABL(8192)) {
       const int col = t.tid & 63, q = t.tid >> 6;
       if (c.a_ok(col >> 5)) {
         const double* ap = As + (col >> 5) * kHalfS + (col & 31) + q * 8 * kLd;
@@ -348,7 +348,7 @@ constexpr int kXpre = 8;
 SCAML_DEVICE void xpre_load(double (&xp)[kXpre], const double* Xm, int I, int J, int nv, int d, int tid) {
   const int a = (tid < kSB) ? I * kSB + tid : J * kSB + (tid - kSB);
 #pragma unroll
-  for (int k = 0; k < kXpre; ++k) xp[k] = (k < d && a < nv) ? __ldg(Xm + (size_t)a * d + k) : 0.0;
+  for (int k = 0; k < kXpre; ++k) xp[k] = (k < d && a < nv && !ABL(65536)) ? __ldg(Xm + (size_t)a * d + k) : 0.0;
 }
 SCAML_DEVICE void xblk_store(double* xblk, const double (&xp)[kXpre], const double* Xm, const double* th, int I,
                              int J, int nv, int d, int tid) {
@@ -691,12 +691,14 @@ SCAML_DEVICE void load_dinvc(double* dinvc, double* stage, const double* W, int 
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
+  if (!ABL(16384)) {
 #pragma unroll
-  for (int b = 0; b < 3; ++b) {
+    for (int b = 0; b < 3; ++b) {
 #pragma unroll 4
-    for (int idx = tid; idx < kTile; idx += kFitThreads) {
-      const int r = idx >> 5, c = idx & 31;
-      dinvc[b * kTileS + c * kLd + r] = stage[b * kTileS + r * kLd + c];
+      for (int idx = tid; idx < kTile; idx += kFitThreads) {
+        const int r = idx >> 5, c = idx & 31;
+        dinvc[b * kTileS + c * kLd + r] = stage[b * kTileS + r * kLd + c];
+      }
     }
   }
   __syncthreads();
@@ -706,7 +708,7 @@ SCAML_DEVICE void load_dinvc(double* dinvc, double* stage, const double* W, int 
 SCAML_DEVICE void dinv_matvec(double* out, const double* dinvc, const double* v, double* red, const FThr& t) {
   const int r = t.tid & 63, q = t.tid >> 6;  // q: 32-wide kk half
   double s = 0.0;
-  for (int kk = q * 32; kk < q * 32 + 32; ++kk) {
+  for (int kk = q * 32; kk < (ABL(32768) ? 0 : q * 32 + 32); ++kk) {
     if (kk > r) break;
     const int rb_ = r >> 5, kb_ = kk >> 5;
     const double* blk = dinvc + ((rb_ == 0) ? 0 : (kb_ == 0 ? kTileS : 2 * kTileS));

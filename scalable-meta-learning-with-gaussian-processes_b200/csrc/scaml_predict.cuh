@@ -32,6 +32,10 @@ struct PredParams {
   double* var;
   double* part;  // [nsplit][2][B] when nsplit > 1
   int M, n_max, n_pad, d, B, nsplit, ntile, ct, alias;
+  // CROSS variant (conditioning on target data, see scaml_cond.cuh)
+  const double* condA;  // [M][n_pad][n_tp]  A_m = K_m^-1 K_m(X_m, X_t)
+  double* cxp;          // [nsplit][B][n_tp] partials of sum_m c_m k*_m^T A_m
+  int n_tp;
 };
 
 // shared memory (doubles): kst | stage | [xst | alp | xcs] (aliased onto stage when alias) | xcr | red | vsq
@@ -98,8 +102,9 @@ SCAML_DEVICE void pred_issue(const double* Lm, const PChunk& c, double* st, int 
   ptile_async(st + kPTile, Lm + (size_t)(tri(2 * c.I + 1) + c.ck) * kTile, tid);
 }
 
-template <int KIND, int CT>
+template <int KIND, int CT, bool CROSS>
 __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const PredParams p) {
+  static_assert(!CROSS || CT == 64, "the fused cross-covariance contraction is written for 64-candidate tiles");
   constexpr int NJ = CT / 32;  // 8-column DMMA tiles per warp (warp tile: 32 rows x 8*NJ candidates)
   constexpr int CBT = CT / 32;  // kst tile columns
   SCAML_DYN_SMEM(double, sm);
@@ -131,6 +136,13 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
       xcr[k * CT + c] = (b0 + c < p.B) ? p.Xc[(size_t)(b0 + c) * d + k] : 0.0;
     }
     double macc = 0.0, vacc = 0.0;
+    // CROSS: cx[i][jj] = 8x8 block (candidates 32 (warp & 1) + 8 i + .., target columns 8 ((warp >> 1) + 4 jj) + ..)
+    // of sum_m c_m k*_m^T A_m, accumulated over ALL tasks of the split by the tensor cores
+    double cx[CROSS ? 4 : 1][CROSS ? 4 : 1][2];
+#pragma unroll
+    for (int i = 0; i < (CROSS ? 4 : 1); ++i)
+#pragma unroll
+      for (int jj = 0; jj < (CROSS ? 4 : 1); ++jj) cx[i][jj][0] = cx[i][jj][1] = 0.0;
     // inputs of the NEXT task (point `tid`, first kPreD dimensions, alpha) are fetched into registers while the
     // tensor-core phase of the current task runs, so that the staging below does not wait on global memory
     constexpr int kPreD = 8;
@@ -185,7 +197,9 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
       // chains per thread keep the FP64 pipe busy (a single chain per thread is latency bound).
       {
         constexpr int QN = kPredThreads / CT;  // row phases (4 for CT = 64, 8 for CT = 32)
-        constexpr int U = 16;
+        // rows per pass = QN * U must divide 64 (npt is a multiple of 64); CROSS keeps 32 more accumulators live
+        constexpr int U = (CT == 64 && !CROSS) ? 16 : 8;
+        static_assert((kPredThreads / CT) * U <= 64, "assembly pass must not run past the task's rows");
         const int c = tid % CT, q = tid / CT;
         double mu = 0.0;
         for (int a0 = q; a0 < npt; a0 += QN * U) {
@@ -218,6 +232,36 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
         }
       }
       __syncthreads();
+      if (CROSS) {
+        // cx += (c_m k*)^T A_m : A-operand = k* (shared, this warp's 32-candidate tile column), B-operand = A_m
+        // straight from L2 (each 4 x 8 fragment is 4 full 64-byte row segments), one k-step prefetched ahead
+        const int njt = p.n_tp >> 3, jw = warp >> 1;
+        const double cm = wm * wm * p.ystd[m] * p.ystd[m];
+        const double* Am = p.condA + (size_t)m * n_pad * p.n_tp + (size_t)t4 * p.n_tp + g;
+        const double* ks = kst + (size_t)(warp & 1) * kPTile + t4 * kPLd + g;
+        double bn[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) bn[jj] = (jw + 4 * jj < njt) ? __ldg(Am + 8 * (jw + 4 * jj)) : 0.0;
+        const int nks = npt >> 2;  // k-steps of 4 rows
+        for (int ks4 = 0; ks4 < nks; ++ks4) {
+          double b[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) b[jj] = bn[jj];
+          if (ks4 + 1 < nks) {
+            const double* An = Am + (size_t)4 * (ks4 + 1) * p.n_tp;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) bn[jj] = (jw + 4 * jj < njt) ? __ldg(An + 8 * (jw + 4 * jj)) : 0.0;
+          }
+          // row 4 ks4 + t4 of k*: tile row block (ks4 >> 3), row (4 (ks4 & 7) + t4) inside it
+          const double* kr = ks + (size_t)(ks4 >> 3) * CBT * kPTile + 4 * (ks4 & 7) * kPLd;
+          const double a[4] = {cm * kr[0], cm * kr[8], cm * kr[16], cm * kr[24]};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              if (jw + 4 * jj < njt) dmma884(cx[i][jj], a[i], b[jj]);
+        }
+      }
       if (p.alias) {
         for (; issued < 2 && issued < L; ++issued, qi.next()) {
           pred_issue(Lm, qi, stage + (issued % kPStages) * 2 * kPTile, tid);
@@ -306,6 +350,21 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
         vacc = fma(wm * wm * ys * ys, os - ssq, vacc);
       }
     }
+    if (CROSS) {
+      const int njt = p.n_tp >> 3, jw = warp >> 1;
+      double* dst = p.cxp + (size_t)spx * p.B * p.n_tp;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int b = b0 + 32 * (warp & 1) + 8 * i + g;
+        if (b < p.B) {
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            if (jw + 4 * jj < njt)
+              *reinterpret_cast<double2*>(dst + (size_t)b * p.n_tp + 8 * (jw + 4 * jj) + 2 * t4) =
+                  make_double2(cx[i][jj][0], cx[i][jj][1]);
+        }
+      }
+    }
     if (tid < CT && b0 + tid < p.B) {
       if (p.nsplit == 1) {
         p.mean[b0 + tid] = macc;
@@ -330,35 +389,41 @@ __global__ void scaml_predict_reduce_kernel(const double* part, double* mean, do
   }
 }
 
-template <int KIND, int CT>
+template <int KIND, int CT, bool CROSS>
 int launch_predict_kc(const PredParams& p, int grid, size_t smem, void* stream) {
 #ifdef SCAML_EMU
   (void)stream;
-  cuemu::launch(dim3(grid), dim3(kPredThreads), smem, scaml_predict_kernel<KIND, CT>, p);
+  cuemu::launch(dim3(grid), dim3(kPredThreads), smem, scaml_predict_kernel<KIND, CT, CROSS>, p);
   return 0;
 #else
-  cudaError_t err =
-      cudaFuncSetAttribute(scaml_predict_kernel<KIND, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t err = cudaFuncSetAttribute(scaml_predict_kernel<KIND, CT, CROSS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return (int)err;
-  scaml_predict_kernel<KIND, CT><<<grid, kPredThreads, smem, (cudaStream_t)stream>>>(p);
+  scaml_predict_kernel<KIND, CT, CROSS><<<grid, kPredThreads, smem, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 #endif
 }
 template <int KIND>
 int launch_predict_k(const PredParams& p, int grid, size_t smem, void* stream) {
-  return p.ct == 64 ? launch_predict_kc<KIND, 64>(p, grid, smem, stream)
-                    : launch_predict_kc<KIND, 32>(p, grid, smem, stream);
+  if (p.condA != nullptr) return launch_predict_kc<KIND, 64, true>(p, grid, smem, stream);
+  return p.ct == 64 ? launch_predict_kc<KIND, 64, false>(p, grid, smem, stream)
+                    : launch_predict_kc<KIND, 32, false>(p, grid, smem, stream);
 }
 
+// condA != null: also accumulate the cross-covariance partials into cxp (needs 64-candidate tiles: SCAML_E_SMEM
+// otherwise); workspace layout: [nsplit][2][B] mean/var partials (nsplit > 1) -- cxp is a separate buffer
 inline int launch_predict_weighted(const double* X, const int32_t* n_valid, const double* theta, const double* linv,
                                    const double* alpha, const double* ybar, const double* ystd, const double* w,
                                    const double* Xc, double* mean, double* var, double* workspace, int M, int n_max,
-                                   int n_pad, int d, int B, int kernel, int num_sms, void* stream) {
+                                   int n_pad, int d, int B, int kernel, int num_sms, void* stream,
+                                   const double* condA = nullptr, double* cxp = nullptr, int n_tp = 0) {
   PredParams p;
+  p.condA = condA, p.cxp = cxp, p.n_tp = n_tp;
   p.X = X, p.n_valid = n_valid, p.theta = theta, p.linv = linv, p.alpha = alpha, p.ybar = ybar, p.ystd = ystd;
   p.w = w, p.Xc = Xc, p.mean = mean, p.var = var, p.part = workspace;
   p.M = M, p.n_max = n_max, p.n_pad = n_pad, p.d = d, p.B = B;
   if (!predict_config(n_pad, d, &p.ct, &p.alias)) return SCAML_E_SMEM;
+  if (condA != nullptr && (p.ct != 64 || n_tp <= 0 || n_tp > 128 || (n_tp & 7))) return SCAML_E_UNSUPPORTED;
   p.ntile = (B + p.ct - 1) / p.ct;
   p.nsplit = predict_nsplit(M, B, num_sms, p.ct);
   const size_t smem = predict_smem_bytes(n_pad, d, p.ct, p.alias);

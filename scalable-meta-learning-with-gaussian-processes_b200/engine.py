@@ -300,6 +300,45 @@ class Engine:
         self.launches += 2 if need else 1
         return mean, cov
 
+    # ---- conditioning at scale (cross-covariance fused into the prediction kernel) ------- #
+    def cond_supported(self, fs: FittedSources, n_t: int) -> bool:
+        """The fused path needs 64-candidate tiles in shared memory (n_max <= 256 at the usual d) and n_t <= 128."""
+        b = fs.batch
+        return 0 < n_t <= 128 and b.n_max <= 256 and b.d <= 16
+
+    def cond_prepare(self, fs: FittedSources, Xt: torch.Tensor) -> torch.Tensor:
+        """A [M, n_pad, n_tp] with A_m = K_m^-1 K_m(X_m, X_t): once per set of target inputs."""
+        b = fs.batch
+        Xt = Xt.to(torch.float64).contiguous()
+        n_t = Xt.shape[0]
+        n_tp = ((n_t + 7) // 8) * 8
+        A = torch.zeros(b.M, pad64(b.n_max), n_tp, dtype=torch.float64, device=self.device)
+        self.lib.cond_prepare(_ptr(b.X), _ptr(b.n_valid), _ptr(fs.theta), _ptr(fs.linv), _ptr(Xt), _ptr(A), b.M, b.n_max,
+                              b.d, n_t, fs.spec.kernel, self._stream())
+        self.launches += 1
+        return A
+
+    def predict_conditioned(self, fs: FittedSources, w: torch.Tensor, Xc: torch.Tensor, Xt: torch.Tensor,
+                            A: torch.Tensor):
+        """Weighted prior mean [B], variance [B] and cross-covariance with the target inputs [B, n_t] (raw-Y units)."""
+        b = fs.batch
+        Xc = Xc.to(torch.float64).contiguous()
+        Xt = Xt.to(torch.float64).contiguous()
+        w = w.to(torch.float64).contiguous()
+        B, n_t = Xc.shape[0], Xt.shape[0]
+        mean = torch.empty(B, dtype=torch.float64, device=self.device)
+        var = torch.empty(B, dtype=torch.float64, device=self.device)
+        cross = torch.empty(B, n_t, dtype=torch.float64, device=self.device)
+        need = self.lib.predict_conditioned_workspace_bytes(b.M, b.n_max, b.d, B, n_t)
+        if self._pws is None or self._pws.numel() * 8 < need:
+            self._pws = torch.empty((need + 7) // 8, dtype=torch.float64, device=self.device)
+        self.lib.predict_conditioned(_ptr(b.X), _ptr(b.n_valid), _ptr(fs.theta), _ptr(fs.linv), _ptr(fs.alpha),
+                                     _ptr(b.ybar), _ptr(b.ystd), _ptr(w), _ptr(Xc), _ptr(Xt), _ptr(A), _ptr(mean),
+                                     _ptr(var), _ptr(cross), _ptr(self._pws), need, b.M, b.n_max, b.d, B, n_t,
+                                     fs.spec.kernel, self._stream())
+        self.launches += 3
+        return mean, var, cross
+
     # ---- a7: target objective ------------------------------------------------------------ #
     def target_lml_grad(self, source_means: torch.Tensor, source_covs: torch.Tensor, Xt: torch.Tensor,
                         yt: torch.Tensor, w: torch.Tensor, theta_raw: torch.Tensor, mu_all: float, s_all: float,

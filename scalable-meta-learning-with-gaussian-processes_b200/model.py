@@ -222,6 +222,7 @@ class ScaMLGP:
         self.raw_weights_constraint = GreaterThan(1e-10, transform=None)
         self.training = True
         self._tstate: Optional[TargetState] = None
+        self._condA: Optional[torch.Tensor] = None  # K_m^-1 K_m(X_m, X_t) of every source task (lazy, once per model)
 
     # ---- parameters ------------------------------------------------------------------------- #
     @property
@@ -334,6 +335,9 @@ class ScaMLGP:
             X = X[:, 0, :]
         Xc = X.to(dev, DT).contiguous()
         w = self.pruned_weights()
+        if self.num_train > 0 and eng.cond_supported(self._fitted, self.num_train):
+            mean, var = self._posterior_fused(Xc, w)
+            return Posterior(mean.to(X.device), var.to(X.device))
         pm, pv = eng.predict_weighted(self._fitted, w, Xc)
         if self.num_train == 0:
             # prior-only model (optimizer.py:135-141): no outcome transform, var + s_t
@@ -342,3 +346,12 @@ class ScaMLGP:
             _, cross = eng.predict_cross(self._fitted, Xc, self._Xt, w=w)
             mean, var = eng.target_posterior(self._target_state(), pm, pv, cross, Xc)
         return Posterior(mean.to(X.device), var.to(X.device))
+
+    def _posterior_fused(self, Xc: torch.Tensor, w: torch.Tensor):
+        """n_t > 0, q = 1: prior mean / variance and the cross-covariance with the target inputs in ONE prediction
+        launch (the k*^T A_m contraction rides on the k* tiles), then the n_t-dimensional conditioning."""
+        eng = self.engine
+        if self._condA is None:
+            self._condA = eng.cond_prepare(self._fitted, self._Xt)
+        pm, pv, cross = eng.predict_conditioned(self._fitted, w, Xc, self._Xt, self._condA)
+        return eng.target_posterior(self._target_state(), pm, pv, cross, Xc)

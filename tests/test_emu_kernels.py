@@ -246,3 +246,43 @@ def test_device_exp_is_accurate_to_two_ulp(emu_lib):
     so = np.empty_like(special)
     f(special.ctypes.data, so.ctypes.data, special.size)
     assert (so[:4] == 0.0).all() and np.isnan(so[4])
+
+
+def test_emu_fused_conditioning_matches_cross_kernel_and_oracle(emu_lib):
+    """scaml_cond_prepare + scaml_predict_conditioned (cross-covariance fused into the prediction kernel) against
+    the stand-alone cross kernel (reduce = 1) and the oracle; ragged tasks, a pruned task, n_t not a multiple of 8."""
+    from tests.emu_engine import EmuEngine
+    from scamlgp_b200.engine import SourceBatch
+
+    eng = EmuEngine(emu_lib)
+    M, n, d, B, nt = 3, 128, 3, 70, 11
+    pb = make_problem(M, 2, n, d, seed=9, n_valid=[128, 70, 9], kernel=0)
+    batch = SourceBatch.from_padded(pb["X"], pb["Y"], torch.tensor(pb["nv"]))
+    th = pb["th"][:, 1].contiguous()
+    fs = eng.factorize(batch, th, pb["cspec"])
+    g = torch.Generator().manual_seed(4)
+    Xc = torch.rand(B, d, dtype=torch.float64, generator=g)
+    Xt = torch.rand(nt, d, dtype=torch.float64, generator=g)
+    for w in (torch.tensor([0.5, 0.3, 0.2], dtype=torch.float64), torch.tensor([0.7, 0.0, 0.3], dtype=torch.float64)):
+        A = eng.cond_prepare(fs, Xt)
+        pm, pv, cross = eng.predict_conditioned(fs, w, Xc, Xt, A)
+        pm0, pv0 = eng.predict_weighted(fs, w, Xc)
+        _, cross0 = eng.predict_cross(fs, Xc, Xt, w=w)
+        assert rel_err(pm.numpy(), pm0.numpy()) < 1e-12 and rel_err(pv.numpy(), pv0.numpy()) < 1e-12
+        scale = float(cross0.abs().max())
+        assert float((cross - cross0).abs().max()) < 1e-10 * scale
+        # oracle: sum_m w_m^2 Sigma_m(x, X_t)
+        ref = torch.zeros(B, nt, dtype=torch.float64)
+        for m in range(M):
+            k = int(pb["nv"][m])
+            st = O.factorize(pb["X"][m, :k], pb["Y"][m, :k], th[m], pb["ospec"])
+            _, c = O.posterior(st, torch.cat([Xc, Xt]), full_cov=True)
+            ref += w[m] ** 2 * c[:B, B:]
+        assert float((cross - ref).abs().max()) < 1e-9 * float(ref.abs().max())
+    # A_m itself: K_m^-1 K_m(X_m, X_t)
+    k = int(pb["nv"][1])
+    st = O.factorize(pb["X"][1, :k], pb["Y"][1, :k], th[1], pb["ospec"])
+    Kmt = O.kernel_matrix(pb["X"][1, :k], Xt, st.ls, st.os, 0)
+    Aref = torch.cholesky_solve(Kmt, st.L)
+    assert float((A[1, :k, :nt] - Aref).abs().max()) < 1e-9 * float(Aref.abs().max())
+    assert float(A[1, k:].abs().max()) == 0.0 and float(A[1, :, nt:].abs().max()) == 0.0
