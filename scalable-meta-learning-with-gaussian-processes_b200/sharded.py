@@ -84,6 +84,8 @@ class ShardedSources:
         self.all_Y = torch.cat([t[1].reshape(-1).to(DT) for t in tasks])
         self.ystd_all: Optional[torch.Tensor] = None
         self.fitted: Optional[FittedSources] = None
+        self._condA: Optional[torch.Tensor] = None  # A_m = K_m^-1 K_m(X_m, X_t) of the local tasks
+        self._cond_key = None
 
     # ---- fit: no collective on the data path ----------------------------------------------------------- #
     def fit(self, spec: HyperSpec, theta_init: torch.Tensor, fit_options: Optional[dict] = None) -> ShardedFit:
@@ -141,9 +143,24 @@ class ShardedSources:
                   prior_outputscale: float = 0.0):
         """ScaML-GP posterior mean / variance at Xc [B, d] (q = 1).  `w` are the (already pruned) weights of
         all M tasks.  tstate None -> prior-only model (n_t = 0, optimizer.py:135-141): var + s_t."""
-        Xc = Xc.to(self.engine.device, DT).contiguous()
-        pm, pv = self.predict_weighted(w, Xc)
+        eng = self.engine
+        Xc = Xc.to(eng.device, DT).contiguous()
         if tstate is None:
+            pm, pv = self.predict_weighted(w, Xc)
             return pm, pv + prior_outputscale
-        _, cross = self.predict_cross(w, Xc, tstate.Xt)
-        return self.engine.target_posterior(tstate, pm.contiguous(), pv.contiguous(), cross.contiguous(), Xc)
+        n_t = tstate.Xt.shape[0]
+        if eng.cond_supported(self.fitted, n_t):
+            # fused path: local prior mean / variance / cross-covariance in one prediction launch, then ONE
+            # all_reduce over the stacked partials [B, 2 + n_t]
+            key = (tstate.Xt.data_ptr(), n_t)
+            if self._cond_key != key:
+                self._condA, self._cond_key = eng.cond_prepare(self.fitted, tstate.Xt), key
+            pm, pv, cross = eng.predict_conditioned(self.fitted, self._local_w(w), Xc, tstate.Xt, self._condA)
+            if self.world > 1:
+                flat = torch.cat([pm.unsqueeze(1), pv.unsqueeze(1), cross], dim=1).contiguous()
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+                pm, pv, cross = flat[:, 0].contiguous(), flat[:, 1].contiguous(), flat[:, 2:].contiguous()
+        else:
+            pm, pv = self.predict_weighted(w, Xc)
+            _, cross = self.predict_cross(w, Xc, tstate.Xt)
+        return eng.target_posterior(tstate, pm.contiguous(), pv.contiguous(), cross.contiguous(), Xc)
