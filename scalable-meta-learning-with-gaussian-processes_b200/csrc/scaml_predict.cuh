@@ -239,27 +239,37 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
         const double cm = wm * wm * p.ystd[m] * p.ystd[m];
         const double* Am = p.condA + (size_t)m * n_pad * p.n_tp + (size_t)t4 * p.n_tp + g;
         const double* ks = kst + (size_t)(warp & 1) * kPTile + t4 * kPLd + g;
-        double bn[4];
+        // work items = (32-row block rbk of k*, column block jj of this warp); the 8 B-fragments of an item are
+        // fetched while the previous item's 32 DMMAs run (double-buffered registers): L2 latency is hidden
+        const int nrb = npt >> 5;
+        const int njw = (njt > jw) ? (njt - jw + 3) >> 2 : 0;  // column blocks jw, jw+4, .. owned by this warp
+        const int nitems = nrb * njw;
+        double bcur[8], bnxt[8];
+        auto fetch = [&](int item, double (&b)[8]) {
+          const int rbk = item / njw, jj = item - rbk * njw;
+          const double* src = Am + (size_t)(32 * rbk) * p.n_tp + 8 * (jw + 4 * jj);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) bn[jj] = (jw + 4 * jj < njt) ? __ldg(Am + 8 * (jw + 4 * jj)) : 0.0;
-        const int nks = npt >> 2;  // k-steps of 4 rows
-        for (int ks4 = 0; ks4 < nks; ++ks4) {
-          double b[4];
+          for (int s = 0; s < 8; ++s) b[s] = __ldg(src + (size_t)(4 * s) * p.n_tp);
+        };
+        if (nitems > 0) fetch(0, bnxt);
+        for (int item = 0; item < nitems; ++item) {
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) b[jj] = bn[jj];
-          if (ks4 + 1 < nks) {
-            const double* An = Am + (size_t)4 * (ks4 + 1) * p.n_tp;
+          for (int s = 0; s < 8; ++s) bcur[s] = bnxt[s];
+          if (item + 1 < nitems) fetch(item + 1, bnxt);
+          const int rbk = item / njw, jj = item - rbk * njw;
+          const double* kr = ks + (size_t)rbk * CBT * kPTile;
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) bn[jj] = (jw + 4 * jj < njt) ? __ldg(An + 8 * (jw + 4 * jj)) : 0.0;
+          for (int s = 0; s < 8; ++s) {
+            const double a[4] = {cm * kr[0], cm * kr[8], cm * kr[16], cm * kr[24]};
+            kr += 4 * kPLd;
+            // jj is warp-uniform but not a compile-time constant: select the accumulator set by unrolled compare
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (q == jj) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dmma884(cx[i][q], a[i], bcur[s]);
+              }
           }
-          // row 4 ks4 + t4 of k*: tile row block (ks4 >> 3), row (4 (ks4 & 7) + t4) inside it
-          const double* kr = ks + (size_t)(ks4 >> 3) * CBT * kPTile + 4 * (ks4 & 7) * kPLd;
-          const double a[4] = {cm * kr[0], cm * kr[8], cm * kr[16], cm * kr[24]};
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-              if (jw + 4 * jj < njt) dmma884(cx[i][jj], a[i], b[jj]);
         }
       }
       if (p.alias) {
