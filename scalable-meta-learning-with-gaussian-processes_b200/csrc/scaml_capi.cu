@@ -135,14 +135,6 @@ int run_fit(scaml::FitParams p, void* workspace, size_t workspace_bytes, void* s
   }
   const long long E = (long long)p.M * p.R;
   if (E < grid) grid = (int)E;
-  // start offset of the co-resident CTAs: ~1/3 of one evaluation (measured 0.67 ms at n_pad = 256, ~n^1.8),
-  // only when every CTA has several evaluations to amortise it over
-  p.stagger_ns = 0;
-  if (E >= 4ll * grid && grid > p.sms) {
-    double ns = 0.0;  // measured: no effect on B200 (sweep 0..450 us, profiles/r1_stagger_sweep.txt)
-    if (const char* env = getenv("SCAML_FIT_STAGGER_NS")) ns = atof(env);
-    p.stagger_ns = (unsigned)(ns < 0 ? 0 : (ns > 4e6 ? 4e6 : ns));
-  }
   return f8 ? dispatch_fit8(p, grid, smem, stream) : dispatch_fit(p, grid, smem, stream);
 }
 

@@ -81,7 +81,6 @@ struct FitParams {
   long long* prof;      // SCAML_PROF builds only: [grid][16] cycle counters per phase
   int M, R, n_max, n_pad, d, mode;
   int sms;  // SM count (co-resident CTAs are blockIdx.x, blockIdx.x + sms, ...)
-  unsigned stagger_ns;  // start offset between the co-resident CTAs of an SM (0 = none)
   scaml_hyper_spec spec;
 };
 
@@ -748,19 +747,6 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
 #endif
   const int E = p.M * p.R;
   const scaml_hyper_spec& sp = p.spec;
-#ifndef SCAML_EMU
-  // Co-resident CTAs run identical work: started together they stay in phase (all in the latency-bound pivot
-  // chains, then all on the tensor pipe).  Offsetting their start by a fraction of one evaluation keeps one
-  // CTA's chains / exp epilogues under the other CTAs' tile products.
-  if (p.stagger_ns != 0 && p.sms > 0) {
-    const unsigned slot = blockIdx.x / (unsigned)p.sms;
-    for (unsigned long long left = (unsigned long long)slot * p.stagger_ns; left > 0;) {
-      const unsigned step = left > 500000ull ? 500000u : (unsigned)left;
-      __nanosleep(step);
-      left -= step;
-    }
-  }
-#endif
   // The four tile roles of a super-tile carry unequal work (on diagonal super-tiles role (1,0) multiplies a
   // full tile, (0,0)/(1,1) the lower 8x8 blocks only and (0,1) nothing, epilogues included), and warp w of
   // every co-resident CTA sits on sub-partition w % 4.  Rotating the warp -> role map by the CTA's slot on
