@@ -102,7 +102,23 @@ class _SingleObjectiveBase:
         return spec
 
     def _model_for_acquisition(self):
-        return self.model
+        """The model the acquisition function sees.  With evaluations pending (max_pending_evaluations > 1) the
+        reference's base class conditions a fantasy model on the pending points; here the pending
+        points are fantasised at the posterior mean ("kriging believer"): the mean is unchanged, the variance
+        collapses around them, so concurrent suggestions spread out.  Hyper-parameters are not refitted."""
+        if not self.pending_specifications or getattr(self.model, "num_train", 0) == 0:
+            return self.model
+        Xp = torch.tensor(np.stack([self.search_space.to_numerical(s.configuration)
+                                    for s in self.pending_specifications.values()]), dtype=self.torch_dtype)
+        Xp = impute_nans_with_constant(Xp)
+        base = self.model
+        yp = base.posterior(Xp).mean.reshape(-1, 1).to(self.torch_dtype).cpu()
+        X_all = torch.cat([base.train_inputs[0].to(self.torch_dtype), Xp], dim=0)
+        Y_all = torch.cat([base._train_Y.to(self.torch_dtype), yp], dim=0)
+        fantasy = ScaMLGP(X_all, Y_all, self.source_gps, likelihood=base.likelihood, covar_module=base.covar_module,
+                          **self.model_kwargs)
+        fantasy.raw_weights = base.raw_weights.clone()
+        return fantasy.eval()
 
     def generate_evaluation_specification(self) -> EvaluationSpecification:
         if (self.max_pending_evaluations is not None

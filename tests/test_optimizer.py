@@ -153,25 +153,26 @@ def _missing_objective_scenario(eng, extra, n_source=32):
     assert len(opt.source_gps) == 1
 
 
-def _spaces_scenario(eng, extra, steps):
-    # sequential optimisation of a single parameter
-    opt = ScaMLGPBO(space_1d(), LOSS, meta_1d(), seed=1, num_initial_random_samples=1, max_pending_evaluations=5,
-                    engine=eng, **extra)
-    evs = _loop(opt, lambda c: (c["p1"] - 0.3) ** 2, steps)
-    assert len(evs) == steps and all(0.0 <= e.configuration["p1"] <= 1.0 for e in evs)
-    # unknown objective
-    with pytest.raises(EvaluationsError):
-        opt.report(Evaluation(configuration={"p1": 0.2}, objectives={"unknown": 1.0}))
-    # fixed parameter is respected
-    opt = ScaMLGPBO(space_fixed(), LOSS, meta_fixed(), seed=1, num_initial_random_samples=1,
-                    max_pending_evaluations=5, engine=eng, **extra)
-    for e in _loop(opt, lambda c: c["x"] ** 2, steps):
-        assert e.configuration["my_fixed_param"] == 1.0
-    # conditional space: inactive parameters never appear, active ones always do
-    opt = ScaMLGPBO(space_conditional(), LOSS, meta_conditional(), seed=1, num_initial_random_samples=1,
-                    max_pending_evaluations=5, engine=eng, **extra)
-    for e in _loop(opt, lambda c: c["lr"], 2):
-        assert ("momentum" in e.configuration) == (e.configuration["optimizer"] == "sgd")
+def _spaces_scenario(eng, extra, steps, parts=("single", "fixed", "conditional", "mixed")):
+    if "single" in parts:  # sequential optimisation of a single parameter
+        opt = ScaMLGPBO(space_1d(), LOSS, meta_1d(), seed=1, num_initial_random_samples=1, max_pending_evaluations=5,
+                        engine=eng, **extra)
+        evs = _loop(opt, lambda c: (c["p1"] - 0.3) ** 2, steps)
+        assert len(evs) == steps and all(0.0 <= e.configuration["p1"] <= 1.0 for e in evs)
+        with pytest.raises(EvaluationsError):  # unknown objective
+            opt.report(Evaluation(configuration={"p1": 0.2}, objectives={"unknown": 1.0}))
+    if "fixed" in parts:  # fixed parameter is respected
+        opt = ScaMLGPBO(space_fixed(), LOSS, meta_fixed(), seed=1, num_initial_random_samples=1,
+                        max_pending_evaluations=5, engine=eng, **extra)
+        for e in _loop(opt, lambda c: c["x"] ** 2, steps):
+            assert e.configuration["my_fixed_param"] == 1.0
+    if "conditional" in parts:  # inactive parameters never appear, active ones always do
+        opt = ScaMLGPBO(space_conditional(), LOSS, meta_conditional(), seed=1, num_initial_random_samples=1,
+                        max_pending_evaluations=5, engine=eng, **extra)
+        for e in _loop(opt, lambda c: c["lr"], 2):
+            assert ("momentum" in e.configuration) == (e.configuration["optimizer"] == "sgd")
+    if "mixed" not in parts:
+        return
     # mixed space, list reporting
     opt = ScaMLGPBO(space_mixed(), LOSS, meta_mixed(), seed=1, num_initial_random_samples=1,
                     max_pending_evaluations=5, engine=eng, **extra)
@@ -206,7 +207,9 @@ def test_missing_objective_emulated(emu_engine):
 
 
 def test_spaces_emulated(emu_engine):
-    _spaces_scenario(emu_engine, TINY, steps=2)
+    # the emulation spawns one OS thread per CUDA thread: keep to the discrete / conditional path here, the
+    # continuous path is covered by test_missing_objective_emulated, everything at full budgets by the gpu tests
+    _spaces_scenario(emu_engine, TINY, steps=2, parts=("conditional",))
 
 
 def test_greater_is_better_flips_sign_and_maximizing_acquisition_is_rejected(emu_engine):
@@ -220,7 +223,28 @@ def test_greater_is_better_flips_sign_and_maximizing_acquisition_is_rejected(emu
         UpperConfidenceBound(opt.model, maximize=True)
 
 
+def _pending_scenario(eng, extra):
+    """Concurrent suggestions (max_pending_evaluations > 1): pending points are fantasised, so the next
+    proposals move away from them instead of repeating the same maximiser of the acquisition function."""
+    opt = ScaMLGPBO(space_1d(), LOSS, meta_1d(), seed=3, num_initial_random_samples=1, max_pending_evaluations=3,
+                    engine=eng, **extra)
+    _loop(opt, lambda c: (c["p1"] - 0.3) ** 2, 3)
+    a = opt.generate_evaluation_specification().configuration["p1"]
+    b = opt.generate_evaluation_specification().configuration["p1"]
+    c = opt.generate_evaluation_specification().configuration["p1"]
+    assert len(opt.pending_specifications) == 3
+    assert abs(a - b) > 1e-4 and abs(b - c) > 1e-4 and abs(a - c) > 1e-4
+    with pytest.raises(OptimizerNotReady):
+        opt.generate_evaluation_specification()
+    assert opt.model.train_inputs[0].shape[0] == 3  # the fantasy model is not kept
+
+
 # ---- GPU (product engine, reference settings) ------------------------------------------------------------ #
+@pytest.mark.gpu
+def test_pending_points_are_fantasised_gpu(engine):
+    _pending_scenario(engine, {})
+
+
 @pytest.mark.gpu
 def test_missing_objective_gpu(engine):
     _missing_objective_scenario(engine, {})
