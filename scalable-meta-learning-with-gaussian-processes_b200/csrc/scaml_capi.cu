@@ -128,6 +128,8 @@ int run_fit(scaml::FitParams p, void* workspace, size_t workspace_bytes, void* s
   p.ws_stride = scaml::fit_ws_doubles_host(p.n_pad, p.d);
   p.prof = g_prof;
   p.sms = num_sms();
+  p.kcache = 1;
+  if (const char* env = getenv("SCAML_FIT_KCACHE")) p.kcache = atoi(env) != 0;
   int grid = fit_grid_slots(p.n_pad, p.d);
   if (f8) {  // register-limited to two 256-thread CTAs per SM
     const int per_sm = (2 * (smem + 1024) <= 228 * 1024) ? 2 : 1;

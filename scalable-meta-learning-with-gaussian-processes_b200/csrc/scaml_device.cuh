@@ -54,6 +54,22 @@ SCAML_DEVICE void cp_async_wait() {
 #endif
 }
 
+// streaming (evict-first) 16-byte global accesses for write-once / read-once scratch
+SCAML_DEVICE void st_stream(double2* p, double2 v) {
+#ifdef SCAML_EMU
+  *p = v;
+#else
+  __stcs(p, v);
+#endif
+}
+SCAML_DEVICE double2 ld_stream(const double2* p) {
+#ifdef SCAML_EMU
+  return *p;
+#else
+  return __ldcs(p);
+#endif
+}
+
 // FP64 tensor-core MMA (DMMA): D(8x8) += A(8x4) * B(4x8).  Fragments (PTX ISA, mma.m8n8k4 .f64):
 //   a    = A[lane>>2][lane&3]        b = B[lane&3][lane>>2]
 //   d[e] = D[lane>>2][2*(lane&3)+e]

@@ -81,14 +81,21 @@ struct FitParams {
   long long* prof;      // SCAML_PROF builds only: [grid][16] cycle counters per phase
   int M, R, n_max, n_pad, d, mode;
   int sms;  // SM count (co-resident CTAs are blockIdx.x, blockIdx.x + sms, ...)
+  int kcache;  // 4-warp RBF kernel: cache kappa between the assembly and the gradient epilogue
   scaml_hyper_spec spec;
 };
 
 // workspace slot: lower tiles, tri(NB) x 1024 doubles
-inline long long fit_ws_doubles_host(int n_pad, int d) {
-  (void)d;
+inline long long fit_tile_doubles_host(int n_pad) {
   const int NB = n_pad / kBS;
   return (long long)((NB * (NB + 1)) / 2) * kTile;
+}
+// + kappa cache of the 4-warp kernel: one 64x64 block per lower super-tile (written by the assembly epilogue,
+// read back by the gradient epilogue instead of recomputing distances and exponentials; RBF only)
+inline long long fit_ws_doubles_host(int n_pad, int d) {
+  (void)d;
+  const int NS = n_pad / kSB;
+  return fit_tile_doubles_host(n_pad) + (long long)((NS * (NS + 1)) / 2) * kSB * kSB;
 }
 // shared memory (doubles): stage 4608 | dinvc 3456 | y,z,alpha 3*n_pad | red 128 |
 //                          gsm 4*kMaxP | par 4*kMaxP+8 | flags 2
@@ -161,6 +168,10 @@ struct ChunkPtrs {
   SCAML_DEVICE bool a_ok(int rb) const { return rb == 0 ? a0 != nullptr : a1 != nullptr; }
   SCAML_DEVICE bool b_ok(int cb) const { return cb == 0 ? b0 != nullptr : b1 != nullptr; }
 };
+SCAML_DEVICE long long fit_tile_doubles(int n_pad) {
+  const int NB = n_pad / kBS;
+  return (long long)((NB * (NB + 1)) / 2) * kTile;
+}
 SCAML_DEVICE const double* wtile(const double* W, int bi, int bj) { return W + (size_t)(tri(bi) + bj) * kTile; }
 SCAML_DEVICE double* wtile_w(double* W, int bi, int bj) { return W + (size_t)(tri(bi) + bj) * kTile; }
 
@@ -382,9 +393,11 @@ SCAML_DEVICE void pair_r2(double (&r2)[16], const double* xblk, int d, int ra, i
 }
 
 // ---- epilogue 1: acc <- K_y(I,J) - acc, K recomputed from the scaled inputs ----------- //
+// kc: this thread's slots of the super-tile's kappa cache ([pass h][8 pairs of values][128 threads] as double2),
+// or null (Matern kernels recompute: their gradient needs a second function of r)
 template <int KIND>
 SCAML_DEVICE void assemble_tile(Acc& acc, int I, int J, const FThr& t, const double* xblk, int d, int nv, double os,
-                                double diag_add) {
+                                double diag_add, double2* kc) {
   const int ra = t.rb * kBS + t.g, cb0 = kSB + t.cb * kBS + 2 * t.t4;
   const int a0 = I * kSB + ra, b0 = J * kSB + t.cb * kBS + 2 * t.t4;
 #pragma unroll
@@ -392,6 +405,10 @@ SCAML_DEVICE void assemble_tile(Acc& acc, int I, int J, const FThr& t, const dou
     double r2[16];  // [i][j][e] -> 8 i + 2 j + e
     pair_r2(r2, xblk, d, ra + 16 * h, cb0);
     if (!ABL(2)) kappa_n<KIND, 16, false>(r2, r2, r2);  // 16 independent exponentials, interleaved
+    if (KIND == SCAML_KERNEL_RBF && kc != nullptr) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) st_stream(kc + (h * 8 + u) * kFitThreads, make_double2(r2[2 * u], r2[2 * u + 1]));
+    }
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
@@ -412,17 +429,24 @@ SCAML_DEVICE void assemble_tile(Acc& acc, int I, int J, const FThr& t, const dou
 // acc is overwritten by t_ab = wgt * W_ab * kd_ab.
 template <int KIND>
 SCAML_DEVICE void grad_tile(Acc& acc, int I, int J, const FThr& t, const double* xblk, const double* av, int d,
-                            int nv, double* gsm) {
+                            int nv, double* gsm, const double2* kc) {
   const int ra = t.rb * kBS + t.g, cb0 = kSB + t.cb * kBS + 2 * t.t4;
   const int a0 = I * kSB + ra, b0 = J * kSB + t.cb * kBS + 2 * t.t4;
   double accS = 0.0, accT = 0.0;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     double r2[16], kdv[16];  // [i][j][e] -> 8 i + 2 j + e
-    pair_r2(r2, xblk, d, ra + 16 * h, cb0);
-    if (KIND == SCAML_KERNEL_RBF) {
+    if (KIND == SCAML_KERNEL_RBF && kc != nullptr) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const double2 v = ld_stream(kc + (h * 8 + u) * kFitThreads);
+        r2[2 * u] = v.x, r2[2 * u + 1] = v.y;
+      }
+    } else if (KIND == SCAML_KERNEL_RBF) {
+      pair_r2(r2, xblk, d, ra + 16 * h, cb0);
       if (!ABL(4)) kappa_n<KIND, 16, false>(r2, r2, r2);  // kd == kappa for the RBF kernel (kdv unused)
     } else {
+      pair_r2(r2, xblk, d, ra + 16 * h, cb0);
       kappa_n<KIND, 16, true>(r2, r2, kdv);
     }
 #pragma unroll
@@ -740,6 +764,11 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
   int* flag = reinterpret_cast<int*>(scal + 8);
 
   double* W = p.workspace + (size_t)blockIdx.x * p.ws_stride;
+  // kappa cache behind the tiles; the mapping thread -> slot depends on the thread id only, so the warp-role
+  // rotation (which is per evaluation) does not matter
+  double2* kcache = (KIND == SCAML_KERNEL_RBF && p.kcache && p.mode == kModeLmlGrad)
+                        ? reinterpret_cast<double2*>(W + fit_tile_doubles(p.n_pad))
+                        : nullptr;
 #ifdef SCAML_PROF
   long long prof_last = clock64();
   if (threadIdx.x < 16) profsm[threadIdx.x] = 0;
@@ -823,7 +852,9 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
         PROF_MARK(1);
         xblk_store(stage, xp, Xm, th, I, J, nv, d, t.tid);  // stage is idle: x-block lives there
         __syncthreads();
-        if (!(diag && upper_warp)) assemble_tile<KIND>(acc, I, J, t, stage, d, nv, os, diag_add);
+        if (!(diag && upper_warp))
+          assemble_tile<KIND>(acc, I, J, t, stage, d, nv, os, diag_add,
+                              kcache ? kcache + ((size_t)(tri(I) + J) * 16) * kFitThreads + t.tid : nullptr);
         __syncthreads();  // x-block consumed before C_in overwrites it
         if (!(diag && upper_warp)) store_tile_C(stage + (t.rb * 2 + t.cb) * kTileS, kLd, acc, t, 1.0);
         __syncthreads();
@@ -932,7 +963,9 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
           if (t.tid < 64) av[I * kSB + t.tid] = red[t.tid] + red[64 + t.tid];
           __syncthreads();
         }
-        if (!(diag && upper_warp)) grad_tile<KIND>(acc, I, J, t, stage, av, d, nv, gsm);
+        if (!(diag && upper_warp))
+          grad_tile<KIND>(acc, I, J, t, stage, av, d, nv, gsm,
+                          kcache ? kcache + ((size_t)(tri(I) + J) * 16) * kFitThreads + t.tid : nullptr);
         __syncthreads();  // x-block consumed before the next product stages tiles over it
         PROF_MARK(9);
       }

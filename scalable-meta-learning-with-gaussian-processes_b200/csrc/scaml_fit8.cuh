@@ -221,14 +221,19 @@ SCAML_DEVICE void pair_r2_8(double (&r2)[16], const double* xblk, int d, int ra,
 }
 
 // ---- epilogue 1: acc <- K_y(I,J) - acc, K recomputed from the scaled inputs ----------- //
+// kc: this thread's slots of the super-tile's kappa cache ([8 pairs of values][256 threads] as double2) or null
 template <int KIND>
 SCAML_DEVICE void assemble8(Acc8& acc, int I, int J, const Thr& t, const double* xblk, int d, int nv, double os,
-                            double diag_add) {
+                            double diag_add, double2* kc) {
   const int ra = t.rb * kBS + t.g, cb0 = kSB + t.cb * kBS + t.cin + 2 * t.t4;
   const int a0 = I * kSB + ra, b0 = J * kSB + t.cb * kBS + t.cin + 2 * t.t4;
   double r2[16];
   pair_r2_8(r2, xblk, d, ra, cb0);
   kappa_n<KIND, 16, false>(r2, r2, r2);  // 16 independent exponentials, interleaved
+  if (KIND == SCAML_KERNEL_RBF && kc != nullptr) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) st_stream(kc + u * kThreads, make_double2(r2[2 * u], r2[2 * u + 1]));
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -248,16 +253,23 @@ SCAML_DEVICE void assemble8(Acc8& acc, int I, int J, const Thr& t, const double*
 // acc is overwritten by t_ab = wgt * W_ab * kd_ab.
 template <int KIND>
 SCAML_DEVICE void grad8(Acc8& acc, int I, int J, const Thr& t, const double* xblk, const double* av, int d, int nv,
-                        double* gsm) {
+                        double* gsm, const double2* kc) {
   const int ra = t.rb * kBS + t.g, cb0 = kSB + t.cb * kBS + t.cin + 2 * t.t4;
   const int a0 = I * kSB + ra, b0 = J * kSB + t.cb * kBS + t.cin + 2 * t.t4;
   double accS = 0.0, accT = 0.0;
   {
     double r2[16], kdv[16];
-    pair_r2_8(r2, xblk, d, ra, cb0);
-    if (KIND == SCAML_KERNEL_RBF) {
+    if (KIND == SCAML_KERNEL_RBF && kc != nullptr) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const double2 v = ld_stream(kc + u * kThreads);
+        r2[2 * u] = v.x, r2[2 * u + 1] = v.y;
+      }
+    } else if (KIND == SCAML_KERNEL_RBF) {
+      pair_r2_8(r2, xblk, d, ra, cb0);
       kappa_n<KIND, 16, false>(r2, r2, r2);  // kd == kappa for the RBF kernel (kdv unused)
     } else {
+      pair_r2_8(r2, xblk, d, ra, cb0);
       kappa_n<KIND, 16, true>(r2, r2, kdv);
     }
 #pragma unroll
@@ -446,6 +458,9 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit8_kernel(const FitParams
   int* flag = reinterpret_cast<int*>(scal + 8);
 
   double* W = p.workspace + (size_t)blockIdx.x * p.ws_stride;
+  double2* kcache = (KIND == SCAML_KERNEL_RBF && p.kcache && p.mode == kModeLmlGrad)
+                        ? reinterpret_cast<double2*>(W + fit_tile_doubles(p.n_pad))
+                        : nullptr;  // kappa cache behind the tiles (see scaml_fit.cuh)
   const int E = p.M * p.R;
   const scaml_hyper_spec& sp = p.spec;
   // warp w of every co-resident CTA sits on sub-partition w % 4; the eight tile roles carry unequal work on
@@ -519,7 +534,9 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit8_kernel(const FitParams
         gemm_global8(acc, src, stage, t, diag, false, pig, nullptr);
         xblk_store8(stage, xp, Xm, th, I, J, nv, d, t.tid);  // stage is idle: x-block lives there
         __syncthreads();
-        if (!idle) assemble8<KIND>(acc, I, J, t, stage, d, nv, os, diag_add);
+        if (!idle)
+          assemble8<KIND>(acc, I, J, t, stage, d, nv, os, diag_add,
+                          kcache ? kcache + ((size_t)(tri(I) + J) * 8) * kThreads + t.tid : nullptr);
         __syncthreads();  // x-block consumed before C_in overwrites it
         if (!idle) store8_C(stage + (t.rb * 2 + t.cb) * kTileS, kLd, acc, t, 1.0);
         __syncthreads();
@@ -624,7 +641,9 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit8_kernel(const FitParams
             av[I * kSB + t.tid] = (red[t.tid] + red[64 + t.tid]) + (red[128 + t.tid] + red[192 + t.tid]);
           __syncthreads();
         }
-        if (!idle) grad8<KIND>(acc, I, J, t, stage, av, d, nv, gsm);
+        if (!idle)
+          grad8<KIND>(acc, I, J, t, stage, av, d, nv, gsm,
+                      kcache ? kcache + ((size_t)(tri(I) + J) * 8) * kThreads + t.tid : nullptr);
         __syncthreads();  // x-block consumed before the next product stages tiles over it
       }
     }
