@@ -94,16 +94,16 @@ int dispatch_fit8(const scaml::FitParams& p, int grid, size_t smem, void* stream
 
 // Two variants of the fit kernel (same algorithm, same results): 4-warp CTAs, three per SM (scaml_fit.cuh), and
 // 8-warp CTAs, two per SM (scaml_fit8.cuh).  Measured on B200 (profiles/r1_fit_variants.txt): the 4-warp
-// kernel wins for the RBF kernel up to n = 320 (661k vs 631k evals/s at n = 256), the 8-warp kernel for larger
-// tasks (115k vs 110k at n = 512, d = 10) and for the Matern family, whose epilogues are heavier (580k vs 509k).
-// SCAML_FIT_IMPL=4|8 forces one (A/B runs).
+// kernel wins up to n = 320 (RBF 722k vs 652k evals/s, Matern-5/2 626k vs 604k at n = 256), the 8-warp kernel
+// for larger tasks (118k vs 110k at n = 512, d = 10).  SCAML_FIT_IMPL=4|8 forces one (A/B runs).
 bool use_fit8(int n_pad, int kernel) {
   if (const char* env = getenv("SCAML_FIT_IMPL")) {
     const int v = atoi(env);
     if (v == 4) return false;
     if (v == 8) return true;
   }
-  return kernel != SCAML_KERNEL_RBF || n_pad >= 384;
+  (void)kernel;
+  return n_pad >= 384;
 }
 
 int dispatch_fit(const scaml::FitParams& p, int grid, size_t smem, void* stream) {

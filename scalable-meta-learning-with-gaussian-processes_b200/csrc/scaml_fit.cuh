@@ -91,11 +91,12 @@ inline long long fit_tile_doubles_host(int n_pad) {
   return (long long)((NB * (NB + 1)) / 2) * kTile;
 }
 // + kappa cache of the 4-warp kernel: one 64x64 block per lower super-tile (written by the assembly epilogue,
-// read back by the gradient epilogue instead of recomputing distances and exponentials; RBF only)
+// read back by the gradient epilogue instead of recomputing distances and exponentials; the Matern kernels
+// cache kd = -2 dkappa/dr^2 as well, in the second half of the block)
 inline long long fit_ws_doubles_host(int n_pad, int d) {
   (void)d;
   const int NS = n_pad / kSB;
-  return fit_tile_doubles_host(n_pad) + (long long)((NS * (NS + 1)) / 2) * kSB * kSB;
+  return fit_tile_doubles_host(n_pad) + (long long)((NS * (NS + 1)) / 2) * kSB * kSB * 2;  // kappa and kd
 }
 // shared memory (doubles): stage 4608 | dinvc 3456 | y,z,alpha 3*n_pad | red 128 |
 //                          gsm 4*kMaxP | par 4*kMaxP+8 | flags 2
@@ -404,8 +405,15 @@ SCAML_DEVICE void assemble_tile(Acc& acc, int I, int J, const FThr& t, const dou
   for (int h = 0; h < 2; ++h) {  // two passes of two row-tiles keep r2 at 32 registers
     double r2[16];  // [i][j][e] -> 8 i + 2 j + e
     pair_r2(r2, xblk, d, ra + 16 * h, cb0);
-    if (!ABL(2)) kappa_n<KIND, 16, false>(r2, r2, r2);  // 16 independent exponentials, interleaved
-    if (KIND == SCAML_KERNEL_RBF && kc != nullptr) {
+    if (KIND != SCAML_KERNEL_RBF && kc != nullptr) {
+      double kdv[16];
+      kappa_n<KIND, 16, true>(r2, r2, kdv);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) st_stream(kc + (16 + h * 8 + u) * kFitThreads, make_double2(kdv[2 * u], kdv[2 * u + 1]));
+    } else if (!ABL(2)) {
+      kappa_n<KIND, 16, false>(r2, r2, r2);  // 16 independent exponentials, interleaved
+    }
+    if (kc != nullptr) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) st_stream(kc + (h * 8 + u) * kFitThreads, make_double2(r2[2 * u], r2[2 * u + 1]));
     }
@@ -436,11 +444,15 @@ SCAML_DEVICE void grad_tile(Acc& acc, int I, int J, const FThr& t, const double*
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     double r2[16], kdv[16];  // [i][j][e] -> 8 i + 2 j + e
-    if (KIND == SCAML_KERNEL_RBF && kc != nullptr) {
+    if (kc != nullptr) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const double2 v = ld_stream(kc + (h * 8 + u) * kFitThreads);
         r2[2 * u] = v.x, r2[2 * u + 1] = v.y;
+        if (KIND != SCAML_KERNEL_RBF) {
+          const double2 q = ld_stream(kc + (16 + h * 8 + u) * kFitThreads);
+          kdv[2 * u] = q.x, kdv[2 * u + 1] = q.y;
+        }
       }
     } else if (KIND == SCAML_KERNEL_RBF) {
       pair_r2(r2, xblk, d, ra + 16 * h, cb0);
@@ -766,7 +778,7 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
   double* W = p.workspace + (size_t)blockIdx.x * p.ws_stride;
   // kappa cache behind the tiles; the mapping thread -> slot depends on the thread id only, so the warp-role
   // rotation (which is per evaluation) does not matter
-  double2* kcache = (KIND == SCAML_KERNEL_RBF && p.kcache && p.mode == kModeLmlGrad)
+  double2* kcache = (p.kcache && p.mode == kModeLmlGrad)
                         ? reinterpret_cast<double2*>(W + fit_tile_doubles(p.n_pad))
                         : nullptr;
 #ifdef SCAML_PROF
@@ -854,7 +866,7 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
         __syncthreads();
         if (!(diag && upper_warp))
           assemble_tile<KIND>(acc, I, J, t, stage, d, nv, os, diag_add,
-                              kcache ? kcache + ((size_t)(tri(I) + J) * 16) * kFitThreads + t.tid : nullptr);
+                              kcache ? kcache + ((size_t)(tri(I) + J) * 32) * kFitThreads + t.tid : nullptr);
         __syncthreads();  // x-block consumed before C_in overwrites it
         if (!(diag && upper_warp)) store_tile_C(stage + (t.rb * 2 + t.cb) * kTileS, kLd, acc, t, 1.0);
         __syncthreads();
@@ -965,7 +977,7 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
         }
         if (!(diag && upper_warp))
           grad_tile<KIND>(acc, I, J, t, stage, av, d, nv, gsm,
-                          kcache ? kcache + ((size_t)(tri(I) + J) * 16) * kFitThreads + t.tid : nullptr);
+                          kcache ? kcache + ((size_t)(tri(I) + J) * 32) * kFitThreads + t.tid : nullptr);
         __syncthreads();  // x-block consumed before the next product stages tiles over it
         PROF_MARK(9);
       }

@@ -229,8 +229,15 @@ SCAML_DEVICE void assemble8(Acc8& acc, int I, int J, const Thr& t, const double*
   const int a0 = I * kSB + ra, b0 = J * kSB + t.cb * kBS + t.cin + 2 * t.t4;
   double r2[16];
   pair_r2_8(r2, xblk, d, ra, cb0);
-  kappa_n<KIND, 16, false>(r2, r2, r2);  // 16 independent exponentials, interleaved
-  if (KIND == SCAML_KERNEL_RBF && kc != nullptr) {
+  if (KIND != SCAML_KERNEL_RBF && kc != nullptr) {
+    double kdv[16];
+    kappa_n<KIND, 16, true>(r2, r2, kdv);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) st_stream(kc + (8 + u) * kThreads, make_double2(kdv[2 * u], kdv[2 * u + 1]));
+  } else {
+    kappa_n<KIND, 16, false>(r2, r2, r2);  // 16 independent exponentials, interleaved
+  }
+  if (kc != nullptr) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) st_stream(kc + u * kThreads, make_double2(r2[2 * u], r2[2 * u + 1]));
   }
@@ -259,11 +266,15 @@ SCAML_DEVICE void grad8(Acc8& acc, int I, int J, const Thr& t, const double* xbl
   double accS = 0.0, accT = 0.0;
   {
     double r2[16], kdv[16];
-    if (KIND == SCAML_KERNEL_RBF && kc != nullptr) {
+    if (kc != nullptr) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const double2 v = ld_stream(kc + u * kThreads);
         r2[2 * u] = v.x, r2[2 * u + 1] = v.y;
+        if (KIND != SCAML_KERNEL_RBF) {
+          const double2 q = ld_stream(kc + (8 + u) * kThreads);
+          kdv[2 * u] = q.x, kdv[2 * u + 1] = q.y;
+        }
       }
     } else if (KIND == SCAML_KERNEL_RBF) {
       pair_r2_8(r2, xblk, d, ra, cb0);
@@ -458,7 +469,7 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit8_kernel(const FitParams
   int* flag = reinterpret_cast<int*>(scal + 8);
 
   double* W = p.workspace + (size_t)blockIdx.x * p.ws_stride;
-  double2* kcache = (KIND == SCAML_KERNEL_RBF && p.kcache && p.mode == kModeLmlGrad)
+  double2* kcache = (p.kcache && p.mode == kModeLmlGrad)
                         ? reinterpret_cast<double2*>(W + fit_tile_doubles(p.n_pad))
                         : nullptr;  // kappa cache behind the tiles (see scaml_fit.cuh)
   const int E = p.M * p.R;
@@ -536,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit8_kernel(const FitParams
         __syncthreads();
         if (!idle)
           assemble8<KIND>(acc, I, J, t, stage, d, nv, os, diag_add,
-                          kcache ? kcache + ((size_t)(tri(I) + J) * 8) * kThreads + t.tid : nullptr);
+                          kcache ? kcache + ((size_t)(tri(I) + J) * 16) * kThreads + t.tid : nullptr);
         __syncthreads();  // x-block consumed before C_in overwrites it
         if (!idle) store8_C(stage + (t.rb * 2 + t.cb) * kTileS, kLd, acc, t, 1.0);
         __syncthreads();
@@ -643,7 +654,7 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit8_kernel(const FitParams
         }
         if (!idle)
           grad8<KIND>(acc, I, J, t, stage, av, d, nv, gsm,
-                      kcache ? kcache + ((size_t)(tri(I) + J) * 8) * kThreads + t.tid : nullptr);
+                      kcache ? kcache + ((size_t)(tri(I) + J) * 16) * kThreads + t.tid : nullptr);
         __syncthreads();  // x-block consumed before the next product stages tiles over it
       }
     }
