@@ -128,6 +128,13 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F kernel, A... args) {
         kernel(args...);
       });
     for (auto& t : th) t.join();
+    // canary: a kernel that writes past the dynamic shared memory it asked for would corrupt a neighbour on the GPU
+    for (size_t i = smem_bytes; i < smem_bytes + 1024; ++i)
+      if (((unsigned char*)mem)[i] != 0xCD) {
+        std::fprintf(stderr, "cuda_emu: CTA %u wrote past its %zu bytes of dynamic shared memory (offset %zu)\n", b,
+                     smem_bytes, i);
+        std::abort();
+      }
     pthread_barrier_destroy(&c.bar);
     for (int w = 0; w < nw; ++w) pthread_barrier_destroy(&c.wbar[w]);
     free(mem);

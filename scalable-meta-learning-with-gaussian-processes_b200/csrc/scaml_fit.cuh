@@ -103,7 +103,7 @@ inline long long fit_ws_doubles_host(int n_pad, int d) {
 inline size_t fit_smem_bytes(int n_pad, int d) {
   (void)d;
   return sizeof(double) *
-         (size_t)(kStage + 3 * kTileS + 3 * (size_t)n_pad + 128 + kFitWarps * kMaxP + 4 * kMaxP + 8 + 2);
+         (size_t)(kStage + 3 * kTileS + 3 * (size_t)n_pad + 128 + kFitWarps * kMaxP + 5 * kMaxP + 8 + 2);
 }
 
 // per-thread coordinates: warp (rb, cb) owns one 32x32 tile of the 64x64 super-tile as a 4x4
@@ -361,14 +361,15 @@ SCAML_DEVICE void xpre_load(double (&xp)[kXpre], const double* Xm, int I, int J,
 #pragma unroll
   for (int k = 0; k < kXpre; ++k) xp[k] = (k < d && a < nv && !ABL(65536)) ? __ldg(Xm + (size_t)a * d + k) : 0.0;
 }
+// `th` here holds the RECIPROCAL lengthscales
 SCAML_DEVICE void xblk_store(double* xblk, const double (&xp)[kXpre], const double* Xm, const double* th, int I,
                              int J, int nv, int d, int tid) {
 #pragma unroll
   for (int k = 0; k < kXpre; ++k)
-    if (k < d) xblk[k * 128 + tid] = ABL(2048) ? xp[k] * th[k] : xp[k] / th[k];
+    if (k < d) xblk[k * 128 + tid] = xp[k] * th[k];
   if (d > kXpre) {
     const int a = (tid < kSB) ? I * kSB + tid : J * kSB + (tid - kSB);
-    for (int k = kXpre; k < d; ++k) xblk[k * 128 + tid] = (a < nv) ? __ldg(Xm + (size_t)a * d + k) / th[k] : 0.0;
+    for (int k = kXpre; k < d; ++k) xblk[k * 128 + tid] = (a < nv) ? __ldg(Xm + (size_t)a * d + k) * th[k] : 0.0;
   }
 }
 
@@ -772,7 +773,8 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
   double* lp = par + kMaxP;
   double* dlp = par + 2 * kMaxP;
   double* chain = par + 3 * kMaxP;
-  double* scal = par + 4 * kMaxP;  // [0] logdet
+  double* invl = par + 4 * kMaxP;  // reciprocal lengthscales (x * (1/l): an FP64 division is ~10 pipe slots)
+  double* scal = par + 5 * kMaxP;  // [0] logdet
   int* flag = reinterpret_cast<int*>(scal + 8);
 
   double* W = p.workspace + (size_t)blockIdx.x * p.ws_stride;
@@ -829,6 +831,7 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
       lp[t.tid] = log_prior(pk, p1, p2, v);
       dlp[t.tid] = dlog_prior(pk, p1, p2, v);
       chain[t.tid] = (hi - lo) * sg * (1.0 - sg);
+      invl[t.tid] = 1.0 / v;
       if (p.mode == kModeFactorize) p.theta_out[(size_t)e * P + t.tid] = v;
     }
     if (t.tid == 0) {
@@ -862,7 +865,7 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
         CholSrc src{W, I, J};
         gemm_global(acc, src, stage, t, diag, false, pig, nullptr);
         PROF_MARK(1);
-        xblk_store(stage, xp, Xm, th, I, J, nv, d, t.tid);  // stage is idle: x-block lives there
+        xblk_store(stage, xp, Xm, invl, I, J, nv, d, t.tid);  // stage is idle: x-block lives there
         __syncthreads();
         if (!(diag && upper_warp))
           assemble_tile<KIND>(acc, I, J, t, stage, d, nv, os, diag_add,
@@ -968,7 +971,7 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
         LauumSrc src{W, I, J, NS};
         gemm_global(acc, src, stage, t, diag, diag, pig, zv);
         PROF_MARK(8);
-        xblk_store(stage, xp, Xm, th, I, J, nv, d, t.tid);
+        xblk_store(stage, xp, Xm, invl, I, J, nv, d, t.tid);
         if (diag) red[t.tid] = pig;
         __syncthreads();
         if (diag) {

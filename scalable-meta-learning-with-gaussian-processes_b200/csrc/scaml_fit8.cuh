@@ -15,10 +15,10 @@ namespace f8 {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 
-// shared memory (doubles): stage 4608 | dinvc 3456 | y,z,alpha 3*n_pad | red 256 | gsm 8*kMaxP | par 4*kMaxP+8 | flags 2
+// shared memory (doubles): stage 4608 | dinvc 3456 | y,z,alpha 3*n_pad | red 256 | gsm 8*kMaxP | par 5*kMaxP+8 | flags 2
 inline size_t smem_bytes(int n_pad, int d) {
   (void)d;
-  return sizeof(double) * (size_t)(kStage + 3 * kTileS + 3 * (size_t)n_pad + 256 + kWarps * kMaxP + 4 * kMaxP + 8 + 2);
+  return sizeof(double) * (size_t)(kStage + 3 * kTileS + 3 * (size_t)n_pad + 256 + kWarps * kMaxP + 5 * kMaxP + 8 + 2);
 }
 
 // warp role r in 0..7: rb = r >> 2 (tile row), cq = r & 3 (16-column group of the 64 columns)
@@ -185,17 +185,18 @@ SCAML_DEVICE void xpre_load8(double (&xp)[kXh], const double* Xm, int I, int J, 
     xp[u] = (k < d && a < nv) ? __ldg(Xm + (size_t)a * d + k) : 0.0;
   }
 }
+// `th` here holds the RECIPROCAL lengthscales
 SCAML_DEVICE void xblk_store8(double* xblk, const double (&xp)[kXh], const double* Xm, const double* th, int I, int J,
                               int nv, int d, int tid) {
   const int pt = tid & 127, kh = tid >> 7;
 #pragma unroll
   for (int u = 0; u < kXh; ++u) {
     const int k = 2 * u + kh;
-    if (k < d) xblk[k * 128 + pt] = xp[u] / th[k];
+    if (k < d) xblk[k * 128 + pt] = xp[u] * th[k];
   }
   if (d > 2 * kXh) {
     const int a = (pt < kSB) ? I * kSB + pt : J * kSB + (pt - kSB);
-    for (int k = 2 * kXh + kh; k < d; k += 2) xblk[k * 128 + pt] = (a < nv) ? __ldg(Xm + (size_t)a * d + k) / th[k] : 0.0;
+    for (int k = 2 * kXh + kh; k < d; k += 2) xblk[k * 128 + pt] = (a < nv) ? __ldg(Xm + (size_t)a * d + k) * th[k] : 0.0;
   }
 }
 
@@ -465,7 +466,8 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit8_kernel(const FitParams
   double* lp = par + kMaxP;
   double* dlp = par + 2 * kMaxP;
   double* chain = par + 3 * kMaxP;
-  double* scal = par + 4 * kMaxP;  // [0] logdet
+  double* invl = par + 4 * kMaxP;  // reciprocal lengthscales (x * (1/l): an FP64 division is ~10 pipe slots)
+  double* scal = par + 5 * kMaxP;  // [0] logdet
   int* flag = reinterpret_cast<int*>(scal + 8);
 
   double* W = p.workspace + (size_t)blockIdx.x * p.ws_stride;
@@ -512,6 +514,7 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit8_kernel(const FitParams
       lp[t.tid] = log_prior(pk, p1, p2, v);
       dlp[t.tid] = dlog_prior(pk, p1, p2, v);
       chain[t.tid] = (hi - lo) * sg * (1.0 - sg);
+      invl[t.tid] = 1.0 / v;
       if (p.mode == kModeFactorize) p.theta_out[(size_t)e * P + t.tid] = v;
     }
     if (t.tid == 0) {
@@ -543,7 +546,7 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit8_kernel(const FitParams
         xpre_load8(xp, Xm, I, J, nv, d, t.tid);
         CholSrc src{W, I, J};
         gemm_global8(acc, src, stage, t, diag, false, pig, nullptr);
-        xblk_store8(stage, xp, Xm, th, I, J, nv, d, t.tid);  // stage is idle: x-block lives there
+        xblk_store8(stage, xp, Xm, invl, I, J, nv, d, t.tid);  // stage is idle: x-block lives there
         __syncthreads();
         if (!idle)
           assemble8<KIND>(acc, I, J, t, stage, d, nv, os, diag_add,
@@ -644,7 +647,7 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit8_kernel(const FitParams
         xpre_load8(xp, Xm, I, J, nv, d, t.tid);
         LauumSrc src{W, I, J, NS};
         gemm_global8(acc, src, stage, t, diag, diag, pig, zv);
-        xblk_store8(stage, xp, Xm, th, I, J, nv, d, t.tid);
+        xblk_store8(stage, xp, Xm, invl, I, J, nv, d, t.tid);
         if (diag) red[t.tid] = pig;
         __syncthreads();
         if (diag) {
