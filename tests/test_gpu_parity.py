@@ -30,6 +30,8 @@ def _batch(pb):
     (4, 1, 128, 4, None, 1),
     (4, 1, 128, 4, None, 2),
     (2, 1, 512, 10, None, 0),           # config 4 shape, sampled
+    (3, 2, 128, 17, [128, 90, 3], 0),   # d > 8: input dimensions beyond the register-prefetched ones
+    (2, 1, 320, 32, None, 3),           # d at the library limit, 5 super-tiles
 ])
 def test_lml_grad_matches_oracle(engine, M, R, n, d, nv, kernel):
     pb = make_problem(M, R, n, d, seed=3, n_valid=nv, kernel=kernel)
