@@ -192,7 +192,13 @@ int scaml_target_posterior(const double* prior_mean, const double* prior_var, co
  * with the k*^T A contraction fused into the prediction kernel (the k* tile is already in shared memory).
  * Together with scaml_target_posterior this replaces the eval branch of `ScaMLGP.forward` for q = 1 candidate
  * batches (reference scamlgp/model.py:364-375 evaluates every source posterior at [X_t; x] jointly).
- * n_max <= 256 (64-candidate tiles must fit shared memory), n_t <= 128. */
+ * scaml_cond_caches: the per-task caches `source_means` [n_t][M] / `source_covs` [n_t][n_t][M] of
+ * `ScaMLGP.__init__` (reference scamlgp/model.py:278-289) from A:
+ *   source_covs[t][t'][m] = ystd_m^2 ( K_m(x_t, x_t') - K_m(x_t, X_m) A_m[:, t'] ).
+ * n_max <= 512 (whatever scaml_predict_weighted accepts), n_t <= 128. */
+int scaml_cond_caches(const double* X, const int32_t* n_valid, const double* theta, const double* alpha,
+                      const double* ybar, const double* ystd, const double* Xt, const double* A, double* mean,
+                      double* cov, int M, int n_max, int d, int n_t, int kernel, void* stream);
 int scaml_cond_prepare(const double* X, const int32_t* n_valid, const double* theta, const double* linv_packed,
                        const double* Xt, double* A, int M, int n_max, int d, int n_t, int kernel, void* stream);
 size_t scaml_predict_conditioned_workspace_bytes(int M, int n_max, int d, int B, int n_t);

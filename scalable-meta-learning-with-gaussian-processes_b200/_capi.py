@@ -108,6 +108,7 @@ EXPORTED_SYMBOLS = (
     "scaml_target_posterior",
     "scaml_lbfgs_step",
     "scaml_cond_prepare",
+    "scaml_cond_caches",
     "scaml_predict_conditioned_workspace_bytes",
     "scaml_predict_conditioned",
 )
@@ -159,6 +160,7 @@ class ScamlLib:
         L.scaml_target_posterior.argtypes = [vp] * 8 + [dbl, dbl, vp, vp, i32, i32, i32, i32, vp]
         L.scaml_lbfgs_step.argtypes = [C.POINTER(CLbfgsState), vp, vp, vp, vp, i32, i32, i32, i32, dbl, dbl, i32, i32, vp]
         L.scaml_cond_prepare.argtypes = [vp] * 6 + [i32] * 5 + [vp]
+        L.scaml_cond_caches.argtypes = [vp] * 10 + [i32] * 5 + [vp]
         L.scaml_predict_conditioned_workspace_bytes.restype = sz
         L.scaml_predict_conditioned_workspace_bytes.argtypes = [i32] * 5
         L.scaml_predict_conditioned.argtypes = [vp] * 15 + [sz] + [i32] * 6 + [vp]
@@ -234,6 +236,10 @@ class ScamlLib:
     def cond_prepare(self, X, n_valid, theta, linv, Xt, A, M, n_max, d, n_t, kernel, stream=0):
         _check(self.lib.scaml_cond_prepare(X, n_valid, theta, linv, Xt, A, M, n_max, d, n_t, kernel, stream),
                "scaml_cond_prepare")
+
+    def cond_caches(self, X, n_valid, theta, alpha, ybar, ystd, Xt, A, mean, cov, M, n_max, d, n_t, kernel, stream=0):
+        _check(self.lib.scaml_cond_caches(X, n_valid, theta, alpha, ybar, ystd, Xt, A, mean, cov, M, n_max, d, n_t, kernel,
+                                          stream), "scaml_cond_caches")
 
     def predict_conditioned_workspace_bytes(self, M, n_max, d, B, n_t) -> int:
         return int(self.lib.scaml_predict_conditioned_workspace_bytes(M, n_max, d, B, n_t))

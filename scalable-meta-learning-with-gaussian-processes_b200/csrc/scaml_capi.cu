@@ -351,9 +351,23 @@ int scaml_cond_prepare(const double* X, const int32_t* n_valid, const double* th
   return scaml::launch_cond_prepare(p, kernel, num_sms(), stream);
 }
 
+int scaml_cond_caches(const double* X, const int32_t* n_valid, const double* theta, const double* alpha,
+                      const double* ybar, const double* ystd, const double* Xt, const double* A, double* mean,
+                      double* cov, int M, int n_max, int d, int n_t, int kernel, void* stream) {
+  if (!X || !theta || !alpha || !ybar || !ystd || !Xt || !A || !mean || !cov) return SCAML_E_ARG;
+  if (M <= 0 || n_max <= 0 || d <= 0 || n_t <= 0 || kernel < 0 || kernel > 3) return SCAML_E_ARG;
+  if (d > scaml::kMaxP - 2 || n_t > 128) return SCAML_E_UNSUPPORTED;
+  scaml::CondCachesParams p{};
+  p.X = X, p.n_valid = n_valid, p.theta = theta, p.alpha = alpha, p.ybar = ybar, p.ystd = ystd, p.Xt = Xt, p.A = A;
+  p.mean = mean, p.cov = cov, p.M = M, p.n_max = n_max, p.n_pad = pad64(n_max), p.d = d, p.n_t = n_t;
+  return scaml::launch_cond_caches(p, kernel, num_sms(), stream);
+}
+
 size_t scaml_predict_conditioned_workspace_bytes(int M, int n_max, int d, int B, int n_t) {
   if (M <= 0 || n_max <= 0 || d <= 0 || B <= 0 || n_t <= 0) return 0;
-  const int ns = scaml::predict_nsplit(M, B, num_sms(), 64);
+  int ct = 64, alias = 0;
+  if (!scaml::predict_config(pad64(n_max), d, &ct, &alias)) return 0;
+  const int ns = scaml::predict_nsplit(M, B, num_sms(), ct);
   const size_t pv = ns > 1 ? sizeof(double) * 2 * (size_t)ns * (size_t)B : 0;
   return pv + sizeof(double) * (size_t)ns * (size_t)B * (size_t)scaml::cond_ntp(n_t);
 }
@@ -370,7 +384,9 @@ int scaml_predict_conditioned(const double* X, const int32_t* n_valid, const dou
   if (d > scaml::kMaxP - 2 || n_t > 128) return SCAML_E_UNSUPPORTED;
   if (workspace_bytes < scaml_predict_conditioned_workspace_bytes(M, n_max, d, B, n_t)) return SCAML_E_WORKSPACE;
   const int n_tp = scaml::cond_ntp(n_t);
-  const int ns = scaml::predict_nsplit(M, B, num_sms(), 64);
+  int ct = 64, alias = 0;
+  if (!scaml::predict_config(pad64(n_max), d, &ct, &alias)) return SCAML_E_SMEM;
+  const int ns = scaml::predict_nsplit(M, B, num_sms(), ct);
   double* part = static_cast<double*>(workspace);
   double* cxp = part + (ns > 1 ? 2 * (size_t)ns * (size_t)B : 0);
   int rc = scaml::launch_predict_weighted(X, n_valid, theta, linv_packed, alpha, ybar, ystd, w, Xc, mean, var, part, M,

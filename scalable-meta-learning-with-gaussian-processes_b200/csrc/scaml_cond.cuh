@@ -268,6 +268,127 @@ __global__ void __launch_bounds__(256) scaml_cond_combine_kernel(const CondCombi
   }
 }
 
+// Per-task caches of ScaMLGP.__init__ (reference scamlgp/model.py:278-289) from A_m:
+//   source_means[t][m]    = ybar_m + ystd_m  K_m(x_t, X_m) alpha_m
+//   source_covs[t][t'][m] = ystd_m^2 ( K_m(x_t, x_t') - K_m(x_t, X_m) A_m[:, t'] )
+// One CTA per task walks X_m in 32-row chunks: K chunk and A chunk in shared memory, the n_t x n_t accumulator
+// tile in shared memory as well (every thread owns its entries: no races, fixed order).
+struct CondCachesParams {
+  const double* X;
+  const int32_t* n_valid;
+  const double* theta;
+  const double* alpha;  // [M][n_pad]
+  const double* ybar;
+  const double* ystd;
+  const double* Xt;   // [n_t][d]
+  const double* A;    // [M][n_pad][n_tp]
+  double* mean;       // [n_t][M]
+  double* cov;        // [n_t][n_t][M]
+  int M, n_max, n_pad, d, n_t, n_tp;
+};
+// shared memory (doubles): acc [n_t][n_t] | macc [n_t] | Kc [32][n_tp+1] | Ac [32][n_tp] | alc [32] | xts [d][n_tp] | invl
+inline size_t cond_caches_smem_bytes(int d, int n_t, int n_tp) {
+  return sizeof(double) * ((size_t)n_t * n_t + n_t + 32 * (size_t)(n_tp + 1) + 32 * (size_t)n_tp + 32 +
+                           (size_t)d * n_tp + kMaxP + 8);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256) scaml_cond_caches_kernel(const CondCachesParams p) {
+  SCAML_DYN_SMEM(double, sm);
+  const int tid = threadIdx.x, d = p.d, P = d + 2, nt = p.n_t, ntp = p.n_tp, ldk = ntp + 1;
+  double* acc = sm;                        // [nt][nt]
+  double* macc = acc + (size_t)nt * nt;    // [nt]
+  double* Kc = macc + nt;                  // [32][ldk]
+  double* Ac = Kc + 32 * (size_t)ldk;      // [32][ntp]
+  double* alc = Ac + 32 * (size_t)ntp;     // [32]
+  double* xts = alc + 32;                  // [d][ntp]
+  double* invl = xts + (size_t)d * ntp;    // [kMaxP]
+  for (int m = blockIdx.x; m < p.M; m += gridDim.x) {
+    const int nv = p.n_valid ? p.n_valid[m] : p.n_max;
+    const double* th = p.theta + (size_t)m * P;
+    const double os = th[d], ys = p.ystd[m];
+    const double* Xm = p.X + (size_t)m * p.n_max * d;
+    __syncthreads();
+    if (tid < d) invl[tid] = 1.0 / th[tid];
+    for (int i = tid; i < nt * nt + nt; i += 256) acc[i] = 0.0;  // acc and macc are contiguous
+    __syncthreads();
+    for (int i = tid; i < d * ntp; i += 256) {
+      const int k = i / ntp, j = i - k * ntp;
+      xts[i] = (j < nt) ? p.Xt[(size_t)j * d + k] * invl[k] : 0.0;
+    }
+    for (int a0 = 0; a0 < nv; a0 += 32) {
+      __syncthreads();
+      for (int i = tid; i < 32 * ntp; i += 256) {
+        const int r = i / ntp, j = i - r * ntp, a = a0 + r;
+        double kv = 0.0;
+        if (a < nv && j < nt) {
+          double r2 = 0.0;
+          for (int k = 0; k < d; ++k) {
+            const double df = Xm[(size_t)a * d + k] * invl[k] - xts[k * ntp + j];
+            r2 = fma(df, df, r2);
+          }
+          kv = os * kappa_of<KIND>(r2);
+        }
+        Kc[r * ldk + j] = kv;
+        Ac[i] = (a < nv) ? p.A[((size_t)m * p.n_pad + a) * ntp + j] : 0.0;
+      }
+      if (tid < 32) alc[tid] = (a0 + tid < nv) ? p.alpha[(size_t)m * p.n_pad + a0 + tid] : 0.0;
+      __syncthreads();
+      for (int e = tid; e < nt * nt; e += 256) {
+        const int t = e / nt, u = e - t * nt;
+        double s = acc[e];
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) s = fma(Kc[r * ldk + t], Ac[r * ntp + u], s);
+        acc[e] = s;
+      }
+      if (tid < nt) {
+        double s = macc[tid];
+        for (int r = 0; r < 32; ++r) s = fma(Kc[r * ldk + tid], alc[r], s);
+        macc[tid] = s;
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < nt * nt; e += 256) {
+      const int t = e / nt, u = e - t * nt;
+      double r2 = 0.0;
+      for (int k = 0; k < d; ++k) {
+        const double df = xts[k * ntp + t] - xts[k * ntp + u];
+        r2 = fma(df, df, r2);
+      }
+      p.cov[(size_t)e * p.M + m] = ys * ys * (os * kappa_of<KIND>(r2) - acc[e]);
+    }
+    if (tid < nt) p.mean[(size_t)tid * p.M + m] = p.ybar[m] + ys * macc[tid];
+  }
+}
+
+template <int KIND>
+int launch_cond_caches_k(const CondCachesParams& p, int grid, size_t smem, void* stream) {
+#ifdef SCAML_EMU
+  (void)stream;
+  cuemu::launch(dim3(grid), dim3(256), smem, scaml_cond_caches_kernel<KIND>, p);
+  return 0;
+#else
+  cudaError_t err =
+      cudaFuncSetAttribute(scaml_cond_caches_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return (int)err;
+  scaml_cond_caches_kernel<KIND><<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
+#endif
+}
+
+inline int launch_cond_caches(CondCachesParams p, int kernel, int num_sms, void* stream) {
+  p.n_tp = cond_ntp(p.n_t);
+  const size_t smem = cond_caches_smem_bytes(p.d, p.n_t, p.n_tp);
+  if (smem > 227 * 1024) return SCAML_E_SMEM;
+  int grid = p.M < 2 * num_sms ? p.M : 2 * num_sms;
+  switch (kernel) {
+    case SCAML_KERNEL_RBF: return launch_cond_caches_k<SCAML_KERNEL_RBF>(p, grid, smem, stream);
+    case SCAML_KERNEL_MATERN12: return launch_cond_caches_k<SCAML_KERNEL_MATERN12>(p, grid, smem, stream);
+    case SCAML_KERNEL_MATERN32: return launch_cond_caches_k<SCAML_KERNEL_MATERN32>(p, grid, smem, stream);
+    default: return launch_cond_caches_k<SCAML_KERNEL_MATERN52>(p, grid, smem, stream);
+  }
+}
+
 template <int KIND>
 int launch_cond_prepare_k(const CondPrepParams& p, int grid, size_t smem, void* stream) {
 #ifdef SCAML_EMU

@@ -104,7 +104,6 @@ SCAML_DEVICE void pred_issue(const double* Lm, const PChunk& c, double* st, int 
 
 template <int KIND, int CT, bool CROSS>
 __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const PredParams p) {
-  static_assert(!CROSS || CT == 64, "the fused cross-covariance contraction is written for 64-candidate tiles");
   constexpr int NJ = CT / 32;  // 8-column DMMA tiles per warp (warp tile: 32 rows x 8*NJ candidates)
   constexpr int CBT = CT / 32;  // kst tile columns
   SCAML_DYN_SMEM(double, sm);
@@ -136,8 +135,11 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
       xcr[k * CT + c] = (b0 + c < p.B) ? p.Xc[(size_t)(b0 + c) * d + k] : 0.0;
     }
     double macc = 0.0, vacc = 0.0;
-    // CROSS: cx[i][jj] = 8x8 block (candidates 32 (warp & 1) + 8 i + .., target columns 8 ((warp >> 1) + 4 jj) + ..)
-    // of sum_m c_m k*_m^T A_m, accumulated over ALL tasks of the split by the tensor cores
+    // CROSS: cx[i][jj] = 8x8 block (candidates 32 xt + 8 i + .., target columns 8 (jw + JS jj) + ..) of
+    // sum_m c_m k*_m^T A_m, accumulated over ALL tasks of the split by the tensor cores.  CT = 64: the warp's
+    // candidate tile column xt = warp & 1 and column blocks jw = warp >> 1, +4, ..; CT = 32: xt = 0, jw = warp, +8, ..
+    constexpr int JS = (CT == 64) ? 4 : 8;
+    const int xt = (CT == 64) ? (warp & 1) : 0, jw = (CT == 64) ? (warp >> 1) : warp;
     double cx[CROSS ? 4 : 1][CROSS ? 4 : 1][2];
 #pragma unroll
     for (int i = 0; i < (CROSS ? 4 : 1); ++i)
@@ -235,19 +237,19 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
       if (CROSS) {
         // cx += (c_m k*)^T A_m : A-operand = k* (shared, this warp's 32-candidate tile column), B-operand = A_m
         // straight from L2 (each 4 x 8 fragment is 4 full 64-byte row segments), one k-step prefetched ahead
-        const int njt = p.n_tp >> 3, jw = warp >> 1;
+        const int njt = p.n_tp >> 3;
         const double cm = wm * wm * p.ystd[m] * p.ystd[m];
         const double* Am = p.condA + (size_t)m * n_pad * p.n_tp + (size_t)t4 * p.n_tp + g;
-        const double* ks = kst + (size_t)(warp & 1) * kPTile + t4 * kPLd + g;
+        const double* ks = kst + (size_t)xt * kPTile + t4 * kPLd + g;
         // work items = (32-row block rbk of k*, column block jj of this warp); the 8 B-fragments of an item are
         // fetched while the previous item's 32 DMMAs run (double-buffered registers): L2 latency is hidden
         const int nrb = npt >> 5;
-        const int njw = (njt > jw) ? (njt - jw + 3) >> 2 : 0;  // column blocks jw, jw+4, .. owned by this warp
+        const int njw = (njt > jw) ? (njt - jw + JS - 1) / JS : 0;  // column blocks jw, jw+JS, .. owned by this warp
         const int nitems = nrb * njw;
         double bcur[8], bnxt[8];
         auto fetch = [&](int item, double (&b)[8]) {
           const int rbk = item / njw, jj = item - rbk * njw;
-          const double* src = Am + (size_t)(32 * rbk) * p.n_tp + 8 * (jw + 4 * jj);
+          const double* src = Am + (size_t)(32 * rbk) * p.n_tp + 8 * (jw + JS * jj);
 #pragma unroll
           for (int s = 0; s < 8; ++s) b[s] = __ldg(src + (size_t)(4 * s) * p.n_tp);
         };
@@ -361,16 +363,16 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
       }
     }
     if (CROSS) {
-      const int njt = p.n_tp >> 3, jw = warp >> 1;
+      const int njt = p.n_tp >> 3;
       double* dst = p.cxp + (size_t)spx * p.B * p.n_tp;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int b = b0 + 32 * (warp & 1) + 8 * i + g;
+        const int b = b0 + 32 * xt + 8 * i + g;
         if (b < p.B) {
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj)
-            if (jw + 4 * jj < njt)
-              *reinterpret_cast<double2*>(dst + (size_t)b * p.n_tp + 8 * (jw + 4 * jj) + 2 * t4) =
+            if (jw + JS * jj < njt)
+              *reinterpret_cast<double2*>(dst + (size_t)b * p.n_tp + 8 * (jw + JS * jj) + 2 * t4) =
                   make_double2(cx[i][jj][0], cx[i][jj][1]);
         }
       }
@@ -415,7 +417,9 @@ int launch_predict_kc(const PredParams& p, int grid, size_t smem, void* stream) 
 }
 template <int KIND>
 int launch_predict_k(const PredParams& p, int grid, size_t smem, void* stream) {
-  if (p.condA != nullptr) return launch_predict_kc<KIND, 64, true>(p, grid, smem, stream);
+  if (p.condA != nullptr)
+    return p.ct == 64 ? launch_predict_kc<KIND, 64, true>(p, grid, smem, stream)
+                      : launch_predict_kc<KIND, 32, true>(p, grid, smem, stream);
   return p.ct == 64 ? launch_predict_kc<KIND, 64, false>(p, grid, smem, stream)
                     : launch_predict_kc<KIND, 32, false>(p, grid, smem, stream);
 }
@@ -433,7 +437,7 @@ inline int launch_predict_weighted(const double* X, const int32_t* n_valid, cons
   p.w = w, p.Xc = Xc, p.mean = mean, p.var = var, p.part = workspace;
   p.M = M, p.n_max = n_max, p.n_pad = n_pad, p.d = d, p.B = B;
   if (!predict_config(n_pad, d, &p.ct, &p.alias)) return SCAML_E_SMEM;
-  if (condA != nullptr && (p.ct != 64 || n_tp <= 0 || n_tp > 128 || (n_tp & 7))) return SCAML_E_UNSUPPORTED;
+  if (condA != nullptr && (n_tp <= 0 || n_tp > 128 || (n_tp & 7))) return SCAML_E_UNSUPPORTED;
   p.ntile = (B + p.ct - 1) / p.ct;
   p.nsplit = predict_nsplit(M, B, num_sms, p.ct);
   const size_t smem = predict_smem_bytes(n_pad, d, p.ct, p.alias);

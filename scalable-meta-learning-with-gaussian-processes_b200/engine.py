@@ -302,9 +302,9 @@ class Engine:
 
     # ---- conditioning at scale (cross-covariance fused into the prediction kernel) ------- #
     def cond_supported(self, fs: FittedSources, n_t: int) -> bool:
-        """The fused path needs 64-candidate tiles in shared memory (n_max <= 256 at the usual d) and n_t <= 128."""
+        """The A_m-based conditioning kernels cover what the prediction kernel covers (n_max <= 512) and n_t <= 128."""
         b = fs.batch
-        return 0 < n_t <= 128 and b.n_max <= 256 and b.d <= 16
+        return 0 < n_t <= 128 and b.n_max <= 512 and b.d <= 16
 
     def cond_prepare(self, fs: FittedSources, Xt: torch.Tensor) -> torch.Tensor:
         """A [M, n_pad, n_tp] with A_m = K_m^-1 K_m(X_m, X_t): once per set of target inputs."""
@@ -317,6 +317,19 @@ class Engine:
                               b.d, n_t, fs.spec.kernel, self._stream())
         self.launches += 1
         return A
+
+    def cond_caches(self, fs: FittedSources, Xt: torch.Tensor, A: torch.Tensor):
+        """`source_means` [n_t, M] / `source_covs` [n_t, n_t, M] (reference model.py:278-289) from A."""
+        b = fs.batch
+        Xt = Xt.to(torch.float64).contiguous()
+        n_t = Xt.shape[0]
+        mean = torch.empty(n_t, b.M, dtype=torch.float64, device=self.device)
+        cov = torch.empty(n_t, n_t, b.M, dtype=torch.float64, device=self.device)
+        self.lib.cond_caches(_ptr(b.X), _ptr(b.n_valid), _ptr(fs.theta), _ptr(fs.alpha), _ptr(b.ybar), _ptr(b.ystd),
+                             _ptr(Xt), _ptr(A), _ptr(mean), _ptr(cov), b.M, b.n_max, b.d, n_t, fs.spec.kernel,
+                             self._stream())
+        self.launches += 1
+        return mean, cov
 
     def predict_conditioned(self, fs: FittedSources, w: torch.Tensor, Xc: torch.Tensor, Xt: torch.Tensor,
                             A: torch.Tensor):

@@ -203,8 +203,14 @@ class ScaMLGP:
         n_t = train_Y.shape[-2]
         self._Xt = train_X.reshape(n_t, d).to(dev, DT).contiguous()
         # cache the source posteriors at the target inputs (model.py:278-289): one launch for all tasks
+        self._condA: Optional[torch.Tensor] = None  # K_m^-1 K_m(X_m, X_t) of every source task
         if n_t > 0:
-            self.source_means, self.source_covs = self.engine.predict_cross(self._fitted, self._Xt)
+            if self.engine.cond_supported(self._fitted, n_t):
+                # A_m once per model; the caches and every later posterior call are contractions with it
+                self._condA = self.engine.cond_prepare(self._fitted, self._Xt)
+                self.source_means, self.source_covs = self.engine.cond_caches(self._fitted, self._Xt, self._condA)
+            else:
+                self.source_means, self.source_covs = self.engine.predict_cross(self._fitted, self._Xt)
         if covar_module is None:
             covar_module = _get_default_kernel(base_kernel=RBFKernel, ard_num_dims=d)
         self.source_gps = source_gps
@@ -222,7 +228,6 @@ class ScaMLGP:
         self.raw_weights_constraint = GreaterThan(1e-10, transform=None)
         self.training = True
         self._tstate: Optional[TargetState] = None
-        self._condA: Optional[torch.Tensor] = None  # K_m^-1 K_m(X_m, X_t) of every source task (lazy, once per model)
 
     # ---- parameters ------------------------------------------------------------------------- #
     @property

@@ -279,6 +279,11 @@ def test_emu_fused_conditioning_matches_cross_kernel_and_oracle(emu_lib):
             _, c = O.posterior(st, torch.cat([Xc, Xt]), full_cov=True)
             ref += w[m] ** 2 * c[:B, B:]
         assert float((cross - ref).abs().max()) < 1e-9 * float(ref.abs().max())
+    # per-task caches from A_m == the stand-alone cross kernel (reduce = 0)
+    sm0, sc0 = eng.predict_cross(fs, Xt)
+    sm1, sc1 = eng.cond_caches(fs, Xt, A)
+    assert rel_err(sm1.numpy(), sm0.numpy()) < 1e-11
+    assert float((sc1 - sc0).abs().max()) < 1e-10 * float(sc0.abs().max())
     # A_m itself: K_m^-1 K_m(X_m, X_t)
     k = int(pb["nv"][1])
     st = O.factorize(pb["X"][1, :k], pb["Y"][1, :k], th[1], pb["ospec"])

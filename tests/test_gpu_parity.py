@@ -344,3 +344,40 @@ def test_full_size_properties_config5(engine):
     om, ov = O.scaml_prior_predict(states, ws[sel], Xc[:3].cpu())
     assert rel_err(mo.cpu().numpy(), om.numpy()) < TOL_MEAN_VAR
     assert rel_err(vo.cpu().numpy(), ov.numpy()) < TOL_MEAN_VAR
+
+
+@pytest.mark.parametrize("n,d,kernel,nvs,nt", [
+    (256, 6, 0, [256, 130, 64, 7], 80),     # 64-candidate tiles, n_t = 80 (10 column blocks)
+    (512, 10, 0, [512, 400, 1], 20),        # config-4 shape: 32-candidate tiles, aliased staging, 16-wide panels
+    (320, 6, 3, [320, 257, 100], 116),      # Matern-5/2, n_t at the target kernels' limit
+])
+def test_conditioning_from_A_matches_oracle(engine, n, d, kernel, nvs, nt):
+    """scaml_cond_prepare / scaml_cond_caches / scaml_predict_conditioned (cross-covariance fused into the
+    prediction kernel) against the oracle at the shapes the stand-alone cross kernel cannot reach (n > 256)."""
+    M, B = len(nvs), 200
+    pb = make_problem(M, 2, n, d, seed=17, n_valid=nvs, kernel=kernel)
+    batch = _batch(pb)
+    th = pb["th"][:, 1].contiguous()
+    fs = engine.factorize(batch, th.cuda(), pb["cspec"])
+    assert int(fs.info.abs().max()) == 0
+    g = torch.Generator().manual_seed(3)
+    Xc = torch.rand(B, d, dtype=torch.float64, generator=g)
+    Xt = torch.rand(nt, d, dtype=torch.float64, generator=g)
+    w = torch.rand(M, dtype=torch.float64, generator=g)
+    A = engine.cond_prepare(fs, Xt.cuda())
+    pm, pv, cross = engine.predict_conditioned(fs, w.cuda(), Xc.cuda(), Xt.cuda(), A)
+    sm, sc = engine.cond_caches(fs, Xt.cuda(), A)
+    ref_cross = torch.zeros(B, nt, dtype=torch.float64)
+    ref_mean = torch.zeros(B, dtype=torch.float64)
+    scale = 0.0
+    for m in range(M):
+        k = int(pb["nv"][m])
+        st = O.factorize(pb["X"][m, :k], pb["Y"][m, :k], th[m], pb["ospec"])
+        mu, c = O.posterior(st, torch.cat([Xc, Xt]), full_cov=True)
+        ref_cross += w[m] ** 2 * c[:B, B:]
+        ref_mean += w[m] * mu[:B]
+        scale += float(w[m] ** 2 * st.os * st.ystd ** 2)
+        assert rel_err(sm[:, m].cpu().numpy(), mu[B:].numpy()) < TOL_MEAN_VAR
+        assert float((sc[:, :, m].cpu() - c[B:, B:]).abs().max()) < TOL_MEAN_VAR * float(st.os * st.ystd ** 2)
+    assert rel_err(pm.cpu().numpy(), ref_mean.numpy()) < TOL_MEAN_VAR
+    assert float((cross.cpu() - ref_cross).abs().max()) < TOL_MEAN_VAR * scale
