@@ -264,6 +264,24 @@ def measure_fp64_peak(torch, lib_path: str, device) -> dict:
             if rep > 0:
                 best = max(best, flops.value / (ms * 1e-3) / 1e12)
         res[name] = best
+    # library DGEMM for reference ("quote roofline fractions of measured DGEMM / DFMA")
+    try:
+        n = 8192
+        a = torch.randn(n, n, dtype=torch.float64, device=device)
+        b = torch.randn(n, n, dtype=torch.float64, device=device)
+        torch.matmul(a, b)
+        best = 0.0
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize(device)
+            best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        res["cublas_dgemm_8192"] = best
+        del a, b
+    except Exception:
+        res["cublas_dgemm_8192"] = None
     return res
 
 
