@@ -25,6 +25,9 @@ from .modules import (DT, GammaPrior, GaussianLikelihood, GreaterThan, Interval,
 from .utils import validate_meta_data
 
 
+MAX_TARGET_POINTS = 116  # scaml_target_* kernels: K_t and L_t^-1 (n_t x n_t each) live in 227 KB of shared memory
+
+
 # ---- defaults (reference model.py:25-105) ---------------------------------------------------- #
 def _get_default_likelihood(batch_shape: torch.Size = torch.Size()) -> GaussianLikelihood:
     return GaussianLikelihood(noise_prior=LogNormalPrior(-8.0, 2.0), noise_constraint=Interval(1e-8, 1e-2, 1e-3),
@@ -201,6 +204,10 @@ class ScaMLGP:
         self.train_inputs = (train_X,)
         self._train_Y = train_Y
         n_t = train_Y.shape[-2]
+        if n_t > MAX_TARGET_POINTS:
+            raise NotImplementedError(
+                f"{n_t} target observations: the target-GP kernels hold the n_t x n_t system in shared memory and "
+                f"support n_t <= {MAX_TARGET_POINTS} in this release (the reference's experiments use <= 80 evaluations)")
         self._Xt = train_X.reshape(n_t, d).to(dev, DT).contiguous()
         # cache the source posteriors at the target inputs (model.py:278-289): one launch for all tasks
         self._condA: Optional[torch.Tensor] = None  # K_m^-1 K_m(X_m, X_t) of every source task

@@ -100,6 +100,8 @@ def test_model_errors_through_emulation(emu_engine):
     assert torch.allclose(model.weights, torch.full((2,), 0.5, dtype=DT))
     with pytest.raises(NotImplementedError):
         model.posterior(torch.rand(4, 2, 2, dtype=DT))  # q > 1
+    with pytest.raises(NotImplementedError, match="n_t <= 116"):
+        ScaMLGP(torch.rand(117, 2, dtype=DT), torch.rand(117, 1, dtype=DT), gps, engine=emu_engine)
     with pytest.raises(ValueError):
         UpperConfidenceBound(model, maximize=True)
     # all restarts failing -> ModelFittingError (utils.py:207-212): NaN targets poison every row
