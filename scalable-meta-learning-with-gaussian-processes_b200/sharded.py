@@ -129,7 +129,14 @@ class ShardedSources:
 
     def target_caches(self, Xt: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """`source_means` [n_t, M], `source_covs` [n_t, n_t, M] for ALL tasks, gathered along the task axis."""
-        sm, sc = self.engine.predict_cross(self.fitted, Xt)
+        eng = self.engine
+        if eng.cond_supported(self.fitted, Xt.shape[0]):  # from A_m (any n the prediction kernel accepts)
+            key = (Xt.data_ptr(), Xt.shape[0])
+            if self._cond_key != key:
+                self._condA, self._cond_key = eng.cond_prepare(self.fitted, Xt), key
+            sm, sc = eng.cond_caches(self.fitted, Xt, self._condA)
+        else:
+            sm, sc = eng.predict_cross(self.fitted, Xt)
         if self.world == 1:
             return sm, sc
         nt = Xt.shape[0]

@@ -47,7 +47,7 @@ def main():
         ref = fit_sources(eng, batch, spec, th0)
         fs = eng.factorize(batch, ref.theta_raw, spec)
         rm, rv = eng.predict_weighted(fs, w.to(dev), Xc.to(dev))
-        rsm, rsc = eng.predict_cross(fs, Xt)
+        rsm, rsc = eng.cond_caches(fs, Xt, eng.cond_prepare(fs, Xt))
         checks = {
             "theta bitwise": torch.equal(ref.theta_raw, fit.theta_raw),
             "lml bitwise": torch.equal(ref.lml, fit.lml),
