@@ -468,6 +468,19 @@ def scaml_posterior(states, weights, cache: Optional[TargetCache], theta_raw, sp
     return cache.mu_all + cache.s_all * mu, cache.s_all**2 * var
 
 
+def scaml_posterior_grad(states, weights, cache: Optional[TargetCache], theta_raw, spec: HyperSpec,
+                         Xs: torch.Tensor, prune_threshold: Optional[float] = 1e-3):
+    """d mean / d x and d var / d x [B, d] of `scaml_posterior` by autograd -- what botorch's optimize_acqf
+    differentiates when it runs L-BFGS-B on the acquisition function over `ScaMLGP.forward` (eval branch,
+    model.py:364-375; consumer utils.py:215-224).  Every candidate's mean / variance depends on its own row of Xs
+    only (q = 1), so the gradient of the sum over candidates is the per-candidate gradient."""
+    Xg = Xs.clone().requires_grad_(True)
+    mean, var = scaml_posterior(states, weights, cache, theta_raw, spec, Xg, prune_threshold)
+    (dmean,) = torch.autograd.grad(mean.sum(), Xg, retain_graph=True)
+    (dvar,) = torch.autograd.grad(var.sum(), Xg)
+    return mean.detach(), var.detach(), dmean, dvar
+
+
 def ucb(mean: torch.Tensor, var: torch.Tensor, beta: float = 9.0) -> torch.Tensor:
     """reference utils.py:215-224: botorch UCB with maximize=False -> -mu + sqrt(beta var)."""
     return -mean + torch.sqrt(beta * var.clamp_min(1e-9))

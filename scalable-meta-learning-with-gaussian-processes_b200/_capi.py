@@ -104,6 +104,9 @@ EXPORTED_SYMBOLS = (
     "scaml_predict_cross",
     "scaml_target_workspace_bytes",
     "scaml_target_lml_grad",
+    "scaml_target_posterior_beta",
+    "scaml_posterior_grad_workspace_bytes",
+    "scaml_posterior_grad",
     "scaml_target_factorize",
     "scaml_target_posterior",
     "scaml_lbfgs_step",
@@ -158,6 +161,10 @@ class ScamlLib:
         L.scaml_target_factorize.argtypes = ([vp] * 6 + [dbl, dbl, dbl] + [vp] * 6 +
                                              [sz, i32, i32, i32, C.POINTER(CHyperSpec), vp])
         L.scaml_target_posterior.argtypes = [vp] * 8 + [dbl, dbl, vp, vp, i32, i32, i32, i32, vp]
+        L.scaml_target_posterior_beta.argtypes = [vp] * 8 + [dbl, dbl, vp, vp, vp, i32, i32, i32, i32, vp]
+        L.scaml_posterior_grad_workspace_bytes.restype = sz
+        L.scaml_posterior_grad_workspace_bytes.argtypes = [i32, i32, i32]
+        L.scaml_posterior_grad.argtypes = [vp] * 13 + [dbl, vp, vp, vp, sz] + [i32] * 7 + [vp]
         L.scaml_lbfgs_step.argtypes = [C.POINTER(CLbfgsState), vp, vp, vp, vp, i32, i32, i32, i32, dbl, dbl, i32, i32, vp]
         L.scaml_cond_prepare.argtypes = [vp] * 6 + [i32] * 5 + [vp]
         L.scaml_cond_caches.argtypes = [vp] * 10 + [i32] * 5 + [vp]
@@ -228,6 +235,21 @@ class ScamlLib:
         _check(self.lib.scaml_target_posterior(pm, pv, cross, Xc, Xt, theta, linv_t, alpha_t, float(mu_all),
                                                float(s_all), mean, var, B, n_t, d, kernel, stream),
                "scaml_target_posterior")
+
+    def target_posterior_beta(self, pm, pv, cross, Xc, Xt, theta, linv_t, alpha_t, mu_all, s_all, mean, var, beta, B,
+                              n_t, d, kernel, stream=0):
+        _check(self.lib.scaml_target_posterior_beta(pm, pv, cross, Xc, Xt, theta, linv_t, alpha_t, float(mu_all),
+                                                    float(s_all), mean, var, beta, B, n_t, d, kernel, stream),
+               "scaml_target_posterior_beta")
+
+    def posterior_grad_workspace_bytes(self, M: int, d: int, B: int) -> int:
+        return int(self.lib.scaml_posterior_grad_workspace_bytes(M, d, B))
+
+    def posterior_grad(self, X, n_valid, theta, alpha, ystd, w, Xc, U, Xt, A, alpha_t, beta, theta_t, s_all, dmean,
+                       dvar, ws, ws_bytes, M, n_max, d, B, n_t, kernel, kernel_t, stream=0):
+        _check(self.lib.scaml_posterior_grad(X, n_valid, theta, alpha, ystd, w, Xc, U, Xt, A, alpha_t, beta, theta_t,
+                                             float(s_all), dmean, dvar, ws, ws_bytes, M, n_max, d, B, n_t, kernel,
+                                             kernel_t, stream), "scaml_posterior_grad")
 
     def lbfgs_step(self, state: "CLbfgsState", xt, ft, gt, lower, E, D, m, init, gtol, ftol, maxiter, max_ls, stream=0):
         _check(self.lib.scaml_lbfgs_step(C.byref(state), xt, ft, gt, lower, E, D, m, int(init), float(gtol),

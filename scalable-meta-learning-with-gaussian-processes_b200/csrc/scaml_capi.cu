@@ -8,6 +8,7 @@
 #include "scaml_cross.cuh"
 #include "scaml_target.cuh"
 #include "scaml_lbfgs.cuh"
+#include "scaml_grad.cuh"
 
 #ifndef SCAML_EMU
 #include <cuda_runtime.h>
@@ -325,6 +326,51 @@ int scaml_target_posterior(const double* prior_mean, const double* prior_var, co
   p.alpha = alpha_t, p.mean = mean, p.var = var, p.mu_all = mu_all, p.s_all = s_all;
   p.B = B, p.nt = n_t, p.d = d, p.kernel = kernel;
   return scaml::launch_target_posterior(p, num_sms(), stream);
+}
+
+int scaml_target_posterior_beta(const double* prior_mean, const double* prior_var, const double* cross,
+                                const double* Xc, const double* Xt, const double* theta, const double* linv_t,
+                                const double* alpha_t, double mu_all, double s_all, double* mean, double* var,
+                                double* beta, int B, int n_t, int d, int kernel, void* stream) {
+  if (!prior_mean || !prior_var || !cross || !Xc || !Xt || !theta || !linv_t || !alpha_t || !mean || !var || !beta)
+    return SCAML_E_ARG;
+  if (B <= 0 || n_t <= 0 || d <= 0 || kernel < 0 || kernel > 3 || !(s_all > 0.0)) return SCAML_E_ARG;
+  if (d > scaml::kMaxP - 2 || n_t > 128) return SCAML_E_UNSUPPORTED;
+  scaml::TargetPostParams p{};
+  p.pm = prior_mean, p.pv = prior_var, p.cross = cross, p.Xc = Xc, p.Xt = Xt, p.theta = theta, p.linv = linv_t;
+  p.alpha = alpha_t, p.mean = mean, p.var = var, p.beta = beta, p.mu_all = mu_all, p.s_all = s_all;
+  p.B = B, p.nt = n_t, p.d = d, p.kernel = kernel, p.n_tp = scaml::cond_ntp(n_t);
+  return scaml::launch_target_posterior(p, num_sms(), stream);
+}
+
+size_t scaml_posterior_grad_workspace_bytes(int M, int d, int B) {
+  if (M <= 0 || d <= 0 || B <= 0) return 0;
+  const int ntile = (B + scaml::kGradCT - 1) / scaml::kGradCT;
+  return sizeof(double) * (size_t)scaml::grad_nsplit(M, ntile, num_sms()) * (size_t)B * 2 * (size_t)d;
+}
+
+int scaml_posterior_grad(const double* X, const int32_t* n_valid, const double* theta, const double* alpha,
+                         const double* ystd, const double* w, const double* Xc, const double* U, const double* Xt,
+                         const double* A, const double* alpha_t, const double* beta, const double* theta_t,
+                         double s_all, double* dmean, double* dvar, void* workspace, size_t workspace_bytes, int M,
+                         int n_max, int d, int B, int n_t, int kernel, int kernel_t, void* stream) {
+  if (!X || !theta || !alpha || !ystd || !w || !Xc || !U || !dmean || !dvar || !workspace) return SCAML_E_ARG;
+  if (M <= 0 || n_max <= 0 || d <= 0 || B <= 0 || n_t < 0 || kernel < 0 || kernel > 3) return SCAML_E_ARG;
+  if (n_t > 0 && (!Xt || !A || !alpha_t || !beta || !theta_t || !(s_all > 0.0) || kernel_t < 0 || kernel_t > 3))
+    return SCAML_E_ARG;
+  if (d > scaml::kMaxP - 2 || n_t > 128 || B > 128) return SCAML_E_UNSUPPORTED;
+  if (workspace_bytes < scaml_posterior_grad_workspace_bytes(M, d, B)) return SCAML_E_WORKSPACE;
+  scaml::GradParams p{};
+  p.X = X, p.n_valid = n_valid, p.theta = theta, p.alpha = alpha, p.ystd = ystd, p.w = w, p.Xc = Xc, p.U = U;
+  p.Xt = Xt, p.A = A, p.alpha_t = alpha_t, p.beta = beta, p.theta_t = theta_t;
+  p.part = static_cast<double*>(workspace), p.dmean = dmean, p.dvar = dvar;
+  p.s_all = n_t > 0 ? s_all : 1.0;
+  p.M = M, p.n_max = n_max, p.n_pad = pad64(n_max), p.d = d, p.B = B, p.B_p = scaml::cond_ntp(B);
+  p.n_t = n_t, p.n_tp = n_t > 0 ? scaml::cond_ntp(n_t) : 0;
+  p.ntile = (B + scaml::kGradCT - 1) / scaml::kGradCT;
+  p.nsplit = scaml::grad_nsplit(M, p.ntile, num_sms());
+  p.kernel_t = kernel_t;
+  return scaml::launch_posterior_grad(p, kernel, num_sms(), stream);
 }
 
 int scaml_lbfgs_step(const scaml_lbfgs_state* st, double* xt, const double* ft, const double* gt, const double* lower,

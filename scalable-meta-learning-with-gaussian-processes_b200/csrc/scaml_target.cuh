@@ -293,13 +293,14 @@ struct TargetPostParams {
   const double* alpha;  // [nt]
   double* mean;         // [B]
   double* var;          // [B]
+  double* beta;         // optional [B][n_tp]: K_t^-1 k_s (needed by the candidate gradient, scaml_grad.cuh)
   double mu_all, s_all;
-  int B, nt, d, kernel;
+  int B, nt, d, kernel, n_tp;
 };
 constexpr int kPostThreads = 256;
 inline size_t target_post_smem_bytes(int nt, int d) {
   const int ld = nt | 1;
-  return sizeof(double) * ((size_t)nt * ld + (size_t)nt * d + nt + (kPostThreads / 32) * (size_t)(nt + d) + kMaxP);
+  return sizeof(double) * ((size_t)nt * ld + (size_t)nt * d + nt + (kPostThreads / 32) * (size_t)(2 * nt + d) + kMaxP);
 }
 __global__ void __launch_bounds__(kPostThreads) scaml_target_posterior_kernel(const TargetPostParams p) {
   SCAML_DYN_SMEM(double, sm);
@@ -307,8 +308,8 @@ __global__ void __launch_bounds__(kPostThreads) scaml_target_posterior_kernel(co
   double* Li = sm;                        // nt x ld
   double* xt = Li + (size_t)nt * ld;      // [nt][d] scaled
   double* al = xt + (size_t)nt * d;       // nt
-  double* wk = al + nt;                   // per warp: k_s [nt] | x_b scaled [d]
-  double* th = wk + (kPostThreads / 32) * (size_t)(nt + d);
+  double* wk = al + nt;                   // per warp: k_s [nt] | x_b scaled [d] | L_t^-1 k_s [nt]
+  double* th = wk + (kPostThreads / 32) * (size_t)(2 * nt + d);
   if (tid < d + 2) th[tid] = p.theta[tid];
   __syncthreads();
   for (int i = tid; i < nt * nt; i += kPostThreads) Li[(i / nt) * ld + (i % nt)] = p.linv[i];
@@ -316,8 +317,9 @@ __global__ void __launch_bounds__(kPostThreads) scaml_target_posterior_kernel(co
   for (int i = tid; i < nt; i += kPostThreads) al[i] = p.alpha[i];
   __syncthreads();
   const double os = th[d], s2 = p.s_all * p.s_all;
-  double* ks = wk + warp * (size_t)(nt + d);
+  double* ks = wk + warp * (size_t)(2 * nt + d);
   double* xb = ks + nt;
+  double* sv = xb + d;
   const int wpg = kPostThreads / 32;
   for (long long b = (long long)blockIdx.x * wpg + warp; b < p.B; b += (long long)gridDim.x * wpg) {
     __syncwarp();
@@ -341,6 +343,15 @@ __global__ void __launch_bounds__(kPostThreads) scaml_target_posterior_kernel(co
       const double* row = Li + (size_t)i * ld;
       for (int j = 0; j <= i; ++j) s = fma(row[j], ks[j], s);
       ssq = fma(s, s, ssq);
+      sv[i] = s;
+    }
+    if (p.beta != nullptr) {  // beta = L_t^-T (L_t^-1 k_s)
+      __syncwarp();
+      for (int j = lane; j < p.n_tp; j += 32) {
+        double s = 0.0;
+        for (int i = j; i < nt; ++i) s = fma(Li[(size_t)i * ld + j], sv[i], s);
+        p.beta[(size_t)b * p.n_tp + j] = s;
+      }
     }
     dot = warp_sum(dot);
     ssq = warp_sum(ssq);

@@ -148,6 +148,7 @@ class Engine:
         self._pws: Optional[torch.Tensor] = None
         self._cws: Optional[torch.Tensor] = None
         self._tws: Optional[torch.Tensor] = None
+        self._gws: Optional[torch.Tensor] = None
         self.launches = 0  # kernels launched through this engine (bench.py reports it)
 
     # ---- workspaces ------------------------------------------------------------------ #
@@ -432,6 +433,50 @@ class Engine:
                                   ts.kernel, self._stream())
         self.launches += 1
         return mean, var
+
+
+    # ---- f3: analytic candidate gradients (reference: autograd through ScaMLGP.forward, model.py:364-375) ---- #
+    def target_posterior_beta(self, ts: "TargetState", prior_mean, prior_var, cross, Xc):
+        """`target_posterior` plus beta [B, n_tp] = K_t^-1 k_s(x_b), the vector the variance gradient contracts with."""
+        B, d = Xc.shape
+        nt = ts.Xt.shape[0]
+        n_tp = ((nt + 7) // 8) * 8
+        mean = torch.empty(B, dtype=torch.float64, device=self.device)
+        var = torch.empty(B, dtype=torch.float64, device=self.device)
+        beta = torch.empty(B, n_tp, dtype=torch.float64, device=self.device)
+        self.lib.target_posterior_beta(_ptr(prior_mean), _ptr(prior_var), _ptr(cross), _ptr(Xc), _ptr(ts.Xt),
+                                       _ptr(ts.theta), _ptr(ts.linv), _ptr(ts.alpha), ts.mu_all, ts.s_all, _ptr(mean),
+                                       _ptr(var), _ptr(beta), B, nt, d, ts.kernel, self._stream())
+        self.launches += 1
+        return mean, var, beta
+
+    def posterior_grad(self, fs: FittedSources, w: torch.Tensor, Xc: torch.Tensor, U: torch.Tensor,
+                       ts: Optional["TargetState"] = None, A: Optional[torch.Tensor] = None,
+                       beta: Optional[torch.Tensor] = None):
+        """d mean / d x and d var / d x [B, d] of the (un-standardised) ScaML-GP posterior at B <= 128 candidates.
+
+        U = cond_prepare(fs, Xc) (K_m^-1 k*_m of every task); with target data: ts / A / beta from
+        `target_factorize`, `cond_prepare(fs, X_t)` and `target_posterior_beta`; without: the weighted prior."""
+        b = fs.batch
+        B, d = Xc.shape
+        n_t = 0 if ts is None else ts.Xt.shape[0]
+        w = w.to(torch.float64).contiguous()
+        dmean = torch.empty(B, d, dtype=torch.float64, device=self.device)
+        dvar = torch.empty(B, d, dtype=torch.float64, device=self.device)
+        need = self.lib.posterior_grad_workspace_bytes(b.M, d, B)
+        if self._gws is None or self._gws.numel() * 8 < need:
+            self._gws = torch.empty((need + 7) // 8, dtype=torch.float64, device=self.device)
+        if n_t > 0:
+            self.lib.posterior_grad(_ptr(b.X), _ptr(b.n_valid), _ptr(fs.theta), _ptr(fs.alpha), _ptr(b.ystd), _ptr(w),
+                                    _ptr(Xc), _ptr(U), _ptr(ts.Xt), _ptr(A), _ptr(ts.alpha), _ptr(beta), _ptr(ts.theta),
+                                    ts.s_all, _ptr(dmean), _ptr(dvar), _ptr(self._gws), need, b.M, b.n_max, d, B, n_t,
+                                    fs.spec.kernel, ts.kernel, self._stream())
+        else:
+            self.lib.posterior_grad(_ptr(b.X), _ptr(b.n_valid), _ptr(fs.theta), _ptr(fs.alpha), _ptr(b.ystd), _ptr(w),
+                                    _ptr(Xc), _ptr(U), None, None, None, None, None, 1.0, _ptr(dmean), _ptr(dvar),
+                                    _ptr(self._gws), need, b.M, b.n_max, d, B, 0, fs.spec.kernel, 0, self._stream())
+        self.launches += 2
+        return dmean, dvar
 
 
 @dataclass

@@ -359,6 +359,41 @@ class ScaMLGP:
             mean, var = eng.target_posterior(self._target_state(), pm, pv, cross, Xc)
         return Posterior(mean.to(X.device), var.to(X.device))
 
+    def posterior_with_grad(self, X: torch.Tensor):
+        """Posterior mean / variance [B] and their gradients wrt the candidates [B, d] (q = 1), un-standardised.
+
+        What botorch's `optimize_acqf` gets by autograd through `ScaMLGP.forward` (eval branch, model.py:364-375) and
+        the exact prediction strategy; here analytic: K_m^-1 k*_m on the tensor cores (`cond_prepare` at the
+        candidates), then one contraction kernel over all tasks (`csrc/scaml_grad.cuh`)."""
+        eng, dev = self.engine, self.engine.device
+        if X.dim() == 3:
+            if X.shape[-2] != 1:
+                raise NotImplementedError("only q = 1 candidate batches (the acquisition path) are supported")
+            X = X[:, 0, :]
+        b = self._fitted.batch
+        if b.n_max > 512 or b.d > 16:
+            raise NotImplementedError("candidate gradients need n <= 512 points per task and d <= 16")
+        Xall = X.to(dev, DT).contiguous()
+        w = self.pruned_weights()
+        n_t = self.num_train
+        if n_t > 0 and self._condA is None:
+            self._condA = eng.cond_prepare(self._fitted, self._Xt)
+        outs = []
+        for lo in range(0, Xall.shape[0], 128):
+            Xc = Xall[lo:lo + 128].contiguous()
+            U = eng.cond_prepare(self._fitted, Xc)
+            if n_t > 0:
+                ts = self._target_state()
+                pm, pv, cross = eng.predict_conditioned(self._fitted, w, Xc, self._Xt, self._condA)
+                mean, var, beta = eng.target_posterior_beta(ts, pm, pv, cross, Xc)
+                dm, dv = eng.posterior_grad(self._fitted, w, Xc, U, ts, self._condA, beta)
+            else:
+                mean, pv = eng.predict_weighted(self._fitted, w, Xc)
+                var = pv + float(self.covar_module.outputscale)
+                dm, dv = eng.posterior_grad(self._fitted, w, Xc, U)
+            outs.append((mean, var, dm, dv))
+        return tuple(torch.cat([o[i] for o in outs]).to(X.device) for i in range(4))
+
     def _posterior_fused(self, Xc: torch.Tensor, w: torch.Tensor):
         """n_t > 0, q = 1: prior mean / variance and the cross-covariance with the target inputs in ONE prediction
         launch (the k*^T A_m contraction rides on the k* tiles), then the n_t-dimensional conditioning."""

@@ -3,9 +3,10 @@
 The reference derives from blackboxopt's `SingleObjectiveBOTorchOptimizer` (not in its tree, not
 installable here); the few behaviours of that base class the reference relies on and its tests assert
 (`X`, `losses`, `pending_specifications`, `report`, `generate_evaluation_specification`,
-`OptimizerNotReady`) are restated in `_SingleObjectiveBase`.  The acquisition optimiser is batched to
-suit the fused prediction kernel: a large raw-sample screening launch followed by shrinking-box
-local refinement rounds, each round one posterior launch over every start x every perturbation.
+`OptimizerNotReady`) are restated in `_SingleObjectiveBase`.  Two acquisition optimisers: `optimize_acqf_lbfgsb`
+(default; botorch's recipe -- raw-sample screening, then L-BFGS-B over all restarts with the analytic posterior
+gradients of `csrc/scaml_grad.cuh`) and `optimize_acqf_batched` (zeroth order: shrinking-box refinement rounds, each
+one posterior launch over every start x every perturbation; `af_optimizer_kwargs={"method": "batched"}`).
 """
 from __future__ import annotations
 
@@ -45,6 +46,38 @@ def optimize_acqf_batched(af: Callable[[torch.Tensor], torch.Tensor], bounds: np
         best = torch.where(better, bv, best)
         radius = radius * 0.5
     return starts[int(torch.argmax(best))]
+
+
+def optimize_acqf_lbfgsb(af, bounds: np.ndarray, generator: torch.Generator, raw_samples: int = 1024,
+                         num_restarts: int = 32, maxiter: int = 60) -> torch.Tensor:
+    """Maximise af over the box `bounds` [d, 2] (q = 1) the way botorch's `optimize_acqf` does for the reference:
+    raw-sample screening, then scipy L-BFGS-B on the SUM of the acquisition values of all restarts (they are
+    independent, so one optimiser run drives them in lock-step; botorch gen_candidates_scipy) with the analytic
+    gradient of `af.value_and_grad` -- one posterior-with-gradient launch sequence per function evaluation."""
+    from scipy.optimize import minimize
+
+    lo = torch.tensor(bounds[:, 0], dtype=torch.float64)
+    hi = torch.tensor(bounds[:, 1], dtype=torch.float64)
+    d = lo.numel()
+    X0 = lo + (hi - lo) * torch.rand(raw_samples, d, dtype=torch.float64, generator=generator)
+    v0 = af(X0).reshape(-1).cpu()
+    top = torch.topk(v0, min(num_restarts, raw_samples))
+    starts = X0[top.indices].clone()
+    S = starts.shape[0]
+
+    def fun(xflat: np.ndarray):
+        X = torch.from_numpy(xflat.reshape(S, d).copy())
+        val, grad = af.value_and_grad(X)
+        return -float(val.sum()), -grad.cpu().numpy().reshape(-1).astype(np.float64)
+
+    res = minimize(fun, starts.numpy().reshape(-1), jac=True, method="L-BFGS-B",
+                   bounds=[(float(lo[k]), float(hi[k])) for _ in range(S) for k in range(d)],
+                   options=dict(maxiter=int(maxiter)))
+    Xo = torch.minimum(torch.maximum(torch.from_numpy(res.x.reshape(S, d).copy()), lo), hi)
+    # never worse than the best raw sample: score the refined points and the starts together
+    cand = torch.cat([Xo, starts])
+    vals = af(cand).reshape(-1).cpu()
+    return cand[int(torch.argmax(vals))]
 
 
 class _SingleObjectiveBase:
@@ -133,7 +166,13 @@ class _SingleObjectiveBase:
             raise ValueError("Only acquisition functions to be minimized are supported")
         d = len(self.search_space)
         kw = self.af_opt_kwargs
-        if self.search_space.is_all_continuous:
+        method = str(kw.get("method", "lbfgsb" if hasattr(af, "value_and_grad") else "batched"))
+        if self.search_space.is_all_continuous and method == "lbfgsb":
+            x = optimize_acqf_lbfgsb(af, self.search_space.numerical_bounds(), self._gen,
+                                     raw_samples=int(kw.get("raw_samples", 1024)),
+                                     num_restarts=int(kw.get("num_restarts", 32)), maxiter=int(kw.get("maxiter", 60)))
+            configuration = self.search_space.from_numerical(x.numpy())
+        elif self.search_space.is_all_continuous:
             x = optimize_acqf_batched(af, self.search_space.numerical_bounds(), self._gen,
                                       raw_samples=int(kw.get("raw_samples", 4096)),
                                       num_restarts=int(kw.get("num_restarts", 8)), rounds=int(kw.get("rounds", 8)),

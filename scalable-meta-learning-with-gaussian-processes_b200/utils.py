@@ -135,3 +135,12 @@ class UpperConfidenceBound:
         mean = post.mean.reshape(-1)
         var = post.variance.reshape(-1).clamp_min(1e-9)  # botorch: sigma = variance.clamp_min(1e-9).sqrt()
         return -mean + torch.sqrt(self.beta * var)
+
+    def value_and_grad(self, X: torch.Tensor):
+        """Acquisition value [B] and its gradient wrt the candidates [B, d] from the analytic posterior gradients
+        (the reference differentiates the same expression by autograd inside botorch's optimize_acqf)."""
+        mean, var, dmean, dvar = self.model.posterior_with_grad(X)
+        live = var > 1e-9  # clamp_min(1e-9): zero variance gradient below the clamp
+        sig = torch.sqrt(self.beta * var.clamp_min(1e-9))
+        grad = -dmean + (0.5 * self.beta / sig * live.to(sig.dtype)).unsqueeze(-1) * dvar
+        return -mean + sig, grad

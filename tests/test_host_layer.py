@@ -124,6 +124,22 @@ def _pipeline(eng, M, n, d, n_t, B, restarts, fit_options, ragged=False):
     # ---- (5) acquisition value (utils.py:215-224) ----------------------------------------------------------- #
     af = UpperConfidenceBound(model)
     assert rel_err(af(Xc.unsqueeze(1)).numpy(), O.ucb(om, ov).numpy()) < 1e-7
+    # ---- (5b) analytic candidate gradients vs autograd through the oracle (what optimize_acqf differentiates) --- #
+    Xg = Xc[: min(B, 40)]
+    for mdl, args in ((prior_model, (states, w0, None, O.initial_theta_raw(d, tspec), tspec)),
+                      (model, (states, w, cache, th, tspec))):
+        gm, gv, gdm, gdv = mdl.posterior_with_grad(Xg.unsqueeze(1))
+        rm, rv, rdm, rdv = O.scaml_posterior_grad(*args, Xg)
+        assert gdm.shape == Xg.shape and gdv.shape == Xg.shape
+        assert rel_err(gm.numpy(), rm.numpy()) < 1e-8 and float((gv - rv).abs().max()) < 1e-8 * float(rv.abs().max())
+        assert rel_err(gdm.numpy(), rdm.numpy()) < TOL_GRAD, rel_err(gdm.numpy(), rdm.numpy())
+        assert rel_err(gdv.numpy(), rdv.numpy()) < TOL_GRAD, rel_err(gdv.numpy(), rdv.numpy())
+    val, grad = af.value_and_grad(Xg)
+    Xa = Xg.clone().requires_grad_(True)
+    om_a, ov_a = O.scaml_posterior(states, w, cache, th, tspec, Xa)
+    oa = O.ucb(om_a, ov_a)
+    (og,) = torch.autograd.grad(oa.sum(), Xa)
+    assert rel_err(val.numpy(), oa.detach().numpy()) < 1e-7 and rel_err(grad.numpy(), og.numpy()) < 1e-6
     # ---- (6) state_dict round trip (utils.py:169,205) ------------------------------------------------------ #
     sd = model.state_dict()
     model.weights = torch.full((M,), 0.5, dtype=DT)
