@@ -193,15 +193,16 @@ int scaml_target_posterior(const double* prior_mean, const double* prior_var, co
  * U [M][n_pad][B_p] = K_m^-1 K_m(X_m, Xc) is the output of scaml_cond_prepare called with the candidates in the place
  * of the target inputs (B_p = 8*ceil(B/8), B <= 128 per call); A [M][n_pad][n_tp] is scaml_cond_prepare at X_t;
  * theta_t [P] / alpha_t [n_t] are the outputs of scaml_target_factorize.  For n_t = 0 pass NULL for Xt, A, alpha_t,
- * beta, theta_t.  Tasks with w == 0 are skipped (pruning).  The sum over tasks runs in a fixed order
+ * beta, theta_t.  U is CONSUMED when n_t > 0: a DMMA pass replaces it by U - A beta(x_b) in place before the
+ * contraction.  Tasks with w == 0 are skipped (pruning).  The sum over tasks runs in a fixed order
  * (deterministic). */
 int scaml_target_posterior_beta(const double* prior_mean, const double* prior_var, const double* cross,
                                 const double* Xc, const double* Xt, const double* theta, const double* linv_t,
                                 const double* alpha_t, double mu_all, double s_all, double* mean, double* var,
                                 double* beta, int B, int n_t, int d, int kernel, void* stream);
-size_t scaml_posterior_grad_workspace_bytes(int M, int d, int B);
+size_t scaml_posterior_grad_workspace_bytes(int M, int n_max, int d, int B);
 int scaml_posterior_grad(const double* X, const int32_t* n_valid, const double* theta, const double* alpha,
-                         const double* ystd, const double* w, const double* Xc, const double* U, const double* Xt,
+                         const double* ystd, const double* w, const double* Xc, double* U, const double* Xt,
                          const double* A, const double* alpha_t, const double* beta, const double* theta_t,
                          double s_all, double* dmean, double* dvar, void* workspace, size_t workspace_bytes, int M,
                          int n_max, int d, int B, int n_t, int kernel, int kernel_t, void* stream);

@@ -163,7 +163,7 @@ class ScamlLib:
         L.scaml_target_posterior.argtypes = [vp] * 8 + [dbl, dbl, vp, vp, i32, i32, i32, i32, vp]
         L.scaml_target_posterior_beta.argtypes = [vp] * 8 + [dbl, dbl, vp, vp, vp, i32, i32, i32, i32, vp]
         L.scaml_posterior_grad_workspace_bytes.restype = sz
-        L.scaml_posterior_grad_workspace_bytes.argtypes = [i32, i32, i32]
+        L.scaml_posterior_grad_workspace_bytes.argtypes = [i32, i32, i32, i32]
         L.scaml_posterior_grad.argtypes = [vp] * 13 + [dbl, vp, vp, vp, sz] + [i32] * 7 + [vp]
         L.scaml_lbfgs_step.argtypes = [C.POINTER(CLbfgsState), vp, vp, vp, vp, i32, i32, i32, i32, dbl, dbl, i32, i32, vp]
         L.scaml_cond_prepare.argtypes = [vp] * 6 + [i32] * 5 + [vp]
@@ -242,8 +242,8 @@ class ScamlLib:
                                                     float(s_all), mean, var, beta, B, n_t, d, kernel, stream),
                "scaml_target_posterior_beta")
 
-    def posterior_grad_workspace_bytes(self, M: int, d: int, B: int) -> int:
-        return int(self.lib.scaml_posterior_grad_workspace_bytes(M, d, B))
+    def posterior_grad_workspace_bytes(self, M: int, n_max: int, d: int, B: int) -> int:
+        return int(self.lib.scaml_posterior_grad_workspace_bytes(M, n_max, d, B))
 
     def posterior_grad(self, X, n_valid, theta, alpha, ystd, w, Xc, U, Xt, A, alpha_t, beta, theta_t, s_all, dmean,
                        dvar, ws, ws_bytes, M, n_max, d, B, n_t, kernel, kernel_t, stream=0):

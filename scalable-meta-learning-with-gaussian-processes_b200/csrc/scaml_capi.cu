@@ -343,14 +343,15 @@ int scaml_target_posterior_beta(const double* prior_mean, const double* prior_va
   return scaml::launch_target_posterior(p, num_sms(), stream);
 }
 
-size_t scaml_posterior_grad_workspace_bytes(int M, int d, int B) {
-  if (M <= 0 || d <= 0 || B <= 0) return 0;
+size_t scaml_posterior_grad_workspace_bytes(int M, int n_max, int d, int B) {
+  if (M <= 0 || n_max <= 0 || d <= 0 || B <= 0) return 0;
   const int ntile = (B + scaml::kGradCT - 1) / scaml::kGradCT;
-  return sizeof(double) * (size_t)scaml::grad_nsplit(M, ntile, num_sms()) * (size_t)B * 2 * (size_t)d;
+  return sizeof(double) * ((size_t)scaml::grad_nsplit(M, ntile, num_sms()) * (size_t)B * 2 * (size_t)d +
+                           (size_t)M * (size_t)pad64(n_max));
 }
 
 int scaml_posterior_grad(const double* X, const int32_t* n_valid, const double* theta, const double* alpha,
-                         const double* ystd, const double* w, const double* Xc, const double* U, const double* Xt,
+                         const double* ystd, const double* w, const double* Xc, double* U, const double* Xt,
                          const double* A, const double* alpha_t, const double* beta, const double* theta_t,
                          double s_all, double* dmean, double* dvar, void* workspace, size_t workspace_bytes, int M,
                          int n_max, int d, int B, int n_t, int kernel, int kernel_t, void* stream) {
@@ -359,16 +360,18 @@ int scaml_posterior_grad(const double* X, const int32_t* n_valid, const double* 
   if (n_t > 0 && (!Xt || !A || !alpha_t || !beta || !theta_t || !(s_all > 0.0) || kernel_t < 0 || kernel_t > 3))
     return SCAML_E_ARG;
   if (d > scaml::kMaxP - 2 || n_t > 128 || B > 128) return SCAML_E_UNSUPPORTED;
-  if (workspace_bytes < scaml_posterior_grad_workspace_bytes(M, d, B)) return SCAML_E_WORKSPACE;
+  if (workspace_bytes < scaml_posterior_grad_workspace_bytes(M, n_max, d, B)) return SCAML_E_WORKSPACE;
   scaml::GradParams p{};
   p.X = X, p.n_valid = n_valid, p.theta = theta, p.alpha = alpha, p.ystd = ystd, p.w = w, p.Xc = Xc, p.U = U;
   p.Xt = Xt, p.A = A, p.alpha_t = alpha_t, p.beta = beta, p.theta_t = theta_t;
-  p.part = static_cast<double*>(workspace), p.dmean = dmean, p.dvar = dvar;
+  p.dmean = dmean, p.dvar = dvar;
   p.s_all = n_t > 0 ? s_all : 1.0;
   p.M = M, p.n_max = n_max, p.n_pad = pad64(n_max), p.d = d, p.B = B, p.B_p = scaml::cond_ntp(B);
   p.n_t = n_t, p.n_tp = n_t > 0 ? scaml::cond_ntp(n_t) : 0;
   p.ntile = (B + scaml::kGradCT - 1) / scaml::kGradCT;
   p.nsplit = scaml::grad_nsplit(M, p.ntile, num_sms());
+  p.part = static_cast<double*>(workspace);
+  p.aal = p.part + (size_t)p.nsplit * (size_t)B * 2 * (size_t)d;
   p.kernel_t = kernel_t;
   return scaml::launch_posterior_grad(p, kernel, num_sms(), stream);
 }

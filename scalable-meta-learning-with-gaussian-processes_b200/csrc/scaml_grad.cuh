@@ -19,10 +19,11 @@
 // u_m for a tile of candidates is exactly what scaml_cond_prepare computes with the candidates in the place of the
 // target inputs (U = K_m^-1 K_m(X_m, Xc), both triangular products on DMMA), so the n^2 work is done there; the
 // kernels here are the O(n (n_t + d)) contraction per (task, candidate):
+//   scaml_grad_mix_kernel      : U <- U - A_m beta and aal <- A_m alpha_t, a [32 x n_t] x [n_t x B] DMMA product per
+//                                (task, 32-row chunk) with beta^T | alpha_t resident in shared memory;
 //   scaml_grad_contract_kernel : lane <-> candidate (32-candidate tiles), the 8 warps split the rows of a task in
-//                                4-row blocks (4 independent exp chains per thread); A_m is staged in 32-row chunks
-//                                and read as warp-uniform broadcasts; the sum over the tasks of a split stays in
-//                                registers (fixed order), one cross-warp reduction at the end;
+//                                4-row blocks (4 independent exp chains per thread); the sum over the tasks of a
+//                                split stays in registers (fixed order), one cross-warp reduction at the end;
 //   scaml_grad_finish_kernel   : fixed-order sum of the task splits + the target-kernel terms, one warp per candidate.
 #pragma once
 #include "scaml_device.cuh"
@@ -37,7 +38,8 @@ struct GradParams {
   const double* ystd;      // [M]
   const double* w;         // [M] (pruned: 0 -> task skipped)
   const double* Xc;        // [B][d]
-  const double* U;         // [M][n_pad][B_p]  K_m^-1 K_m(X_m, Xc)
+  double* U;               // [M][n_pad][B_p]  in: K_m^-1 K_m(X_m, Xc); the mix kernel turns it into U - A beta in place
+  double* aal;             // [M][n_pad] workspace: A_m alpha_t (n_t > 0)
   const double* Xt;        // [n_t][d]               (n_t > 0)
   const double* A;         // [M][n_pad][n_tp]       (n_t > 0)
   const double* alpha_t;   // [n_t]                  (n_t > 0)
@@ -53,16 +55,19 @@ struct GradParams {
 constexpr int kGradThreads = 256;
 constexpr int kGradWarps = kGradThreads / 32;
 constexpr int kGradCT = 32;  // candidates per tile (lane <-> candidate)
+#ifndef SCAML_GRAD_ROWS
+#define SCAML_GRAD_ROWS 4
+#endif
+constexpr int kGR = SCAML_GRAD_ROWS;  // rows per thread and step = independent exp chains in flight
 
 // shared memory (doubles): xs [max(n_pad, 512)][d] (aliased by red [warps][2 d][32] at the end) | al [n_pad]
-//                          | Ach [32][n_tp] | xts [n_tp][d] | bt [n_tp][32] | at [n_tp] | il2 [kMaxP]
+//                          | xts [n_tp][d] | bt [n_tp][32] | at [n_tp] | il2 [kMaxP]
 #ifndef SCAML_EMU
 __host__ __device__
 #endif
 inline size_t grad_xs_rows(int n_pad) { return n_pad > 2 * 32 * kGradWarps ? n_pad : 2 * 32 * kGradWarps; }
 inline size_t grad_smem_bytes(int n_pad, int d, int n_tp) {
-  return sizeof(double) * (grad_xs_rows(n_pad) * d + n_pad + 32 * (size_t)n_tp + (size_t)n_tp * d +
-                           (size_t)n_tp * 32 + n_tp + kMaxP + 8);
+  return sizeof(double) * (grad_xs_rows(n_pad) * d + n_pad + (size_t)n_tp * d + (size_t)n_tp * 32 + n_tp + kMaxP + 8);
 }
 inline int grad_nsplit(int M, int ntile, int num_sms) {
   int ns = (2 * num_sms + ntile - 1) / ntile;
@@ -71,15 +76,77 @@ inline int grad_nsplit(int M, int ntile, int num_sms) {
   return ns;
 }
 
+// U <- U - A_m beta (all candidates of the call) and aal <- A_m alpha_t: per (task, 32-row chunk) one
+// [32 x n_tp] x [n_tp x (B_p + 8)] product on the FP64 tensor cores (column B_p of the right-hand side is alpha_t).
+// Staged operands are padded to a row stride = 4 (mod 8) doubles (conflict-free DMMA fragment loads).
+constexpr int kMixMaxCB = 9;  // column blocks per warp: (128 + 8) / 8 = 17 over two warp groups
+inline int mix_ldb(int B_p) { return B_p + 8 + 4; }
+inline size_t grad_mix_smem_bytes(int n_tp, int B_p) {
+  return sizeof(double) * ((size_t)n_tp * mix_ldb(B_p) + 32 * (size_t)(n_tp + 4));
+}
+__global__ void __launch_bounds__(kGradThreads) scaml_grad_mix_kernel(const GradParams p) {
+  SCAML_DYN_SMEM(double, sm);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  const int ntp = p.n_tp, nt = p.n_t, Bp = p.B_p, ldb = Bp + 12, lda = ntp + 4, n_pad = p.n_pad;
+  double* bts = sm;                        // [ntp][ldb]: beta^T | alpha_t | 0
+  double* Ach = bts + (size_t)ntp * ldb;   // [32][lda]
+  for (int i = tid; i < ntp * (Bp + 8); i += kGradThreads) {
+    const int j = i / (Bp + 8), c = i - j * (Bp + 8);
+    double v = 0.0;
+    if (j < nt) {
+      if (c < p.B) v = p.beta[(size_t)c * ntp + j];
+      else if (c == Bp) v = p.alpha_t[j];
+    }
+    bts[(size_t)j * ldb + c] = v;
+  }
+  const int nchunk = n_pad / 32, ncb = Bp / 8 + 1;  // column blocks incl. the alpha_t block
+  const int rb = warp & 3, cb0 = warp >> 2;
+  const long long items = (long long)p.M * nchunk;
+  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+    const int m = (int)(it / nchunk), ch = (int)(it - (long long)m * nchunk);
+    const int nv = p.n_valid ? p.n_valid[m] : p.n_max;
+    if (p.w[m] == 0.0 || 32 * ch >= nv) continue;  // uniform over the CTA
+    __syncthreads();  // previous chunk consumed (and bts staged)
+    const double* src = p.A + ((size_t)m * n_pad + 32 * ch) * ntp;
+    for (int i = tid; i < 32 * ntp; i += kGradThreads) Ach[(i / ntp) * lda + (i % ntp)] = src[i];
+    __syncthreads();
+    double acc[kMixMaxCB][2];
+#pragma unroll
+    for (int c = 0; c < kMixMaxCB; ++c) acc[c][0] = acc[c][1] = 0.0;
+    const double* ar = Ach + (size_t)(8 * rb + g) * lda + t4;
+    const double* br = bts + (size_t)t4 * ldb + 8 * cb0 + g;
+    for (int s = 0; s < ntp / 4; ++s) {
+      const double a = ar[4 * s];
+#pragma unroll
+      for (int c = 0; c < kMixMaxCB; ++c)
+        if (cb0 + 2 * c < ncb) dmma884(acc[c], a, br[(size_t)4 * s * ldb + 16 * c]);
+    }
+    const int row = 32 * ch + 8 * rb + g;
+    double* ur = p.U + ((size_t)m * n_pad + row) * Bp;
+#pragma unroll
+    for (int c = 0; c < kMixMaxCB; ++c) {
+      const int cb = cb0 + 2 * c;
+      if (cb < ncb - 1) {
+        double2* q = reinterpret_cast<double2*>(ur + 8 * cb + 2 * t4);
+        double2 v = *q;
+        v.x -= acc[c][0];
+        v.y -= acc[c][1];
+        *q = v;
+      } else if (cb == ncb - 1 && t4 == 0) {
+        p.aal[(size_t)m * n_pad + row] = acc[c][0];
+      }
+    }
+  }
+}
+
 template <int KIND, int DMAX>
 __global__ void __launch_bounds__(kGradThreads, 1) scaml_grad_contract_kernel(const GradParams p) {
   SCAML_DYN_SMEM(double, sm);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int d = p.d, P = d + 2, n_pad = p.n_pad, nt = p.n_t, ntp = p.n_tp;
   double* xs = sm;                               // [n_pad][d] raw inputs of the task
-  double* al = xs + grad_xs_rows(n_pad) * d;     // [n_pad]
-  double* Ach = al + n_pad;                      // [32][ntp]
-  double* xts = Ach + 32 * (size_t)ntp;          // [ntp][d] raw target inputs
+  double* al = xs + grad_xs_rows(n_pad) * d;     // [n_pad] mean coefficient of the training rows
+  double* xts = al + n_pad;                      // [ntp][d] raw target inputs
   double* bt = xts + (size_t)ntp * d;            // [ntp][32] beta of this tile, candidate fastest
   double* at = bt + (size_t)ntp * 32;            // [ntp] alpha_t
   double* il2 = at + ntp;                        // [kMaxP] 1 / l_k^2 of the task
@@ -113,47 +180,28 @@ __global__ void __launch_bounds__(kGradThreads, 1) scaml_grad_contract_kernel(co
       const double os = th[d], sy = p.ystd[m];
       const double cmw = wm * sy, c = cmw * cmw, cS = c / p.s_all;
       const double* Xm = p.X + (size_t)m * p.n_max * d;
-      const double* Um = p.U + (size_t)m * n_pad * p.B_p;
-      const double* Am = nt > 0 ? p.A + (size_t)m * n_pad * ntp : nullptr;
+      const double* Um = p.U + (size_t)m * n_pad * p.B_p;  // already U - A beta when n_t > 0 (mix kernel)
       __syncthreads();  // previous task's xs / al / il2 are no longer read
       for (int i = tid; i < nv * d; i += kGradThreads) xs[i] = Xm[i];
-      for (int i = tid; i < nv; i += kGradThreads) al[i] = p.alpha[(size_t)m * n_pad + i];
+      for (int i = tid; i < nv; i += kGradThreads) {
+        const double a = cmw * p.alpha[(size_t)m * n_pad + i];
+        al[i] = nt > 0 ? a - cS * p.aal[(size_t)m * n_pad + i] : a;
+      }
       if (tid < d) {
         const double l = th[tid];
         il2[tid] = 1.0 / (l * l);
       }
-      const int nchunk = (nv + 31) >> 5;
-      for (int ch = 0; ch < nchunk; ++ch) {
-        __syncthreads();  // staging visible / previous chunk of A consumed
-        if (nt > 0) {
-          const double* src = Am + (size_t)ch * 32 * ntp;  // rows 32 ch .. 32 ch + 31 are contiguous ([n_pad][ntp])
-          for (int i = tid; i < 32 * ntp; i += kGradThreads) Ach[i] = src[i];
-          __syncthreads();
-        }
-        const int r0 = 4 * warp, i0 = 32 * ch + r0;  // this warp: rows i0 .. i0 + 3
-        if (i0 >= nv) continue;                       // no barrier below this point in the chunk
-        double tb[4] = {0.0, 0.0, 0.0, 0.0}, ta[4] = {0.0, 0.0, 0.0, 0.0};
-        if (nt > 0) {
-          const double* a0 = Ach + (size_t)r0 * ntp;
-          for (int j = 0; j < nt; ++j) {
-            const double bj = bt[j * 32 + lane], aj = at[j];
+      __syncthreads();
+      for (int i0 = kGR * warp; i0 < nv; i0 += kGR * kGradWarps) {  // this warp: rows i0 .. i0 + kGR - 1
+        double r2[kGR], kap[kGR], kd[kGR], gm[kGR], gv[kGR];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const double a = a0[u * ntp + j];
-              tb[u] = fma(a, bj, tb[u]);
-              ta[u] = fma(a, aj, ta[u]);
-            }
-          }
-        }
-        double r2[4], kap[4], kd[4], gm[4], gv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kGR; ++u) {
           const int i = i0 + u;
           const bool ok = i < nv;
           const int ic = ok ? i : nv - 1;
           const double uu = Um[(size_t)ic * p.B_p + bc];
-          gm[u] = ok ? cmw * al[ic] - cS * ta[u] : 0.0;
-          gv[u] = ok ? -2.0 * c * (uu - tb[u]) : 0.0;
+          gm[u] = ok ? al[ic] : 0.0;
+          gv[u] = ok ? -2.0 * c * uu : 0.0;
           double s = 0.0;
 #pragma unroll
           for (int k = 0; k < DMAX; ++k)
@@ -163,9 +211,9 @@ __global__ void __launch_bounds__(kGradThreads, 1) scaml_grad_contract_kernel(co
             }
           r2[u] = s;
         }
-        kappa_n<KIND, 4, true>(r2, kap, kd);
+        kappa_n<KIND, kGR, true>(r2, kap, kd);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kGR; ++u) {
           const double f = os * kd[u];
           gm[u] *= f;
           gv[u] *= f;
@@ -175,7 +223,7 @@ __global__ void __launch_bounds__(kGradThreads, 1) scaml_grad_contract_kernel(co
           if (k < d) {
             const double xk = x[k], ik = il2[k];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kGR; ++u) {
               const int ic = (i0 + u < nv) ? i0 + u : nv - 1;
               const double df = (xk - xs[ic * d + k]) * ik;
               accm[k] = fma(gm[u], df, accm[k]);
@@ -324,6 +372,24 @@ int launch_grad_contract_k(const GradParams& p, int grid, size_t smem, void* str
 inline int launch_posterior_grad(GradParams p, int kernel, int num_sms, void* stream) {
   const size_t smem = grad_smem_bytes(p.n_pad, p.d, p.n_tp);
   if (smem > 227 * 1024) return SCAML_E_SMEM;
+  if (p.n_t > 0) {
+    const size_t msm = grad_mix_smem_bytes(p.n_tp, p.B_p);
+    if (msm > 227 * 1024) return SCAML_E_SMEM;
+    const long long mitems = (long long)p.M * (p.n_pad / 32);
+#ifdef SCAML_EMU
+    cuemu::launch(dim3((unsigned)(mitems < 2 ? mitems : 2)), dim3(kGradThreads), msm, scaml_grad_mix_kernel, p);
+#else
+    int per_sm = (int)((227 * 1024) / (msm + 1024));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    const long long mg = mitems < (long long)per_sm * num_sms ? mitems : (long long)per_sm * num_sms;
+    cudaError_t merr = cudaFuncSetAttribute(scaml_grad_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm);
+    if (merr != cudaSuccess) return (int)merr;
+    scaml_grad_mix_kernel<<<(unsigned)mg, kGradThreads, msm, (cudaStream_t)stream>>>(p);
+    merr = cudaGetLastError();
+    if (merr != cudaSuccess) return (int)merr;
+#endif
+  }
   const int items = p.nsplit * p.ntile;
 #ifdef SCAML_EMU
   const int grid = items < 2 ? items : 2;

@@ -456,14 +456,15 @@ class Engine:
         """d mean / d x and d var / d x [B, d] of the (un-standardised) ScaML-GP posterior at B <= 128 candidates.
 
         U = cond_prepare(fs, Xc) (K_m^-1 k*_m of every task); with target data: ts / A / beta from
-        `target_factorize`, `cond_prepare(fs, X_t)` and `target_posterior_beta`; without: the weighted prior."""
+        `target_factorize`, `cond_prepare(fs, X_t)` and `target_posterior_beta`; without: the weighted prior.
+        With target data U is consumed (overwritten by U - A beta)."""
         b = fs.batch
         B, d = Xc.shape
         n_t = 0 if ts is None else ts.Xt.shape[0]
         w = w.to(torch.float64).contiguous()
         dmean = torch.empty(B, d, dtype=torch.float64, device=self.device)
         dvar = torch.empty(B, d, dtype=torch.float64, device=self.device)
-        need = self.lib.posterior_grad_workspace_bytes(b.M, d, B)
+        need = self.lib.posterior_grad_workspace_bytes(b.M, b.n_max, d, B)
         if self._gws is None or self._gws.numel() * 8 < need:
             self._gws = torch.empty((need + 7) // 8, dtype=torch.float64, device=self.device)
         if n_t > 0:

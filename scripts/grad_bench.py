@@ -13,7 +13,9 @@ from scamlgp_b200 import HyperSpec
 from scamlgp_b200.engine import Engine, SourceBatch
 
 M, n, d, nt, B = (int(a) for a in (sys.argv[1:6] + ["4096", "256", "6", "32", "64"][len(sys.argv) - 1:]))
-eng = Engine(torch.device("cuda:0"))
+from scamlgp_b200._capi import ScamlLib
+lib = ScamlLib(os.environ["SCAML_LIB"]) if os.environ.get("SCAML_LIB") else None
+eng = Engine(torch.device("cuda:0"), lib=lib)
 dev = eng.device
 X, Y = O.synthetic_tasks(M, n, d, seed=0)
 batch = SourceBatch.from_padded(X.to(dev), Y.to(dev))
@@ -53,8 +55,8 @@ mean, var, beta = eng.target_posterior_beta(ts, pm, pv, cross, Xc)
 t_u = timed(lambda: eng.cond_prepare(fs, Xc))
 t_p = timed(lambda: eng.predict_conditioned(fs, w, Xc, Xt, A))
 t_b = timed(lambda: eng.target_posterior_beta(ts, pm, pv, cross, Xc))
-t_g = timed(lambda: eng.posterior_grad(fs, w, Xc, U, ts, A, beta))
 t_g0 = timed(lambda: eng.posterior_grad(fs, w, Xc, U))
+t_g = timed(lambda: eng.posterior_grad(fs, w, Xc, U, ts, A, beta))  # consumes U (timing only: U is re-mixed every call)
 print(f"  cond_prepare(Xc)  U = K^-1 k*  (DMMA)    {t_u:8.3f} ms")
 print(f"  predict_conditioned (values + cross)     {t_p:8.3f} ms")
 print(f"  target_posterior_beta                    {t_b:8.3f} ms")

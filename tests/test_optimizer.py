@@ -332,3 +332,39 @@ def test_lbfgsb_acquisition_optimiser_finds_the_box_constrained_maximiser(opt):
     # the zeroth-order search gets close, the gradient search gets there
     xb = optimize_acqf_batched(af, bounds, torch.Generator().manual_seed(0), raw_samples=64, num_restarts=8)
     assert float(af(x.unsqueeze(0))) >= float(af(xb.unsqueeze(0))) - 1e-12
+
+
+@pytest.mark.gpu
+def test_lbfgsb_reaches_a_stationary_point_of_the_real_ucb_surface(engine):
+    """On a fitted ScaML-GP (8 Hartmann-6 meta-tasks, 10 target evaluations) the L-BFGS-B acquisition optimiser
+    ends at a KKT point of UCB on the unit box (projected analytic gradient ~ 0) whose value is at least the
+    zeroth-order search's, with both starting from the same raw samples."""
+    from oracle import scaml_oracle as O
+    from scamlgp_b200.model import ScaMLGP, meta_fit_scamlgp
+    from scamlgp_b200.modules import SupervisedDataset
+    from scamlgp_b200.optimizer import optimize_acqf_batched, optimize_acqf_lbfgsb
+    from scamlgp_b200.utils import optimize_marginal_likelihood
+
+    M, n, d, n_t = 8, 64, 6, 10
+    X, Y = O.synthetic_tasks(M, n, d, seed=21)
+    md = {i: SupervisedDataset(X[i], Y[i].reshape(-1, 1)) for i in range(M)}
+    gps = meta_fit_scamlgp(md, seed=0, engine=engine)
+    g = torch.Generator().manual_seed(3)
+    Xt = torch.rand(n_t, d, dtype=torch.float64, generator=g)
+    Yt = O.hartmann6(Xt, torch.tensor([1.0, 1.2, 3.0, 3.2], dtype=torch.float64)).reshape(-1, 1)
+    model = ScaMLGP(Xt, Yt, gps, engine=engine)
+    optimize_marginal_likelihood(model, 2, generator=torch.Generator().manual_seed(1))
+    model.eval()
+    af = UpperConfidenceBound(model)
+    bounds = np.array([[0.0, 1.0]] * d)
+    xg = optimize_acqf_lbfgsb(af, bounds, torch.Generator().manual_seed(7), raw_samples=512, num_restarts=16, maxiter=100)
+    xb = optimize_acqf_batched(af, bounds, torch.Generator().manual_seed(7), raw_samples=512, num_restarts=16)
+    vg, gg = af.value_and_grad(xg.unsqueeze(0))
+    vb = af(xb.unsqueeze(0))
+    assert float(vg) >= float(vb) - 1e-9 * abs(float(vb)), (float(vg), float(vb))
+    # KKT on the box: gradient component may only point outwards at an active bound
+    gg = gg.reshape(-1).cpu()
+    proj = torch.where((xg <= 1e-12) & (gg < 0), torch.zeros_like(gg), gg)
+    proj = torch.where((xg >= 1 - 1e-12) & (gg > 0), torch.zeros_like(proj), proj)
+    scale = max(1.0, float(af.value_and_grad(torch.rand(64, d, dtype=torch.float64, generator=g))[1].abs().max()))
+    assert float(proj.abs().max()) < 1e-3 * scale, (proj, scale)
