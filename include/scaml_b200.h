@@ -195,7 +195,8 @@ int scaml_target_posterior(const double* prior_mean, const double* prior_var, co
  * theta_t [P] / alpha_t [n_t] are the outputs of scaml_target_factorize.  For n_t = 0 pass NULL for Xt, A, alpha_t,
  * beta, theta_t.  U is CONSUMED when n_t > 0: a DMMA pass replaces it by U - A beta(x_b) in place before the
  * contraction.  Tasks with w == 0 are skipped (pruning).  The sum over tasks runs in a fixed order
- * (deterministic). */
+ * (deterministic).  kernel_t = -1 leaves out the terms of the target kernel itself: with the tasks sharded over
+ * GPUs every rank contracts its block and exactly one rank adds those terms before the all-reduce(sum). */
 int scaml_target_posterior_beta(const double* prior_mean, const double* prior_var, const double* cross,
                                 const double* Xc, const double* Xt, const double* theta, const double* linv_t,
                                 const double* alpha_t, double mu_all, double s_all, double* mean, double* var,
@@ -225,6 +226,12 @@ int scaml_cond_caches(const double* X, const int32_t* n_valid, const double* the
                       double* cov, int M, int n_max, int d, int n_t, int kernel, void* stream);
 int scaml_cond_prepare(const double* X, const int32_t* n_valid, const double* theta, const double* linv_packed,
                        const double* Xt, double* A, int M, int n_max, int d, int n_t, int kernel, void* stream);
+/* scaml_cond_prepare restricted to the tasks with w[m] != 0 (the pruned tasks of `significant_weights_mask`,
+ * reference scamlgp/model.py:192-215,365-372, are skipped; their slices of A are left untouched).  Used for
+ * U = K_m^-1 K_m(X_m, Xc) of scaml_posterior_grad. */
+int scaml_cond_prepare_pruned(const double* X, const int32_t* n_valid, const double* theta,
+                              const double* linv_packed, const double* Xt, const double* w, double* A, int M,
+                              int n_max, int d, int n_t, int kernel, void* stream);
 size_t scaml_predict_conditioned_workspace_bytes(int M, int n_max, int d, int B, int n_t);
 int scaml_predict_conditioned(const double* X, const int32_t* n_valid, const double* theta,
                               const double* linv_packed, const double* alpha, const double* ybar,

@@ -107,6 +107,7 @@ EXPORTED_SYMBOLS = (
     "scaml_target_posterior_beta",
     "scaml_posterior_grad_workspace_bytes",
     "scaml_posterior_grad",
+    "scaml_cond_prepare_pruned",
     "scaml_target_factorize",
     "scaml_target_posterior",
     "scaml_lbfgs_step",
@@ -167,6 +168,7 @@ class ScamlLib:
         L.scaml_posterior_grad.argtypes = [vp] * 13 + [dbl, vp, vp, vp, sz] + [i32] * 7 + [vp]
         L.scaml_lbfgs_step.argtypes = [C.POINTER(CLbfgsState), vp, vp, vp, vp, i32, i32, i32, i32, dbl, dbl, i32, i32, vp]
         L.scaml_cond_prepare.argtypes = [vp] * 6 + [i32] * 5 + [vp]
+        L.scaml_cond_prepare_pruned.argtypes = [vp] * 7 + [i32] * 5 + [vp]
         L.scaml_cond_caches.argtypes = [vp] * 10 + [i32] * 5 + [vp]
         L.scaml_predict_conditioned_workspace_bytes.restype = sz
         L.scaml_predict_conditioned_workspace_bytes.argtypes = [i32] * 5
@@ -258,6 +260,10 @@ class ScamlLib:
     def cond_prepare(self, X, n_valid, theta, linv, Xt, A, M, n_max, d, n_t, kernel, stream=0):
         _check(self.lib.scaml_cond_prepare(X, n_valid, theta, linv, Xt, A, M, n_max, d, n_t, kernel, stream),
                "scaml_cond_prepare")
+
+    def cond_prepare_pruned(self, X, n_valid, theta, linv, Xt, w, A, M, n_max, d, n_t, kernel, stream=0):
+        _check(self.lib.scaml_cond_prepare_pruned(X, n_valid, theta, linv, Xt, w, A, M, n_max, d, n_t, kernel, stream),
+               "scaml_cond_prepare_pruned")
 
     def cond_caches(self, X, n_valid, theta, alpha, ybar, ystd, Xt, A, mean, cov, M, n_max, d, n_t, kernel, stream=0):
         _check(self.lib.scaml_cond_caches(X, n_valid, theta, alpha, ybar, ystd, Xt, A, mean, cov, M, n_max, d, n_t, kernel,

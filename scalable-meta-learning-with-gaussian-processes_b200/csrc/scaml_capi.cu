@@ -357,7 +357,7 @@ int scaml_posterior_grad(const double* X, const int32_t* n_valid, const double* 
                          int n_max, int d, int B, int n_t, int kernel, int kernel_t, void* stream) {
   if (!X || !theta || !alpha || !ystd || !w || !Xc || !U || !dmean || !dvar || !workspace) return SCAML_E_ARG;
   if (M <= 0 || n_max <= 0 || d <= 0 || B <= 0 || n_t < 0 || kernel < 0 || kernel > 3) return SCAML_E_ARG;
-  if (n_t > 0 && (!Xt || !A || !alpha_t || !beta || !theta_t || !(s_all > 0.0) || kernel_t < 0 || kernel_t > 3))
+  if (n_t > 0 && (!Xt || !A || !alpha_t || !beta || !theta_t || !(s_all > 0.0) || kernel_t < -1 || kernel_t > 3))
     return SCAML_E_ARG;
   if (d > scaml::kMaxP - 2 || n_t > 128 || B > 128) return SCAML_E_UNSUPPORTED;
   if (workspace_bytes < scaml_posterior_grad_workspace_bytes(M, n_max, d, B)) return SCAML_E_WORKSPACE;
@@ -396,6 +396,18 @@ int scaml_cond_prepare(const double* X, const int32_t* n_valid, const double* th
   if (d > scaml::kMaxP - 2 || n_t > 128) return SCAML_E_UNSUPPORTED;
   scaml::CondPrepParams p{};
   p.X = X, p.n_valid = n_valid, p.theta = theta, p.linv = linv_packed, p.Xt = Xt, p.A = A;
+  p.M = M, p.n_max = n_max, p.n_pad = pad64(n_max), p.d = d, p.n_t = n_t;
+  return scaml::launch_cond_prepare(p, kernel, num_sms(), stream);
+}
+
+int scaml_cond_prepare_pruned(const double* X, const int32_t* n_valid, const double* theta, const double* linv_packed,
+                              const double* Xt, const double* w, double* A, int M, int n_max, int d, int n_t,
+                              int kernel, void* stream) {
+  if (!X || !theta || !linv_packed || !Xt || !w || !A) return SCAML_E_ARG;
+  if (M <= 0 || n_max <= 0 || d <= 0 || n_t <= 0 || kernel < 0 || kernel > 3) return SCAML_E_ARG;
+  if (d > scaml::kMaxP - 2 || n_t > 128) return SCAML_E_UNSUPPORTED;
+  scaml::CondPrepParams p{};
+  p.X = X, p.n_valid = n_valid, p.theta = theta, p.linv = linv_packed, p.Xt = Xt, p.skip_w = w, p.A = A;
   p.M = M, p.n_max = n_max, p.n_pad = pad64(n_max), p.d = d, p.n_t = n_t;
   return scaml::launch_cond_prepare(p, kernel, num_sms(), stream);
 }

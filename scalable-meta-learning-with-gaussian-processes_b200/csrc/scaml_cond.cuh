@@ -24,6 +24,7 @@ struct CondPrepParams {
   const double* theta;  // [M][P] constrained
   const double* linv;   // packed C-layout tiles
   const double* Xt;     // [n_t][d]
+  const double* skip_w; // optional [M]: tasks with skip_w[m] == 0 are left untouched (pruned tasks)
   double* A;            // [M][n_pad][n_tp]
   int M, n_max, n_pad, d, n_t, n_tp, pw, npanel;
 };
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_cond_prepare_kernel(con
   const int items = p.M * p.npanel;
   for (int it = blockIdx.x; it < items; it += gridDim.x) {
     const int m = it / p.npanel, pn = it - m * p.npanel;
+    if (p.skip_w != nullptr && p.skip_w[m] == 0.0) continue;  // uniform over the CTA
     const int j0 = pn * pw;
     const int njt = ((p.n_tp - j0 < pw ? p.n_tp - j0 : pw) + 7) / 8;  // 8-column blocks of this panel
     const int nv = p.n_valid ? p.n_valid[m] : p.n_max;

@@ -192,6 +192,12 @@ __global__ void __launch_bounds__(kGradThreads, 1) scaml_grad_contract_kernel(co
         il2[tid] = 1.0 / (l * l);
       }
       __syncthreads();
+      double un[kGR];  // U of the next row block, in flight under the current block's exponentials
+#pragma unroll
+      for (int u = 0; u < kGR; ++u) {
+        const int i = kGR * warp + u;
+        un[u] = Um[(size_t)(i < nv ? i : nv - 1) * p.B_p + bc];
+      }
       for (int i0 = kGR * warp; i0 < nv; i0 += kGR * kGradWarps) {  // this warp: rows i0 .. i0 + kGR - 1
         double r2[kGR], kap[kGR], kd[kGR], gm[kGR], gv[kGR];
 #pragma unroll
@@ -199,7 +205,9 @@ __global__ void __launch_bounds__(kGradThreads, 1) scaml_grad_contract_kernel(co
           const int i = i0 + u;
           const bool ok = i < nv;
           const int ic = ok ? i : nv - 1;
-          const double uu = Um[(size_t)ic * p.B_p + bc];
+          const double uu = un[u];
+          const int inx = i + kGR * kGradWarps;
+          un[u] = Um[(size_t)(inx < nv ? inx : nv - 1) * p.B_p + bc];
           gm[u] = ok ? al[ic] : 0.0;
           gv[u] = ok ? -2.0 * c * uu : 0.0;
           double s = 0.0;
@@ -291,12 +299,13 @@ __global__ void __launch_bounds__(kGradThreads, 1) scaml_grad_contract_kernel(co
 }
 
 // dmean[b][k] = sum_split part + S s_t sum_j alpha_t[j] dkappa_t/dx_k ;  dvar[b][k] = sum_split part - 2 S^2 s_t sum_j beta[b][j] dkappa_t/dx_k
-__global__ void __launch_bounds__(256) scaml_grad_finish_kernel(const GradParams p) {
+__global__ void __launch_bounds__(64) scaml_grad_finish_kernel(const GradParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, d = p.d, nt = p.n_t;
   const int wpg = blockDim.x >> 5;
   for (long long b = (long long)blockIdx.x * wpg + warp; b < p.B; b += (long long)gridDim.x * wpg) {
     double gmj[4] = {0.0, 0.0, 0.0, 0.0}, gvj[4] = {0.0, 0.0, 0.0, 0.0};
-    if (nt > 0) {
+    const bool tterms = nt > 0 && p.kernel_t >= 0;  // kernel_t < 0: task-sharded partial sums, another rank adds them
+    if (tterms) {
       const double os = p.theta_t[d], S = p.s_all;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -321,7 +330,7 @@ __global__ void __launch_bounds__(256) scaml_grad_finish_kernel(const GradParams
     }
     for (int k = 0; k < d; ++k) {
       double sm_ = 0.0, sv_ = 0.0;
-      if (nt > 0) {
+      if (tterms) {
         const double l = p.theta_t[k], il2 = 1.0 / (l * l);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -335,12 +344,14 @@ __global__ void __launch_bounds__(256) scaml_grad_finish_kernel(const GradParams
         sm_ = -warp_sum(sm_);
         sv_ = -warp_sum(sv_);
       }
+      double am = 0.0, av = 0.0;  // lanes stride over the task splits, then a fixed-order warp tree
+      for (int s = lane; s < p.nsplit; s += 32) {
+        am += p.part[((size_t)s * p.B + b) * 2 * d + k];
+        av += p.part[((size_t)s * p.B + b) * 2 * d + d + k];
+      }
+      am = warp_sum(am);
+      av = warp_sum(av);
       if (lane == 0) {
-        double am = 0.0, av = 0.0;
-        for (int s = 0; s < p.nsplit; ++s) {
-          am += p.part[((size_t)s * p.B + b) * 2 * d + k];
-          av += p.part[((size_t)s * p.B + b) * 2 * d + d + k];
-        }
         p.dmean[(size_t)b * d + k] = am + sm_;
         p.dvar[(size_t)b * d + k] = av + sv_;
       }
@@ -404,13 +415,13 @@ inline int launch_posterior_grad(GradParams p, int kernel, int num_sms, void* st
     default: rc = launch_grad_contract_k<SCAML_KERNEL_MATERN52>(p, grid, smem, stream); break;
   }
   if (rc) return rc;
-  long long gx = ((long long)p.B + 7) / 8;
+  long long gx = ((long long)p.B + 1) / 2;  // one warp per candidate, two warps per CTA
 #ifdef SCAML_EMU
-  cuemu::launch(dim3((unsigned)(gx < 2 ? gx : 2)), dim3(256), 0, scaml_grad_finish_kernel, p);
+  cuemu::launch(dim3((unsigned)(gx < 2 ? gx : 2)), dim3(64), 0, scaml_grad_finish_kernel, p);
   return 0;
 #else
   if (gx > 4LL * num_sms) gx = 4LL * num_sms;
-  scaml_grad_finish_kernel<<<(unsigned)gx, 256, 0, (cudaStream_t)stream>>>(p);
+  scaml_grad_finish_kernel<<<(unsigned)gx, 64, 0, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 #endif
 }

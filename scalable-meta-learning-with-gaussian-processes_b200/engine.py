@@ -307,15 +307,21 @@ class Engine:
         b = fs.batch
         return 0 < n_t <= 128 and b.n_max <= 512 and b.d <= 16
 
-    def cond_prepare(self, fs: FittedSources, Xt: torch.Tensor) -> torch.Tensor:
-        """A [M, n_pad, n_tp] with A_m = K_m^-1 K_m(X_m, X_t): once per set of target inputs."""
+    def cond_prepare(self, fs: FittedSources, Xt: torch.Tensor, w: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """A [M, n_pad, n_tp] with A_m = K_m^-1 K_m(X_m, X_t): once per set of target inputs.  With w given, tasks
+        with w == 0 (pruned) are skipped and their slices stay zero."""
         b = fs.batch
         Xt = Xt.to(torch.float64).contiguous()
         n_t = Xt.shape[0]
         n_tp = ((n_t + 7) // 8) * 8
         A = torch.zeros(b.M, pad64(b.n_max), n_tp, dtype=torch.float64, device=self.device)
-        self.lib.cond_prepare(_ptr(b.X), _ptr(b.n_valid), _ptr(fs.theta), _ptr(fs.linv), _ptr(Xt), _ptr(A), b.M, b.n_max,
-                              b.d, n_t, fs.spec.kernel, self._stream())
+        if w is not None:
+            w = w.to(torch.float64).contiguous()
+            self.lib.cond_prepare_pruned(_ptr(b.X), _ptr(b.n_valid), _ptr(fs.theta), _ptr(fs.linv), _ptr(Xt), _ptr(w),
+                                         _ptr(A), b.M, b.n_max, b.d, n_t, fs.spec.kernel, self._stream())
+        else:
+            self.lib.cond_prepare(_ptr(b.X), _ptr(b.n_valid), _ptr(fs.theta), _ptr(fs.linv), _ptr(Xt), _ptr(A), b.M,
+                                  b.n_max, b.d, n_t, fs.spec.kernel, self._stream())
         self.launches += 1
         return A
 
@@ -452,12 +458,13 @@ class Engine:
 
     def posterior_grad(self, fs: FittedSources, w: torch.Tensor, Xc: torch.Tensor, U: torch.Tensor,
                        ts: Optional["TargetState"] = None, A: Optional[torch.Tensor] = None,
-                       beta: Optional[torch.Tensor] = None):
+                       beta: Optional[torch.Tensor] = None, target_terms: bool = True):
         """d mean / d x and d var / d x [B, d] of the (un-standardised) ScaML-GP posterior at B <= 128 candidates.
 
         U = cond_prepare(fs, Xc) (K_m^-1 k*_m of every task); with target data: ts / A / beta from
         `target_factorize`, `cond_prepare(fs, X_t)` and `target_posterior_beta`; without: the weighted prior.
-        With target data U is consumed (overwritten by U - A beta)."""
+        With target data U is consumed (overwritten by U - A beta).  target_terms=False leaves out the target-kernel
+        terms (task-sharded partial sums: only one rank may add them)."""
         b = fs.batch
         B, d = Xc.shape
         n_t = 0 if ts is None else ts.Xt.shape[0]
@@ -471,7 +478,7 @@ class Engine:
             self.lib.posterior_grad(_ptr(b.X), _ptr(b.n_valid), _ptr(fs.theta), _ptr(fs.alpha), _ptr(b.ystd), _ptr(w),
                                     _ptr(Xc), _ptr(U), _ptr(ts.Xt), _ptr(A), _ptr(ts.alpha), _ptr(beta), _ptr(ts.theta),
                                     ts.s_all, _ptr(dmean), _ptr(dvar), _ptr(self._gws), need, b.M, b.n_max, d, B, n_t,
-                                    fs.spec.kernel, ts.kernel, self._stream())
+                                    fs.spec.kernel, ts.kernel if target_terms else -1, self._stream())
         else:
             self.lib.posterior_grad(_ptr(b.X), _ptr(b.n_valid), _ptr(fs.theta), _ptr(fs.alpha), _ptr(b.ystd), _ptr(w),
                                     _ptr(Xc), _ptr(U), None, None, None, None, None, 1.0, _ptr(dmean), _ptr(dvar),

@@ -381,7 +381,7 @@ class ScaMLGP:
         outs = []
         for lo in range(0, Xall.shape[0], 128):
             Xc = Xall[lo:lo + 128].contiguous()
-            U = eng.cond_prepare(self._fitted, Xc)
+            U = eng.cond_prepare(self._fitted, Xc, w)  # pruned tasks skipped
             if n_t > 0:
                 ts = self._target_state()
                 pm, pv, cross = eng.predict_conditioned(self._fitted, w, Xc, self._Xt, self._condA)

@@ -171,3 +171,43 @@ class ShardedSources:
             pm, pv = self.predict_weighted(w, Xc)
             _, cross = self.predict_cross(w, Xc, tstate.Xt)
         return eng.target_posterior(tstate, pm.contiguous(), pv.contiguous(), cross.contiguous(), Xc)
+
+    def posterior_with_grad(self, w: torch.Tensor, Xc: torch.Tensor, tstate: Optional[TargetState] = None,
+                            prior_outputscale: float = 0.0):
+        """`posterior` plus the analytic gradients d mean / dx, d var / dx [B, d] (B <= 128 candidates per call).
+
+        Every rank contracts its own block of tasks (csrc/scaml_grad.cuh); the target-kernel terms are added on rank
+        0 only, so ONE all_reduce(sum) over [B, 2 d] gives the full gradient (the values need the [B, 2 + n_t]
+        all_reduce of `posterior` first: beta depends on the cross-covariance over ALL tasks)."""
+        eng = self.engine
+        Xc = Xc.to(eng.device, DT).contiguous()
+        wl = self._local_w(w)
+        has_tasks = self.hi > self.lo
+        U = eng.cond_prepare(self.fitted, Xc, wl) if has_tasks else None
+        d = Xc.shape[1]
+        if tstate is None:
+            mean, var = self.posterior(w, Xc, None, prior_outputscale)
+            if has_tasks:
+                dm, dv = eng.posterior_grad(self.fitted, wl, Xc, U)
+            else:
+                dm, dv = torch.zeros_like(Xc), torch.zeros_like(Xc)
+        else:
+            n_t = tstate.Xt.shape[0]
+            if not eng.cond_supported(self.fitted, n_t):
+                raise NotImplementedError("candidate gradients need n <= 512 points per task, d <= 16, n_t <= 128")
+            key = (tstate.Xt.data_ptr(), n_t)
+            if self._cond_key != key:
+                self._condA, self._cond_key = eng.cond_prepare(self.fitted, tstate.Xt), key
+            pm, pv, cross = eng.predict_conditioned(self.fitted, wl, Xc, tstate.Xt, self._condA)
+            if self.world > 1:
+                flat = torch.cat([pm.unsqueeze(1), pv.unsqueeze(1), cross], dim=1).contiguous()
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+                pm, pv, cross = flat[:, 0].contiguous(), flat[:, 1].contiguous(), flat[:, 2:].contiguous()
+            mean, var, beta = eng.target_posterior_beta(tstate, pm, pv, cross, Xc)
+            dm, dv = eng.posterior_grad(self.fitted, wl, Xc, U, tstate, self._condA, beta,
+                                        target_terms=(self.rank == 0))
+        if self.world > 1:
+            g = torch.cat([dm, dv], dim=1).contiguous()
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+            dm, dv = g[:, :d].contiguous(), g[:, d:].contiguous()
+        return mean, var, dm, dv

@@ -30,7 +30,10 @@ def _case(eng, M, n, d, B, nt, nvs, kernel, kernel_t, w, seed=3):
     otspec, ctspec = O.HyperSpec.target(kernel_t), HyperSpec.target(kernel_t)
     tht = O.initial_theta_raw(d, otspec) + 0.3 * torch.randn(d + 2, dtype=DT, generator=g)
     Xcd, wd = Xc.to(dev), w.to(dev)
-    U = eng.cond_prepare(fs, Xcd)
+    U = eng.cond_prepare(fs, Xcd, wd)  # pruned tasks (w == 0) are skipped: their slices stay zero
+    for m in range(M):
+        if float(w[m]) == 0.0:
+            assert float(U[m].abs().max()) == 0.0
     # ---- prior only (n_t = 0): gradient of sum_m w_m mu_m and sum_m w_m^2 var_m ------------------------------------ #
     dm, dv = eng.posterior_grad(fs, wd, Xcd, U)
     _, _, rdm, rdv = O.scaml_posterior_grad(states, w, None, tht, otspec, Xc, None)

@@ -48,8 +48,11 @@ def _run(engine, group):
     sm, sc = src.target_caches(Xt)
     ts = engine.target_factorize(sm, sc, Xt, yt, w, O.initial_theta_raw(D, O.HyperSpec.target()), 0.1, 1.3, tspec)
     mean, var = src.posterior(w, Xc, ts)
+    # analytic candidate gradients: local contraction per rank, target-kernel terms on rank 0, one all_reduce
+    gmean, gvar, dm, dv = src.posterior_with_grad(w, Xc, ts)
+    _, _, dm0, dv0 = src.posterior_with_grad(w, Xc, None, prior_outputscale=0.1)
     return dict(theta=fit.theta_raw, lml=fit.lml, ystd=src.ystd_all, pm=pm.clone(), pv=pv.clone(), sm=sm, sc=sc,
-                mean=mean, var=var)
+                mean=mean, var=var, gmean=gmean, gvar=gvar, dm=dm, dv=dv, dm0=dm0, dv0=dv0)
 
 
 def _worker(rank, world, port, out_dir):
@@ -85,6 +88,7 @@ def test_two_rank_gloo_matches_single_process(emu_lib, tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     r0 = torch.load(os.path.join(tmp_path, "rank0.pt"))
     r1 = torch.load(os.path.join(tmp_path, "rank1.pt"))
+    assert torch.equal(single["gmean"], single["mean"]) and torch.equal(single["gvar"], single["var"])
     for k in single:
         # every rank ends with the same replicated result ...
         assert torch.equal(r0[k], r1[k]), k
