@@ -442,7 +442,7 @@ def run_ours(args) -> None:
 
         def step_grad():
             U = eng.cond_prepare(fs, Xg)
-            a_, b_, c_ = eng.predict_conditioned(fs, w, Xg, Xt, A)
+            a_, b_, c_ = eng.values_from_u(fs, w, Xg, U, Xt, A)
             _, _, beta = eng.target_posterior_beta(tstate, a_, b_, c_, Xg)
             return eng.posterior_grad(fs, w, Xg, U, tstate, A, beta)
 
@@ -473,7 +473,7 @@ def run_ours(args) -> None:
                              "value": float(M) * Bg * world * 3 / (ms_g * 1e-3), "unit": "(task, candidate) gradients/s",
                              "finite": grad_finite,
                              "what": "posterior value + analytic d mean/dx, d var/dx (conditioned on n_t target points): "
-                                     "cond_prepare at the candidates, fused prediction, beta, gradient contraction"},
+                                     "cond_prepare at the candidates, values from U, beta, DMMA mix, gradient contraction"},
                 "roofline": {"bound": "tensor", "pipe": "FP64 tensor cores (DMMA)", "achieved": ach, "unit": "TFLOP/s", "flops_per_point": Fp,
                              "traffic": ncu_traffic("scaml_predict_kernel<RBF>"),
                              "traffic_unit": "DRAM bytes per launch (ncu)",

@@ -208,6 +208,18 @@ int scaml_posterior_grad(const double* X, const int32_t* n_valid, const double* 
                          double s_all, double* dmean, double* dvar, void* workspace, size_t workspace_bytes, int M,
                          int n_max, int d, int B, int n_t, int kernel, int kernel_t, void* stream);
 
+/* The same quantities as scaml_predict_conditioned (weighted prior mean [B], variance [B], cross-covariance with the
+ * target inputs [B][n_t]; reference scamlgp/model.py:364-375, q = 1) computed from U = K_m^-1 K_m(X_m, Xc) instead of a
+ * second pass over the packed factors: mean = sum w (ybar + ystd k*^T alpha), var = sum c (s - k*^T u),
+ * cross = sum c (K_m(x, x_tj) - k*^T A_m[:, j]).  The value half of a value-and-gradient evaluation (call it BEFORE
+ * scaml_posterior_grad, which consumes U).  B <= 128; n_t = 0: pass NULL for Xt, A, cross. */
+size_t scaml_posterior_values_from_u_workspace_bytes(int M, int B, int n_t);
+int scaml_posterior_values_from_u(const double* X, const int32_t* n_valid, const double* theta, const double* alpha,
+                                  const double* ybar, const double* ystd, const double* w, const double* Xc,
+                                  const double* U, const double* Xt, const double* A, double* mean, double* var,
+                                  double* cross, void* workspace, size_t workspace_bytes, int M, int n_max, int d,
+                                  int B, int n_t, int kernel, void* stream);
+
 /* Conditioning at scale.  scaml_cond_prepare: A_m = K_m^-1 K_m(X_m, X_t) for every source task, A [M][n_pad][n_tp]
  * with n_pad = 64*ceil(n_max/64), n_tp = 8*ceil(n_t/8) (rows >= n_valid and columns >= n_t are zero; the caller
  * zero-initialises A).  It depends only on the fitted source GPs and the target inputs: once per

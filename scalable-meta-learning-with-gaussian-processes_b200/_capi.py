@@ -108,6 +108,8 @@ EXPORTED_SYMBOLS = (
     "scaml_posterior_grad_workspace_bytes",
     "scaml_posterior_grad",
     "scaml_cond_prepare_pruned",
+    "scaml_posterior_values_from_u_workspace_bytes",
+    "scaml_posterior_values_from_u",
     "scaml_target_factorize",
     "scaml_target_posterior",
     "scaml_lbfgs_step",
@@ -166,6 +168,9 @@ class ScamlLib:
         L.scaml_posterior_grad_workspace_bytes.restype = sz
         L.scaml_posterior_grad_workspace_bytes.argtypes = [i32, i32, i32, i32]
         L.scaml_posterior_grad.argtypes = [vp] * 13 + [dbl, vp, vp, vp, sz] + [i32] * 7 + [vp]
+        L.scaml_posterior_values_from_u_workspace_bytes.restype = sz
+        L.scaml_posterior_values_from_u_workspace_bytes.argtypes = [i32, i32, i32]
+        L.scaml_posterior_values_from_u.argtypes = [vp] * 15 + [sz] + [i32] * 6 + [vp]
         L.scaml_lbfgs_step.argtypes = [C.POINTER(CLbfgsState), vp, vp, vp, vp, i32, i32, i32, i32, dbl, dbl, i32, i32, vp]
         L.scaml_cond_prepare.argtypes = [vp] * 6 + [i32] * 5 + [vp]
         L.scaml_cond_prepare_pruned.argtypes = [vp] * 7 + [i32] * 5 + [vp]
@@ -252,6 +257,15 @@ class ScamlLib:
         _check(self.lib.scaml_posterior_grad(X, n_valid, theta, alpha, ystd, w, Xc, U, Xt, A, alpha_t, beta, theta_t,
                                              float(s_all), dmean, dvar, ws, ws_bytes, M, n_max, d, B, n_t, kernel,
                                              kernel_t, stream), "scaml_posterior_grad")
+
+    def posterior_values_from_u_workspace_bytes(self, M: int, B: int, n_t: int) -> int:
+        return int(self.lib.scaml_posterior_values_from_u_workspace_bytes(M, B, n_t))
+
+    def posterior_values_from_u(self, X, n_valid, theta, alpha, ybar, ystd, w, Xc, U, Xt, A, mean, var, cross, ws,
+                                ws_bytes, M, n_max, d, B, n_t, kernel, stream=0):
+        _check(self.lib.scaml_posterior_values_from_u(X, n_valid, theta, alpha, ybar, ystd, w, Xc, U, Xt, A, mean, var,
+                                                      cross, ws, ws_bytes, M, n_max, d, B, n_t, kernel, stream),
+               "scaml_posterior_values_from_u")
 
     def lbfgs_step(self, state: "CLbfgsState", xt, ft, gt, lower, E, D, m, init, gtol, ftol, maxiter, max_ls, stream=0):
         _check(self.lib.scaml_lbfgs_step(C.byref(state), xt, ft, gt, lower, E, D, m, int(init), float(gtol),

@@ -17,7 +17,7 @@ CUDA_LIB = os.path.join(CSRC, "libscaml_b200.so")
 EMU_LIB = os.path.join(CSRC, "libscaml_emu.so")
 
 CUDA_SOURCES = ["scaml_capi.cu", "scaml_microbench.cu"]
-HEADERS = ["scaml_device.cuh", "scaml_fit.cuh", "scaml_fit8.cuh", "scaml_kmat.cuh", "scaml_predict.cuh", "scaml_cond.cuh", "scaml_cross.cuh", "scaml_target.cuh", "scaml_lbfgs.cuh", "scaml_grad.cuh", "scaml_tile256.cuh",
+HEADERS = ["scaml_device.cuh", "scaml_fit.cuh", "scaml_fit8.cuh", "scaml_kmat.cuh", "scaml_predict.cuh", "scaml_cond.cuh", "scaml_cross.cuh", "scaml_target.cuh", "scaml_lbfgs.cuh", "scaml_grad.cuh", "scaml_gradval.cuh", "scaml_tile256.cuh",
            os.path.join("emu", "cuda_emu.h"), os.path.join("..", "..", "include", "scaml_b200.h")]
 
 NVCC_FLAGS = [

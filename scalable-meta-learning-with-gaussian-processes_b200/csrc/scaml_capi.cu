@@ -9,6 +9,7 @@
 #include "scaml_target.cuh"
 #include "scaml_lbfgs.cuh"
 #include "scaml_grad.cuh"
+#include "scaml_gradval.cuh"
 
 #ifndef SCAML_EMU
 #include <cuda_runtime.h>
@@ -374,6 +375,40 @@ int scaml_posterior_grad(const double* X, const int32_t* n_valid, const double* 
   p.aal = p.part + (size_t)p.nsplit * (size_t)B * 2 * (size_t)d;
   p.kernel_t = kernel_t;
   return scaml::launch_posterior_grad(p, kernel, num_sms(), stream);
+}
+
+size_t scaml_posterior_values_from_u_workspace_bytes(int M, int B, int n_t) {
+  if (M <= 0 || B <= 0 || n_t < 0) return 0;
+  const int ntile = (B + scaml::kGvCT - 1) / scaml::kGvCT;
+  const size_t ns = (size_t)scaml::gradval_nsplit(M, ntile, num_sms());
+  return sizeof(double) * ns * (size_t)B * ((size_t)scaml::cond_ntp(n_t) + 2);
+}
+
+int scaml_posterior_values_from_u(const double* X, const int32_t* n_valid, const double* theta, const double* alpha,
+                                  const double* ybar, const double* ystd, const double* w, const double* Xc,
+                                  const double* U, const double* Xt, const double* A, double* mean, double* var,
+                                  double* cross, void* workspace, size_t workspace_bytes, int M, int n_max, int d,
+                                  int B, int n_t, int kernel, void* stream) {
+  if (!X || !theta || !alpha || !ybar || !ystd || !w || !Xc || !U || !mean || !var || !workspace) return SCAML_E_ARG;
+  if (M <= 0 || n_max <= 0 || d <= 0 || B <= 0 || n_t < 0 || kernel < 0 || kernel > 3) return SCAML_E_ARG;
+  if (n_t > 0 && (!Xt || !A || !cross)) return SCAML_E_ARG;
+  if (d > scaml::kMaxP - 2 || n_t > 128 || B > 128) return SCAML_E_UNSUPPORTED;
+  if (workspace_bytes < scaml_posterior_values_from_u_workspace_bytes(M, B, n_t)) return SCAML_E_WORKSPACE;
+  scaml::GradValParams p{};
+  p.X = X, p.n_valid = n_valid, p.theta = theta, p.alpha = alpha, p.ybar = ybar, p.ystd = ystd, p.w = w, p.Xc = Xc;
+  p.U = U, p.A = A, p.mean = mean, p.var = var;
+  p.M = M, p.n_max = n_max, p.n_pad = pad64(n_max), p.d = d, p.B = B, p.B_p = scaml::cond_ntp(B);
+  p.n_t = n_t, p.n_tp = n_t > 0 ? scaml::cond_ntp(n_t) : 0;
+  p.ntile = (B + scaml::kGvCT - 1) / scaml::kGvCT;
+  p.nsplit = scaml::gradval_nsplit(M, p.ntile, num_sms());
+  p.cxp = static_cast<double*>(workspace);
+  p.mvp = p.cxp + (size_t)p.nsplit * (size_t)B * (size_t)p.n_tp;
+  int rc = scaml::launch_grad_values(p, kernel, num_sms(), stream);
+  if (rc != 0 || n_t == 0) return rc;
+  scaml::CondCombineParams c{};
+  c.theta = theta, c.ystd = ystd, c.w = w, c.Xc = Xc, c.Xt = Xt, c.cxp = p.cxp, c.cross = cross;
+  c.M = M, c.d = d, c.B = B, c.n_t = n_t, c.n_tp = p.n_tp, c.nsplit = p.nsplit;
+  return scaml::launch_cond_combine(c, kernel, stream);
 }
 
 int scaml_lbfgs_step(const scaml_lbfgs_state* st, double* xt, const double* ft, const double* gt, const double* lower,

@@ -149,6 +149,7 @@ class Engine:
         self._cws: Optional[torch.Tensor] = None
         self._tws: Optional[torch.Tensor] = None
         self._gws: Optional[torch.Tensor] = None
+        self._vws: Optional[torch.Tensor] = None
         self.launches = 0  # kernels launched through this engine (bench.py reports it)
 
     # ---- workspaces ------------------------------------------------------------------ #
@@ -455,6 +456,27 @@ class Engine:
                                        _ptr(var), _ptr(beta), B, nt, d, ts.kernel, self._stream())
         self.launches += 1
         return mean, var, beta
+
+    def values_from_u(self, fs: FittedSources, w: torch.Tensor, Xc: torch.Tensor, U: torch.Tensor,
+                      Xt: Optional[torch.Tensor] = None, A: Optional[torch.Tensor] = None):
+        """Weighted prior mean [B], variance [B] (and cross-covariance [B, n_t] when Xt / A are given) from
+        U = cond_prepare(fs, Xc): the quantities of `predict_conditioned` without a second pass over the factors."""
+        b = fs.batch
+        B, d = Xc.shape
+        n_t = 0 if Xt is None else Xt.shape[0]
+        w = w.to(torch.float64).contiguous()
+        mean = torch.empty(B, dtype=torch.float64, device=self.device)
+        var = torch.empty(B, dtype=torch.float64, device=self.device)
+        cross = torch.empty(B, n_t, dtype=torch.float64, device=self.device) if n_t > 0 else None
+        need = self.lib.posterior_values_from_u_workspace_bytes(b.M, B, n_t)
+        if self._vws is None or self._vws.numel() * 8 < need:
+            self._vws = torch.empty((need + 7) // 8, dtype=torch.float64, device=self.device)
+        self.lib.posterior_values_from_u(_ptr(b.X), _ptr(b.n_valid), _ptr(fs.theta), _ptr(fs.alpha), _ptr(b.ybar),
+                                         _ptr(b.ystd), _ptr(w), _ptr(Xc), _ptr(U), _ptr(Xt), _ptr(A), _ptr(mean), _ptr(var),
+                                         _ptr(cross), _ptr(self._vws), need, b.M, b.n_max, d, B, n_t, fs.spec.kernel,
+                                         self._stream())
+        self.launches += 3 if n_t > 0 else 2
+        return mean, var, cross
 
     def posterior_grad(self, fs: FittedSources, w: torch.Tensor, Xc: torch.Tensor, U: torch.Tensor,
                        ts: Optional["TargetState"] = None, A: Optional[torch.Tensor] = None,

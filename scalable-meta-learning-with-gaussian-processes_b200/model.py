@@ -364,7 +364,8 @@ class ScaMLGP:
 
         What botorch's `optimize_acqf` gets by autograd through `ScaMLGP.forward` (eval branch, model.py:364-375) and
         the exact prediction strategy; here analytic: K_m^-1 k*_m on the tensor cores (`cond_prepare` at the
-        candidates), then one contraction kernel over all tasks (`csrc/scaml_grad.cuh`)."""
+        candidates), the values from it (`csrc/scaml_gradval.cuh`), then the gradient contraction over all tasks
+        (`csrc/scaml_grad.cuh`)."""
         eng, dev = self.engine, self.engine.device
         if X.dim() == 3:
             if X.shape[-2] != 1:
@@ -384,11 +385,11 @@ class ScaMLGP:
             U = eng.cond_prepare(self._fitted, Xc, w)  # pruned tasks skipped
             if n_t > 0:
                 ts = self._target_state()
-                pm, pv, cross = eng.predict_conditioned(self._fitted, w, Xc, self._Xt, self._condA)
+                pm, pv, cross = eng.values_from_u(self._fitted, w, Xc, U, self._Xt, self._condA)
                 mean, var, beta = eng.target_posterior_beta(ts, pm, pv, cross, Xc)
                 dm, dv = eng.posterior_grad(self._fitted, w, Xc, U, ts, self._condA, beta)
             else:
-                mean, pv = eng.predict_weighted(self._fitted, w, Xc)
+                mean, pv, _ = eng.values_from_u(self._fitted, w, Xc, U)
                 var = pv + float(self.covar_module.outputscale)
                 dm, dv = eng.posterior_grad(self._fitted, w, Xc, U)
             outs.append((mean, var, dm, dv))

@@ -182,15 +182,16 @@ class ShardedSources:
         eng = self.engine
         Xc = Xc.to(eng.device, DT).contiguous()
         wl = self._local_w(w)
-        has_tasks = self.hi > self.lo
-        U = eng.cond_prepare(self.fitted, Xc, wl) if has_tasks else None
+        U = eng.cond_prepare(self.fitted, Xc, wl)
         d = Xc.shape[1]
         if tstate is None:
-            mean, var = self.posterior(w, Xc, None, prior_outputscale)
-            if has_tasks:
-                dm, dv = eng.posterior_grad(self.fitted, wl, Xc, U)
-            else:
-                dm, dv = torch.zeros_like(Xc), torch.zeros_like(Xc)
+            pm, pv, _ = eng.values_from_u(self.fitted, wl, Xc, U)
+            if self.world > 1:
+                flat = torch.stack([pm, pv]).contiguous()
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+                pm, pv = flat[0].contiguous(), flat[1].contiguous()
+            mean, var = pm, pv + prior_outputscale
+            dm, dv = eng.posterior_grad(self.fitted, wl, Xc, U)
         else:
             n_t = tstate.Xt.shape[0]
             if not eng.cond_supported(self.fitted, n_t):
@@ -198,7 +199,7 @@ class ShardedSources:
             key = (tstate.Xt.data_ptr(), n_t)
             if self._cond_key != key:
                 self._condA, self._cond_key = eng.cond_prepare(self.fitted, tstate.Xt), key
-            pm, pv, cross = eng.predict_conditioned(self.fitted, wl, Xc, tstate.Xt, self._condA)
+            pm, pv, cross = eng.values_from_u(self.fitted, wl, Xc, U, tstate.Xt, self._condA)
             if self.world > 1:
                 flat = torch.cat([pm.unsqueeze(1), pv.unsqueeze(1), cross], dim=1).contiguous()
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)

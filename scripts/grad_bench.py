@@ -54,14 +54,19 @@ pm, pv, cross = eng.predict_conditioned(fs, w, Xc, Xt, A)
 mean, var, beta = eng.target_posterior_beta(ts, pm, pv, cross, Xc)
 t_u = timed(lambda: eng.cond_prepare(fs, Xc))
 t_p = timed(lambda: eng.predict_conditioned(fs, w, Xc, Xt, A))
+t_v = timed(lambda: eng.values_from_u(fs, w, Xc, U, Xt, A))
+vm, vv, vc = eng.values_from_u(fs, w, Xc, U, Xt, A)
+print(f"  values_from_u vs predict_conditioned: mean {float((vm - pm).abs().max() / pm.abs().max()):.1e} "
+      f"var {float((vv - pv).abs().max() / pv.abs().max()):.1e} cross {float((vc - cross).abs().max() / cross.abs().max()):.1e}")
 t_b = timed(lambda: eng.target_posterior_beta(ts, pm, pv, cross, Xc))
 t_g0 = timed(lambda: eng.posterior_grad(fs, w, Xc, U))
 t_g = timed(lambda: eng.posterior_grad(fs, w, Xc, U, ts, A, beta))  # consumes U (timing only: U is re-mixed every call)
 print(f"  cond_prepare(Xc)  U = K^-1 k*  (DMMA)    {t_u:8.3f} ms")
-print(f"  predict_conditioned (values + cross)     {t_p:8.3f} ms")
+print(f"  predict_conditioned (values + cross)     {t_p:8.3f} ms   (not on the gradient path any more)")
+print(f"  values_from_u (mean, var, cross from U)  {t_v:8.3f} ms")
 print(f"  target_posterior_beta                    {t_b:8.3f} ms")
 print(f"  posterior_grad (contract + finish)       {t_g:8.3f} ms   (prior only: {t_g0:.3f} ms)")
-tot = t_u + t_p + t_b + t_g
+tot = t_u + t_v + t_b + t_g
 print(f"  value + gradient at {B} candidates        {tot:8.3f} ms  = {M * B / tot * 1e3 / 1e6:.1f} M (task, candidate) gradients/s")
 # 2 d + 1 central finite-difference evaluations through the value path would need
 t_fd = timed(lambda: eng.predict_conditioned(fs, w, Xc.repeat(2 * d + 1, 1).contiguous(), Xt, A))

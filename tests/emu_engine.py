@@ -15,7 +15,7 @@ class EmuEngine(Engine):
     def __init__(self, lib):
         self.device = torch.device("cpu")
         self.lib = lib
-        self._ws = self._pws = self._cws = self._tws = self._gws = None
+        self._ws = self._pws = self._cws = self._tws = self._gws = self._vws = None
         self.launches = 0
 
     def _stream(self) -> int:

@@ -34,6 +34,11 @@ def _case(eng, M, n, d, B, nt, nvs, kernel, kernel_t, w, seed=3):
     for m in range(M):
         if float(w[m]) == 0.0:
             assert float(U[m].abs().max()) == 0.0
+    # ---- values from U (no second pass over the factors) == the prediction kernel ---------------------------------- #
+    pm0, pv0 = eng.predict_weighted(fs, wd, Xcd)
+    vm, vv, _ = eng.values_from_u(fs, wd, Xcd, U)
+    assert rel_err(vm.cpu().numpy(), pm0.cpu().numpy()) < 1e-11
+    assert float((vv - pv0).abs().max()) < 1e-10 * float(pv0.abs().max())
     # ---- prior only (n_t = 0): gradient of sum_m w_m mu_m and sum_m w_m^2 var_m ------------------------------------ #
     dm, dv = eng.posterior_grad(fs, wd, Xcd, U)
     _, _, rdm, rdv = O.scaml_posterior_grad(states, w, None, tht, otspec, Xc, None)
@@ -52,6 +57,10 @@ def _case(eng, M, n, d, B, nt, nvs, kernel, kernel_t, w, seed=3):
                               cache.mu_all, cache.s_all, ctspec)
     assert ts.info == 0
     pm, pv, cross = eng.predict_conditioned(fs, wd, Xcd, Xtd, A)
+    vm, vv, vc = eng.values_from_u(fs, wd, Xcd, U, Xtd, A)
+    assert rel_err(vm.cpu().numpy(), pm.cpu().numpy()) < 1e-11
+    assert float((vv - pv).abs().max()) < 1e-10 * float(pv.abs().max())
+    assert float((vc - cross).abs().max()) < 1e-10 * float(cross.abs().max())
     mean0, var0 = eng.target_posterior(ts, pm, pv, cross, Xcd)
     mean, var, beta = eng.target_posterior_beta(ts, pm, pv, cross, Xcd)
     assert torch.equal(mean, mean0) and torch.equal(var, var0)  # the beta output does not disturb the values

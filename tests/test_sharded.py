@@ -88,7 +88,9 @@ def test_two_rank_gloo_matches_single_process(emu_lib, tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     r0 = torch.load(os.path.join(tmp_path, "rank0.pt"))
     r1 = torch.load(os.path.join(tmp_path, "rank1.pt"))
-    assert torch.equal(single["gmean"], single["mean"]) and torch.equal(single["gvar"], single["var"])
+    # the value half of posterior_with_grad comes from U (no second pass over the factors): same numbers to rounding
+    assert float((single["gmean"] - single["mean"]).abs().max()) <= 1e-11 * float(single["mean"].abs().max())
+    assert float((single["gvar"] - single["var"]).abs().max()) <= 1e-10 * float(single["var"].abs().max())
     for k in single:
         # every rank ends with the same replicated result ...
         assert torch.equal(r0[k], r1[k]), k
