@@ -244,6 +244,9 @@ int scaml_cond_prepare(const double* X, const int32_t* n_valid, const double* th
 int scaml_cond_prepare_pruned(const double* X, const int32_t* n_valid, const double* theta,
                               const double* linv_packed, const double* Xt, const double* w, double* A, int M,
                               int n_max, int d, int n_t, int kernel, void* stream);
+/* Number of task splits the direct term sum_m c_m K_m(x_b, x_tj) of the cross-covariance is summed over (> 1 for
+ * small candidate batches, where one CTA per 256 (b, j) pairs would leave the GPU idle; one more launch then). */
+int scaml_cond_combine_task_splits(int M, int B, int n_t);
 size_t scaml_predict_conditioned_workspace_bytes(int M, int n_max, int d, int B, int n_t);
 int scaml_predict_conditioned(const double* X, const int32_t* n_valid, const double* theta,
                               const double* linv_packed, const double* alpha, const double* ybar,

@@ -108,6 +108,7 @@ EXPORTED_SYMBOLS = (
     "scaml_posterior_grad_workspace_bytes",
     "scaml_posterior_grad",
     "scaml_cond_prepare_pruned",
+    "scaml_cond_combine_task_splits",
     "scaml_posterior_values_from_u_workspace_bytes",
     "scaml_posterior_values_from_u",
     "scaml_target_factorize",
@@ -175,6 +176,7 @@ class ScamlLib:
         L.scaml_cond_prepare.argtypes = [vp] * 6 + [i32] * 5 + [vp]
         L.scaml_cond_prepare_pruned.argtypes = [vp] * 7 + [i32] * 5 + [vp]
         L.scaml_cond_caches.argtypes = [vp] * 10 + [i32] * 5 + [vp]
+        L.scaml_cond_combine_task_splits.argtypes = [i32, i32, i32]
         L.scaml_predict_conditioned_workspace_bytes.restype = sz
         L.scaml_predict_conditioned_workspace_bytes.argtypes = [i32] * 5
         L.scaml_predict_conditioned.argtypes = [vp] * 15 + [sz] + [i32] * 6 + [vp]
@@ -282,6 +284,9 @@ class ScamlLib:
     def cond_caches(self, X, n_valid, theta, alpha, ybar, ystd, Xt, A, mean, cov, M, n_max, d, n_t, kernel, stream=0):
         _check(self.lib.scaml_cond_caches(X, n_valid, theta, alpha, ybar, ystd, Xt, A, mean, cov, M, n_max, d, n_t, kernel,
                                           stream), "scaml_cond_caches")
+
+    def cond_combine_task_splits(self, M: int, B: int, n_t: int) -> int:
+        return int(self.lib.scaml_cond_combine_task_splits(M, B, n_t))
 
     def predict_conditioned_workspace_bytes(self, M, n_max, d, B, n_t) -> int:
         return int(self.lib.scaml_predict_conditioned_workspace_bytes(M, n_max, d, B, n_t))

@@ -381,7 +381,8 @@ size_t scaml_posterior_values_from_u_workspace_bytes(int M, int B, int n_t) {
   if (M <= 0 || B <= 0 || n_t < 0) return 0;
   const int ntile = (B + scaml::kGvCT - 1) / scaml::kGvCT;
   const size_t ns = (size_t)scaml::gradval_nsplit(M, ntile, num_sms());
-  return sizeof(double) * ns * (size_t)B * ((size_t)scaml::cond_ntp(n_t) + 2);
+  return sizeof(double) * (ns * (size_t)B * ((size_t)scaml::cond_ntp(n_t) + 2) +
+                           (n_t > 0 ? scaml::comb_dpart_doubles(M, B, n_t, num_sms()) : 0));
 }
 
 int scaml_posterior_values_from_u(const double* X, const int32_t* n_valid, const double* theta, const double* alpha,
@@ -408,6 +409,8 @@ int scaml_posterior_values_from_u(const double* X, const int32_t* n_valid, const
   scaml::CondCombineParams c{};
   c.theta = theta, c.ystd = ystd, c.w = w, c.Xc = Xc, c.Xt = Xt, c.cxp = p.cxp, c.cross = cross;
   c.M = M, c.d = d, c.B = B, c.n_t = n_t, c.n_tp = p.n_tp, c.nsplit = p.nsplit;
+  c.ntsplit = scaml::comb_ntsplit(M, B, n_t, num_sms());
+  c.dpart = p.mvp + (size_t)p.nsplit * (size_t)B * 2;
   return scaml::launch_cond_combine(c, kernel, stream);
 }
 
@@ -459,13 +462,19 @@ int scaml_cond_caches(const double* X, const int32_t* n_valid, const double* the
   return scaml::launch_cond_caches(p, kernel, num_sms(), stream);
 }
 
+int scaml_cond_combine_task_splits(int M, int B, int n_t) {
+  if (M <= 0 || B <= 0 || n_t <= 0) return 0;
+  return scaml::comb_ntsplit(M, B, n_t, num_sms());
+}
+
 size_t scaml_predict_conditioned_workspace_bytes(int M, int n_max, int d, int B, int n_t) {
   if (M <= 0 || n_max <= 0 || d <= 0 || B <= 0 || n_t <= 0) return 0;
   int ct = 64, alias = 0;
   if (!scaml::predict_config(pad64(n_max), d, &ct, &alias)) return 0;
   const int ns = scaml::predict_nsplit(M, B, num_sms(), ct);
   const size_t pv = ns > 1 ? sizeof(double) * 2 * (size_t)ns * (size_t)B : 0;
-  return pv + sizeof(double) * (size_t)ns * (size_t)B * (size_t)scaml::cond_ntp(n_t);
+  return pv + sizeof(double) * ((size_t)ns * (size_t)B * (size_t)scaml::cond_ntp(n_t) +
+                                scaml::comb_dpart_doubles(M, B, n_t, num_sms()));
 }
 
 int scaml_predict_conditioned(const double* X, const int32_t* n_valid, const double* theta, const double* linv_packed,
@@ -491,6 +500,8 @@ int scaml_predict_conditioned(const double* X, const int32_t* n_valid, const dou
   scaml::CondCombineParams c{};
   c.theta = theta, c.ystd = ystd, c.w = w, c.Xc = Xc, c.Xt = Xt, c.cxp = cxp, c.cross = cross;
   c.M = M, c.d = d, c.B = B, c.n_t = n_t, c.n_tp = n_tp, c.nsplit = ns;
+  c.ntsplit = scaml::comb_ntsplit(M, B, n_t, num_sms());
+  c.dpart = cxp + (size_t)ns * (size_t)B * (size_t)n_tp;
   return scaml::launch_cond_combine(c, kernel, stream);
 }
 

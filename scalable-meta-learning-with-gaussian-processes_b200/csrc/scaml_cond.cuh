@@ -14,6 +14,8 @@
 // Before: scaml_predict_cross(reduce = 1) recomputed L^-1 K(X_m, X_t) for every 32-candidate tile and took 9x
 // the time of the prior prediction (722 ms vs 80 ms for 4096 tasks x 4096 candidates).
 #pragma once
+#include <cstdlib>
+
 #include "scaml_predict.cuh"
 
 namespace scaml {
@@ -199,6 +201,9 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_cond_prepare_kernel(con
 }
 
 // cross[b][j] = sum_m c_m os_m kappa_m(x_b, x_tj) - sum_s cxp[s][b][j],  c_m = w_m^2 ystd_m^2 (tasks with w = 0 skipped)
+// With few (candidate, target) pairs the sum over the M tasks is split over `ntsplit` CTAs per pair block (partials in
+// dpart, summed in a fixed order by scaml_cond_combine_finish_kernel): at 64 candidates x 32 target points the
+// unsplit kernel ran on 8 CTAs and took 1.4 ms for 4096 tasks -- half of a small-batch posterior call.
 struct CondCombineParams {
   const double* theta;
   const double* ystd;
@@ -207,10 +212,26 @@ struct CondCombineParams {
   const double* Xt;   // [n_t][d]
   const double* cxp;  // [nsplit][B][n_tp]
   double* cross;      // [B][n_t]
-  int M, d, B, n_t, n_tp, nsplit;
+  double* dpart;      // [ntsplit][B][n_t] (ntsplit > 1)
+  int M, d, B, n_t, n_tp, nsplit, ntsplit;
 };
 
 constexpr int kCombTasks = 32;
+inline int comb_ntsplit(int M, int B, int n_t, int num_sms) {
+  const long long nblk = ((long long)B * n_t + 255) / 256;
+  long long ns = (2LL * num_sms) / nblk;
+  const long long cap = (M + 4 * kCombTasks - 1) / (4 * kCombTasks);  // at least 128 tasks per split
+  if (ns > cap) ns = cap;
+  if (const char* env = getenv("SCAML_COMB_TSPLIT")) {  // test knob: force the split path at tiny sizes
+    const int v = atoi(env);
+    if (v >= 1) ns = v < M ? v : M;
+  }
+  return ns < 1 ? 1 : (int)ns;
+}
+inline size_t comb_dpart_doubles(int M, int B, int n_t, int num_sms) {
+  const int ns = comb_ntsplit(M, B, n_t, num_sms);
+  return ns > 1 ? (size_t)ns * (size_t)B * (size_t)n_t : 0;
+}
 
 template <int KIND>
 __global__ void __launch_bounds__(256) scaml_cond_combine_kernel(const CondCombineParams p) {
@@ -219,18 +240,21 @@ __global__ void __launch_bounds__(256) scaml_cond_combine_kernel(const CondCombi
   double* invl = sm + kCombTasks;
   const int d = p.d, P = d + 2;
   const long long pairs = (long long)p.B * p.n_t;
-  for (long long base = (long long)blockIdx.x * blockDim.x; base < pairs; base += (long long)gridDim.x * blockDim.x) {
-    const long long pr = base + threadIdx.x;
+  const long long nblk = (pairs + blockDim.x - 1) / blockDim.x;
+  for (long long item = blockIdx.x; item < nblk * p.ntsplit; item += gridDim.x) {
+    const int ts = (int)(item / nblk);
+    const long long pr = (item - (long long)ts * nblk) * blockDim.x + threadIdx.x;
+    const int m_lo = (int)((long long)p.M * ts / p.ntsplit), m_hi = (int)((long long)p.M * (ts + 1) / p.ntsplit);
     const bool live = pr < pairs;
     const int b = live ? (int)(pr / p.n_t) : 0, j = live ? (int)(pr - (long long)b * p.n_t) : 0;
     double dx[kMaxP];
     for (int k = 0; k < d; ++k) dx[k] = p.Xc[(size_t)b * d + k] - p.Xt[(size_t)j * d + k];
     double acc = 0.0;
-    for (int m0 = 0; m0 < p.M; m0 += kCombTasks) {
+    for (int m0 = m_lo; m0 < m_hi; m0 += kCombTasks) {
       __syncthreads();
       for (int i = threadIdx.x; i < kCombTasks * (d + 1); i += blockDim.x) {
         const int mm = i / (d + 1), k = i - mm * (d + 1), m = m0 + mm;
-        if (m < p.M) {
+        if (m < m_hi) {
           const double* th = p.theta + (size_t)m * P;
           if (k == d) {
             const double wy = p.w[m] * p.ystd[m];
@@ -263,10 +287,26 @@ __global__ void __launch_bounds__(256) scaml_cond_combine_kernel(const CondCombi
       }
     }
     if (live) {
-      double sub = 0.0;
-      for (int s = 0; s < p.nsplit; ++s) sub += p.cxp[((size_t)s * p.B + b) * p.n_tp + j];
-      p.cross[(size_t)b * p.n_t + j] = acc - sub;
+      if (p.ntsplit > 1) {
+        p.dpart[(size_t)ts * pairs + pr] = acc;
+      } else {
+        double sub = 0.0;
+        for (int s = 0; s < p.nsplit; ++s) sub += p.cxp[((size_t)s * p.B + b) * p.n_tp + j];
+        p.cross[(size_t)b * p.n_t + j] = acc - sub;
+      }
     }
+  }
+}
+
+// ntsplit > 1: cross = (sum of the task-split partials, fixed order) - (sum of the fused partials, fixed order)
+__global__ void __launch_bounds__(256) scaml_cond_combine_finish_kernel(const CondCombineParams p) {
+  const long long pairs = (long long)p.B * p.n_t;
+  for (long long pr = (long long)blockIdx.x * blockDim.x + threadIdx.x; pr < pairs; pr += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(pr / p.n_t), j = (int)(pr - (long long)b * p.n_t);
+    double acc = 0.0, sub = 0.0;
+    for (int t = 0; t < p.ntsplit; ++t) acc += p.dpart[(size_t)t * pairs + pr];
+    for (int s = 0; s < p.nsplit; ++s) sub += p.cxp[((size_t)s * p.B + b) * p.n_tp + j];
+    p.cross[(size_t)b * p.n_t + j] = acc - sub;
   }
 }
 
@@ -426,14 +466,20 @@ template <int KIND>
 int launch_cond_combine_k(const CondCombineParams& p, void* stream) {
   const size_t smem = sizeof(double) * kCombTasks * (p.d + 1);
   const long long pairs = (long long)p.B * p.n_t;
-  long long blocks = (pairs + 255) / 256;
+  long long blocks = ((pairs + 255) / 256) * p.ntsplit;
 #ifdef SCAML_EMU
   (void)stream;
   cuemu::launch(dim3((unsigned)(blocks < 2 ? blocks : 2)), dim3(256), smem, scaml_cond_combine_kernel<KIND>, p);
+  if (p.ntsplit > 1) cuemu::launch(dim3(1), dim3(256), 0, scaml_cond_combine_finish_kernel, p);
   return 0;
 #else
   if (blocks > 148 * 8) blocks = 148 * 8;
   scaml_cond_combine_kernel<KIND><<<(int)blocks, 256, smem, (cudaStream_t)stream>>>(p);
+  int rc = (int)cudaGetLastError();
+  if (rc || p.ntsplit <= 1) return rc;
+  long long fb = (pairs + 255) / 256;
+  if (fb > 148 * 8) fb = 148 * 8;
+  scaml_cond_combine_finish_kernel<<<(int)fb, 256, 0, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 #endif
 }

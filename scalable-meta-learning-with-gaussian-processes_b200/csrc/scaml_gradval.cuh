@@ -47,8 +47,8 @@ inline size_t gradval_smem_bytes(int d, int n_tp) {
                            4 * kGvCT + 8);
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(kGvThreads) scaml_grad_values_kernel(const GradValParams p) {
+template <int KIND, int NCB>
+__global__ void __launch_bounds__(kGvThreads, (NCB <= 9 ? 2 : 1)) scaml_grad_values_kernel(const GradValParams p) {
   SCAML_DYN_SMEM(double, sm);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
   const int d = p.d, P = d + 2, n_pad = p.n_pad, nt = p.n_t, ntp = p.n_tp, lda = ntp + 12;
@@ -72,9 +72,9 @@ __global__ void __launch_bounds__(kGvThreads) scaml_grad_values_kernel(const Gra
       const int bb = b0 + c < p.B ? b0 + c : p.B - 1;
       xcs[i] = p.Xc[(size_t)bb * d + k];
     }
-    double acc[kGvMaxCB][2];
+    double acc[NCB][2];
 #pragma unroll
-    for (int c = 0; c < kGvMaxCB; ++c) acc[c][0] = acc[c][1] = 0.0;
+    for (int c = 0; c < NCB; ++c) acc[c][0] = acc[c][1] = 0.0;
     double vacc = 0.0;
     for (int m = m_lo; m < m_hi; ++m) {
       const double wm = p.w[m];
@@ -102,9 +102,13 @@ __global__ void __launch_bounds__(kGvThreads) scaml_grad_values_kernel(const Gra
         }
         __syncthreads();
         {  // scaled k* chunk: ks[r][c] = c_m s_m kappa(x_c, X_m[row]); variance term with U (coalesced over candidates)
-          double r2[8], kap[8];
+          double r2[8], kap[8], uq[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) r2[u] = 0.0;
+          for (int u = 0; u < 8; ++u) {  // U first: the loads fly under the distance / exp chains
+            const int row = 32 * ch + rg + 4 * u;
+            uq[u] = row < nv ? p.U[((size_t)m * n_pad + row) * p.B_p + bme] : 0.0;
+            r2[u] = 0.0;
+          }
           for (int k = 0; k < d; ++k) {
             const double xk = xcs[k * kGvCT + cb_], ik = il[k];
 #pragma unroll
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(kGvThreads) scaml_grad_values_kernel(const Gra
             const int r = rg + 4 * u, row = 32 * ch + r;
             const double kv = row < nv ? cos_ * kap[u] : 0.0;
             ks[r * kGvLdk + cb_] = kv;
-            if (row < nv) vacc = fma(kv, p.U[((size_t)m * n_pad + row) * p.B_p + bme], vacc);
+            vacc = fma(kv, uq[u], vacc);
           }
         }
         __syncthreads();
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(kGvThreads) scaml_grad_values_kernel(const Gra
           for (int s = 0; s < 8; ++s) {
             const double a = ar[(size_t)4 * s * kGvLdk];
 #pragma unroll
-            for (int c = 0; c < kGvMaxCB; ++c)
+            for (int c = 0; c < NCB; ++c)
               if (c < ncb) dmma884(acc[c], a, br[(size_t)4 * s * lda + 8 * c]);
           }
         }
@@ -140,7 +144,7 @@ __global__ void __launch_bounds__(kGvThreads) scaml_grad_values_kernel(const Gra
     {
       const int cand = b0 + 8 * warp + g;  // d[e] = D[g][2 t4 + e]
 #pragma unroll
-      for (int c = 0; c < kGvMaxCB; ++c) {
+      for (int c = 0; c < NCB; ++c) {
         if (c < ncb - 1) {
           if (cand < p.B)
             *reinterpret_cast<double2*>(p.cxp + ((size_t)split * p.B + cand) * ntp + 8 * c + 2 * t4) =
@@ -190,24 +194,31 @@ __global__ void __launch_bounds__(64) scaml_grad_values_finish_kernel(const Grad
 }
 
 inline int gradval_nsplit(int M, int ntile, int num_sms) {
-  int ns = (2 * num_sms + ntile - 1) / ntile;
+  int ns = (4 * num_sms + ntile - 1) / ntile;  // 2 CTAs / SM resident, 2 waves
   if (ns > M) ns = M;
   return ns < 1 ? 1 : ns;
 }
 
-template <int KIND>
-int launch_grad_values_k(const GradValParams& p, int grid, size_t smem, void* stream) {
+template <int KIND, int NCB>
+int launch_grad_values_kn(const GradValParams& p, int grid, size_t smem, void* stream) {
 #ifdef SCAML_EMU
   (void)stream;
-  cuemu::launch(dim3(grid), dim3(kGvThreads), smem, scaml_grad_values_kernel<KIND>, p);
+  cuemu::launch(dim3(grid), dim3(kGvThreads), smem, scaml_grad_values_kernel<KIND, NCB>, p);
   return 0;
 #else
-  cudaError_t err =
-      cudaFuncSetAttribute(scaml_grad_values_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t err = cudaFuncSetAttribute(scaml_grad_values_kernel<KIND, NCB>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return (int)err;
-  scaml_grad_values_kernel<KIND><<<grid, kGvThreads, smem, (cudaStream_t)stream>>>(p);
+  scaml_grad_values_kernel<KIND, NCB><<<grid, kGvThreads, smem, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 #endif
+}
+template <int KIND>
+int launch_grad_values_k(const GradValParams& p, int grid, size_t smem, void* stream) {
+  const int ncb = p.n_tp / 8 + 1;  // accumulator column blocks per warp: register variants 5 / 9 / 17
+  if (ncb <= 5) return launch_grad_values_kn<KIND, 5>(p, grid, smem, stream);
+  if (ncb <= 9) return launch_grad_values_kn<KIND, 9>(p, grid, smem, stream);
+  return launch_grad_values_kn<KIND, kGvMaxCB>(p, grid, smem, stream);
 }
 
 inline int launch_grad_values(const GradValParams& p, int kernel, int num_sms, void* stream) {
@@ -217,7 +228,7 @@ inline int launch_grad_values(const GradValParams& p, int kernel, int num_sms, v
 #ifdef SCAML_EMU
   const int grid = items < 2 ? items : 2;
 #else
-  const int grid = items < 2 * num_sms ? items : 2 * num_sms;
+  const int grid = items < 4 * num_sms ? items : 4 * num_sms;
 #endif
   int rc;
   switch (kernel) {

@@ -385,7 +385,7 @@ class ScaMLGP:
             U = eng.cond_prepare(self._fitted, Xc, w)  # pruned tasks skipped
             if n_t > 0:
                 ts = self._target_state()
-                pm, pv, cross = eng.values_from_u(self._fitted, w, Xc, U, self._Xt, self._condA)
+                pm, pv, cross = eng.prior_values(self._fitted, w, Xc, U, self._Xt, self._condA)
                 mean, var, beta = eng.target_posterior_beta(ts, pm, pv, cross, Xc)
                 dm, dv = eng.posterior_grad(self._fitted, w, Xc, U, ts, self._condA, beta)
             else:

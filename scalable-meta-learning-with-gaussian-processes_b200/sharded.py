@@ -199,7 +199,7 @@ class ShardedSources:
             key = (tstate.Xt.data_ptr(), n_t)
             if self._cond_key != key:
                 self._condA, self._cond_key = eng.cond_prepare(self.fitted, tstate.Xt), key
-            pm, pv, cross = eng.values_from_u(self.fitted, wl, Xc, U, tstate.Xt, self._condA)
+            pm, pv, cross = eng.prior_values(self.fitted, wl, Xc, U, tstate.Xt, self._condA)
             if self.world > 1:
                 flat = torch.cat([pm.unsqueeze(1), pv.unsqueeze(1), cross], dim=1).contiguous()
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)

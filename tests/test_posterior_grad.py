@@ -144,3 +144,28 @@ def test_gpu_posterior_grad_is_deterministic_and_split_invariant(engine):
     g2 = engine.posterior_grad(fs, w2, Xc, U)
     for i in range(2):
         assert float((g1[i] + g2[i] - a[i]).abs().max()) < 1e-12 * float(a[i].abs().max())
+
+
+def test_emu_cross_covariance_direct_term_split_over_tasks(emu_engine, monkeypatch):
+    """Small candidate batches sum the direct term sum_m c_m K_m(x, x_tj) over task splits (partials + fixed-order
+    finish kernel); forced here with the test knob, must equal the unsplit result to rounding."""
+    from scamlgp_b200.engine import SourceBatch
+
+    eng = emu_engine
+    M, n, d, B, nt = 5, 40, 3, 7, 5
+    pb = make_problem(M, 2, n, d, seed=5, n_valid=[40, 33, 20, 9, 1])
+    batch = SourceBatch.from_padded(pb["X"], pb["Y"], torch.tensor(pb["nv"]))
+    fs = eng.factorize(batch, pb["th"][:, 1].contiguous(), pb["cspec"])
+    g = torch.Generator().manual_seed(8)
+    Xc, Xt = torch.rand(B, d, dtype=DT, generator=g), torch.rand(nt, d, dtype=DT, generator=g)
+    w = torch.tensor([0.3, 0.0, 0.3, 0.2, 0.2], dtype=DT)
+    A = eng.cond_prepare(fs, Xt)
+    ref = eng.predict_conditioned(fs, w, Xc, Xt, A)
+    monkeypatch.setenv("SCAML_COMB_TSPLIT", "3")
+    assert eng.lib.cond_combine_task_splits(M, B, nt) == 3
+    got = eng.predict_conditioned(fs, w, Xc, Xt, A)
+    U = eng.cond_prepare(fs, Xc, w)
+    got_u = eng.values_from_u(fs, w, Xc, U, Xt, A)
+    for r, a, b_ in zip(ref, got, got_u):
+        assert float((a - r).abs().max()) <= 1e-13 * float(r.abs().max())
+        assert float((b_ - r).abs().max()) <= 1e-10 * float(r.abs().max())
