@@ -157,6 +157,16 @@ int scaml_target_lml_grad(const double* source_means, const double* source_covs,
                           const scaml_hyper_spec* spec, int w_prior, double w_p1, double w_p2,
                           void* stream);
 
+/* scaml_target_lml_grad with linear_operator's psd_safe_cholesky jitter ladder applied INSIDE the kernel: a row whose
+ * factorisation fails is retried with +1e-8, +1e-7, +1e-6 on the diagonal before it is reported (info > 0, NaN
+ * outputs).  Same results as re-running the failed rows from the host with those jitters, without reading `info`
+ * back between the rounds of the L-BFGS driver (reference call site scamlgp/utils.py:171-177,190-192). */
+int scaml_target_lml_grad_ladder(const double* source_means, const double* source_covs, const double* Xt,
+                                 const double* yt, const double* w, const double* theta_raw, double mu_all,
+                                 double s_all, double* lml, double* grad_w, double* grad_theta, int32_t* info,
+                                 void* workspace, size_t workspace_bytes, int M, int n_t, int d, int R,
+                                 const scaml_hyper_spec* spec, int w_prior, double w_p1, double w_p2, void* stream);
+
 /* Target-GP prediction state at the fitted parameters (R = 1): row-major L_t^-1 [n_t][n_t] of
  * K = (sum_i w_i^2 C_i)/s_all^2 + s k(X_t) + (noise + jitter) I, alpha_t = K^-1 (y_t - mean) [n_t], the
  * constrained kernel parameters theta [P] and the objective value lml[1].  Replaces the prediction

@@ -104,6 +104,7 @@ EXPORTED_SYMBOLS = (
     "scaml_predict_cross",
     "scaml_target_workspace_bytes",
     "scaml_target_lml_grad",
+    "scaml_target_lml_grad_ladder",
     "scaml_target_posterior_beta",
     "scaml_posterior_grad_workspace_bytes",
     "scaml_posterior_grad",
@@ -182,6 +183,9 @@ class ScamlLib:
         L.scaml_predict_conditioned.argtypes = [vp] * 15 + [sz] + [i32] * 6 + [vp]
         L.scaml_target_workspace_bytes.restype = sz
         L.scaml_target_workspace_bytes.argtypes = [i32, i32]
+        L.scaml_target_lml_grad_ladder.argtypes = ([vp] * 6 + [C.c_double, C.c_double] + [vp] * 5 +
+                                                   [sz, i32, i32, i32, i32, C.POINTER(CHyperSpec), i32, C.c_double,
+                                                    C.c_double, vp])
         L.scaml_target_lml_grad.argtypes = ([vp] * 7 + [C.c_double, C.c_double] + [vp] * 5 +
                                             [sz, i32, i32, i32, i32, C.POINTER(CHyperSpec), i32, C.c_double,
                                              C.c_double, vp])
@@ -307,6 +311,15 @@ class ScamlLib:
                                               lml, grad_w, grad_theta, info, ws, ws_bytes, M, n_t, d, R, C.byref(cs),
                                               int(w_prior[0]), float(w_prior[1]), float(w_prior[2]), stream),
                "scaml_target_lml_grad")
+
+
+    def target_lml_grad_ladder(self, smeans, scovs, Xt, yt, w, theta_raw, mu_all, s_all, lml, grad_w, grad_theta, info,
+                               ws, ws_bytes, M, n_t, d, R, spec: HyperSpec, w_prior=(PRIOR_GAMMA, 1.0, 1.0), stream=0):
+        cs = spec.to_c()
+        _check(self.lib.scaml_target_lml_grad_ladder(smeans, scovs, Xt, yt, w, theta_raw, float(mu_all), float(s_all),
+                                                     lml, grad_w, grad_theta, info, ws, ws_bytes, M, n_t, d, R,
+                                                     C.byref(cs), int(w_prior[0]), float(w_prior[1]),
+                                                     float(w_prior[2]), stream), "scaml_target_lml_grad_ladder")
 
 
 _cuda_lib: Optional[ScamlLib] = None

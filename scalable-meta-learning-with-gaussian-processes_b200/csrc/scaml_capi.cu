@@ -285,6 +285,32 @@ int scaml_target_lml_grad(const double* source_means, const double* source_covs,
   return scaml::launch_target(p, num_sms(), stream);
 }
 
+int scaml_target_lml_grad_ladder(const double* source_means, const double* source_covs, const double* Xt,
+                                 const double* yt, const double* w, const double* theta_raw, double mu_all,
+                                 double s_all, double* lml, double* grad_w, double* grad_theta, int32_t* info,
+                                 void* workspace, size_t workspace_bytes, int M, int n_t, int d, int R,
+                                 const scaml_hyper_spec* spec, int w_prior, double w_p1, double w_p2, void* stream) {
+  if (!source_means || !source_covs || !Xt || !yt || !w || !theta_raw || !lml || !grad_w || !grad_theta || !info ||
+      !workspace || !spec)
+    return SCAML_E_ARG;
+  if (M <= 0 || n_t <= 0 || d <= 0 || R <= 0 || !(s_all > 0.0)) return SCAML_E_ARG;
+  if (d > scaml::kMaxP - 2) return SCAML_E_UNSUPPORTED;
+  if (workspace_bytes < scaml_target_workspace_bytes(n_t, R)) return SCAML_E_WORKSPACE;
+  scaml::TargetParams p{};
+  p.smeans = source_means, p.scovs = source_covs, p.Xt = Xt, p.yt = yt, p.w = w, p.theta_raw = theta_raw;
+  p.jitter = nullptr, p.jitter_value = 0.0, p.ladder = 1;
+  p.lml = lml, p.grad_w = grad_w, p.grad_theta = grad_theta, p.info = info;
+  double* ws = static_cast<double*>(workspace);
+  p.covw = ws;
+  p.Wmat = ws + (size_t)R * n_t * n_t;
+  p.meanw = ws + 2 * (size_t)R * n_t * n_t;
+  p.alpha = p.meanw + (size_t)R * n_t;
+  p.mu_all = mu_all, p.s_all = s_all;
+  p.M = M, p.nt = n_t, p.d = d, p.R = R, p.w_prior = w_prior, p.w_p1 = w_p1, p.w_p2 = w_p2;
+  p.spec = *spec;
+  return scaml::launch_target(p, num_sms(), stream);
+}
+
 int scaml_target_factorize(const double* source_means, const double* source_covs, const double* Xt, const double* yt,
                            const double* w, const double* theta_raw, double jitter_value, double mu_all, double s_all,
                            double* linv_t, double* alpha_t, double* theta, double* lml, int32_t* info, void* workspace,

@@ -38,6 +38,7 @@ struct TargetParams {
   double* theta_out;        // factorize: [P] constrained, or null
   double mu_all, s_all;
   double jitter_value;      // used when `jitter` is null
+  int ladder;               // 1: psd_safe_cholesky jitter ladder (+1e-8, +1e-7, +1e-6) inside the kernel on failure
   int M, nt, d, R, w_prior;
   double w_p1, w_p2;
   scaml_hyper_spec spec;
@@ -125,13 +126,24 @@ __global__ void __launch_bounds__(kTgtThreads) scaml_target_factor_kernel(const 
   }
   if (tid == 0) *flag = 0;
   __syncthreads();
-  const double os = th[d], diag_add = th[d + 1] + (p.jitter ? p.jitter[r] : p.jitter_value);
+  const double os = th[d], base_add = th[d + 1] + (p.jitter ? p.jitter[r] : p.jitter_value);
   for (int i = tid; i < nt * d; i += kTgtThreads) {
     const int a = i / d, k = i - a * d;
     xs[k * nt + a] = p.Xt[i] / th[k];
   }
   for (int i = tid; i < nt; i += kTgtThreads) rv[i] = p.yt[i] - p.meanw[(size_t)r * nt + i];
   __syncthreads();
+  // linear_operator's psd_safe_cholesky retries a failed factorisation with jitter 1e-8, 1e-7, 1e-6 (fp64); with
+  // p.ladder the retries happen here, so the host never has to read `info` back between L-BFGS rounds
+  double logdet = 0.0;
+  const int nlev = p.ladder ? 4 : 1;
+  for (int lev = 0; lev < nlev; ++lev) {
+  const double diag_add = base_add + (lev == 0 ? 0.0 : (lev == 1 ? 1e-8 : (lev == 2 ? 1e-7 : 1e-6)));
+  if (lev > 0) {
+    __syncthreads();  // every thread has read the flag of the failed attempt
+    if (tid == 0) *flag = 0;
+    __syncthreads();
+  }
   // ---- K_y -------------------------------------------------------------------------- //
   for (int i = tid; i < nt * nt; i += kTgtThreads) {
     const int a = i / nt, b = i - a * nt;
@@ -146,7 +158,7 @@ __global__ void __launch_bounds__(kTgtThreads) scaml_target_factor_kernel(const 
   }
   __syncthreads();
   // ---- Cholesky (right-looking, in place, lower) -------------------------------------- //
-  double logdet = 0.0;
+  logdet = 0.0;
   for (int k = 0; k < nt; ++k) {
     const double dkk = K[k * ld + k];
     if (!(dkk > 0.0) || !(dkk < 1e300)) {
@@ -167,6 +179,8 @@ __global__ void __launch_bounds__(kTgtThreads) scaml_target_factor_kernel(const 
     __syncthreads();
   }
   __syncthreads();
+  if (*flag == 0) break;  // uniform
+  }  // jitter levels
   if (*flag != 0) {
     if (tid == 0) {
       p.info[r] = *flag;

@@ -46,6 +46,6 @@ for name in ("report", "suggest"):
         if name == "report":
             pr.disable()
     buf = io.StringIO()
-    pstats.Stats(pr, stream=buf).sort_stats("cumulative").print_stats(28)
+    pstats.Stats(pr, stream=buf).strip_dirs().sort_stats("tottime").print_stats(22)
     print(f"===== {name} x {steps} =====")
     print("\n".join(l[:150] for l in buf.getvalue().splitlines() if l.strip())[:6000])

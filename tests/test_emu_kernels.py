@@ -291,3 +291,45 @@ def test_emu_fused_conditioning_matches_cross_kernel_and_oracle(emu_lib):
     Aref = torch.cholesky_solve(Kmt, st.L)
     assert float((A[1, :k, :nt] - Aref).abs().max()) < 1e-9 * float(Aref.abs().max())
     assert float(A[1, k:].abs().max()) == 0.0 and float(A[1, :, nt:].abs().max()) == 0.0
+
+
+def test_emu_target_jitter_ladder_inside_the_kernel_matches_the_host_ladder(emu_lib):
+    from tests.emu_engine import EmuEngine
+
+    _target_ladder_case(EmuEngine(emu_lib))
+
+
+@pytest.mark.gpu
+def test_gpu_target_jitter_ladder_inside_the_kernel_matches_the_host_ladder(engine):
+    _target_ladder_case(engine)
+
+
+def _target_ladder_case(eng):
+    """A weighted prior covariance that is slightly negative definite: the factorisation fails at jitter 0 and 1e-8
+    and succeeds at 1e-7 (psd_safe_cholesky semantics).  The in-kernel ladder must give exactly what re-running the
+    failed row from the host gives; a healthy row is untouched; a hopeless row reports info > 0 and NaN."""
+    dev = eng.device
+    M, nt, d, R = 3, 3, 2, 3
+    spec = HyperSpec.target()
+    ospec = O.HyperSpec.target()
+    th = O.initial_theta_raw(d, ospec).reshape(1, -1).repeat(R, 1).contiguous()
+    ls, os_, noise = O.split_theta(th[0], ospec)
+    Xt = torch.tensor([[0.0, 0.0], [40.0, 0.0], [0.0, 40.0]], dtype=torch.float64)  # kappa ~ 0 off the diagonal
+    yt = torch.tensor([0.1, -0.2, 0.05], dtype=torch.float64)
+    sm = torch.zeros(nt, M, dtype=torch.float64)
+    sc = torch.zeros(nt, nt, M, dtype=torch.float64)
+    w = torch.full((R, M), 1e-6, dtype=torch.float64)  # (weights of exactly 0 have no Gamma(1, 1) log density)
+    w[0, 0] = w[1, 1] = w[2, 2] = 1.0
+    for a in range(nt):
+        sc[a, a, 0] = -(float(os_) + float(noise)) - 3e-8   # row 0: K_y = -3e-8 I  -> recovers at +1e-7
+        sc[a, a, 1] = 0.5                                   # row 1: healthy
+        sc[a, a, 2] = -(float(os_) + float(noise)) - 1.0    # row 2: hopeless
+    sm, sc, Xt, yt, w, th = (t.to(dev) for t in (sm, sc, Xt, yt, w, th))
+    a_ = eng.target_lml_grad_safe(sm, sc, Xt, yt, w, th, 0.0, 1.0, spec)
+    b_ = eng.target_lml_grad_host_ladder(sm, sc, Xt, yt, w, th, 0.0, 1.0, spec)
+    assert a_[3].tolist() == b_[3].tolist() and a_[3][0] == 0 and a_[3][1] == 0 and a_[3][2] > 0
+    for x, y in zip(a_[:3], b_[:3]):
+        assert torch.equal(torch.nan_to_num(x, nan=-7.0), torch.nan_to_num(y, nan=-7.0))
+    assert torch.isfinite(a_[0][:2]).all() and torch.isnan(a_[0][2])
+    plain = eng.target_lml_grad(sm, sc, Xt, yt, w, th, 0.0, 1.0, spec)
+    assert plain[3][0] > 0 and torch.equal(plain[0][1], a_[0][1])
