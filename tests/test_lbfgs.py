@@ -111,6 +111,26 @@ def _device_vs_torch(eng):
                                      options=dict(ftol=0, gtol=1e-10, maxiter=2000))
         assert np.abs(res.x[e].cpu().numpy() - sp.x).max() < 1e-6
         assert bool((res.x[e, : D - 8] >= 1e-10).all())
+    # (2b) long rows (D >= 512): the 8-warp CTA-per-row variant of the kernel (target fit: D = M + d + 2); diagonal
+    #      quadratic + bounds, against the torch statement of the algorithm and the closed-form minimiser
+    E, D = 2, 700
+    qd = (0.5 + torch.rand(E, D, dtype=torch.float64, generator=gen)).to(dev)
+    cd = torch.randn(E, D, dtype=torch.float64, generator=gen).to(dev)
+    lower = torch.cat([torch.full((D - 20,), 1e-10), torch.full((20,), float("-inf"))]).to(torch.float64).to(dev)
+
+    def fun_w(x, active):
+        return 0.5 * (qd * x * x).sum(1) - (cd * x).sum(1), qd * x - cd
+
+    x0w = torch.full((E, D), 0.3, dtype=torch.float64, device=dev)
+    res = lbfgs_minimize_device(eng, fun_w, x0w, lower=lower, maxiter=300, gtol=1e-9, ftol=0.0)
+    exact = torch.maximum(cd / qd, lower)
+    assert bool(res.converged.all())
+    assert float((res.x - exact).abs().max()) < 1e-6
+    ref = lbfgs_minimize(fun_w, x0w, lower=lower, maxiter=300, gtol=1e-9, ftol=0.0)  # torch statement, same device
+    assert float((res.x - ref.x).abs().max()) < 1e-6
+    assert abs(int(res.iterations.sum()) - int(ref.iterations.sum())) <= 0.25 * int(ref.iterations.sum()) + 2
+    again = lbfgs_minimize_device(eng, fun_w, x0w, lower=lower, maxiter=300, gtol=1e-9, ftol=0.0)
+    assert torch.equal(again.x, res.x)  # fixed-order reductions: bit-reproducible
     # (3) NaN at the start fails the row; NaN at a trial point backtracks
     def fun_nan(x, active):
         f = (x * x).sum(1)
