@@ -109,6 +109,15 @@ __global__ void __launch_bounds__(kGradThreads) scaml_grad_mix_kernel(const Grad
     __syncthreads();  // previous chunk consumed (and bts staged)
     const double* src = p.A + ((size_t)m * n_pad + 32 * ch) * ntp;
     for (int i = tid; i < 32 * ntp; i += kGradThreads) Ach[(i / ntp) * lda + (i % ntp)] = src[i];
+    // the U entries this thread will update: loaded now, so that their DRAM latency overlaps the A chunk and the DMMAs
+    double2 uq[kMixMaxCB];
+    {
+      const double* ur0 = p.U + ((size_t)m * n_pad + 32 * ch + 8 * rb + g) * Bp;
+#pragma unroll
+      for (int c = 0; c < kMixMaxCB; ++c)
+        uq[c] = (cb0 + 2 * c < ncb - 1) ? *reinterpret_cast<const double2*>(ur0 + 8 * (cb0 + 2 * c) + 2 * t4)
+                                        : make_double2(0.0, 0.0);
+    }
     __syncthreads();
     double acc[kMixMaxCB][2];
 #pragma unroll
@@ -127,11 +136,7 @@ __global__ void __launch_bounds__(kGradThreads) scaml_grad_mix_kernel(const Grad
     for (int c = 0; c < kMixMaxCB; ++c) {
       const int cb = cb0 + 2 * c;
       if (cb < ncb - 1) {
-        double2* q = reinterpret_cast<double2*>(ur + 8 * cb + 2 * t4);
-        double2 v = *q;
-        v.x -= acc[c][0];
-        v.y -= acc[c][1];
-        *q = v;
+        *reinterpret_cast<double2*>(ur + 8 * cb + 2 * t4) = make_double2(uq[c].x - acc[c][0], uq[c].y - acc[c][1]);
       } else if (cb == ncb - 1 && t4 == 0) {
         p.aal[(size_t)m * n_pad + row] = acc[c][0];
       }
