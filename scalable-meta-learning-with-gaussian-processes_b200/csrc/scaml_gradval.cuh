@@ -30,7 +30,7 @@ struct GradValParams {
   const double* U;         // [M][n_pad][B_p]
   const double* A;         // [M][n_pad][n_tp] (n_t > 0)
   double* cxp;             // [nsplit][B][n_tp] partial sum_m c_m k*_m^T A_m (n_t > 0)
-  double* mvp;             // [nsplit][B][2]    partial sum_m w_m ystd_m k*^T alpha | sum_m c_m k*^T u
+  double* mvp;             // [nsplit][B][2]    partial sum_m w_m (ybar_m + ystd_m k*^T alpha) | sum_m c_m (s_m - k*^T u)
   double* mean;            // [B]
   double* var;             // [B]
   int M, n_max, n_pad, d, B, B_p, n_t, n_tp, nsplit, ntile;
@@ -75,13 +75,15 @@ __global__ void __launch_bounds__(kGvThreads, (NCB <= 9 ? 2 : 1)) scaml_grad_val
     double acc[NCB][2];
 #pragma unroll
     for (int c = 0; c < NCB; ++c) acc[c][0] = acc[c][1] = 0.0;
-    double vacc = 0.0;
+    double vacc = 0.0, c0 = 0.0, c1 = 0.0;  // c0 / c1: the split's share of sum_m w_m ybar_m and sum_m c_m s_m
     for (int m = m_lo; m < m_hi; ++m) {
       const double wm = p.w[m];
       if (wm == 0.0) continue;  // pruned task (uniform over the CTA)
       const int nv = p.n_valid ? p.n_valid[m] : p.n_max;
       const double* th = p.theta + (size_t)m * P;
       const double sy = p.ystd[m], cmw = wm * sy, cos_ = cmw * cmw * th[d], ia = 1.0 / cmw;
+      c0 = fma(wm, p.ybar[m], c0);
+      c1 += cos_;
       const double* Xm = p.X + (size_t)m * p.n_max * d;
       const int nchunk = (nv + 31) >> 5;
       for (int ch = 0; ch < nchunk; ++ch) {
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(kGvThreads, (NCB <= 9 ? 2 : 1)) scaml_grad_val
             *reinterpret_cast<double2*>(p.cxp + ((size_t)split * p.B + cand) * ntp + 8 * c + 2 * t4) =
                 make_double2(acc[c][0], acc[c][1]);
         } else if (c == ncb - 1) {
-          if (cand < p.B && t4 == 0) p.mvp[((size_t)split * p.B + cand) * 2] = acc[c][0];
+          if (cand < p.B && t4 == 0) p.mvp[((size_t)split * p.B + cand) * 2] = c0 + acc[c][0];
         }
       }
     }
@@ -159,24 +161,14 @@ __global__ void __launch_bounds__(kGvThreads, (NCB <= 9 ? 2 : 1)) scaml_grad_val
     __syncthreads();
     if (tid < kGvCT && b0 + tid < p.B)
       p.mvp[((size_t)split * p.B + b0 + tid) * 2 + 1] =
-          (red[tid] + red[kGvCT + tid]) + (red[2 * kGvCT + tid] + red[3 * kGvCT + tid]);
+          c1 - ((red[tid] + red[kGvCT + tid]) + (red[2 * kGvCT + tid] + red[3 * kGvCT + tid]));
   }
 }
 
-// mean[b] = sum_m w_m ybar_m + sum_s mvp[s][b][0];  var[b] = sum_m c_m s_m - sum_s mvp[s][b][1]   (fixed order)
+// mean[b] = sum_s mvp[s][b][0];  var[b] = sum_s mvp[s][b][1]   (the splits carry their share of the constants; lanes
+// stride over the splits, fixed-order warp tree)
 __global__ void __launch_bounds__(64) scaml_grad_values_finish_kernel(const GradValParams p) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, P = p.d + 2;
-  double c0 = 0.0, c1 = 0.0;  // every warp recomputes the two constants (M terms, lanes strided, fixed tree)
-  for (int m = lane; m < p.M; m += 32) {
-    const double wm = p.w[m];
-    if (wm != 0.0) {
-      const double cw = wm * p.ystd[m];
-      c0 = fma(wm, p.ybar[m], c0);
-      c1 = fma(cw * cw, p.theta[(size_t)m * P + p.d], c1);
-    }
-  }
-  c0 = warp_sum(c0);
-  c1 = warp_sum(c1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int wpg = blockDim.x >> 5;
   for (long long b = (long long)blockIdx.x * wpg + warp; b < p.B; b += (long long)gridDim.x * wpg) {
     double a = 0.0, v = 0.0;
@@ -187,8 +179,8 @@ __global__ void __launch_bounds__(64) scaml_grad_values_finish_kernel(const Grad
     a = warp_sum(a);
     v = warp_sum(v);
     if (lane == 0) {
-      p.mean[b] = c0 + a;
-      p.var[b] = c1 - v;
+      p.mean[b] = a;
+      p.var[b] = v;
     }
   }
 }

@@ -401,6 +401,25 @@ __global__ void scaml_predict_reduce_kernel(const double* part, double* mean, do
   }
 }
 
+// many splits (few candidates): one warp per candidate, lanes stride over the splits, fixed-order warp tree
+__global__ void __launch_bounds__(128) scaml_predict_reduce_wide_kernel(const double* part, double* mean, double* var,
+                                                                        int nsplit, int B) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpg = blockDim.x >> 5;
+  for (int b = blockIdx.x * wpg + warp; b < B; b += gridDim.x * wpg) {
+    double m = 0.0, v = 0.0;
+    for (int s = lane; s < nsplit; s += 32) {
+      m += part[((size_t)s * 2 + 0) * B + b];
+      v += part[((size_t)s * 2 + 1) * B + b];
+    }
+    m = warp_sum(m);
+    v = warp_sum(v);
+    if (lane == 0) {
+      mean[b] = m;
+      var[b] = v;
+    }
+  }
+}
+
 template <int KIND, int CT, bool CROSS>
 int launch_predict_kc(const PredParams& p, int grid, size_t smem, void* stream) {
 #ifdef SCAML_EMU
@@ -451,13 +470,21 @@ inline int launch_predict_weighted(const double* X, const int32_t* n_valid, cons
     default: rc = launch_predict_k<SCAML_KERNEL_MATERN52>(p, grid, smem, stream); break;
   }
   if (rc != 0 || p.nsplit == 1) return rc;
+  const bool wide = p.nsplit >= 32;  // by shape only
 #ifdef SCAML_EMU
-  cuemu::launch(dim3(1), dim3(64), 0, scaml_predict_reduce_kernel, (const double*)workspace, mean, var, p.nsplit, B);
+  if (wide) cuemu::launch(dim3(1), dim3(128), 0, scaml_predict_reduce_wide_kernel, (const double*)workspace, mean, var, p.nsplit, B);
+  else cuemu::launch(dim3(1), dim3(64), 0, scaml_predict_reduce_kernel, (const double*)workspace, mean, var, p.nsplit, B);
   return 0;
 #else
-  const int rb = (B + 255) / 256;
-  scaml_predict_reduce_kernel<<<rb < 1184 ? rb : 1184, 256, 0, (cudaStream_t)stream>>>(workspace, mean, var,
-                                                                                      p.nsplit, B);
+  if (wide) {
+    const int wb = (B + 3) / 4;
+    scaml_predict_reduce_wide_kernel<<<wb < 1184 ? wb : 1184, 128, 0, (cudaStream_t)stream>>>(workspace, mean, var,
+                                                                                             p.nsplit, B);
+  } else {
+    const int rb = (B + 255) / 256;
+    scaml_predict_reduce_kernel<<<rb < 1184 ? rb : 1184, 256, 0, (cudaStream_t)stream>>>(workspace, mean, var,
+                                                                                        p.nsplit, B);
+  }
   return (int)cudaGetLastError();
 #endif
 }
