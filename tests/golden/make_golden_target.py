@@ -3,7 +3,7 @@
 test data (tests/meta_data_examples.py:141-175: y = a f(x) + b (x - 0.5) - c with f the Forrester function):
 3 source tasks x 12 points, 5 target points, 9 candidates.  Stored: inputs, the source hyper-parameters used,
 the per-task caches, the training-branch objective + gradients at two (w, theta) rows, and the conditioned
-posterior mean / variance with weight pruning (tau = 1e-3).
+posterior mean / variance with weight pruning (tau = 1e-3), and their gradients wrt the candidates.
 Run:  python tests/golden/make_golden_target.py
 """
 import os
@@ -50,6 +50,14 @@ def main():
         m_, v_ = O.scaml_posterior(states, W[r], cache, TH[r], tspec, torch.tensor(Xc), prune_threshold=1e-3)
         pm.append(m_.numpy())
         pv.append(v_.numpy())
+    # candidate gradients d mean / dx, d var / dx (autograd through the oracle: what botorch's optimize_acqf differentiates)
+    dpm, dpv = [], []
+    for r in range(2):
+        _, _, dm_, dv_ = O.scaml_posterior_grad(states, W[r], cache, TH[r], tspec, torch.tensor(Xc), prune_threshold=1e-3)
+        dpm.append(dm_.numpy())
+        dpv.append(dv_.numpy())
+    _, _, dprior_m, dprior_v = O.scaml_posterior_grad(states, W[0], None, TH[0], tspec, torch.tensor(Xc),
+                                                      prune_threshold=1e-3)
     prior_m, prior_v = O.scaml_posterior(states, W[0], None, TH[0], tspec, torch.tensor(Xc), prune_threshold=1e-3)
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "scaml_golden_target_v1.npz")
     np.savez_compressed(
@@ -57,7 +65,8 @@ def main():
         source_means=cache.source_means.numpy(), source_covs=cache.source_covs.numpy(), mu_all=cache.mu_all,
         s_all=cache.s_all, yt_std=cache.yt_std.numpy(), objective=np.array(obj), grad_w=np.stack(gw),
         grad_theta=np.stack(gt), post_mean=np.stack(pm), post_var=np.stack(pv), prior_mean=prior_m.numpy(),
-        prior_var=prior_v.numpy())
+        prior_var=prior_v.numpy(), dpost_mean=np.stack(dpm), dpost_var=np.stack(dpv), dprior_mean=dprior_m.numpy(),
+        dprior_var=dprior_v.numpy())
     print("wrote", out, os.path.getsize(out), "bytes")
 
 
