@@ -359,6 +359,13 @@ class ScaMLGP:
             mean, var = eng.target_posterior(self._target_state(), pm, pv, cross, Xc)
         return Posterior(mean.to(X.device), var.to(X.device))
 
+    @property
+    def supports_candidate_gradients(self) -> bool:
+        """Shapes the analytic-gradient kernels cover (n <= 512 points per task, d <= 16, n_t <= 128); outside them
+        the optimizer falls back to its zeroth-order acquisition search."""
+        b = self._fitted.batch
+        return b.n_max <= 512 and b.d <= 16 and self.num_train <= 128
+
     def posterior_with_grad(self, X: torch.Tensor):
         """Posterior mean / variance [B] and their gradients wrt the candidates [B, d] (q = 1), un-standardised.
 
@@ -372,8 +379,8 @@ class ScaMLGP:
                 raise NotImplementedError("only q = 1 candidate batches (the acquisition path) are supported")
             X = X[:, 0, :]
         b = self._fitted.batch
-        if b.n_max > 512 or b.d > 16:
-            raise NotImplementedError("candidate gradients need n <= 512 points per task and d <= 16")
+        if not self.supports_candidate_gradients:
+            raise NotImplementedError("candidate gradients need n <= 512 points per task, d <= 16 and n_t <= 128")
         Xall = X.to(dev, DT).contiguous()
         w = self.pruned_weights()
         n_t = self.num_train

@@ -166,7 +166,9 @@ class _SingleObjectiveBase:
             raise ValueError("Only acquisition functions to be minimized are supported")
         d = len(self.search_space)
         kw = self.af_opt_kwargs
-        method = str(kw.get("method", "lbfgsb" if hasattr(af, "value_and_grad") else "batched"))
+        has_grad = hasattr(af, "value_and_grad") and bool(getattr(getattr(af, "model", None),
+                                                                 "supports_candidate_gradients", False))
+        method = str(kw.get("method", "lbfgsb" if has_grad else "batched"))
         if self.search_space.is_all_continuous and method == "lbfgsb":
             x = optimize_acqf_lbfgsb(af, self.search_space.numerical_bounds(), self._gen,
                                      raw_samples=int(kw.get("raw_samples", 1024)),

@@ -108,3 +108,54 @@ def test_model_errors_through_emulation(emu_engine):
     bad = {"a": SupervisedDataset(torch.rand(5, 2, dtype=DT), torch.full((5, 1), float("nan"), dtype=DT))}
     with pytest.raises(ModelFittingError, match="failed for all attempts"):
         meta_fit_scamlgp(bad, num_restarts_log_likelihood=1, seed=0, engine=emu_engine, fit_options=dict(maxiter=2))
+
+
+def test_acquisition_optimiser_falls_back_without_gradient_support():
+    """Models outside the shapes of the analytic-gradient kernels (or custom acquisition functions without
+    `value_and_grad`) take the zeroth-order search: the default method follows `supports_candidate_gradients`."""
+    import numpy as np
+    import torch
+
+    from scamlgp_b200 import optimizer as opt_mod
+
+    calls = []
+
+    class _Model:
+        supports_candidate_gradients = False
+
+    class _AF:
+        maximize = False
+        model = _Model()
+
+        def __call__(self, X):
+            return -((X - 0.5) ** 2).sum(-1)
+
+        def value_and_grad(self, X):  # must not be used
+            raise AssertionError("gradient path taken for a model without gradient support")
+
+    class _Space:
+        is_all_continuous = True
+        parameter_names = ["x"]
+
+        def __len__(self):
+            return 1
+
+        def numerical_bounds(self):
+            return np.array([[0.0, 1.0]])
+
+        def from_numerical(self, x):
+            calls.append(float(x[0]))
+            return {"x": float(x[0])}
+
+        def seed(self, s):
+            pass
+
+    base = opt_mod._SingleObjectiveBase.__new__(opt_mod._SingleObjectiveBase)
+    base.search_space, base.max_pending_evaluations, base.pending_specifications = _Space(), None, {}
+    base.losses, base.X = torch.zeros(1, 1, dtype=torch.float64), torch.zeros(1, 1, dtype=torch.float64)
+    base.num_initial_random, base.af_opt_kwargs, base._next_id = 0, dict(raw_samples=64, num_restarts=4, rounds=3), 0
+    base._gen = torch.Generator().manual_seed(0)
+    base.model = _Model()
+    base.acquisition_function_factory = lambda model: _AF()
+    spec = base.generate_evaluation_specification()
+    assert abs(spec.configuration["x"] - 0.5) < 0.05 and len(calls) == 1
