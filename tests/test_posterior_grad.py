@@ -169,3 +169,31 @@ def test_emu_cross_covariance_direct_term_split_over_tasks(emu_engine, monkeypat
     for r, a, b_ in zip(ref, got, got_u):
         assert float((a - r).abs().max()) <= 1e-13 * float(r.abs().max())
         assert float((b_ - r).abs().max()) <= 1e-10 * float(r.abs().max())
+
+
+def test_emu_value_half_switches_kernel_with_the_number_of_target_points(emu_engine):
+    """`Engine.prior_values`: values from U for n_t <= 64, the fused prediction kernel above (the 17-column-block
+    variant of the values kernel is register-bound on the GPU); both must give the same numbers."""
+    from scamlgp_b200.engine import SourceBatch
+
+    eng = emu_engine
+    M, n, d, B = 2, 40, 2, 5
+    pb = make_problem(M, 2, n, d, seed=6)
+    batch = SourceBatch.from_padded(pb["X"], pb["Y"], torch.tensor(pb["nv"]))
+    fs = eng.factorize(batch, pb["th"][:, 1].contiguous(), pb["cspec"])
+    g = torch.Generator().manual_seed(2)
+    Xc = torch.rand(B, d, dtype=DT, generator=g)
+    w = torch.tensor([0.6, 0.4], dtype=DT)
+    U = eng.cond_prepare(fs, Xc, w)
+    for nt in (64, 70):
+        Xt = torch.rand(nt, d, dtype=DT, generator=g)
+        A = eng.cond_prepare(fs, Xt)
+        launches0 = eng.launches
+        a = eng.prior_values(fs, w, Xc, U, Xt, A)
+        used = eng.launches - launches0
+        b_ = eng.values_from_u(fs, w, Xc, U, Xt, A)
+        c = eng.predict_conditioned(fs, w, Xc, Xt, A)
+        for x, y, z in zip(a, b_, c):
+            assert float((x - y).abs().max()) <= 1e-10 * float(y.abs().max())
+            assert float((x - z).abs().max()) <= 1e-10 * float(z.abs().max())
+        assert used >= 2
