@@ -487,65 +487,13 @@ def ucb(mean: torch.Tensor, var: torch.Tensor, beta: float = 9.0) -> torch.Tenso
 
 
 # --------------------------------------------------------------------------- #
-# synthetic meta-data (formulas from benchmarking/functions/hartmann.py:170-185,
-# alpha ranges benchmarks/hartmann_3d.py:31-34)
+# synthetic meta-data: the generators live in the neutral `datagen.py` at the repo root (bench.py's product arm
+# must not import the oracle); re-exported here for the tests that take their inputs from the oracle namespace
 # --------------------------------------------------------------------------- #
-_H6_A = [[10, 3, 17, 3.5, 1.7, 8], [0.05, 10, 17, 0.1, 8, 14], [3, 3.5, 1.7, 10, 17, 8], [17, 8, 0.05, 10, 0.1, 14]]
-_H6_P = [[1312, 1696, 5569, 124, 8283, 5886], [2329, 4135, 8307, 3736, 1004, 9991],
-         [2348, 1451, 3522, 2883, 3047, 6650], [4047, 8828, 8732, 5743, 1091, 381]]
+import os as _os
+import sys as _sys
 
-
-def hartmann6(X: torch.Tensor, alpha: torch.Tensor) -> torch.Tensor:
-    A = torch.tensor(_H6_A, dtype=DT)
-    P = 1e-4 * torch.tensor(_H6_P, dtype=DT)
-    e = torch.exp(-(A[None] * (X[:, None, :] - P[None]) ** 2).sum(-1))  # n x 4
-    return -(e * alpha[None]).sum(-1)
-
-
-def synthetic_tasks(M: int, n: int, d: int, seed: int = 0, noise_sd: float = 0.1):
-    """Hartmann-6 family for d == 6, separable smooth family otherwise.  Returns X[M,n,d], Y[M,n]."""
-    g = torch.Generator().manual_seed(seed)
-    X = torch.rand(M, n, d, dtype=DT, generator=g)
-    if d == 6:
-        lo = torch.tensor([1.0, 1.18, 2.8, 3.2], dtype=DT)
-        hi = torch.tensor([1.02, 1.2, 3.0, 3.4], dtype=DT)
-        al = lo + (hi - lo) * torch.rand(M, 4, dtype=DT, generator=g)
-        Y = torch.stack([hartmann6(X[i], al[i]) for i in range(M)])
-    else:
-        a = 1.0 + torch.rand(M, 1, d, dtype=DT, generator=g)
-        ph = torch.rand(M, 1, d, dtype=DT, generator=g)
-        Y = (torch.sin(3.0 * a * X + 6.28 * ph) + (X - ph) ** 2).sum(-1) / math.sqrt(d)
-    Y = Y + noise_sd * torch.randn(M, n, dtype=DT, generator=g)
-    return X, Y
-
-
-def sample_theta_raw(M: int, R: int, d: int, spec: HyperSpec, seed: int = 0) -> torch.Tensor:
-    """Row 0 = reference initial values; rows 1.. = prior samples clipped into the Interval
-    (1 warm start + (R-1) prior restarts, utils.py:173-203)."""
-    g = torch.Generator().manual_seed(seed + 12345)
-    out = torch.empty(M, R, d + 2, dtype=DT)
-    out[:, 0] = initial_theta_raw(d, spec)
-
-    def draw(prior, shape, bounds):
-        kind, p1, p2 = prior
-        if kind == PRIOR_GAMMA:
-            # Gamma(k, rate) via generator-aware normal approximation-free method:
-            # sum of k exponentials for integer k (all reference Gamma priors have integer k)
-            k = int(p1)
-            assert float(k) == p1
-            u = torch.rand(*shape, k, dtype=DT, generator=g)
-            v = -torch.log(u).sum(-1) / p2
-        else:
-            v = torch.exp(p1 + p2 * torch.randn(*shape, dtype=DT, generator=g))
-        lo, hi = bounds
-        eps = 1e-6 * (hi - lo)
-        return v.clamp(lo + eps, hi - eps)
-
-    if R > 1:
-        ls = draw(spec.ls_prior, (M, R - 1, d), spec.ls_bounds)
-        os_ = draw(spec.os_prior, (M, R - 1), spec.os_bounds)
-        nz = draw(spec.noise_prior, (M, R - 1), spec.noise_bounds)
-        out[:, 1:, :d] = unconstrain(ls, *spec.ls_bounds)
-        out[:, 1:, d] = unconstrain(os_, *spec.os_bounds)
-        out[:, 1:, d + 1] = unconstrain(nz, *spec.noise_bounds)
-    return out
+_ROOT = _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+if _ROOT not in _sys.path:
+    _sys.path.insert(0, _ROOT)
+from datagen import hartmann6, sample_theta_raw, synthetic_tasks  # noqa: E402,F401

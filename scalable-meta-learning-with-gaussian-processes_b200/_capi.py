@@ -126,6 +126,11 @@ class ScamlError(RuntimeError):
     pass
 
 
+class NotPSDError(ScamlError):
+    """linear_operator.utils.errors.NotPSDError stand-in: a covariance is not positive definite even after the
+    psd_safe_cholesky jitter ladder (1e-8, 1e-7, 1e-6)."""
+
+
 _ERRORS = {-1: "bad argument", -2: "workspace too small", -3: "unsupported size (d or n_max)",
            -4: "configuration does not fit shared memory"}
 

@@ -1,8 +1,8 @@
 """In-tree builds of the native code (explicit nvcc / g++ command lines, no JIT cache).
 
 build_cuda(): csrc/*.cu -> csrc/libscaml_b200.so for sm_100a (the product library).
-build_emu():  the same kernel sources with -DSCAML_EMU via g++ -> csrc/libscaml_emu.so,
-              a CPU *logic emulation* used only by tests/ (see csrc/emu/cuda_emu.h).
+The CPU logic-emulation build of the same kernel sources (-DSCAML_EMU, g++) is test infrastructure and lives
+in tests/emu_build.py; nothing in this package builds or loads it.
 """
 from __future__ import annotations
 
@@ -14,16 +14,21 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 CUDA_LIB = os.path.join(CSRC, "libscaml_b200.so")
-EMU_LIB = os.path.join(CSRC, "libscaml_emu.so")
 
 CUDA_SOURCES = ["scaml_capi.cu", "scaml_microbench.cu"]
 HEADERS = ["scaml_device.cuh", "scaml_fit.cuh", "scaml_fit8.cuh", "scaml_kmat.cuh", "scaml_predict.cuh", "scaml_cond.cuh", "scaml_cross.cuh", "scaml_target.cuh", "scaml_lbfgs.cuh", "scaml_grad.cuh", "scaml_gradval.cuh", "scaml_tile256.cuh",
            os.path.join("emu", "cuda_emu.h"), os.path.join("..", "..", "include", "scaml_b200.h")]
 
-NVCC_FLAGS = [
+NVCC_COMPILE_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
+]
+NVCC_LINK_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-shared",
+    # link the CUDA runtime dynamically (libcudart.so.12: the one torch has already loaded into the process, else the
+    # toolkit's via rpath) instead of embedding a static copy in the artefact
+    "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64",
 ]
 
 
@@ -41,16 +46,47 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+PARTS = (0, 1, 2, 3)  # scaml_capi.cu is compiled once per part (see its header), in parallel
+
+
+def _compile_parts(extra, out: str, verbose: bool = False) -> None:
+    """nvcc -c per part (parallel processes) + scaml_microbench.cu, then one link."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    nvcc = _nvcc()
+    tag = os.path.splitext(os.path.basename(out))[0]
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    jobs = []
+    for part in PARTS:
+        obj = os.path.join(objdir, f"{tag}_part{part}.o")
+        jobs.append((obj, [nvcc] + NVCC_COMPILE_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) +
+                     [f"-DSCAML_PART={part}", "-c", "-o", obj, "scaml_capi.cu"]))
+    obj = os.path.join(objdir, f"{tag}_microbench.o")
+    jobs.append((obj, [nvcc] + NVCC_COMPILE_FLAGS + extra + ["-c", "-o", obj, "scaml_microbench.cu"]))
+
+    def run(job):
+        res = subprocess.run(job[1], cwd=CSRC, capture_output=True, text=True)
+        return job, res
+
+    with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+        results = list(ex.map(run, jobs))
+    for (obj, cmd), res in results:
+        if verbose:
+            sys.stderr.write(res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    cmd = [nvcc] + NVCC_LINK_FLAGS + ["-o", out] + [j[0] for j in jobs]
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+
+
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
     deps = [os.path.join(CSRC, s) for s in CUDA_SOURCES + HEADERS]
     if not force and _newer(CUDA_LIB, deps):
         return CUDA_LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", CUDA_LIB] + CUDA_SOURCES
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if verbose:
-        sys.stderr.write(res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    _compile_parts([], CUDA_LIB, verbose)
     return CUDA_LIB
 
 
@@ -60,10 +96,7 @@ def build_prof(force: bool = False) -> str:
     deps = [os.path.join(CSRC, s) for s in CUDA_SOURCES + HEADERS]
     if not force and _newer(out, deps):
         return out
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-DSCAML_PROF", "-o", out] + CUDA_SOURCES
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc (prof build) failed:\n" + res.stdout + res.stderr)
+    _compile_parts(["-DSCAML_PROF"], out)
     return out
 
 
@@ -73,26 +106,9 @@ def build_ablate(force: bool = False) -> str:
     deps = [os.path.join(CSRC, s) for s in CUDA_SOURCES + HEADERS]
     if not force and _newer(out, deps):
         return out
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-DSCAML_ABLATE", "-o", out] + CUDA_SOURCES
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc (ablation build) failed:\n" + res.stdout + res.stderr)
+    _compile_parts(["-DSCAML_ABLATE"], out)
     return out
-
-
-def build_emu(force: bool = False) -> str:
-    deps = [os.path.join(CSRC, s) for s in ["scaml_capi.cu"] + HEADERS]
-    if not force and _newer(EMU_LIB, deps):
-        return EMU_LIB
-    cmd = ["g++", "-std=c++17", "-O2", "-mfma", "-DSCAML_EMU", "-x", "c++", "-fPIC", "-shared", "-pthread",
-           "-o", EMU_LIB, "scaml_capi.cu"]
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("g++ (emulation build) failed:\n" + res.stdout + res.stderr)
-    return EMU_LIB
 
 
 if __name__ == "__main__":
     print(build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv))
-    if "--emu" in sys.argv:
-        print(build_emu(force=True))

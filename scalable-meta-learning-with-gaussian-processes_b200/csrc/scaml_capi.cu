@@ -1,15 +1,34 @@
 // extern "C" entry points of libscaml_b200.so (see include/scaml_b200.h).
 // No torch types, no allocation: raw device pointers + sizes + stream.
+//
+// The file is compiled once per PART (-DSCAML_PART=0..3, build.py runs the four nvcc jobs in parallel and links the
+// objects) or, with SCAML_PART undefined, as one translation unit (the -DSCAML_EMU test build):
+//   part 0  fit kernel (4-warp), limits / version / workspace queries
+//   part 1  fit kernel (8-warp)
+//   part 2  kernel matrix, prediction, conditioning, values-from-U
+//   part 3  cross blocks, target GP, L-BFGS update, candidate gradients
+#ifndef SCAML_PART
+#define SCAML_PART (-1)
+#endif
+#define SCAML_HAS(k) (SCAML_PART == -1 || SCAML_PART == (k))
+
+#if SCAML_HAS(0) || SCAML_HAS(1)
 #include "scaml_fit.cuh"
 #include "scaml_fit8.cuh"
+#endif
+#if SCAML_HAS(2)
 #include "scaml_kmat.cuh"
 #include "scaml_predict.cuh"
 #include "scaml_cond.cuh"
+#include "scaml_gradval.cuh"
+#endif
+#if SCAML_HAS(3)
 #include "scaml_cross.cuh"
 #include "scaml_target.cuh"
 #include "scaml_lbfgs.cuh"
 #include "scaml_grad.cuh"
-#include "scaml_gradval.cuh"
+#endif
+#include "scaml_device.cuh"
 
 #ifndef SCAML_EMU
 #include <cuda_runtime.h>
@@ -21,24 +40,27 @@ namespace {
 
 constexpr size_t kMaxSmem = 227 * 1024;
 
-int g_num_sms = 0;
+int g_num_sms[64] = {0};      // SM count of the CURRENT device, cached per device ordinal
 long long* g_prof = nullptr;  // SCAML_PROF builds: per-CTA phase cycle counters
 int num_sms() {
 #ifdef SCAML_EMU
   return 2;
 #else
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& slot = g_num_sms[(dev >= 0 && dev < 64) ? dev : 0];
+  if (slot == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    slot = n > 0 ? n : 148;
   }
-  return g_num_sms;
+  return slot;
 #endif
 }
 
 inline int pad64(int n) { return ((n + 63) / 64) * 64; }
 
+#if SCAML_HAS(0)
 // persistent grid of the fit kernels: CTAs per SM allowed by shared memory (<= 3)
 int fit_ctas_per_sm(int n_pad, int d) {
   const size_t s = scaml::fit_smem_bytes(n_pad, d) + 1024;
@@ -69,6 +91,8 @@ int launch_fit(const scaml::FitParams& p, int grid, size_t smem, void* stream) {
 #endif
 }
 
+#endif
+#if SCAML_HAS(1)
 template <int KIND>
 int launch_fit8(const scaml::FitParams& p, int grid, size_t smem, void* stream) {
 #ifdef SCAML_EMU
@@ -84,7 +108,9 @@ int launch_fit8(const scaml::FitParams& p, int grid, size_t smem, void* stream) 
 #endif
 }
 
-int dispatch_fit8(const scaml::FitParams& p, int grid, size_t smem, void* stream) {
+}  // namespace
+__attribute__((visibility("hidden"))) int scaml_detail_dispatch_fit8(const scaml::FitParams& p, int grid, size_t smem,
+                                                                   void* stream) {
   switch (p.spec.kernel) {
     case SCAML_KERNEL_RBF: return launch_fit8<SCAML_KERNEL_RBF>(p, grid, smem, stream);
     case SCAML_KERNEL_MATERN12: return launch_fit8<SCAML_KERNEL_MATERN12>(p, grid, smem, stream);
@@ -93,11 +119,18 @@ int dispatch_fit8(const scaml::FitParams& p, int grid, size_t smem, void* stream
     default: return SCAML_E_ARG;
   }
 }
+namespace {
 
+#endif
+#if SCAML_HAS(0)
 // Two variants of the fit kernel (same algorithm, same results): 4-warp CTAs, three per SM (scaml_fit.cuh), and
 // 8-warp CTAs, two per SM (scaml_fit8.cuh).  Measured on B200 (profiles/r1_fit_variants.txt): the 4-warp
 // kernel wins up to n = 320 (RBF 722k vs 652k evals/s, Matern-5/2 626k vs 604k at n = 256), the 8-warp kernel
 // for larger tasks (118k vs 110k at n = 512, d = 10).  SCAML_FIT_IMPL=4|8 forces one (A/B runs).
+}  // namespace
+__attribute__((visibility("hidden"))) int scaml_detail_dispatch_fit8(const scaml::FitParams& p, int grid, size_t smem,
+                                                                   void* stream);
+namespace {
 bool use_fit8(int n_pad, int kernel) {
   if (const char* env = getenv("SCAML_FIT_IMPL")) {
     const int v = atoi(env);
@@ -139,13 +172,15 @@ int run_fit(scaml::FitParams p, void* workspace, size_t workspace_bytes, void* s
   }
   const long long E = (long long)p.M * p.R;
   if (E < grid) grid = (int)E;
-  return f8 ? dispatch_fit8(p, grid, smem, stream) : dispatch_fit(p, grid, smem, stream);
+  return f8 ? scaml_detail_dispatch_fit8(p, grid, smem, stream) : dispatch_fit(p, grid, smem, stream);
 }
 
+#endif
 }  // namespace
 
 extern "C" {
 
+#if SCAML_HAS(0)
 #ifdef SCAML_EMU
 // tests only: the device exponential evaluated on the host (same source, same FMA semantics)
 void scaml_debug_exp_nonpos(const double* x, double* out, int n) {
@@ -210,6 +245,8 @@ int scaml_factorize(const double* X, const double* y, const int32_t* n_valid, co
   return run_fit(p, workspace, workspace_bytes, stream);
 }
 
+#endif
+#if SCAML_HAS(2)
 int scaml_kernel_matrix(const double* X, const int32_t* n_valid, const double* theta, double* K, int M, int n_max,
                         int d, int kernel, void* stream) {
   if (!X || !theta || !K || M <= 0 || n_max <= 0 || d <= 0) return SCAML_E_ARG;
@@ -236,6 +273,8 @@ int scaml_predict_weighted(const double* X, const int32_t* n_valid, const double
                                         num_sms(), stream);
 }
 
+#endif
+#if SCAML_HAS(3)
 size_t scaml_predict_cross_workspace_bytes(int M, int nA, int nB, int reduce) {
   return scaml::cross_workspace_bytes(M, nA, nB, reduce, num_sms());
 }
@@ -403,6 +442,8 @@ int scaml_posterior_grad(const double* X, const int32_t* n_valid, const double* 
   return scaml::launch_posterior_grad(p, kernel, num_sms(), stream);
 }
 
+#endif
+#if SCAML_HAS(2)
 size_t scaml_posterior_values_from_u_workspace_bytes(int M, int B, int n_t) {
   if (M <= 0 || B <= 0 || n_t < 0) return 0;
   const int ntile = (B + scaml::kGvCT - 1) / scaml::kGvCT;
@@ -440,6 +481,8 @@ int scaml_posterior_values_from_u(const double* X, const int32_t* n_valid, const
   return scaml::launch_cond_combine(c, kernel, stream);
 }
 
+#endif
+#if SCAML_HAS(3)
 int scaml_lbfgs_step(const scaml_lbfgs_state* st, double* xt, const double* ft, const double* gt, const double* lower,
                      int E, int D, int m, int init, double gtol, double ftol, int maxiter, int max_ls, void* stream) {
   if (!st || !xt || !ft || !gt || !st->x || !st->f || !st->g || !st->d || !st->t || !st->S || !st->Y || !st->rho ||
@@ -453,6 +496,8 @@ int scaml_lbfgs_step(const scaml_lbfgs_state* st, double* xt, const double* ft, 
   return scaml::launch_lbfgs_step(p, stream);
 }
 
+#endif
+#if SCAML_HAS(2)
 int scaml_cond_prepare(const double* X, const int32_t* n_valid, const double* theta, const double* linv_packed,
                        const double* Xt, double* A, int M, int n_max, int d, int n_t, int kernel, void* stream) {
   if (!X || !theta || !linv_packed || !Xt || !A) return SCAML_E_ARG;
@@ -531,4 +576,5 @@ int scaml_predict_conditioned(const double* X, const int32_t* n_valid, const dou
   return scaml::launch_cond_combine(c, kernel, stream);
 }
 
+#endif
 }  // extern "C"

@@ -31,7 +31,6 @@ struct CondPrepParams {
   int M, n_max, n_pad, d, n_t, n_tp, pw, npanel;
 };
 
-inline int cond_ntp(int n_t) { return ((n_t + 7) / 8) * 8; }
 // shared memory (doubles): KV [n_pad][pw+4] | stage kPStages x 2 tiles | xst [d][n_pad] | xts [d][pw] | invl
 inline size_t cond_prep_smem_bytes(int n_pad, int d, int pw) {
   return sizeof(double) * ((size_t)n_pad * (pw + 4) + (size_t)kPStages * 2 * kPTile + (size_t)d * n_pad +

@@ -276,4 +276,7 @@ SCAML_DEVICE double dlog_prior(int kind, double p1, double p2, double x) {
 }
 SCAML_DEVICE double sigmoid(double x) { return 1.0 / (1.0 + exp(-x)); }
 
+// target points padded to whole 8-column DMMA blocks (shared by the conditioning and the gradient kernels)
+inline int cond_ntp(int n_t) { return ((n_t + 7) / 8) * 8; }
+
 }  // namespace scaml

@@ -19,7 +19,8 @@ from typing import List, Optional, Sequence, Tuple
 
 import torch
 
-from ._capi import PRIOR_GAMMA, HyperSpec, ScamlError, ScamlLib, load_cuda_library, pad64, packed_tiles
+from ._capi import (PRIOR_GAMMA, HyperSpec, NotPSDError, ScamlError, ScamlLib, load_cuda_library, pad64,
+                    packed_tiles)
 
 JITTER_LADDER = (1e-8, 1e-7, 1e-6)  # linear_operator psd_safe_cholesky (fp64), SURVEY A.5
 
@@ -136,14 +137,38 @@ class FittedSources:
                              self.alpha[i:i + 1], self.info[i:i + 1], self.spec)
 
 
+class _DeviceGuardedLib:
+    """View of the library that makes `device` current around every call that is made while another device is
+    current: the C ABI launches on the CURRENT device (attributes, SM count, kernel launches), while the engine's
+    buffers and stream live on `Engine.device`."""
+
+    def __init__(self, lib: ScamlLib, device: torch.device):
+        self._lib, self._index = lib, device.index if device.index is not None else torch.cuda.current_device()
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if not callable(fn):
+            return fn
+        index = self._index
+
+        def guarded(*args, **kwargs):
+            if torch.cuda.current_device() == index:
+                return fn(*args, **kwargs)
+            with torch.cuda.device(index):
+                return fn(*args, **kwargs)
+
+        self.__dict__[name] = guarded  # resolved once per entry point
+        return guarded
+
+
 class Engine:
-    """One engine per process / GPU.  All methods run on torch's current CUDA stream."""
+    """One engine per process / GPU.  All methods run on torch's current CUDA stream of `device`."""
 
     def __init__(self, device: Optional[torch.device] = None, lib: Optional[ScamlLib] = None):
         if not torch.cuda.is_available():
             raise ScamlError("scamlgp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-        self.lib = lib if lib is not None else load_cuda_library()
+        self.lib = _DeviceGuardedLib(lib if lib is not None else load_cuda_library(), self.device)
         self._ws: Optional[torch.Tensor] = None
         self._pws: Optional[torch.Tensor] = None
         self._cws: Optional[torch.Tensor] = None
@@ -225,7 +250,12 @@ class Engine:
         return lml, grad, info
 
     # ---- K1-K3 for prediction ------------------------------------------------------------ #
-    def factorize(self, batch: SourceBatch, theta_raw: torch.Tensor, spec: HyperSpec) -> FittedSources:
+    def factorize(self, batch: SourceBatch, theta_raw: torch.Tensor, spec: HyperSpec,
+                  check: bool = True) -> FittedSources:
+        """L^-1 (packed), alpha and the constrained parameters of every task; psd_safe_cholesky jitter ladder on the
+        failed tasks.  check=True raises NotPSDError when a task is still not positive definite afterwards (the
+        reference surfaces linear_operator's NotPSDError out of `posterior`); check=False returns the state with
+        `info > 0` / NaN rows for the caller to inspect."""
         M, P = theta_raw.shape
         assert M == batch.M and P == batch.d + 2
         theta_raw = theta_raw.contiguous()
@@ -248,6 +278,12 @@ class Engine:
             jitter = torch.where(bad, torch.full((M,), JITTER_LADDER[attempt], dtype=torch.float64, device=self.device),
                                  torch.zeros(M, dtype=torch.float64, device=self.device) if jitter is None else jitter)
             jitter = jitter.contiguous()
+        if check and bool((info != 0).any()):
+            # linear_operator's psd_safe_cholesky raises NotPSDError once the jitter ladder is exhausted; handing the
+            # NaN factors on would poison every weighted prediction (and topk / argmax rank NaN first)
+            bad = torch.nonzero(info != 0).flatten().tolist()
+            raise NotPSDError(f"Matrix not positive definite after repeatedly adding jitter up to "
+                              f"{JITTER_LADDER[-1]:.1e} (source tasks {bad[:16]}{'...' if len(bad) > 16 else ''})")
         return FittedSources(batch, theta_raw, theta, linv, alpha, info, spec)
 
     # ---- K6-K9 fused --------------------------------------------------------------------- #
@@ -431,9 +467,10 @@ class Engine:
         return lml, gw, gt, info
 
     # ---- target prediction state + conditioning ---------------------------------------- #
-    def target_factorize(self, source_means, source_covs, Xt, yt, w, theta_raw, mu_all, s_all, spec) -> "TargetState":
+    def target_factorize(self, source_means, source_covs, Xt, yt, w, theta_raw, mu_all, s_all, spec,
+                         check: bool = True) -> "TargetState":
         """L_t^-1, alpha_t and constrained kernel parameters of the target GP at (w [M], theta_raw [P]);
-        psd_safe_cholesky jitter ladder on failure."""
+        psd_safe_cholesky jitter ladder on failure, NotPSDError when it is exhausted (check=True)."""
         nt, d = Xt.shape
         M, P = w.numel(), d + 2
         linv = torch.empty(nt, nt, dtype=torch.float64, device=self.device)
@@ -451,6 +488,9 @@ class Engine:
             self.launches += 2
             if int(info.item()) == 0:
                 break
+        if check and int(info.item()) != 0:
+            raise NotPSDError(f"Target covariance not positive definite after repeatedly adding jitter up to "
+                              f"{JITTER_LADDER[-1]:.1e} (first failing pivot {int(info.item())})")
         return TargetState(Xt, linv, alpha, theta, float(mu_all), float(s_all), int(info.item()), float(lml.item()),
                            spec.kernel)
 

@@ -100,8 +100,9 @@ def _batch_from_sources(source_gps: Dict[Hashable, SourceGP], engine: Engine) ->
 
 def fitted_sources_of(source_gps: Dict[Hashable, SourceGP], engine: Optional[Engine] = None) -> FittedSources:
     """The device batch behind a dict of source GPs, in the dict's iteration order."""
-    if isinstance(source_gps, SourceGPDict) and [g._index for g in source_gps.values()] == list(range(len(source_gps))):
-        return source_gps.fitted
+    if (isinstance(source_gps, SourceGPDict) and len(source_gps) == source_gps.fitted.batch.M
+            and [g._index for g in source_gps.values()] == list(range(len(source_gps)))):
+        return source_gps.fitted  # untouched dict: the device batch as fitted (a dict with tasks deleted re-selects)
     eng = engine or (source_gps.engine if isinstance(source_gps, SourceGPDict) else default_engine())
     owner = next(iter(source_gps.values()))._owner
     idx = [g._index for g in source_gps.values()]

@@ -85,13 +85,16 @@ class ShardedSources:
         self.ystd_all: Optional[torch.Tensor] = None
         self.fitted: Optional[FittedSources] = None
         self._condA: Optional[torch.Tensor] = None  # A_m = K_m^-1 K_m(X_m, X_t) of the local tasks
-        self._cond_key = None
+        self._cond_Xt: Optional[torch.Tensor] = None  # the target inputs `_condA` was prepared for (a private copy)
+        self._cond_gen = -1  # fit generation `_condA` belongs to
+        self._gen = 0  # bumped by every fit() / set_parameters(): A_m depends on the hyper-parameters
 
     # ---- fit: no collective on the data path ----------------------------------------------------------- #
     def fit(self, spec: HyperSpec, theta_init: torch.Tensor, fit_options: Optional[dict] = None) -> ShardedFit:
         """theta_init [M, R, P] for ALL tasks (identical on every rank: restart draws are positional)."""
         local = fit_sources(self.engine, self.batch, spec, theta_init[self.lo:self.hi].contiguous(), fit_options)
         self.fitted = self.engine.factorize(self.batch, local.theta_raw, spec)
+        self._invalidate()
         rows = torch.cat([local.theta_raw, local.lml.unsqueeze(1), self.batch.ystd.unsqueeze(1)], dim=1)
         rows = _all_gather_rows(rows, self.counts, self.group)
         P = local.theta_raw.shape[1]
@@ -102,7 +105,23 @@ class ShardedSources:
         """Factorise this rank's block at given parameters [M, P] (e.g. restored from a previous fit)."""
         th = theta_raw_all[self.lo:self.hi].to(self.engine.device, DT).contiguous()
         self.fitted = self.engine.factorize(self.batch, th, spec)
+        self._invalidate()
         self.ystd_all = _all_gather_rows(self.batch.ystd.unsqueeze(1), self.counts, self.group).squeeze(1).contiguous()
+
+    def _invalidate(self) -> None:
+        self._gen += 1
+        self._condA = self._cond_Xt = None
+
+    def cond_A(self, Xt: torch.Tensor) -> torch.Tensor:
+        """A_m = K_m^-1 K_m(X_m, X_t) of the local tasks, cached per (fit generation, CONTENTS of X_t): a refit or
+        a different set of target inputs -- even one that re-uses the old tensor's address -- recomputes it."""
+        Xt = Xt.to(self.engine.device, DT).contiguous()
+        hit = (self._condA is not None and self._cond_gen == self._gen and self._cond_Xt is not None
+               and self._cond_Xt.shape == Xt.shape and bool(torch.equal(self._cond_Xt, Xt)))
+        if not hit:
+            self._condA = self.engine.cond_prepare(self.fitted, Xt)
+            self._cond_Xt, self._cond_gen = Xt.clone(), self._gen
+        return self._condA
 
     def _local_w(self, w: torch.Tensor) -> torch.Tensor:
         return w.to(self.engine.device, DT)[self.lo:self.hi].contiguous()
@@ -131,10 +150,7 @@ class ShardedSources:
         """`source_means` [n_t, M], `source_covs` [n_t, n_t, M] for ALL tasks, gathered along the task axis."""
         eng = self.engine
         if eng.cond_supported(self.fitted, Xt.shape[0]):  # from A_m (any n the prediction kernel accepts)
-            key = (Xt.data_ptr(), Xt.shape[0])
-            if self._cond_key != key:
-                self._condA, self._cond_key = eng.cond_prepare(self.fitted, Xt), key
-            sm, sc = eng.cond_caches(self.fitted, Xt, self._condA)
+            sm, sc = eng.cond_caches(self.fitted, Xt, self.cond_A(Xt))
         else:
             sm, sc = eng.predict_cross(self.fitted, Xt)
         if self.world == 1:
@@ -159,10 +175,8 @@ class ShardedSources:
         if eng.cond_supported(self.fitted, n_t):
             # fused path: local prior mean / variance / cross-covariance in one prediction launch, then ONE
             # all_reduce over the stacked partials [B, 2 + n_t]
-            key = (tstate.Xt.data_ptr(), n_t)
-            if self._cond_key != key:
-                self._condA, self._cond_key = eng.cond_prepare(self.fitted, tstate.Xt), key
-            pm, pv, cross = eng.predict_conditioned(self.fitted, self._local_w(w), Xc, tstate.Xt, self._condA)
+            pm, pv, cross = eng.predict_conditioned(self.fitted, self._local_w(w), Xc, tstate.Xt,
+                                                    self.cond_A(tstate.Xt))
             if self.world > 1:
                 flat = torch.cat([pm.unsqueeze(1), pv.unsqueeze(1), cross], dim=1).contiguous()
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
@@ -196,16 +210,14 @@ class ShardedSources:
             n_t = tstate.Xt.shape[0]
             if not eng.cond_supported(self.fitted, n_t):
                 raise NotImplementedError("candidate gradients need n <= 512 points per task, d <= 16, n_t <= 128")
-            key = (tstate.Xt.data_ptr(), n_t)
-            if self._cond_key != key:
-                self._condA, self._cond_key = eng.cond_prepare(self.fitted, tstate.Xt), key
-            pm, pv, cross = eng.prior_values(self.fitted, wl, Xc, U, tstate.Xt, self._condA)
+            condA = self.cond_A(tstate.Xt)
+            pm, pv, cross = eng.prior_values(self.fitted, wl, Xc, U, tstate.Xt, condA)
             if self.world > 1:
                 flat = torch.cat([pm.unsqueeze(1), pv.unsqueeze(1), cross], dim=1).contiguous()
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
                 pm, pv, cross = flat[:, 0].contiguous(), flat[:, 1].contiguous(), flat[:, 2:].contiguous()
             mean, var, beta = eng.target_posterior_beta(tstate, pm, pv, cross, Xc)
-            dm, dv = eng.posterior_grad(self.fitted, wl, Xc, U, tstate, self._condA, beta,
+            dm, dv = eng.posterior_grad(self.fitted, wl, Xc, U, tstate, condA, beta,
                                         target_terms=(self.rank == 0))
         if self.world > 1:
             g = torch.cat([dm, dv], dim=1).contiguous()

@@ -15,10 +15,10 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def emu_lib():
     """CPU logic-emulation build of the kernel sources (tests only, never the product path)."""
-    from scamlgp_b200 import build
     from scamlgp_b200._capi import ScamlLib
+    from tests.emu_build import build_emu
 
-    return ScamlLib(build.build_emu())
+    return ScamlLib(build_emu())
 
 
 @pytest.fixture(scope="session")

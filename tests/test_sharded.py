@@ -60,13 +60,13 @@ def _worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
 
-    from scamlgp_b200 import build
     from scamlgp_b200._capi import ScamlLib
+    from tests.emu_build import build_emu
     from tests.emu_engine import EmuEngine
 
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        res = _run(EmuEngine(ScamlLib(build.build_emu())), None)
+        res = _run(EmuEngine(ScamlLib(build_emu())), None)
         torch.save(res, os.path.join(out_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
