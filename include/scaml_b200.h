@@ -149,6 +149,10 @@ int scaml_predict_cross(const double* X, const int32_t* n_valid, const double* t
  * Replaces `mll(model(X_t), y_t)` + backward on the `ScaMLGP.forward` training branch
  * (reference scamlgp/model.py:359-363,376-383; weights prior :325-330).  n_t <= 116. */
 size_t scaml_target_workspace_bytes(int n_t, int R);
+/* Largest n_t the shared-memory target-GP kernels accept at input dimension d (their n_t x n_t system plus the
+ * d x n_t scaled inputs must fit 227 KB: 116 for small d); the host mirrors raise above it
+ * (scamlgp_b200/model.py: ScaMLGP.__init__) where the reference (model.py:359-384) has no limit. */
+int scaml_target_max_points(int d);
 int scaml_target_lml_grad(const double* source_means, const double* source_covs, const double* Xt,
                           const double* yt, const double* w, const double* theta_raw,
                           const double* jitter, double mu_all, double s_all, double* lml,

@@ -431,8 +431,9 @@ def target_objective(cache: TargetCache, weights: torch.Tensor, theta_raw: torch
 
 
 def scaml_posterior(states, weights, cache: Optional[TargetCache], theta_raw, spec: HyperSpec,
-                    Xs: torch.Tensor, prune_threshold: Optional[float] = 1e-3):
-    """Full ScaML-GP posterior mean/variance at Xs (q=1 per candidate), un-standardised.
+                    Xs: torch.Tensor, prune_threshold: Optional[float] = 1e-3, full_cov: bool = False):
+    """Full ScaML-GP posterior mean/variance at Xs (q=1 per candidate), un-standardised; full_cov=True returns the
+    JOINT covariance [q, q] of the points Xs instead of their variances (one q-batch of model.py:364-375).
 
     n_t = 0  -> prior: sum_i w_i mu_i(x), sum_i w_i^2 var_i(x) + s_t   (A.8 last bullets)
     n_t > 0  -> exact conditioning on the target data in the all-data standardised space.
@@ -444,6 +445,14 @@ def scaml_posterior(states, weights, cache: Optional[TargetCache], theta_raw, sp
         std_y = torch.tensor([s.ystd for s in states], dtype=DT)
         mask = significant_weights_mask(weights, std_y, prune_threshold)
     if cache is None or cache.Xt.shape[0] == 0:
+        if full_cov:
+            mean = torch.zeros(Xs.shape[0], dtype=DT)
+            cov = kernel_matrix(Xs, Xs, ls, os_, spec.kernel)
+            for st, w, keep in zip(states, weights, mask):
+                if bool(keep):
+                    m, c = posterior(st, Xs, full_cov=True)
+                    mean, cov = mean + w * m, cov + w * w * c
+            return mean, cov
         mean, var = scaml_prior_predict(states, weights, Xs, prune_threshold)
         return mean, var + os_
     nt = cache.Xt.shape[0]
@@ -464,6 +473,8 @@ def scaml_posterior(states, weights, cache: Optional[TargetCache], theta_raw, sp
     a = torch.cholesky_solve((cache.yt_std - mean_j[:nt]).reshape(-1, 1), L).reshape(-1)
     mu = mean_j[nt:] + Kst @ a
     V = torch.linalg.solve_triangular(L, Kst.T, upper=False)
+    if full_cov:
+        return cache.mu_all + cache.s_all * mu, cache.s_all**2 * (cov_j[nt:, nt:] - V.T @ V)
     var = torch.diagonal(cov_j[nt:, nt:]) - (V * V).sum(0)
     return cache.mu_all + cache.s_all * mu, cache.s_all**2 * var
 

@@ -299,6 +299,13 @@ size_t scaml_target_workspace_bytes(int n_t, int R) {
   return scaml::target_workspace_doubles(n_t, R) * sizeof(double);
 }
 
+int scaml_target_max_points(int d) {
+  if (d <= 0 || d > scaml::kMaxP - 2) return 0;
+  int nt = 0;
+  while (scaml::target_smem_bytes(nt + 1, d) <= (size_t)227 * 1024) ++nt;
+  return nt;
+}
+
 int scaml_target_lml_grad(const double* source_means, const double* source_covs, const double* Xt, const double* yt,
                           const double* w, const double* theta_raw, const double* jitter, double mu_all, double s_all,
                           double* lml, double* grad_w, double* grad_theta, int32_t* info, void* workspace,

@@ -28,6 +28,15 @@ from .utils import validate_meta_data
 MAX_TARGET_POINTS = 116  # scaml_target_* kernels: K_t and L_t^-1 (n_t x n_t each) live in 227 KB of shared memory
 
 
+def max_target_points(engine: Engine, d: int) -> int:
+    """Largest n_t whose target-GP kernels fit 227 KB of shared memory at input dimension d (the footprint grows with
+    d * n_t: 116 for small d, ~113 at d = 16), asked of the library (`scaml_target_max_points`)."""
+    try:
+        return int(engine.lib.target_max_points(int(d)))
+    except AttributeError:
+        return MAX_TARGET_POINTS
+
+
 # ---- defaults (reference model.py:25-105) ---------------------------------------------------- #
 def _get_default_likelihood(batch_shape: torch.Size = torch.Size()) -> GaussianLikelihood:
     return GaussianLikelihood(noise_prior=LogNormalPrior(-8.0, 2.0), noise_constraint=Interval(1e-8, 1e-2, 1e-3),
@@ -73,7 +82,11 @@ class SourceGP:
 
     def posterior(self, X: torch.Tensor) -> Posterior:
         """Posterior of this source GP at X [n, d] (un-standardised, noise-free), full covariance."""
-        fs = self._owner.fitted.task_slice(self._index)
+        sh = getattr(self._owner, "sharded", None)
+        if sh is not None and not (sh.lo <= self._index < sh.hi):
+            raise NotImplementedError(f"source task {self._index} lives on another rank (this rank owns tasks "
+                                      f"[{sh.lo}, {sh.hi})); query it there or use the weighted ScaMLGP posterior")
+        fs = self._owner.fitted.task_slice(self._index - (sh.lo if sh is not None else 0))
         eng = self._owner.engine
         Xd = X.reshape(-1, X.shape[-1]).to(eng.device, DT).contiguous()
         mean, cov = eng.predict_cross(fs, Xd)
@@ -82,10 +95,13 @@ class SourceGP:
 
 
 class SourceGPDict(dict):
-    """Dict[task_id, SourceGP] that also carries the device-resident batch of all fitted tasks."""
+    """Dict[task_id, SourceGP] that also carries the device-resident batch of all fitted tasks -- or, after a
+    task-sharded meta-fit (`meta_fit_scamlgp(..., group=...)`), this rank's block of them plus the collectives
+    (`sharded`: scamlgp_b200.sharded.ShardedSources)."""
 
     engine: Engine
     fitted: FittedSources
+    sharded = None
 
 
 def _batch_from_sources(source_gps: Dict[Hashable, SourceGP], engine: Engine) -> FittedSources:
@@ -100,6 +116,9 @@ def _batch_from_sources(source_gps: Dict[Hashable, SourceGP], engine: Engine) ->
 
 def fitted_sources_of(source_gps: Dict[Hashable, SourceGP], engine: Optional[Engine] = None) -> FittedSources:
     """The device batch behind a dict of source GPs, in the dict's iteration order."""
+    if getattr(source_gps, "sharded", None) is not None:
+        raise NotImplementedError("task-sharded source GPs are queried through their ShardedSources "
+                                  "(ScaMLGP does this); there is no single device batch of all tasks")
     if (isinstance(source_gps, SourceGPDict) and len(source_gps) == source_gps.fitted.batch.M
             and [g._index for g in source_gps.values()] == list(range(len(source_gps)))):
         return source_gps.fitted  # untouched dict: the device batch as fitted (a dict with tasks deleted re-selects)
@@ -114,11 +133,17 @@ def fitted_sources_of(source_gps: Dict[Hashable, SourceGP], engine: Optional[Eng
 def meta_fit_scamlgp(meta_data: Dict[Hashable, SupervisedDataset], likelihood: Optional[GaussianLikelihood] = None,
                      covar_module: Optional[ScaleKernel] = None, num_restarts_log_likelihood: int = 5,
                      seed: Optional[int] = None, *, engine: Optional[Engine] = None,
-                     fit_options: Optional[dict] = None) -> Dict[Hashable, SourceGP]:
+                     fit_options: Optional[dict] = None, group=None) -> Dict[Hashable, SourceGP]:
     """Train the source GPs on the given meta-data (reference scamlgp/model.py:138-189).
 
     All tasks and all restarts are optimised together on the GPU; returns {task_id: SourceGP} in the
-    order of `meta_data` (a SourceGPDict, which also owns the packed device state used for prediction)."""
+    order of `meta_data` (a SourceGPDict, which also owns the packed device state used for prediction).
+
+    group: a torch.distributed process group (or True for the default group) -> the tasks are block-partitioned
+    over its ranks (one process per GPU; the reference's loop over independent tasks, model.py:176-188, fans out):
+    every rank fits and factorises only its block, one all_gather shares the fitted rows, and the returned dict
+    carries `sharded` (ShardedSources) through which `ScaMLGP` / `ScaMLGPBO` predict with one all_reduce per call.
+    Every rank must pass the same meta-data and seed and gets the same dict back."""
     generator = None
     if seed is not None:
         torch.manual_seed(seed)
@@ -138,17 +163,25 @@ def meta_fit_scamlgp(meta_data: Dict[Hashable, SupervisedDataset], likelihood: O
     spec = hyper_spec_of(likelihood, covar_module)
     theta0 = theta_raw_of(likelihood, covar_module, d)
     tasks = [(ds.X(), ds.Y()) for ds in meta_data.values()]
-    batch = SourceBatch.from_ragged(tasks, eng.device)
     M, R = len(tasks), 1 + int(num_restarts_log_likelihood)
     rows = [theta0.reshape(1, 1, -1).expand(M, 1, -1)]
     if R > 1:
-        rows.append(sample_theta_raw(spec, theta0, M, R - 1, generator))
-    fit = fit_sources(eng, batch, spec, torch.cat(rows, dim=1), fit_options)
-    fitted = eng.factorize(batch, fit.theta_raw, spec)
+        rows.append(sample_theta_raw(spec, theta0, M, R - 1, generator))  # positional: identical on every rank
     out = SourceGPDict()
-    out.engine, out.fitted, out.fit = eng, fitted, fit
-    theta_host = fit.theta_raw.cpu()
-    ybar, ystd = batch.ybar.cpu(), batch.ystd.cpu()
+    if group is not None:
+        from .sharded import ShardedSources
+
+        src = ShardedSources(eng, tasks, group=None if group is True else group)
+        sfit = src.fit(spec, torch.cat(rows, dim=1), fit_options)
+        out.engine, out.fitted, out.fit, out.sharded = eng, src.fitted, sfit, src
+        theta_host, ybar, ystd = sfit.theta_raw.cpu(), src.ybar_all.cpu(), src.ystd_all.cpu()
+    else:
+        batch = SourceBatch.from_ragged(tasks, eng.device)
+        fit = fit_sources(eng, batch, spec, torch.cat(rows, dim=1), fit_options)
+        fitted = eng.factorize(batch, fit.theta_raw, spec)
+        out.engine, out.fitted, out.fit = eng, fitted, fit
+        theta_host = fit.theta_raw.cpu()
+        ybar, ystd = batch.ybar.cpu(), batch.ystd.cpu()
     for i, (task_id, (X, Y)) in enumerate(zip(meta_data.keys(), tasks)):
         lk, cm = copy.deepcopy(likelihood), copy.deepcopy(covar_module)
         set_theta_raw(lk, cm, theta_host[i])
@@ -193,27 +226,38 @@ class ScaMLGP:
         gps = list(source_gps.values())
         self.engine = engine or (source_gps.engine if isinstance(source_gps, SourceGPDict) else gps[0]._owner.engine)
         dev = self.engine.device
-        self._fitted = fitted_sources_of(source_gps, self.engine)
+        # task-sharded source GPs (meta_fit_scamlgp(..., group=)): this rank holds a block of the tasks; caches are
+        # all_gathered, predictions all_reduced (sharded.py).  Every rank builds the same model object.
+        self._sharded = getattr(source_gps, "sharded", None)
+        if self._sharded is not None and len(source_gps) != self._sharded.M:
+            raise NotImplementedError("a task-sharded SourceGPDict must be used whole (all tasks, original order)")
+        self._fitted = self._sharded.fitted if self._sharded is not None else fitted_sources_of(source_gps, self.engine)
         d = train_X.shape[-1]
         # all-data normaliser (model.py:264-276): every source task's raw Y + the target Y, frozen
-        b = self._fitted.batch
-        mask = torch.arange(b.n_max, device=dev).unsqueeze(0) < b.n_valid.unsqueeze(1)
-        Y_all = torch.cat([b.Y_raw[mask], train_Y.reshape(-1).to(dev, DT)])
+        if self._sharded is not None:
+            Y_all = torch.cat([self._sharded.all_Y.to(dev, DT), train_Y.reshape(-1).to(dev, DT)])
+        else:
+            b = self._fitted.batch
+            mask = torch.arange(b.n_max, device=dev).unsqueeze(0) < b.n_valid.unsqueeze(1)
+            Y_all = torch.cat([b.Y_raw[mask], train_Y.reshape(-1).to(dev, DT)])
         outcome_transform = Standardize(1)
         outcome_transform(Y_all.cpu())
         outcome_transform.eval()
         self.train_inputs = (train_X,)
         self._train_Y = train_Y
         n_t = train_Y.shape[-2]
-        if n_t > MAX_TARGET_POINTS:
+        limit = max_target_points(self.engine, d)
+        if n_t > limit:
             raise NotImplementedError(
                 f"{n_t} target observations: the target-GP kernels hold the n_t x n_t system in shared memory and "
-                f"support n_t <= {MAX_TARGET_POINTS} in this release (the reference's experiments use <= 80 evaluations)")
+                f"support n_t <= {limit} at d = {d} in this release (the reference's experiments use <= 80 evaluations)")
         self._Xt = train_X.reshape(n_t, d).to(dev, DT).contiguous()
         # cache the source posteriors at the target inputs (model.py:278-289): one launch for all tasks
         self._condA: Optional[torch.Tensor] = None  # K_m^-1 K_m(X_m, X_t) of every source task
         if n_t > 0:
-            if self.engine.cond_supported(self._fitted, n_t):
+            if self._sharded is not None:
+                self.source_means, self.source_covs = self._sharded.target_caches(self._Xt)
+            elif self.engine.cond_supported(self._fitted, n_t):
                 # A_m once per model; the caches and every later posterior call are contractions with it
                 self._condA = self.engine.cond_prepare(self._fitted, self._Xt)
                 self.source_means, self.source_covs = self.engine.cond_caches(self._fitted, self._Xt, self._condA)
@@ -294,6 +338,8 @@ class ScaMLGP:
         return theta_raw_of(self.likelihood, self.covar_module, self._Xt.shape[1])
 
     def _std_Y_vals(self) -> torch.Tensor:
+        if self._sharded is not None:
+            return self._sharded.ystd_all.to(self.engine.device, DT)
         return self._fitted.batch.ystd
 
     def pruned_weights(self) -> torch.Tensor:
@@ -316,13 +362,22 @@ class ScaMLGP:
 
     # ---- forward / posterior ------------------------------------------------------------------ #
     def forward(self, x: torch.Tensor) -> MultivariateNormal:
-        """Prior of the target process at x [n, d] in the (all-data) standardised space (model.py:359-384)."""
+        """Prior of the target process at x [n, d] (or batch_shape x n x d: one joint prior per batch element) in the
+        (all-data) standardised space (model.py:359-384)."""
+        if x.dim() > 2:
+            lead = x.shape[:-2]
+            parts = [self.forward(xi) for xi in x.reshape(-1, x.shape[-2], x.shape[-1])]
+            return MultivariateNormal(torch.stack([p.mean for p in parts]).reshape(*lead, -1),
+                                      torch.stack([p.covariance_matrix for p in parts]).reshape(
+                                          *lead, x.shape[-2], x.shape[-2]))
         eng, dev = self.engine, self.engine.device
         xd = x.reshape(-1, x.shape[-1]).to(dev, DT).contiguous()
         if self.training:
             w = self.weights.to(dev, DT)
             mean = self.source_means @ w
             cov = self.source_covs @ w ** 2
+        elif self._sharded is not None:
+            mean, cov = self._sharded.predict_cross(self.pruned_weights(), xd)
         else:
             mean, cov = eng.predict_cross(self._fitted, xd, None, w=self.pruned_weights())
         if self.outcome_transform is not None:
@@ -330,35 +385,117 @@ class ScaMLGP:
             mean = (mean - mu) / sd
             cov = cov / sd ** 2
         spec = self.hyper_spec()
-        ls = self.covar_module.base_kernel.lengthscale.reshape(-1).to(dev)
-        if ls.numel() == 1:
-            ls = ls.expand(xd.shape[1])
-        theta = torch.cat([ls, self.covar_module.outputscale.reshape(1).to(dev), torch.zeros(1, dtype=DT, device=dev)])
-        kt = eng.kernel_matrix(xd.unsqueeze(0), theta.reshape(1, -1).contiguous(), spec.kernel)[0]
+        kt = eng.kernel_matrix(xd.unsqueeze(0), self._target_kernel_theta(xd.shape[1]), spec.kernel)[0]
         return MultivariateNormal(mean, cov + kt)
 
     def posterior(self, X: torch.Tensor, observation_noise: bool = False) -> Posterior:
-        """Posterior at candidates X [B, d] or [B, 1, d] (q = 1), un-standardised: mean/variance [B, 1]."""
+        """Posterior at X, un-standardised (botorch `Model.posterior` shapes, reference model.py:359-384).
+
+        X [B, d] or [B, 1, d]: B independent candidates (q = 1, the acquisition path) -> mean / variance [B, 1].
+        X [b..., q, d] with q > 1: joint posterior over the q points of every batch element -> mean / variance
+        [b..., q, 1] and `.mvn.covariance_matrix` [b..., q, q]."""
         if observation_noise:
             raise NotImplementedError("observation_noise=True is not used on the reference path")
         eng, dev = self.engine, self.engine.device
-        if X.dim() == 3:
-            if X.shape[-2] != 1:
-                raise NotImplementedError("only q = 1 candidate batches (the acquisition path) are supported")
-            X = X[:, 0, :]
+        if X.dim() >= 3 and X.shape[-2] != 1:
+            return self._posterior_joint(X)
+        if X.dim() >= 3:
+            lead = X.shape[:-2]
+            X = X.reshape(-1, X.shape[-1])
+        else:
+            lead = None
         Xc = X.to(dev, DT).contiguous()
         w = self.pruned_weights()
-        if self.num_train > 0 and eng.cond_supported(self._fitted, self.num_train):
+        if self._sharded is not None:
+            ts = self._target_state() if self.num_train > 0 else None
+            mean, var = self._sharded.posterior(w, Xc, ts, float(self.covar_module.outputscale))
+        elif self.num_train > 0 and eng.cond_supported(self._fitted, self.num_train):
             mean, var = self._posterior_fused(Xc, w)
-            return Posterior(mean.to(X.device), var.to(X.device))
-        pm, pv = eng.predict_weighted(self._fitted, w, Xc)
-        if self.num_train == 0:
-            # prior-only model (optimizer.py:135-141): no outcome transform, var + s_t
-            mean, var = pm, pv + float(self.covar_module.outputscale)
         else:
-            _, cross = eng.predict_cross(self._fitted, Xc, self._Xt, w=w)
-            mean, var = eng.target_posterior(self._target_state(), pm, pv, cross, Xc)
-        return Posterior(mean.to(X.device), var.to(X.device))
+            pm, pv = eng.predict_weighted(self._fitted, w, Xc)
+            if self.num_train == 0:
+                # prior-only model (optimizer.py:135-141): no outcome transform, var + s_t
+                mean, var = pm, pv + float(self.covar_module.outputscale)
+            else:
+                _, cross = eng.predict_cross(self._fitted, Xc, self._Xt, w=w)
+                mean, var = eng.target_posterior(self._target_state(), pm, pv, cross, Xc)
+        mean, var = mean.to(X.device), var.to(X.device)
+        if lead is not None and len(lead) > 1:
+            return Posterior(mean.reshape(*lead, 1), var.reshape(*lead, 1))
+        return Posterior(mean, var)
+
+    def _target_kernel_theta(self, d: int) -> torch.Tensor:
+        dev = self.engine.device
+        ls = self.covar_module.base_kernel.lengthscale.reshape(-1).to(dev)
+        if ls.numel() == 1:
+            ls = ls.expand(d)
+        return torch.cat([ls, self.covar_module.outputscale.reshape(1).to(dev),
+                          torch.zeros(1, dtype=DT, device=dev)]).reshape(1, -1).contiguous()
+
+    def _posterior_joint(self, X: torch.Tensor) -> Posterior:
+        """q > 1: the joint blocks of the eval branch (model.py:364-375 evaluates every source posterior at
+        [X_t; X*] jointly).  The weighted source blocks Sigma(X*, X*) and Sigma(X*, X_t) come from the fused
+        prediction kernel -- the candidates of a chunk of batch elements play the role of the "target inputs" of
+        `cond_prepare` / `predict_conditioned`, so one launch gives all their pair covariances, n <= 512 -- and the
+        n_t-dimensional conditioning (q x n_t blocks against the cached L_t^-1, alpha_t) is torch on the device."""
+        eng, dev = self.engine, self.engine.device
+        lead, q, d = X.shape[:-2], X.shape[-2], X.shape[-1]
+        if q > 128:
+            raise NotImplementedError("joint posteriors are supported for q <= 128 points per batch element")
+        Xall = X.reshape(-1, q, d).to(dev, DT)
+        nb_all, n_t = Xall.shape[0], self.num_train
+        w = self.pruned_weights()
+        ts = self._target_state() if n_t > 0 else None
+        spec = self.hyper_spec()
+        theta_t = self._target_kernel_theta(d)
+        means, covs = [], []
+        step = max(1, 128 // q)
+        for lo in range(0, nb_all, step):
+            Xf = Xall[lo:lo + step].reshape(-1, d).contiguous()  # [nb * q, d]
+            nb = Xf.shape[0] // q
+            pm, cqq, cqt = self._weighted_blocks(Xf, w)
+            Z = torch.cat([self._Xt, Xf]) if n_t > 0 else Xf
+            kt = eng.kernel_matrix(Z.unsqueeze(0).contiguous(), theta_t, spec.kernel)[0]
+            kqq = kt[n_t:, n_t:]
+            idx = torch.arange(nb * q, device=dev).reshape(nb, q)
+            blk = lambda A: A[idx.unsqueeze(2), idx.unsqueeze(1)]  # noqa: E731  [nb, q, q] diagonal blocks
+            if n_t == 0:  # prior-only model (optimizer.py:135-141): no outcome transform
+                mean, cov = pm.reshape(nb, q), blk(cqq) + blk(kqq)
+            else:
+                mu, sd = ts.mu_all, ts.s_all
+                cst = cqt / sd ** 2 + kt[n_t:, :n_t]  # [nb q, n_t] standardised cross-covariance with X_t
+                V = ts.linv @ cst.t()  # [n_t, nb q]
+                mean_s = (pm - mu) / sd + cst @ ts.alpha
+                cov_s = blk(cqq) / sd ** 2 + blk(kqq) - blk(V.t() @ V)
+                mean, cov = (mu + sd * mean_s).reshape(nb, q), sd ** 2 * cov_s
+            means.append(mean)
+            covs.append(cov)
+        mean = torch.cat(means).reshape(*lead, q).to(X.device)
+        cov = torch.cat(covs).reshape(*lead, q, q).to(X.device)
+        return Posterior(mean, cov.diagonal(dim1=-2, dim2=-1), cov)
+
+    def _weighted_blocks(self, Xf: torch.Tensor, w: torch.Tensor):
+        """Weighted source prior at the points Xf [B, d] (raw-Y units): mean [B], Sigma(Xf, Xf) [B, B] and
+        Sigma(Xf, X_t) [B, n_t] (None without target data), summed over ALL tasks."""
+        eng, n_t = self.engine, self.num_train
+        if self._sharded is not None:
+            mean, cqq = self._sharded.predict_cross(w, Xf)
+            cqt = self._sharded.predict_cross(w, Xf, self._Xt)[1] if n_t > 0 else None
+            return mean, cqq, cqt
+        fs = self._fitted
+        if eng.cond_supported(fs, Xf.shape[0]):
+            U = eng.cond_prepare(fs, Xf, w)  # K_m^-1 K_m(X_m, Xf): the points are their own "target inputs"
+            mean, _, cqq = eng.predict_conditioned(fs, w, Xf, Xf, U)
+            cqq = 0.5 * (cqq + cqq.t())
+            cqt = None
+            if n_t > 0:
+                if self._condA is None:
+                    self._condA = eng.cond_prepare(fs, self._Xt)
+                cqt = eng.predict_conditioned(fs, w, Xf, self._Xt, self._condA)[2]
+            return mean, cqq, cqt
+        mean, cqq = eng.predict_cross(fs, Xf, None, w=w)
+        cqt = eng.predict_cross(fs, Xf, self._Xt, w=w)[1] if n_t > 0 else None
+        return mean, cqq, cqt
 
     @property
     def supports_candidate_gradients(self) -> bool:
@@ -377,7 +514,7 @@ class ScaMLGP:
         eng, dev = self.engine, self.engine.device
         if X.dim() == 3:
             if X.shape[-2] != 1:
-                raise NotImplementedError("only q = 1 candidate batches (the acquisition path) are supported")
+                raise NotImplementedError("candidate gradients cover q = 1 batches (the acquisition path)")
             X = X[:, 0, :]
         b = self._fitted.batch
         if not self.supports_candidate_gradients:
@@ -385,11 +522,15 @@ class ScaMLGP:
         Xall = X.to(dev, DT).contiguous()
         w = self.pruned_weights()
         n_t = self.num_train
-        if n_t > 0 and self._condA is None:
+        if n_t > 0 and self._condA is None and self._sharded is None:
             self._condA = eng.cond_prepare(self._fitted, self._Xt)
         outs = []
         for lo in range(0, Xall.shape[0], 128):
             Xc = Xall[lo:lo + 128].contiguous()
+            if self._sharded is not None:
+                outs.append(self._sharded.posterior_with_grad(w, Xc, self._target_state() if n_t > 0 else None,
+                                                              float(self.covar_module.outputscale)))
+                continue
             U = eng.cond_prepare(self._fitted, Xc, w)  # pruned tasks skipped
             if n_t > 0:
                 ts = self._target_state()

@@ -198,9 +198,14 @@ class ScaMLGPBO(_SingleObjectiveBase):
                  max_pending_evaluations: Optional[int] = 1, num_restarts_log_likelihood: int = 5,
                  model_kwargs: Optional[Dict[str, Any]] = None, logger: Optional[logging.Logger] = None,
                  seed: Optional[int] = None, torch_dtype: torch.dtype = torch.float64, *, engine=None,
-                 fit_options: Optional[dict] = None):
+                 fit_options: Optional[dict] = None, group=None):
         """Single objective meta-learning BO optimizer with ScaML-GP as surrogate
-        (reference scamlgp/optimizer.py:28-154: same arguments; `engine` / `fit_options` are additions)."""
+        (reference scamlgp/optimizer.py:28-154: same arguments; `engine` / `fit_options` / `group` are additions).
+
+        group: torch.distributed process group (True = default group): the meta-tasks are block-partitioned over its
+        ranks -- the meta-fit (optimizer.py:128-133), the per-report caches (model.py:278-289) and every posterior
+        (model.py:364-375) fan out over the GPUs with one all_gather / all_reduce each (sharded.py).  Every rank
+        runs the same optimizer with the same seed and proposes the same configurations."""
         n_features = len(search_space)
         batch_shape = torch.Size()
         if acquisition_function_factory is None:
@@ -210,7 +215,7 @@ class ScaMLGPBO(_SingleObjectiveBase):
         self.fit_options = fit_options
         # NOTE: like the reference (optimizer.py:128-133) the meta-fit always uses the default 5 restarts
         self.source_gps = meta_fit_scamlgp(metadata_numerical, likelihood=gp_likelihood, covar_module=base_gp_kernel,
-                                           seed=seed, engine=engine, fit_options=fit_options)
+                                           seed=seed, engine=engine, fit_options=fit_options, group=group)
         self.model_kwargs = {} if model_kwargs is None else model_kwargs
         model = ScaMLGP(train_X=torch.empty((*batch_shape, 0, n_features), dtype=torch_dtype),
                         train_Y=torch.empty((*batch_shape, 0, 1), dtype=torch_dtype), source_gps=self.source_gps,
@@ -225,6 +230,12 @@ class ScaMLGPBO(_SingleObjectiveBase):
     def report(self, evaluations: Union[Evaluation, Iterable[Evaluation]]):
         """Book-keep the evaluations and refit the ScaML-GP target model (reference optimizer.py:156-185)."""
         _evals = evaluations if isinstance(evaluations, list) else [evaluations]
+        from .model import max_target_points
+
+        limit = max_target_points(self.source_gps.engine, len(self.search_space))
+        if int((~torch.isnan(self.losses)).sum()) + len(_evals) > limit:  # before any book-keeping is changed
+            raise NotImplementedError(f"more than {limit} target observations are not supported in this release "
+                                      "(shared-memory target-GP kernels); the optimizer state is unchanged")
         super()._update_internal_evaluation_data(_evals)
         if len(self.X) < self.num_initial_random:
             return

@@ -82,7 +82,8 @@ class ShardedSources:
         self.batch = SourceBatch.from_ragged(local, engine.device, n_max=n_max)
         # the all-data Standardize of the target model needs every raw Y (model.py:264-276): cheap, host side
         self.all_Y = torch.cat([t[1].reshape(-1).to(DT) for t in tasks])
-        self.ystd_all: Optional[torch.Tensor] = None
+        self.ystd_all: Optional[torch.Tensor] = None  # [M] per-task Standardize state of ALL tasks (gathered)
+        self.ybar_all: Optional[torch.Tensor] = None
         self.fitted: Optional[FittedSources] = None
         self._condA: Optional[torch.Tensor] = None  # A_m = K_m^-1 K_m(X_m, X_t) of the local tasks
         self._cond_Xt: Optional[torch.Tensor] = None  # the target inputs `_condA` was prepared for (a private copy)
@@ -95,10 +96,12 @@ class ShardedSources:
         local = fit_sources(self.engine, self.batch, spec, theta_init[self.lo:self.hi].contiguous(), fit_options)
         self.fitted = self.engine.factorize(self.batch, local.theta_raw, spec)
         self._invalidate()
-        rows = torch.cat([local.theta_raw, local.lml.unsqueeze(1), self.batch.ystd.unsqueeze(1)], dim=1)
+        rows = torch.cat([local.theta_raw, local.lml.unsqueeze(1), self.batch.ystd.unsqueeze(1),
+                          self.batch.ybar.unsqueeze(1)], dim=1)
         rows = _all_gather_rows(rows, self.counts, self.group)
         P = local.theta_raw.shape[1]
         self.ystd_all = rows[:, P + 1].contiguous()
+        self.ybar_all = rows[:, P + 2].contiguous()
         return ShardedFit(local, rows[:, :P].contiguous(), rows[:, P].contiguous())
 
     def set_parameters(self, spec: HyperSpec, theta_raw_all: torch.Tensor) -> None:
@@ -106,7 +109,8 @@ class ShardedSources:
         th = theta_raw_all[self.lo:self.hi].to(self.engine.device, DT).contiguous()
         self.fitted = self.engine.factorize(self.batch, th, spec)
         self._invalidate()
-        self.ystd_all = _all_gather_rows(self.batch.ystd.unsqueeze(1), self.counts, self.group).squeeze(1).contiguous()
+        rows = _all_gather_rows(torch.stack([self.batch.ystd, self.batch.ybar], dim=1), self.counts, self.group)
+        self.ystd_all, self.ybar_all = rows[:, 0].contiguous(), rows[:, 1].contiguous()
 
     def _invalidate(self) -> None:
         self._gen += 1

@@ -84,11 +84,16 @@ def optimize_marginal_likelihood(model, num_restarts: int = 0, generator: Option
     (one batched objective launch per L-BFGS round); the best final value wins, failed rows are skipped
     with a warning, all failed -> ModelFittingError."""
     from .fit import fit_target
-    from .model import ScaMLGP
+    from .model import ScaMLGP, SourceGP
     from .modules import set_theta_raw
 
+    if isinstance(model, SourceGP):
+        # the reference calls this on every source GP (model.py:187); here meta_fit_scamlgp batches those fits, and
+        # this is the single-model form of the same driver (refit of one task, e.g. after its data changed)
+        return _optimize_source_gp(model, num_restarts, generator, **fit_options)
     if not isinstance(model, ScaMLGP):
-        raise TypeError("optimize_marginal_likelihood expects a ScaMLGP (source GPs are fitted by meta_fit_scamlgp)")
+        raise TypeError("optimize_marginal_likelihood expects a ScaMLGP or a SourceGP of meta_fit_scamlgp, got "
+                        f"{type(model).__name__}")
     if model.num_train == 0:
         raise ValueError("cannot optimise the marginal likelihood of a model without training data")
     fit_options.pop("max_attempts", None)
@@ -113,6 +118,45 @@ def optimize_marginal_likelihood(model, num_restarts: int = 0, generator: Option
     set_theta_raw(model.likelihood, model.covar_module, fit.theta_raw)
     model._tstate = None
     model.last_fit = fit
+    return fit
+
+
+def _optimize_source_gp(gp, num_restarts: int, generator: Optional[torch.Generator], **fit_options):
+    """(LML + log priors)/n of ONE source GP maximised from its current parameters + `num_restarts` prior draws
+    (reference utils.py:139-212 on a SingleTaskGP, as called at model.py:187); the winner is written back to the
+    GP's modules and to its slice of the owner's packed device state (factor, alpha, parameters)."""
+    from .engine import SourceBatch
+    from .fit import fit_sources, sample_theta_raw
+    from .modules import hyper_spec_of, set_theta_raw, theta_raw_of
+
+    fit_options.pop("max_attempts", None)
+    fit_options.pop("caught_exception_types", None)
+    owner = gp._owner
+    eng = owner.engine
+    X, Y = gp.train_inputs[0], gp._raw_Y
+    d = X.shape[-1]
+    spec = hyper_spec_of(gp.likelihood, gp.covar_module)
+    theta0 = theta_raw_of(gp.likelihood, gp.covar_module, d)
+    rows = [theta0.reshape(1, 1, -1)]
+    if num_restarts > 0:
+        rows.append(sample_theta_raw(spec, theta0, 1, int(num_restarts), generator))
+    sh = getattr(owner, "sharded", None)
+    fitted = getattr(owner, "fitted", None)
+    local = fitted is not None and (sh is None or sh.lo <= gp._index < sh.hi)
+    n_max = fitted.batch.n_max if local else None
+    batch = SourceBatch.from_ragged([(X, Y)], eng.device, n_max=n_max)
+    fit = fit_sources(eng, batch, spec, torch.cat(rows, dim=1), fit_options or None)
+    nfail = int(torch.isinf(fit.all_lml).sum())
+    if nfail:
+        logger.warning(f"Error occurred while optimizing the model hyperparameters: {nfail} restart(s) skipped.")
+    set_theta_raw(gp.likelihood, gp.covar_module, fit.theta_raw[0].cpu())
+    if local:
+        i = gp._index - (sh.lo if sh is not None else 0)
+        one = eng.factorize(batch, fit.theta_raw, spec)
+        fitted.theta_raw[i], fitted.theta[i] = one.theta_raw[0], one.theta[0]
+        fitted.linv[i], fitted.alpha[i], fitted.info[i] = one.linv[0], one.alpha[0], one.info[0]
+        if sh is not None:
+            sh._invalidate()
     return fit
 
 

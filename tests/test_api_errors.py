@@ -98,10 +98,19 @@ def test_model_errors_through_emulation(emu_engine):
     model = ScaMLGP(torch.empty(0, 2, dtype=DT), torch.empty(0, 1, dtype=DT), gps, engine=emu_engine)
     assert model.outcome_transform is None and model.num_train == 0  # empty input: no standardisation (model.py:307-308)
     assert torch.allclose(model.weights, torch.full((2,), 0.5, dtype=DT))
-    with pytest.raises(NotImplementedError):
-        model.posterior(torch.rand(4, 2, 2, dtype=DT))  # q > 1
-    with pytest.raises(NotImplementedError, match="n_t <= 116"):
-        ScaMLGP(torch.rand(117, 2, dtype=DT), torch.rand(117, 1, dtype=DT), gps, engine=emu_engine)
+    pj = model.posterior(torch.rand(4, 2, 2, dtype=DT))  # q > 1: joint posterior per batch element
+    assert pj.mean.shape == (4, 2, 1) and pj.mvn.covariance_matrix.shape == (4, 2, 2)
+    with pytest.raises(NotImplementedError, match="q <= 128"):
+        model.posterior(torch.rand(1, 129, 2, dtype=DT))
+    with pytest.raises(TypeError, match="ScaMLGP or a SourceGP"):
+        from scamlgp_b200.utils import optimize_marginal_likelihood
+
+        optimize_marginal_likelihood(object())
+    from scamlgp_b200.model import max_target_points
+
+    assert max_target_points(emu_engine, 2) == 117 and max_target_points(emu_engine, 16) == 113  # 227 KB, grows with d
+    with pytest.raises(NotImplementedError, match="n_t <= 117 at d = 2"):
+        ScaMLGP(torch.rand(118, 2, dtype=DT), torch.rand(118, 1, dtype=DT), gps, engine=emu_engine)
     with pytest.raises(ValueError):
         UpperConfidenceBound(model, maximize=True)
     # all restarts failing -> ModelFittingError (utils.py:207-212): NaN targets poison every row

@@ -121,6 +121,23 @@ def _pipeline(eng, M, n, d, n_t, B, restarts, fit_options, ragged=False):
     vscale = float(ov.abs().max())
     assert rel_err(post.mean.reshape(-1).numpy(), om.numpy()) < 1e-8
     assert float((post.variance.reshape(-1) - ov).abs().max()) < 1e-8 * vscale
+    # ---- (4b) q > 1 / batch-shaped inputs: joint posterior over the q points of every batch element --------- #
+    nb, q = 3, 4
+    Xq = torch.rand(nb, q, d, dtype=DT, generator=g)
+    th0 = O.initial_theta_raw(d, tspec)
+    for mdl, args in ((prior_model, (states, w0, None, th0, tspec)), (model, (states, w, cache, th, tspec))):
+        pj = mdl.posterior(Xq)
+        assert pj.mean.shape == (nb, q, 1) and pj.variance.shape == (nb, q, 1)
+        assert pj.mvn.covariance_matrix.shape == (nb, q, q)
+        for i in range(nb):
+            om_j, oc_j = O.scaml_posterior(*args, Xq[i], full_cov=True)
+            assert rel_err(pj.mean[i].reshape(-1).numpy(), om_j.numpy()) < 1e-8
+            assert float((pj.mvn.covariance_matrix[i] - oc_j).abs().max()) < 1e-8 * float(oc_j.abs().max())
+        # the diagonal of the joint covariance is the q = 1 variance of the same points
+        p1 = mdl.posterior(Xq.reshape(-1, 1, d))
+        assert float((p1.variance.reshape(nb, q) - pj.variance.reshape(nb, q)).abs().max()) < 1e-9 * vscale
+        mv = mdl.forward(Xq)  # batch_shape x n x d -> one joint prior per batch element (model.py:114-121)
+        assert mv.mean.shape == (nb, q) and mv.covariance_matrix.shape == (nb, q, q)
     # ---- (5) acquisition value (utils.py:215-224) ----------------------------------------------------------- #
     af = UpperConfidenceBound(model)
     assert rel_err(af(Xc.unsqueeze(1)).numpy(), O.ucb(om, ov).numpy()) < 1e-7
@@ -145,6 +162,23 @@ def _pipeline(eng, M, n, d, n_t, B, restarts, fit_options, ragged=False):
     model.weights = torch.full((M,), 0.5, dtype=DT)
     model.load_state_dict(sd)
     assert torch.equal(model.weights, w)
+    # ---- (7) optimize_marginal_likelihood on ONE source GP (the reference calls it per task, model.py:187) --- #
+    from scamlgp_b200.modules import set_theta_raw
+
+    gp_last = list(gps.values())[-1]
+    Xl, Yl = gp_last.train_inputs[0], gp_last._raw_Y.reshape(-1)
+    ytl = O.standardize(Yl)[0]
+    set_theta_raw(gp_last.likelihood, gp_last.covar_module, th0)  # back to the defaults, then refit this task alone
+    sfit = optimize_marginal_likelihood(gp_last, 1, generator=torch.Generator().manual_seed(2), **(fit_options or {}))
+    th_new = theta_raw_of(gp_last.likelihood, gp_last.covar_module, d)
+    v_new = float(O.lml_objective(Xl, ytl, th_new, ospec))
+    assert v_new >= float(O.lml_objective(Xl, ytl, th0, ospec)) - 1e-12
+    assert abs(float(sfit.lml[0]) - v_new) <= TOL_LML * abs(v_new)
+    st_new = O.factorize(Xl, Yl, th_new, ospec)  # the owner's packed device state was refreshed for this task
+    pl = gp_last.posterior(Xc[:7])
+    oml, ocl = O.posterior(st_new, Xc[:7], full_cov=True)
+    assert rel_err(pl.mean.reshape(-1).numpy(), oml.numpy()) < TOL_MEAN_VAR
+    assert float((pl.mvn.covariance_matrix - ocl).abs().max()) < TOL_MEAN_VAR * float(st_new.os) * st_new.ystd ** 2
     return gps, model
 
 

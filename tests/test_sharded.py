@@ -55,6 +55,36 @@ def _run(engine, group):
                 mean=mean, var=var, gmean=gmean, gvar=gvar, dm=dm, dv=dv, dm0=dm0, dv0=dv0)
 
 
+def _bo_run(engine, group):
+    """The public drop-in on sharded meta-tasks: `ScaMLGPBO(..., group=)` -- meta-fit (optimizer.py:128-133), report
+    (:176-185: caches + target refit) and suggestions (eval branch, model.py:364-375) with 3 tasks over the ranks."""
+    from scamlgp_b200.optimizer import ScaMLGPBO
+    from scamlgp_b200.space import ContinuousParameter, Evaluation, Objective, ParameterSpace
+
+    space = ParameterSpace()
+    space.add(ContinuousParameter("x0", (0.0, 1.0)))
+    space.add(ContinuousParameter("x1", (0.0, 1.0)))
+    loss = Objective("loss", greater_is_better=False)
+    md = {f"t{i}": [Evaluation(configuration={"x0": float(x[0]), "x1": float(x[1])}, objectives={"loss": float(y)})
+                    for x, y in zip(X, Y)] for i, (X, Y) in enumerate(_tasks())}
+    opt = ScaMLGPBO(space, loss, md, seed=5, num_initial_random_samples=0, max_pending_evaluations=3, engine=engine,
+                    num_restarts_log_likelihood=1, fit_options=dict(maxiter=4), group=group,
+                    af_optimizer_kwargs=dict(raw_samples=16, num_restarts=2, maxiter=4))
+    out = []
+    for step in range(3):
+        spec = opt.generate_evaluation_specification()  # step 0: prior-only model (n_t = 0)
+        c = spec.configuration
+        out.append([c["x0"], c["x1"]])
+        opt.report(spec.create_evaluation(objectives={"loss": (c["x0"] - 0.3) ** 2 + (c["x1"] - 0.6) ** 2}))
+    post = opt.model.posterior(torch.tensor([[0.2, 0.4], [0.7, 0.1]], dtype=DT))
+    joint = opt.model.posterior(torch.tensor([[[0.2, 0.4], [0.7, 0.1], [0.5, 0.5]]], dtype=DT))  # q = 3
+    theta = torch.stack([torch.cat([g.covar_module.base_kernel.raw_lengthscale.reshape(-1),
+                                    g.covar_module.raw_outputscale.reshape(-1)]) for g in opt.source_gps.values()])
+    return dict(bo_x=torch.tensor(out, dtype=DT), bo_w=opt.model.weights.clone(), bo_mean=post.mean.reshape(-1),
+                bo_var=post.variance.reshape(-1), bo_jmean=joint.mean.reshape(-1),
+                bo_jcov=joint.mvn.covariance_matrix.reshape(-1), bo_theta=theta)
+
+
 def _worker(rank, world, port, out_dir):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -66,7 +96,9 @@ def _worker(rank, world, port, out_dir):
 
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        res = _run(EmuEngine(ScamlLib(build_emu())), None)
+        eng = EmuEngine(ScamlLib(build_emu()))
+        res = _run(eng, None)
+        res.update(_bo_run(eng, True))
         torch.save(res, os.path.join(out_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -84,6 +116,7 @@ def test_two_rank_gloo_matches_single_process(emu_lib, tmp_path):
     from tests.emu_engine import EmuEngine
 
     single = _run(EmuEngine(emu_lib), None)
+    single.update(_bo_run(EmuEngine(emu_lib), None))  # group=None: the un-sharded product path
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     r0 = torch.load(os.path.join(tmp_path, "rank0.pt"))
@@ -95,8 +128,13 @@ def test_two_rank_gloo_matches_single_process(emu_lib, tmp_path):
         # every rank ends with the same replicated result ...
         assert torch.equal(r0[k], r1[k]), k
         # ... equal to the single-process one: bit-identical where nothing is re-associated across ranks
-        if k in ("theta", "lml", "ystd", "sm", "sc"):
+        if k in ("theta", "lml", "ystd", "sm", "sc", "bo_theta"):
             assert torch.equal(r0[k], single[k]), k
+        elif k.startswith("bo_"):
+            # a 2-rank ScaMLGPBO proposes the same configurations as one rank: the sums over tasks are
+            # re-associated across ranks (1e-13), the optimisers on top of them amplify that only mildly
+            scale = float(single[k].abs().max())
+            assert float((r0[k] - single[k]).abs().max()) <= 1e-6 * scale, (k, r0[k], single[k])
         else:
             scale = float(single[k].abs().max())
             assert float((r0[k] - single[k]).abs().max()) <= 1e-13 * scale, k
