@@ -71,10 +71,12 @@ typedef struct scaml_hyper_spec {
 const char* scaml_version(void);
 
 /* Largest n_max / d the fit kernels accept (shared-memory budget), and the number of
- * workspace bytes scaml_lml_grad / scaml_factorize need for (n_max, device).  The
- * workspace is scratch: contents are undefined between calls. */
+ * workspace bytes scaml_lml_grad / scaml_factorize need for M tasks x R rows of (n_max, d)
+ * on this device: the per-CTA tile workspaces plus the scheduling block (work counter and
+ * the list of active rows, most expensive first).  The workspace is scratch: contents are
+ * undefined between calls.  scaml_factorize: R = 1. */
 int scaml_fit_limits(int* n_max_limit, int* d_limit);
-size_t scaml_fit_workspace_bytes(int n_max, int d);
+size_t scaml_fit_workspace_bytes(int M, int R, int n_max, int d);
 
 /* K1 standalone: K[m] = s_m * kappa(X_m / l_m) + noise_m * I for every task, written dense
  * [M][n_max][n_max] (rows/cols >= n_valid are the identity).  `theta` holds CONSTRAINED
@@ -98,6 +100,16 @@ int scaml_lml_grad(const double* X, const double* y, const int32_t* n_valid,
                    size_t workspace_bytes, int M, int R, int n_max, int d,
                    const scaml_hyper_spec* spec, void* stream);
 
+/* The same evaluation with linear_operator's psd_safe_cholesky jitter ladder applied INSIDE the
+ * kernel: a row whose factorisation meets a non-positive pivot is repeated with 1e-8, 1e-7, 1e-6
+ * added to the diagonal of the original matrix; info > 0 / NaN only when 1e-6 fails too.  No
+ * device -> host read of `info` is needed between the rounds of an optimiser (the reference gets
+ * this behaviour from gpytorch inside the closure, scamlgp/utils.py:171-177). */
+int scaml_lml_grad_ladder(const double* X, const double* y, const int32_t* n_valid,
+                          const double* theta_raw, const int32_t* skip, double* lml, double* grad,
+                          int32_t* info, void* workspace, size_t workspace_bytes, int M, int R,
+                          int n_max, int d, const scaml_hyper_spec* spec, void* stream);
+
 /* K1-K3 for prediction: factorise K_y of every task at its fitted parameters
  * (theta_raw [M][P]) and emit the packed L^-1 tiles, alpha = K_y^-1 y~ [M][n_pad], and
  * the constrained parameters theta [M][P].  Replaces the prediction-strategy caches
@@ -107,6 +119,12 @@ int scaml_factorize(const double* X, const double* y, const int32_t* n_valid,
                     double* alpha, double* theta, int32_t* info, void* workspace,
                     size_t workspace_bytes, int M, int n_max, int d,
                     const scaml_hyper_spec* spec, void* stream);
+/* scaml_factorize with the in-kernel jitter ladder (see scaml_lml_grad_ladder). */
+int scaml_factorize_ladder(const double* X, const double* y, const int32_t* n_valid,
+                           const double* theta_raw, double* linv_packed, double* alpha,
+                           double* theta, int32_t* info, void* workspace, size_t workspace_bytes,
+                           int M, int n_max, int d, const scaml_hyper_spec* spec, void* stream);
+
 
 /* Bytes of partial-sum scratch scaml_predict_weighted needs for B candidates. */
 size_t scaml_predict_workspace_bytes(int M, int n_max, int d, int B);

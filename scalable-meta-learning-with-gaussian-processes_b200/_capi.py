@@ -97,7 +97,9 @@ EXPORTED_SYMBOLS = (
     "scaml_fit_workspace_bytes",
     "scaml_kernel_matrix",
     "scaml_lml_grad",
+    "scaml_lml_grad_ladder",
     "scaml_factorize",
+    "scaml_factorize_ladder",
     "scaml_predict_workspace_bytes",
     "scaml_predict_weighted",
     "scaml_predict_cross_workspace_bytes",
@@ -158,10 +160,12 @@ class ScamlLib:
         L.scaml_version.restype = C.c_char_p
         L.scaml_fit_limits.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.scaml_fit_workspace_bytes.restype = sz
-        L.scaml_fit_workspace_bytes.argtypes = [i32, i32]
+        L.scaml_fit_workspace_bytes.argtypes = [i32, i32, i32, i32]
         L.scaml_kernel_matrix.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, vp]
         L.scaml_lml_grad.argtypes = [vp] * 10 + [sz, i32, i32, i32, i32, C.POINTER(CHyperSpec), vp]
         L.scaml_factorize.argtypes = [vp] * 10 + [sz, i32, i32, i32, C.POINTER(CHyperSpec), vp]
+        L.scaml_lml_grad_ladder.argtypes = [vp] * 9 + [sz, i32, i32, i32, i32, C.POINTER(CHyperSpec), vp]
+        L.scaml_factorize_ladder.argtypes = [vp] * 9 + [sz, i32, i32, i32, C.POINTER(CHyperSpec), vp]
         L.scaml_predict_workspace_bytes.restype = sz
         L.scaml_predict_workspace_bytes.argtypes = [i32, i32, i32, i32]
         L.scaml_predict_weighted.argtypes = [vp] * 12 + [sz, i32, i32, i32, i32, i32, vp]
@@ -207,8 +211,8 @@ class ScamlLib:
         self.lib.scaml_fit_limits(C.byref(n), C.byref(d))
         return n.value, d.value
 
-    def fit_workspace_bytes(self, n_max: int, d: int) -> int:
-        return int(self.lib.scaml_fit_workspace_bytes(n_max, d))
+    def fit_workspace_bytes(self, M: int, R: int, n_max: int, d: int) -> int:
+        return int(self.lib.scaml_fit_workspace_bytes(M, R, n_max, d))
 
     def predict_workspace_bytes(self, M: int, n_max: int, d: int, B: int) -> int:
         return int(self.lib.scaml_predict_workspace_bytes(M, n_max, d, B))
@@ -221,6 +225,18 @@ class ScamlLib:
         cs = spec.to_c()
         _check(self.lib.scaml_lml_grad(X, y, n_valid, theta_raw, jitter, skip, lml, grad, info, ws, ws_bytes,
                                        M, R, n_max, d, C.byref(cs), stream), "scaml_lml_grad")
+
+    def lml_grad_ladder(self, X, y, n_valid, theta_raw, skip, lml, grad, info, ws, ws_bytes, M, R, n_max, d,
+                        spec: HyperSpec, stream=0):
+        cs = spec.to_c()
+        _check(self.lib.scaml_lml_grad_ladder(X, y, n_valid, theta_raw, skip, lml, grad, info, ws, ws_bytes,
+                                              M, R, n_max, d, C.byref(cs), stream), "scaml_lml_grad_ladder")
+
+    def factorize_ladder(self, X, y, n_valid, theta_raw, linv, alpha, theta, info, ws, ws_bytes, M, n_max, d,
+                         spec: HyperSpec, stream=0):
+        cs = spec.to_c()
+        _check(self.lib.scaml_factorize_ladder(X, y, n_valid, theta_raw, linv, alpha, theta, info, ws, ws_bytes,
+                                               M, n_max, d, C.byref(cs), stream), "scaml_factorize_ladder")
 
     def factorize(self, X, y, n_valid, theta_raw, jitter, linv, alpha, theta, info, ws, ws_bytes, M, n_max, d,
                   spec: HyperSpec, stream=0):

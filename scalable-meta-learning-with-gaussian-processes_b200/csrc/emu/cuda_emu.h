@@ -27,6 +27,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __shared__ static  // one CTA runs at a time; its OS threads share the static
 #define __align__(n) alignas(n)
 
 typedef void* cudaStream_t;
@@ -176,6 +177,7 @@ template <class T>
 inline T __ldg(const T* p) {
   return *p;
 }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline double fma_emu(double a, double b, double c) { return std::fma(a, b, c); }
 using std::exp;

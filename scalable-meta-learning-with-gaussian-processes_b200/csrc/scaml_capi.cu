@@ -151,6 +151,11 @@ int dispatch_fit(const scaml::FitParams& p, int grid, size_t smem, void* stream)
   }
 }
 
+size_t fit_tile_workspace_bytes(int n_max, int d) {
+  const int n_pad = pad64(n_max);
+  return (size_t)fit_grid_slots(n_pad, d) * (size_t)scaml::fit_ws_doubles_host(n_pad, d) * sizeof(double);
+}
+
 int run_fit(scaml::FitParams p, void* workspace, size_t workspace_bytes, void* stream) {
   if (p.M <= 0 || p.R <= 0 || p.n_max <= 0 || p.d <= 0) return SCAML_E_ARG;
   if (p.d > scaml::kMaxP - 2) return SCAML_E_UNSUPPORTED;
@@ -158,13 +163,36 @@ int run_fit(scaml::FitParams p, void* workspace, size_t workspace_bytes, void* s
   const bool f8 = use_fit8(p.n_pad, p.spec.kernel);
   const size_t smem = f8 ? scaml::f8::smem_bytes(p.n_pad, p.d) : scaml::fit_smem_bytes(p.n_pad, p.d);
   if (smem > kMaxSmem) return SCAML_E_SMEM;
-  if (workspace_bytes < scaml_fit_workspace_bytes(p.n_max, p.d)) return SCAML_E_WORKSPACE;
+  if (workspace_bytes < scaml_fit_workspace_bytes(p.M, p.R, p.n_max, p.d)) return SCAML_E_WORKSPACE;
   p.workspace = static_cast<double*>(workspace);
   p.ws_stride = scaml::fit_ws_doubles_host(p.n_pad, p.d);
   p.prof = g_prof;
   p.sms = num_sms();
   p.kcache = 1;
   if (const char* env = getenv("SCAML_FIT_KCACHE")) p.kcache = atoi(env) != 0;
+  // scheduling block behind the tile workspace: [counter, #items, order[M R]]
+  const long long E64 = (long long)p.M * p.R;
+  if (E64 > (1LL << 30)) return SCAML_E_UNSUPPORTED;
+  p.sched = reinterpret_cast<int32_t*>(static_cast<char*>(workspace) + fit_tile_workspace_bytes(p.n_max, p.d));
+  p.order = nullptr;
+  if (p.skip != nullptr || p.n_valid != nullptr) {  // active rows, largest tasks first
+    int32_t* order = p.sched + 2;
+#ifdef SCAML_EMU
+    cuemu::launch(dim3(1), dim3(scaml::kSchedThreads), 0, scaml::scaml_fit_schedule_kernel<0>, p.skip, p.n_valid, p.M, p.R,
+                  p.n_max, p.sched, order);
+#else
+    scaml::scaml_fit_schedule_kernel<0><<<1, scaml::kSchedThreads, 0, (cudaStream_t)stream>>>(p.skip, p.n_valid, p.M, p.R,
+                                                                                         p.n_max, p.sched, order);
+    if (cudaGetLastError() != cudaSuccess) return SCAML_E_ARG;
+#endif
+    p.order = order;
+  } else {
+#ifdef SCAML_EMU
+    p.sched[0] = 0;
+#else
+    if (cudaMemsetAsync(p.sched, 0, 2 * sizeof(int32_t), (cudaStream_t)stream) != cudaSuccess) return SCAML_E_ARG;
+#endif
+  }
   int grid = fit_grid_slots(p.n_pad, p.d);
   if (f8) {  // register-limited to two 256-thread CTAs per SM
     const int per_sm = (2 * (smem + 1024) <= 228 * 1024) ? 2 : 1;
@@ -213,10 +241,11 @@ int scaml_fit_limits(int* n_max_limit, int* d_limit) {
   return 0;
 }
 
-size_t scaml_fit_workspace_bytes(int n_max, int d) {
-  if (n_max <= 0 || d <= 0) return 0;
-  const int n_pad = pad64(n_max);
-  return (size_t)fit_grid_slots(n_pad, d) * (size_t)scaml::fit_ws_doubles_host(n_pad, d) * sizeof(double);
+size_t scaml_fit_workspace_bytes(int M, int R, int n_max, int d) {
+  if (M <= 0 || R <= 0 || n_max <= 0 || d <= 0) return 0;
+  // per-CTA tile workspaces + the scheduling block [counter, #items, order[M R]] (int32), rounded up to 16 bytes
+  const size_t sched = ((2 + (size_t)M * R) * sizeof(int32_t) + 15) / 16 * 16;
+  return fit_tile_workspace_bytes(n_max, d) + sched;
 }
 
 int scaml_lml_grad(const double* X, const double* y, const int32_t* n_valid, const double* theta_raw,
@@ -228,6 +257,32 @@ int scaml_lml_grad(const double* X, const double* y, const int32_t* n_valid, con
   p.X = X, p.y = y, p.n_valid = n_valid, p.theta_raw = theta_raw, p.jitter = jitter, p.skip = skip;
   p.lml = lml, p.grad = grad, p.info = info;
   p.M = M, p.R = R, p.n_max = n_max, p.d = d, p.mode = scaml::kModeLmlGrad;
+  p.spec = *spec;
+  return run_fit(p, workspace, workspace_bytes, stream);
+}
+
+int scaml_lml_grad_ladder(const double* X, const double* y, const int32_t* n_valid, const double* theta_raw,
+                          const int32_t* skip, double* lml, double* grad, int32_t* info, void* workspace,
+                          size_t workspace_bytes, int M, int R, int n_max, int d, const scaml_hyper_spec* spec,
+                          void* stream) {
+  if (!X || !y || !theta_raw || !lml || !grad || !info || !workspace || !spec) return SCAML_E_ARG;
+  scaml::FitParams p{};
+  p.X = X, p.y = y, p.n_valid = n_valid, p.theta_raw = theta_raw, p.jitter = nullptr, p.skip = skip;
+  p.lml = lml, p.grad = grad, p.info = info;
+  p.M = M, p.R = R, p.n_max = n_max, p.d = d, p.mode = scaml::kModeLmlGrad, p.ladder = 1;
+  p.spec = *spec;
+  return run_fit(p, workspace, workspace_bytes, stream);
+}
+
+int scaml_factorize_ladder(const double* X, const double* y, const int32_t* n_valid, const double* theta_raw,
+                           double* linv_packed, double* alpha, double* theta, int32_t* info, void* workspace,
+                           size_t workspace_bytes, int M, int n_max, int d, const scaml_hyper_spec* spec,
+                           void* stream) {
+  if (!X || !y || !theta_raw || !linv_packed || !alpha || !theta || !info || !workspace || !spec) return SCAML_E_ARG;
+  scaml::FitParams p{};
+  p.X = X, p.y = y, p.n_valid = n_valid, p.theta_raw = theta_raw, p.jitter = nullptr, p.skip = nullptr;
+  p.info = info, p.linv_out = linv_packed, p.alpha_out = alpha, p.theta_out = theta;
+  p.M = M, p.R = 1, p.n_max = n_max, p.d = d, p.mode = scaml::kModeFactorize, p.ladder = 1;
   p.spec = *spec;
   return run_fit(p, workspace, workspace_bytes, stream);
 }

@@ -80,6 +80,12 @@ struct FitParams {
   long long ws_stride;  // doubles per CTA slot
   long long* prof;      // SCAML_PROF builds only: [grid][16] cycle counters per phase
   int M, R, n_max, n_pad, d, mode;
+  // dynamic scheduling: sched[0] = next-item counter (zeroed before the launch), sched[1] = number of items when
+  // `order` is given; order = active evaluations sorted by descending cost (scaml_fit_schedule_kernel) or null
+  // (items are the evaluations 0 .. M R - 1 themselves)
+  int32_t* sched;
+  const int32_t* order;
+  int ladder;  // 1: psd_safe_cholesky jitter ladder (+1e-8, +1e-7, +1e-6) inside the kernel when a pivot fails
   int sms;  // SM count (co-resident CTAs are blockIdx.x, blockIdx.x + sms, ...)
   int kcache;  // 4-warp RBF kernel: cache kappa between the assembly and the gradient epilogue
   scaml_hyper_spec spec;
@@ -756,6 +762,49 @@ SCAML_DEVICE void dinv_matvec(double* out, const double* dinvc, const double* v,
   __syncthreads();
 }
 
+// ---- schedule: active evaluations, most expensive first --------------------------------------------------- //
+// One CTA.  Buckets the rows that are not skipped by their super-tile count NS = ceil(n_valid / 64) (cost ~ NS^3) with
+// shared-memory counters and writes them to `order` bucket by bucket, largest first; sched[0] = 0 (the work counter of
+// the fit kernel), sched[1] = number of active rows.  The order inside a bucket is whatever the atomics give: results
+// do not depend on the schedule.  Rows with an invalid n_valid stay in the list (the fit kernel reports info = -1).
+constexpr int kSchedThreads = 1024;
+constexpr int kSchedBuckets = 64;
+template <int UNUSED = 0>  // a template only so that the header can be included in several translation units
+__global__ void __launch_bounds__(kSchedThreads) scaml_fit_schedule_kernel(const int32_t* skip, const int32_t* n_valid,
+                                                                           int M, int R, int n_max, int32_t* sched,
+                                                                           int32_t* order) {
+  __shared__ int cnt[kSchedBuckets], base[kSchedBuckets];
+  const int tid = threadIdx.x, E = M * R;
+  if (tid < kSchedBuckets) cnt[tid] = 0;
+  __syncthreads();
+  for (int e = tid; e < E; e += kSchedThreads) {
+    if (skip != nullptr && skip[e] != 0) continue;
+    const int nv = n_valid ? n_valid[e / R] : n_max;
+    int b = (nv + kSB - 1) / kSB;
+    b = b < 1 ? 1 : (b > kSchedBuckets - 1 ? kSchedBuckets - 1 : b);
+    atomicAdd(&cnt[b], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int b = kSchedBuckets - 1; b >= 0; --b) {
+      base[b] = run;
+      run += cnt[b];
+      cnt[b] = 0;
+    }
+    sched[0] = 0;
+    sched[1] = run;
+  }
+  __syncthreads();
+  for (int e = tid; e < E; e += kSchedThreads) {
+    if (skip != nullptr && skip[e] != 0) continue;
+    const int nv = n_valid ? n_valid[e / R] : n_max;
+    int b = (nv + kSB - 1) / kSB;
+    b = b < 1 ? 1 : (b > kSchedBuckets - 1 ? kSchedBuckets - 1 : b);
+    order[base[b] + atomicAdd(&cnt[b], 1)] = e;
+  }
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitParams p) {
   SCAML_DYN_SMEM(double, sm);
@@ -797,8 +846,19 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
   // on the warp that holds the lightest role.  Results do not depend on the rotation (role-indexed reductions).
   const int slot = p.sms > 0 ? (int)(blockIdx.x / p.sms) : 0;
 
-  for (int e = blockIdx.x; e < E; e += gridDim.x) {
-    if (p.skip != nullptr && p.skip[e] != 0) continue;
+  // Work distribution: every CTA pulls the next item from a global counter (one atomic per evaluation), so CTAs
+  // that drew short evaluations (small n_i, rows that fail early) or skipped rows simply pull more; with `order`
+  // the items are the active rows only, most expensive (largest n_i) first.  Results do not depend on which CTA
+  // runs an evaluation (tested bit-identical under permutation), so the schedule is free.
+  const int n_items = (p.order != nullptr) ? p.sched[1] : E;
+  for (int it = 0;; ++it) {
+    __syncthreads();  // previous evaluation fully retired before shared state (and the work slot) is rewritten
+    if (t.tid == 0) flag[2] = atomicAdd(p.sched, 1);
+    __syncthreads();
+    const int item = flag[2];
+    if (item >= n_items) break;
+    const int e = (p.order != nullptr) ? p.order[item] : item;
+    if (p.order == nullptr && p.skip != nullptr && p.skip[e] != 0) continue;
     const int m = e / p.R;
     const int nv = p.n_valid ? p.n_valid[m] : p.n_max;
     if (nv < 1 || nv > p.n_max) {
@@ -806,12 +866,11 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
       continue;
     }
     const int NS = (nv + kSB - 1) / kSB, n_pad = NS * kSB;
-    const int rot = slot + e / (int)gridDim.x;
+    const int rot = slot + it;
     t.role = (t.warp + rot) & (kFitWarps - 1);
     t.rb = t.role >> 1;
     t.cb = t.role & 1;
     const int chain_warp = (1 - rot) & (kFitWarps - 1);  // the warp whose role is (0,1)
-    __syncthreads();  // previous evaluation fully retired before shared state is rewritten
 
     // ---- parameters: Interval transform, priors, chain rule -------------------------- //
     if (t.tid < P) {
@@ -841,7 +900,6 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
     for (int i = t.tid; i < kFitWarps * kMaxP; i += kFitThreads) gsm[i] = 0.0;
     __syncthreads();
     const double os = th[d];
-    const double diag_add = th[d + 1] + (p.jitter ? p.jitter[e] : 0.0);
     const double* Xm = p.X + (size_t)m * p.n_max * d;
     {
       const double* ym = p.y + (size_t)m * p.n_max;
@@ -856,6 +914,13 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
 
     // ================= phase B: blocked left-looking Cholesky ========================== //
     const bool upper_warp = (t.rb == 0 && t.cb == 1);  // idle on diagonal super-tiles
+    // psd_safe_cholesky (linear_operator): on a failed pivot the factorisation is repeated with 1e-8,
+    // 1e-7, 1e-6 added to the diagonal of the ORIGINAL matrix -- here inside the kernel (p.ladder), so that the host
+    // never reads `info` back between the rounds of the L-BFGS driver.
+    double jit = p.jitter ? p.jitter[e] : 0.0;
+    for (int attempt = 0;; ++attempt) {
+    const double diag_add = th[d + 1] + jit;
+    failed = false;
     for (int J = 0; J < NS && !failed; ++J) {
       for (int I = J; I < NS; ++I) {
         const bool diag = (I == J);
@@ -891,6 +956,15 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
           PROF_MARK(4);
         }
       }
+    }
+    if (!failed || !p.ladder || attempt == 3) break;
+    jit = (attempt == 0) ? 1e-8 : ((attempt == 1) ? 1e-7 : 1e-6);
+    __syncthreads();
+    if (t.tid == 0) {
+      scal[0] = 0.0;
+      *flag = 0;
+    }
+    __syncthreads();
     }
     if (failed) {
       if (t.tid == 0) {

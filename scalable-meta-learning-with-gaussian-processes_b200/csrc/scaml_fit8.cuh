@@ -482,8 +482,16 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit8_kernel(const FitParams
   // rotation (role-indexed reductions).
   const int slot = p.sms > 0 ? (int)(blockIdx.x / p.sms) : 0;
 
-  for (int e = blockIdx.x; e < E; e += gridDim.x) {
-    if (p.skip != nullptr && p.skip[e] != 0) continue;
+  // dynamic work distribution over a global counter (see scaml_fit.cuh)
+  const int n_items = (p.order != nullptr) ? p.sched[1] : E;
+  for (int it = 0;; ++it) {
+    __syncthreads();  // previous evaluation fully retired before shared state (and the work slot) is rewritten
+    if (t.tid == 0) flag[2] = atomicAdd(p.sched, 1);
+    __syncthreads();
+    const int item = flag[2];
+    if (item >= n_items) break;
+    const int e = (p.order != nullptr) ? p.order[item] : item;
+    if (p.order == nullptr && p.skip != nullptr && p.skip[e] != 0) continue;
     const int m = e / p.R;
     const int nv = p.n_valid ? p.n_valid[m] : p.n_max;
     if (nv < 1 || nv > p.n_max) {
@@ -491,10 +499,9 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit8_kernel(const FitParams
       continue;
     }
     const int NS = (nv + kSB - 1) / kSB, n_pad = NS * kSB;
-    const int rot = 2 * slot + e / (int)gridDim.x;
+    const int rot = 2 * slot + it;
     set_role(t, (t.warp + rot) & (kWarps - 1));
     const int chain_warp = (2 - rot) & (kWarps - 1);  // the warp whose role is 2: tile (0,1), idle on diagonals
-    __syncthreads();  // previous evaluation fully retired before shared state is rewritten
 
     // ---- parameters: Interval transform, priors, chain rule -------------------------- //
     if (t.tid < P) {
@@ -524,7 +531,6 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit8_kernel(const FitParams
     for (int i = t.tid; i < kWarps * kMaxP; i += kThreads) gsm[i] = 0.0;
     __syncthreads();
     const double os = th[d];
-    const double diag_add = th[d + 1] + (p.jitter ? p.jitter[e] : 0.0);
     const double* Xm = p.X + (size_t)m * p.n_max * d;
     {
       const double* ym = p.y + (size_t)m * p.n_max;
@@ -537,6 +543,11 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit8_kernel(const FitParams
     bool failed = false;
 
     // ================= phase B: blocked left-looking Cholesky ========================== //
+    // in-kernel psd_safe_cholesky jitter ladder (p.ladder), see scaml_fit.cuh
+    double jit = p.jitter ? p.jitter[e] : 0.0;
+    for (int attempt = 0;; ++attempt) {
+    const double diag_add = th[d + 1] + jit;
+    failed = false;
     for (int J = 0; J < NS && !failed; ++J) {
       for (int I = J; I < NS; ++I) {
         const bool diag = (I == J);
@@ -569,6 +580,15 @@ __global__ void __launch_bounds__(kThreads, 2) scaml_fit8_kernel(const FitParams
           __syncthreads();
         }
       }
+    }
+    if (!failed || !p.ladder || attempt == 3) break;
+    jit = (attempt == 0) ? 1e-8 : ((attempt == 1) ? 1e-7 : 1e-6);
+    __syncthreads();
+    if (t.tid == 0) {
+      scal[0] = 0.0;
+      *flag = 0;
+    }
+    __syncthreads();
     }
     if (failed) {
       if (t.tid == 0) {

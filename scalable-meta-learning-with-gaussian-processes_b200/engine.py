@@ -62,6 +62,7 @@ class SourceBatch:
     ybar: torch.Tensor
     ystd: torch.Tensor
     Y_raw: torch.Tensor
+    uniform: bool = False  # every task has n_max points (known on the host: lets the fit skip its schedule pre-pass)
 
     @property
     def M(self) -> int:
@@ -79,11 +80,12 @@ class SourceBatch:
     def from_padded(X: torch.Tensor, Y: torch.Tensor, n_valid: Optional[torch.Tensor] = None) -> "SourceBatch":
         X = X.to(torch.float64).contiguous()
         Y = Y.to(torch.float64).reshape(X.shape[0], X.shape[1]).contiguous()
+        uniform = n_valid is None
         if n_valid is None:
             n_valid = torch.full((X.shape[0],), X.shape[1], dtype=torch.int32, device=X.device)
         n_valid = n_valid.to(device=X.device, dtype=torch.int32).contiguous()
         y, ybar, ystd = standardize_rows(Y, n_valid)
-        return SourceBatch(X, y.contiguous(), n_valid, ybar.contiguous(), ystd.contiguous(), Y)
+        return SourceBatch(X, y.contiguous(), n_valid, ybar.contiguous(), ystd.contiguous(), Y, uniform)
 
     @staticmethod
     def from_ragged(tasks: Sequence[Tuple[torch.Tensor, torch.Tensor]], device,
@@ -100,11 +102,14 @@ class SourceBatch:
             X[i, :n] = xi.detach().to("cpu", torch.float64)
             Y[i, :n] = yi.detach().to("cpu", torch.float64).reshape(-1)
             nv[i] = n
-        return SourceBatch.from_padded(X.to(device), Y.to(device), nv.to(device))
+        b = SourceBatch.from_padded(X.to(device), Y.to(device), nv.to(device))
+        b.uniform = bool((nv == n_max).all())
+        return b
 
     def slice(self, lo: int, hi: int) -> "SourceBatch":
         return SourceBatch(self.X[lo:hi].contiguous(), self.y[lo:hi].contiguous(), self.n_valid[lo:hi].contiguous(),
-                           self.ybar[lo:hi].contiguous(), self.ystd[lo:hi].contiguous(), self.Y_raw[lo:hi].contiguous())
+                           self.ybar[lo:hi].contiguous(), self.ystd[lo:hi].contiguous(), self.Y_raw[lo:hi].contiguous(),
+                           self.uniform)
 
 
 @dataclass
@@ -178,8 +183,8 @@ class Engine:
         self.launches = 0  # kernels launched through this engine (bench.py reports it)
 
     # ---- workspaces ------------------------------------------------------------------ #
-    def _fit_ws(self, n_max: int, d: int) -> torch.Tensor:
-        need = self.lib.fit_workspace_bytes(n_max, d)
+    def _fit_ws(self, M: int, R: int, n_max: int, d: int) -> torch.Tensor:
+        need = self.lib.fit_workspace_bytes(M, R, n_max, d)
         if self._ws is None or self._ws.numel() * 8 < need:
             self._ws = torch.empty((need + 7) // 8, dtype=torch.float64, device=self.device)
         return self._ws
@@ -218,20 +223,47 @@ class Engine:
             info = torch.empty(M, R, dtype=torch.int32, device=self.device)
         else:
             lml, grad, info = out
-        ws = self._fit_ws(batch.n_max, batch.d)
-        self.lib.lml_grad(_ptr(batch.X), _ptr(batch.y), _ptr(batch.n_valid), _ptr(theta_raw), _ptr(jitter), _ptr(skip),
-                          _ptr(lml), _ptr(grad), _ptr(info), _ptr(ws), ws.numel() * 8, M, R, batch.n_max, batch.d,
-                          spec, self._stream())
-        self.launches += 1
+        ws = self._fit_ws(M, R, batch.n_max, batch.d)
+        uniform = batch.uniform and skip is None  # full batch of equal-size tasks: no schedule pre-pass needed
+        self.lib.lml_grad(_ptr(batch.X), _ptr(batch.y), None if uniform else _ptr(batch.n_valid), _ptr(theta_raw),
+                          _ptr(jitter), _ptr(skip), _ptr(lml), _ptr(grad), _ptr(info), _ptr(ws), ws.numel() * 8, M, R,
+                          batch.n_max, batch.d, spec, self._stream())
+        self.launches += 1 if uniform else 2
         return lml, grad, info
 
     def lml_grad(self, batch: SourceBatch, theta_raw: torch.Tensor, spec: HyperSpec,
-                 skip: Optional[torch.Tensor] = None):
-        """LML+grad with the psd_safe_cholesky jitter ladder (only failed rows are re-run).
+                 skip: Optional[torch.Tensor] = None,
+                 out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):
+        """LML+grad with the psd_safe_cholesky jitter ladder applied inside the kernel (`scaml_lml_grad_ladder`): no
+        device -> host read of `info`, so an optimiser driving this call never synchronises with the device.
 
         skip [M, R] int32 (optional): non-zero rows are neither evaluated nor written (their outputs
-        are NaN / info 0).  Rows that still fail keep info > 0 and NaN outputs -- the reference hands
+        are NaN / info 0).  Rows that still fail at jitter 1e-6 keep info > 0 and NaN outputs -- the reference hands
         NaN to scipy in that case."""
+        M, R, P = theta_raw.shape
+        assert M == batch.M and P == batch.d + 2 and theta_raw.is_contiguous()
+        if out is not None:
+            lml, grad, info = out
+        elif skip is not None:
+            lml = torch.full((M, R), float("nan"), dtype=torch.float64, device=self.device)
+            grad = torch.full((M, R, P), float("nan"), dtype=torch.float64, device=self.device)
+            info = torch.zeros(M, R, dtype=torch.int32, device=self.device)
+        else:
+            lml = torch.empty(M, R, dtype=torch.float64, device=self.device)
+            grad = torch.empty(M, R, P, dtype=torch.float64, device=self.device)
+            info = torch.empty(M, R, dtype=torch.int32, device=self.device)
+        ws = self._fit_ws(M, R, batch.n_max, batch.d)
+        uniform = batch.uniform and skip is None
+        self.lib.lml_grad_ladder(_ptr(batch.X), _ptr(batch.y), None if uniform else _ptr(batch.n_valid),
+                                 _ptr(theta_raw), _ptr(skip), _ptr(lml), _ptr(grad), _ptr(info), _ptr(ws),
+                                 ws.numel() * 8, M, R, batch.n_max, batch.d, spec, self._stream())
+        self.launches += 1 if uniform else 2
+        return lml, grad, info
+
+    def lml_grad_host_ladder(self, batch: SourceBatch, theta_raw: torch.Tensor, spec: HyperSpec,
+                             skip: Optional[torch.Tensor] = None):
+        """The same ladder driven from the host (failed rows re-run with explicit jitters, one `info` read-back per
+        step); kept as the checker of the in-kernel ladder (tests)."""
         out = None
         if skip is not None:
             M, R, P = theta_raw.shape
@@ -264,20 +296,12 @@ class Engine:
         alpha = torch.zeros(M, n_pad, dtype=torch.float64, device=self.device)
         theta = torch.empty(M, P, dtype=torch.float64, device=self.device)
         info = torch.empty(M, dtype=torch.int32, device=self.device)
-        ws = self._fit_ws(batch.n_max, batch.d)
-        jitter = None
-        for attempt in range(len(JITTER_LADDER) + 1):
-            self.lib.factorize(_ptr(batch.X), _ptr(batch.y), _ptr(batch.n_valid), _ptr(theta_raw), _ptr(jitter),
-                               _ptr(linv), _ptr(alpha), _ptr(theta), _ptr(info), _ptr(ws), ws.numel() * 8,
-                               M, batch.n_max, batch.d, spec, self._stream())
-            self.launches += 1
-            bad = info > 0
-            if attempt == len(JITTER_LADDER) or not bool(bad.any()):
-                break
-            # re-run everything with jitter on the failed tasks only (rare path)
-            jitter = torch.where(bad, torch.full((M,), JITTER_LADDER[attempt], dtype=torch.float64, device=self.device),
-                                 torch.zeros(M, dtype=torch.float64, device=self.device) if jitter is None else jitter)
-            jitter = jitter.contiguous()
+        ws = self._fit_ws(M, 1, batch.n_max, batch.d)
+        # psd_safe_cholesky jitter ladder inside the kernel: one launch, `info` is read once (the check below)
+        self.lib.factorize_ladder(_ptr(batch.X), _ptr(batch.y), None if batch.uniform else _ptr(batch.n_valid),
+                                  _ptr(theta_raw), _ptr(linv), _ptr(alpha), _ptr(theta), _ptr(info), _ptr(ws),
+                                  ws.numel() * 8, M, batch.n_max, batch.d, spec, self._stream())
+        self.launches += 1 if batch.uniform else 2
         if check and bool((info != 0).any()):
             # linear_operator's psd_safe_cholesky raises NotPSDError once the jitter ladder is exhausted; handing the
             # NaN factors on would poison every weighted prediction (and topk / argmax rank NaN first)

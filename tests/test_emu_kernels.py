@@ -25,7 +25,7 @@ def emu_lml_grad(lib, pb, jitter=None):
     lml = np.full((M, R), -7.0)
     grad = np.full((M, R, d + 2), -7.0)
     info = np.full((M, R), -9, dtype=np.int32)
-    wsb = lib.fit_workspace_bytes(n, d)
+    wsb = lib.fit_workspace_bytes(M, R, n, d)
     ws = np.zeros(wsb // 8 + 8)
     lib.lml_grad(P(X), P(y), P(pb["nv"]), P(th), P(jitter), None, P(lml), P(grad), P(info), P(ws), wsb, M, R, n, d,
                  pb["cspec"])
@@ -81,7 +81,7 @@ def test_emu_factorize_and_weighted_prediction(emu_lib):
     alpha = np.full((M, pad64(n)), np.nan)
     theta = np.zeros((M, d + 2))
     info = np.full(M, -9, dtype=np.int32)
-    wsb = lib.fit_workspace_bytes(n, d)
+    wsb = lib.fit_workspace_bytes(M, 1, n, d)
     ws = np.zeros(wsb // 8 + 8)
     lib.factorize(P(X), P(y), P(pb["nv"]), P(thn), None, P(linv), P(alpha), P(theta), P(info), P(ws), wsb, M, n, d,
                   pb["cspec"])
@@ -141,7 +141,7 @@ def test_emu_predict_cross_per_task_and_reduced(emu_lib):
     alpha = np.zeros((M, pad64(n)))
     theta = np.zeros((M, d + 2))
     info = np.zeros(M, dtype=np.int32)
-    wsb = lib.fit_workspace_bytes(n, d)
+    wsb = lib.fit_workspace_bytes(M, 1, n, d)
     ws = np.zeros(wsb // 8 + 8)
     lib.factorize(P(X), P(y), P(pb["nv"]), P(thn), None, P(linv), P(alpha), P(theta), P(info), P(ws), wsb, M, n, d,
                   pb["cspec"])
@@ -333,3 +333,43 @@ def _target_ladder_case(eng):
     assert torch.isfinite(a_[0][:2]).all() and torch.isnan(a_[0][2])
     plain = eng.target_lml_grad(sm, sc, Xt, yt, w, th, 0.0, 1.0, spec)
     assert plain[3][0] > 0 and torch.equal(plain[0][1], a_[0][1])
+
+
+def _source_ladder_case(eng, n=64):
+    """Source fit: psd_safe_cholesky ladder inside the kernel == the host-driven ladder (bit for bit), on a ragged
+    batch with a skip mask -- which also exercises the schedule pre-pass (active rows, largest tasks first)."""
+    from scamlgp_b200.engine import SourceBatch
+
+    dev = eng.device
+    pb = make_problem(4, 2, n, 2, seed=1, n_valid=[n, n, n // 2 + 1, 3])
+    pb["X"][1, n // 2:] = pb["X"][1, : n // 2]  # task 1: duplicated inputs -> singular without noise
+    for sp in (pb["ospec"], pb["cspec"]):
+        sp.noise_bounds = (1e-30, 1e-2)
+    pb["th"][1, 0] = O.pack_theta(torch.full((2,), 50.0, dtype=torch.float64), 99.0, 1e-25, pb["ospec"])
+    batch = SourceBatch.from_padded(pb["X"].to(dev), pb["Y"].to(dev), torch.tensor(pb["nv"]).to(dev))
+    th = pb["th"].to(dev).contiguous()
+    skip = torch.zeros(4, 2, dtype=torch.int32, device=dev)
+    skip[0, 1] = skip[3, 0] = 1
+    raw = eng.lml_grad_raw(batch, th, pb["cspec"])
+    assert int(raw[2][1, 0]) > 0 and bool(torch.isnan(raw[0][1, 0]))  # fails without jitter
+    a_ = eng.lml_grad(batch, th, pb["cspec"], skip=skip)
+    b_ = eng.lml_grad_host_ladder(batch, th, pb["cspec"], skip=skip)
+    for x, y in zip(a_, b_):
+        assert torch.equal(torch.nan_to_num(x.to(torch.float64), nan=-7.0), torch.nan_to_num(y.to(torch.float64), nan=-7.0))
+    assert int(a_[2].abs().max()) == 0 and bool(torch.isfinite(a_[0][skip == 0]).all())
+    assert bool(torch.isnan(a_[0][skip != 0]).all())  # skipped rows are neither evaluated nor written
+    assert torch.equal(a_[0][2], raw[0][2]) and torch.equal(a_[1][0, 0], raw[1][0, 0])  # healthy rows untouched
+    fs = eng.factorize(batch, th[:, 0].contiguous(), pb["cspec"])
+    assert int(fs.info.abs().max()) == 0 and bool(torch.isfinite(fs.alpha).all())
+
+
+def test_emu_source_jitter_ladder_inside_the_kernel_matches_the_host_ladder(emu_lib):
+    from tests.emu_engine import EmuEngine
+
+    _source_ladder_case(EmuEngine(emu_lib))
+
+
+@pytest.mark.gpu
+def test_gpu_source_jitter_ladder_inside_the_kernel_matches_the_host_ladder(engine):
+    _source_ladder_case(engine)
+    _source_ladder_case(engine, n=192)

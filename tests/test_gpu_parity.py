@@ -110,9 +110,13 @@ def test_non_psd_pivot_reported_and_jitter_ladder(engine):
     lml, grad, info = engine.lml_grad_raw(batch, th, pb["cspec"])
     assert int(info[1, 0]) > 0 and bool(torch.isnan(lml[1, 0])) and bool(torch.isnan(grad[1, 0]).all())
     assert int(info[0, 0]) == 0 and int(info[2, 0]) == 0  # the batch is not aborted
-    lml2, grad2, info2 = engine.lml_grad(batch, th, pb["cspec"])  # host-driven ladder
+    lml2, grad2, info2 = engine.lml_grad(batch, th, pb["cspec"])  # psd_safe_cholesky ladder inside the kernel
     assert int(info2.abs().max()) == 0 and bool(torch.isfinite(lml2).all())
     assert torch.equal(lml2[[0, 2]], lml[[0, 2]])  # untouched rows are bit-identical
+    lml3, grad3, info3 = engine.lml_grad_host_ladder(batch, th, pb["cspec"])  # the host-driven ladder: the checker
+    assert torch.equal(lml3, lml2) and torch.equal(grad3, grad2) and torch.equal(info3, info2)
+    fs = engine.factorize(batch, th[:, 0].contiguous(), pb["cspec"])  # same ladder on the prediction state
+    assert int(fs.info.abs().max()) == 0 and bool(torch.isfinite(fs.alpha).all())
 
 
 def test_factorize_and_weighted_prediction(engine):

@@ -47,6 +47,16 @@ def _oracle_states(gps):
     return states
 
 
+def _record(line: str) -> None:
+    import os
+
+    print(line)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out) and torch.cuda.is_available():
+        with open(os.path.join(out, "parity_r2.txt"), "a") as f:
+            f.write(line + "\n")
+
+
 def _pipeline(eng, M, n, d, n_t, B, restarts, fit_options, ragged=False):
     from scamlgp_b200.model import ScaMLGP, meta_fit_scamlgp
     from scamlgp_b200.modules import theta_raw_of
@@ -114,13 +124,22 @@ def _pipeline(eng, M, n, d, n_t, B, restarts, fit_options, ragged=False):
     assert bool((w >= 1e-10).all())
     v_end = float(O.target_objective(cache, w, th, tspec))
     assert v_end >= v_start - 1e-12
-    assert abs(tfit.lml - v_end) <= 1e-8 * abs(v_end)
+    e_fit = abs(tfit.lml - v_end) / abs(v_end)
     model.eval()
     post = model.posterior(Xc)
     om, ov = O.scaml_posterior(states, w, cache, th, tspec, Xc)
     vscale = float(ov.abs().max())
-    assert rel_err(post.mean.reshape(-1).numpy(), om.numpy()) < 1e-8
-    assert float((post.variance.reshape(-1) - ov).abs().max()) < 1e-8 * vscale
+    e_mean = rel_err(post.mean.reshape(-1).numpy(), om.numpy())
+    e_var = float((post.variance.reshape(-1) - ov).abs().max()) / vscale
+    e_var_self = float(((post.variance.reshape(-1) - ov).abs() / ov).max())
+    # conditioning of the n_t x n_t target system the posterior solves with (oracle side)
+    ls_t, os_t, nz_t = O.split_theta(th, tspec)
+    Ktt = (cache.source_covs @ w ** 2) / cache.s_all ** 2 + O.kernel_matrix(Xt, Xt, ls_t, os_t, tspec.kernel) \
+        + nz_t * torch.eye(n_t, dtype=DT)
+    _record(f"public API (M={M}, n={n}, d={d}, n_t={n_t}): fitted target objective rel {e_fit:.2e}; conditioned posterior "
+            f"mean rel {e_mean:.2e}, variance rel-to-max {e_var:.2e}, rel-to-itself {e_var_self:.2e}; "
+            f"cond(K_tt) {float(torch.linalg.cond(Ktt)):.2e}")
+    assert e_fit <= TOL_LML and e_mean < TOL_MEAN_VAR and e_var < TOL_MEAN_VAR
     # ---- (4b) q > 1 / batch-shaped inputs: joint posterior over the q points of every batch element --------- #
     nb, q = 3, 4
     Xq = torch.rand(nb, q, d, dtype=DT, generator=g)
@@ -131,8 +150,8 @@ def _pipeline(eng, M, n, d, n_t, B, restarts, fit_options, ragged=False):
         assert pj.mvn.covariance_matrix.shape == (nb, q, q)
         for i in range(nb):
             om_j, oc_j = O.scaml_posterior(*args, Xq[i], full_cov=True)
-            assert rel_err(pj.mean[i].reshape(-1).numpy(), om_j.numpy()) < 1e-8
-            assert float((pj.mvn.covariance_matrix[i] - oc_j).abs().max()) < 1e-8 * float(oc_j.abs().max())
+            assert rel_err(pj.mean[i].reshape(-1).numpy(), om_j.numpy()) < TOL_MEAN_VAR
+            assert float((pj.mvn.covariance_matrix[i] - oc_j).abs().max()) < TOL_MEAN_VAR * float(oc_j.abs().max())
         # the diagonal of the joint covariance is the q = 1 variance of the same points
         p1 = mdl.posterior(Xq.reshape(-1, 1, d))
         assert float((p1.variance.reshape(nb, q) - pj.variance.reshape(nb, q)).abs().max()) < 1e-9 * vscale
@@ -148,7 +167,8 @@ def _pipeline(eng, M, n, d, n_t, B, restarts, fit_options, ragged=False):
         gm, gv, gdm, gdv = mdl.posterior_with_grad(Xg.unsqueeze(1))
         rm, rv, rdm, rdv = O.scaml_posterior_grad(*args, Xg)
         assert gdm.shape == Xg.shape and gdv.shape == Xg.shape
-        assert rel_err(gm.numpy(), rm.numpy()) < 1e-8 and float((gv - rv).abs().max()) < 1e-8 * float(rv.abs().max())
+        assert rel_err(gm.numpy(), rm.numpy()) < TOL_MEAN_VAR
+        assert float((gv - rv).abs().max()) < TOL_MEAN_VAR * float(rv.abs().max())
         assert rel_err(gdm.numpy(), rdm.numpy()) < TOL_GRAD, rel_err(gdm.numpy(), rdm.numpy())
         assert rel_err(gdv.numpy(), rdv.numpy()) < TOL_GRAD, rel_err(gdv.numpy(), rdv.numpy())
     val, grad = af.value_and_grad(Xg)
