@@ -110,5 +110,16 @@ def build_ablate(force: bool = False) -> str:
     return out
 
 
+def build_variant(tag: str, defines, force: bool = False) -> str:
+    """A/B experiment builds (e.g. build_variant("nosplit", ["-DSCAML_FIT_NOSPLIT"])) -> csrc/libscaml_b200_<tag>.so;
+    experiments only, never loaded by the package."""
+    out = os.path.join(CSRC, f"libscaml_b200_{tag}.so")
+    deps = [os.path.join(CSRC, s) for s in CUDA_SOURCES + HEADERS]
+    if not force and _newer(out, deps):
+        return out
+    _compile_parts(list(defines), out)
+    return out
+
+
 if __name__ == "__main__":
     print(build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -95,11 +95,37 @@ SCAML_DEVICE int tri(int i) { return (i * (i + 1)) >> 1; }
 // exp(x) for x <= 0, branch-free.  libdevice's exp() carries a slow-path branch, so the 8..16
 // independent exponentials of an unrolled epilogue are emitted one after the other and each
 // is a ~20-deep dependent DFMA chain (measured: "wait" stalls dominate the k* assembly).
-// Without control flow the compiler interleaves them.  Cody-Waite reduction x = n ln2 + r,
-// |r| <= ln2/2, degree-13 Taylor polynomial (remainder 4e-18), 2^n applied through the
-// exponent field.  Max error < 1.5 ulp on [-707, 0] (tests/test_emu_kernels.py); results
-// below 1e-307 are flushed to 0, NaN propagates, -inf -> 0.
+// Without control flow the compiler interleaves them.  Table-driven: x = (64 n + j) ln2/64 + r,
+// |r| <= ln2/128, exp(x) = 2^n * T[j] * (1 + r (1 + r/2 + r^2/6 + r^3/24 + r^4/120)) with
+// T[j] = 2^(j/64) correctly rounded (64 doubles, read through the read-only data path: L1
+// resident) -- 10 FP64 instructions and a dependent chain of 9 instead of 17 / 16 for the
+// table-free degree-13 polynomial; truncation r^6/720 < 3.6e-17.  Max error < 1.5 ulp on
+// [-707, 0] (tests/test_emu_kernels.py); results below 1e-307 are flushed to 0, NaN
+// propagates, -inf -> 0.
 // ----------------------------------------------------------------------------------- //
+#ifdef SCAML_EMU
+#define SCAML_TABLE static const
+#else
+#define SCAML_TABLE __device__ const
+#endif
+SCAML_TABLE double kExp2Tab[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0,
+};
 #ifdef SCAML_EMU
 SCAML_DEVICE int dbl_hi(double x) {
   int64_t b;
@@ -117,12 +143,56 @@ SCAML_DEVICE double dbl_make(int hi, int lo) {
   std::memcpy(&x, &b, 8);
   return x;
 }
+SCAML_DEVICE double exp2_tab(int j) { return kExp2Tab[j]; }
 #else
 SCAML_DEVICE int dbl_hi(double x) { return __double2hiint(x); }
 SCAML_DEVICE int dbl_lo(double x) { return __double2loint(x); }
 SCAML_DEVICE double dbl_make(int hi, int lo) { return __hiloint2double(hi, lo); }
+SCAML_DEVICE double exp2_tab(int j) { return __ldg(kExp2Tab + j); }
 #endif
 
+#ifndef SCAML_EXP_POLY
+// U independent exponentials, written step-major so that the U dependent chains are interleaved in the
+// instruction stream (in[u] <= 0; out may alias in).
+template <int U>
+SCAML_DEVICE void exp_nonpos_n(const double (&in)[U], double (&out)[U]) {
+  const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
+  double r[U], p[U], tab[U];
+  int n[U], xh[U], xl[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const double x = in[u];
+    xh[u] = dbl_hi(x);
+    xl[u] = dbl_lo(x);
+    const double t = fma(x, 92.33248261689366, kMagic);  // 64 / ln 2
+    const int k = dbl_lo(t);                             // round(64 x / ln 2) = 64 n + j
+    const bool big0 = ((unsigned)xh[u] & 0x7fffffffu) >= 0x40861800u;
+    tab[u] = exp2_tab(big0 ? 0 : (k & 63));
+    n[u] = k >> 6;
+    const double kf = t - kMagic;
+    // ln2/64 split: the high part has 35 significant bits, so kf * hi is exact for |kf| < 2^17
+    r[u] = fma(kf, -0x1.1cf79abc9e3b4p-42, fma(kf, -0x1.62e42fef80000p-7, x));
+    p[u] = fma(8.3333333333333332177e-03, r[u], 4.1666666666666664354e-02);  // 1/5!, 1/4!
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], 1.6666666666666665741e-01);
+#pragma unroll
+  for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], 0.5);
+#pragma unroll
+  for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], 1.0);
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const double q = fma(tab[u], p[u] * r[u], tab[u]);  // T (1 + r poly): in [0.99, 2)
+    int hi = dbl_hi(q) + n[u] * 1048576, lo = dbl_lo(q);
+    // |x| >= 707 (incl. -inf / NaN): 0, or NaN for NaN -- selects only, no branch
+    const bool big = ((unsigned)xh[u] & 0x7fffffffu) >= 0x40861800u;
+    const bool neg = in[u] < 0.0;  // false for NaN
+    hi = big ? (neg ? 0 : xh[u]) : hi;
+    lo = big ? (neg ? 0 : xl[u]) : lo;
+    out[u] = dbl_make(hi, lo);
+  }
+}
+#else  // A/B variant: table-free degree-13 polynomial (17 FP64 instructions per value)
 // U independent exponentials, written step-major so that the U dependent chains are interleaved in the
 // instruction stream (in[u] <= 0; out may alias in).
 template <int U>
@@ -160,6 +230,7 @@ SCAML_DEVICE void exp_nonpos_n(const double (&in)[U], double (&out)[U]) {
     out[u] = dbl_make(hi, lo);
   }
 }
+#endif
 SCAML_DEVICE double exp_nonpos(double x) {
   const double in[1] = {x};
   double out[1];

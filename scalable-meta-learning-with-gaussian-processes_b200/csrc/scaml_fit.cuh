@@ -163,6 +163,34 @@ SCAML_DEVICE void fmma(Acc& acc, const double* __restrict__ Ap, const double* __
   }
 }
 
+// The same product when an operand tile is triangular: the 8-row blocks that are identically zero in a k4-step are
+// skipped (a predicated-off DMMA costs an issue slot, not 16 cycles of the FP64 pipe).  kbase = index of the first kk
+// row of this call inside its 32 x 32 tile.  Modes (warp-uniform):
+//   1  operand[kk][x] != 0 only for x <= kk  (rows of L^-1, R-layout)      -> blocks  <= (kk0 + 3) / 8
+//   2  operand[kk][x] != 0 only for x >= kk  (D^-1 of a diagonal block, C-layout) -> blocks >= kk0 / 8
+template <int NK4>
+SCAML_DEVICE void fmma_tri(Acc& acc, const double* __restrict__ Ap, const double* __restrict__ Bp, const FThr& t,
+                           bool lower, int amode, int bmode, int kbase) {
+  const double* ar = Ap + t.t4 * kLd + t.g;
+  const double* br = Bp + t.t4 * kLd + t.g;
+#pragma unroll 2
+  for (int s = 0; s < NK4; ++s) {
+    const int kk0 = kbase + 4 * s;
+    const int up = (kk0 + 3) >> 3, lo = kk0 >> 3;
+    const int ihi = (amode == 1) ? up : 3, ilo = (amode == 2) ? lo : 0;
+    const int jhi = (bmode == 1) ? up : 3, jlo = (bmode == 2) ? lo : 0;
+    const double a[4] = {ar[0], ar[8], ar[16], ar[24]};
+    const double b[4] = {br[0], br[8], br[16], br[24]};
+    ar += 4 * kLd;
+    br += 4 * kLd;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (i >= ilo && i <= ihi && j >= jlo && j <= jhi && (j <= i || !lower)) dmma884(acc[i][j], a[i], b[j]);
+  }
+}
+
 // ---- chunk sources: which global tiles feed chunk `ck` of a super-tile product ------- //
 // Scalar fields only: arrays indexed by the (runtime) warp coordinates would be placed in local memory
 // and put LDL/STL round trips on the critical path of every pipeline step.
@@ -188,6 +216,8 @@ struct CholSrc {
   int I, J;
   SCAML_DEVICE int count() const { return 2 * J; }
   SCAML_DEVICE bool same() const { return I == J; }
+  SCAML_DEVICE int a_tri(int, int) const { return 0; }
+  SCAML_DEVICE int b_tri(int, int) const { return 0; }
   SCAML_DEVICE ChunkPtrs get(int ck) const {
     ChunkPtrs c;
     c.a0 = wtile(W, 2 * I, ck);
@@ -205,6 +235,9 @@ struct TrtriSrc {
   int I, J;
   SCAML_DEVICE int count() const { return 2 * (I - J); }
   SCAML_DEVICE bool same() const { return false; }
+  SCAML_DEVICE int a_tri(int, int) const { return 0; }
+  // chunk 0 / 1 read the lower-triangular diagonal tiles Linv(2J, 2J) / Linv(2J+1, 2J+1) as the B operand of cb = 0 / 1
+  SCAML_DEVICE int b_tri(int ck, int cb) const { return (ck < 2 && ck == cb) ? 1 : 0; }
   SCAML_DEVICE ChunkPtrs get(int ck) const {
     ChunkPtrs c;
     const int kcol = 2 * J + ck;
@@ -222,6 +255,10 @@ struct LauumSrc {
   int I, J, NS;
   SCAML_DEVICE int count() const { return 2 * (NS - I); }
   SCAML_DEVICE bool same() const { return I == J; }
+  // chunk 0 / 1 read the lower-triangular diagonal tiles Linv(2I, 2I) / Linv(2I+1, 2I+1) as the A operand of rb = 0 / 1
+  // (and as the B operand of cb = 0 / 1 on diagonal super-tiles)
+  SCAML_DEVICE int a_tri(int ck, int rb) const { return (ck < 2 && ck == rb) ? 1 : 0; }
+  SCAML_DEVICE int b_tri(int ck, int cb) const { return (I == J && ck < 2 && ck == cb) ? 1 : 0; }
   SCAML_DEVICE ChunkPtrs get(int ck) const {
     ChunkPtrs c;
     const int krow = 2 * I + ck;
@@ -261,15 +298,53 @@ SCAML_DEVICE void stage_issue(const Src& src, int s, double* st, int tid) {
 
 // acc += sum over chunks; optional piggy-backed GEMV  pig[c] += sum_kk A[kk][c] * zv[zoff+kk]
 // (c = tid & 63 over the 64 A columns of the super-tile, kk-half = tid >> 6).
-// DIAG: super-tile on the diagonal -> warp (0,1) idles, warps (0,0),(1,1) compute lower 8x8 tiles only.
+// DIAG: super-tile on the diagonal -> roles (0,0), (1,1) compute the lower 8x8 tiles only (10 of 16), role (0,1) idles.
+// Two work-trimming variants are kept behind compile-time switches because they measured SLOWER on the B200
+// (profiles/r2_fit_split_tri_ab.txt: three co-resident CTAs keep the shared FP64 pipe fed, so shortening one role's
+// critical path buys nothing, while the extra predicates / merges cost issue slots):
+//   -DSCAML_FIT_SPLIT  the one full tile (1,0) is split along the contraction between its own warp and the idle
+//                      role's warp (40 / 32 / 32 / 40 DMMAs per step instead of 40 / 64 / 0 / 40), partial sums merged
+//                      by `split_merge` in a fixed order: -0.7 %
+//   -DSCAML_FIT_TRI    8-row blocks of triangular operand tiles that are identically zero in a k4-step are skipped
+//                      (predicated-off DMMAs, `fmma_tri`): -5 %
 // On return every thread has passed a __syncthreads after its last read of `stage`.
 template <class Src>
 SCAML_DEVICE void gemm_global(Acc& acc, const Src& src, double* stage, const FThr& t, bool diag, bool piggy,
                               double& pig, const double* zv) {
   const int n = 2 * src.count();
   if (n <= 0) return;
-  const bool active = !(diag && t.rb < t.cb);
-  const bool lower = diag && (t.rb == t.cb);
+#ifndef SCAML_FIT_SPLIT
+  const bool helper = false;
+  if (diag && t.rb < t.cb) {  // A/B variant: role (0,1) idles, role (1,0) multiplies the whole tile
+    stage_issue(src, 0, stage, t.tid);
+    for (int s = 0; s < n; ++s) {
+      cp_async_wait<0>();
+      __syncthreads();
+      if (s + 1 < n) stage_issue(src, s + 1, stage + ((s + 1) & 1) * 4 * kHalfS, t.tid);
+      if (piggy) {
+        const ChunkPtrs c = src.get(s >> 1);
+        const double* As = stage + (s & 1) * 4 * kHalfS;
+        const int col = t.tid & 63, q = t.tid >> 6;
+        if (c.a_ok(col >> 5)) {
+          const double* ap = As + (col >> 5) * kHalfS + (col & 31) + q * 8 * kLd;
+          const double* zp = zv + c.zoff + (s & 1) * 16 + q * 8;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) pig = fma(ap[kk * kLd], zp[kk], pig);
+        }
+      }
+    }
+    __syncthreads();
+    return;
+  }
+  const int erb = t.rb, ecb = t.cb;
+  const bool split = false;
+#else
+  const bool helper = diag && t.rb < t.cb;  // role (0,1): works on tile (1,0)
+  const int erb = helper ? 1 : t.rb, ecb = helper ? 0 : t.cb;
+  const bool split = diag && erb == 1 && ecb == 0;
+#endif
+  const bool lower = diag && (erb == ecb);
+  const int koff = helper ? 8 : 0;  // first kk row (inside a 16-deep sub-chunk) of this warp's share of a split tile
   stage_issue(src, 0, stage, t.tid);
   for (int s = 0; s < n; ++s) {
     double* st = stage + (s & 1) * 4 * kHalfS;
@@ -284,12 +359,28 @@ SCAML_DEVICE void gemm_global(Acc& acc, const Src& src, double* stage, const FTh
 #ifdef SCAML_PROF
     const long long pc1 = clock64();
 #endif
-    const ChunkPtrs c = src.get(s >> 1);
+    const int ck = s >> 1;
+    const ChunkPtrs c = src.get(ck);
     const double* As = st;
     const double* Bs = src.same() ? st : st + 2 * kHalfS;
-    const bool bvalid = src.same() ? c.a_ok(t.cb) : c.b_ok(t.cb);
-    if (active && c.a_ok(t.rb) && bvalid && !ABL(8))
-      fmma<4>(acc, As + t.rb * kHalfS, Bs + t.cb * kHalfS, t, lower);
+    const bool bvalid = src.same() ? c.a_ok(ecb) : c.b_ok(ecb);
+    if (c.a_ok(erb) && bvalid && !ABL(8)) {
+#ifndef SCAML_FIT_TRI
+      const int amode = 0, bmode = 0;
+#else
+      const int amode = src.a_tri(ck, erb), bmode = src.b_tri(ck, ecb);
+#endif
+      const double* ap = As + erb * kHalfS + koff * kLd;
+      const double* bp = Bs + ecb * kHalfS + koff * kLd;
+      const int kbase = (s & 1) * 16 + koff;
+      if (split) {
+        if (amode | bmode) fmma_tri<2>(acc, ap, bp, t, false, amode, bmode, kbase);
+        else fmma<2>(acc, ap, bp, t, false);
+      } else {
+        if (amode | bmode) fmma_tri<4>(acc, ap, bp, t, lower, amode, bmode, kbase);
+        else fmma<4>(acc, ap, bp, t, lower);
+      }
+    }
     if (piggy && !ABL(8192)) {
       const int col = t.tid & 63, q = t.tid >> 6;
       if (c.a_ok(col >> 5)) {
@@ -299,7 +390,7 @@ SCAML_DEVICE void gemm_global(Acc& acc, const Src& src, double* stage, const FTh
         for (int kk = 0; kk < 8; ++kk) pig = fma(ap[kk * kLd], zp[kk], pig);
       }
     }
-#ifdef SCAML_PROF
+#ifdef SCAML_PROF_GEMM
     if (threadIdx.x == 0) {
       profsm[14] += pc1 - pc0;          // wait + barrier + issue next
       profsm[15] += clock64() - pc1;    // compute
@@ -307,6 +398,27 @@ SCAML_DEVICE void gemm_global(Acc& acc, const Src& src, double* stage, const FTh
 #endif
   }
   __syncthreads();
+}
+
+// partial sums of the split tile (1,0) of a diagonal super-tile: the helper warp (role (0,1)) parks its accumulators in
+// `scratch` (thread-private slots, >= 1024 doubles) BEFORE a __syncthreads, the owner adds them AFTER it
+SCAML_DEVICE void split_put(double* scratch, const Acc& acc, const FThr& t) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      scratch[(8 * i + 2 * j) * 32 + t.lane] = acc[i][j][0];
+      scratch[(8 * i + 2 * j + 1) * 32 + t.lane] = acc[i][j][1];
+    }
+}
+SCAML_DEVICE void split_merge(Acc& acc, const double* scratch, const FThr& t) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[i][j][0] += scratch[(8 * i + 2 * j) * 32 + t.lane];
+      acc[i][j][1] += scratch[(8 * i + 2 * j + 1) * 32 + t.lane];
+    }
 }
 
 // products of shared-memory resident 64x64 operands (2 chunks of full padded tiles); tile addresses are
@@ -320,7 +432,13 @@ SCAML_DEVICE void gemm_smem_trsm(Acc& acc, const double* cin, const double* dinv
 #pragma unroll
   for (int ck = 0; ck < 2; ++ck) {
     if (t.cb < ck) continue;
+    // D^-1 tiles (0,0) and (1,1) are lower triangular: B[kk][c] = D^-1(c, kk) vanishes for c < kk
+#ifndef SCAML_FIT_TRI
     fmma<8>(acc, cin + (2 * t.rb + ck) * kTileS, dinvc + (t.cb + ck) * kTileS, t, false);
+#else
+    fmma_tri<8>(acc, cin + (2 * t.rb + ck) * kTileS, dinvc + (t.cb + ck) * kTileS, t, false, 0,
+                (t.cb + ck != 1) ? 2 : 0, 0);
+#endif
   }
 }
 // trtri (phase C): acc = D^-1 * S ; A[kk][r] = D^-1(r, kk): chunk ck, row-tile rb -> D tile (rb, ck), null for
@@ -330,7 +448,13 @@ SCAML_DEVICE void gemm_smem_trtri(Acc& acc, const double* dinvc, const double* s
 #pragma unroll
   for (int ck = 0; ck < 2; ++ck) {
     if (t.rb < ck) continue;
+    // A[kk][r] = D^-1(r, kk) vanishes for r < kk on the triangular tiles (0,0), (1,1)
+#ifndef SCAML_FIT_TRI
     fmma<8>(acc, dinvc + (t.rb + ck) * kTileS, sst + (2 * ck + t.cb) * kTileS, t, false);
+#else
+    fmma_tri<8>(acc, dinvc + (t.rb + ck) * kTileS, sst + (2 * ck + t.cb) * kTileS, t, false,
+                (t.rb + ck != 1) ? 2 : 0, 0, 0);
+#endif
   }
 }
 
@@ -575,6 +699,9 @@ SCAML_DEVICE void inv_steps(double (&b)[kBS], int j0, const double* Lc, double* 
 }
 SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* XC, double* XRs, double* XRg,
                              double* logdet, int lane) {
+#if defined(SCAML_PROF) && !defined(SCAML_PROF_GEMM)
+  const long long pc_a = clock64();
+#endif
   double a[kBS];
 #pragma unroll
   for (int c = 0; c < kBS; ++c) a[c] = Dsm[c * kLd + lane];
@@ -588,6 +715,10 @@ SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* 
     chol_steps<16>(a, 16, Lc, lane, fail, mydiag, myrs, dnext, rsnext);
     chol_steps<8>(a, 24, Lc, lane, fail, mydiag, myrs, dnext, rsnext);
   }
+#if defined(SCAML_PROF) && !defined(SCAML_PROF_GEMM)
+  const long long pc_b = clock64();
+  if (lane == 0) profsm[14] += pc_b - pc_a;  // chain warp: load + 32 Cholesky pivot steps
+#endif
   double ld = log(mydiag);
   ld = warp_sum(ld);
   if (lane == 0) *logdet += ld;
@@ -611,6 +742,9 @@ SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* 
     }
   }
   __syncwarp();
+#if defined(SCAML_PROF) && !defined(SCAML_PROF_GEMM)
+  if (lane == 0) profsm[15] += clock64() - pc_b;  // chain warp: log det + 32 inverse steps + transposed outputs
+#endif
   return fail;
 }
 
@@ -930,8 +1064,15 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
         CholSrc src{W, I, J};
         gemm_global(acc, src, stage, t, diag, false, pig, nullptr);
         PROF_MARK(1);
+        // split tile (1,0) of a diagonal super-tile: dinvc is free here (all trsm of column J-1 have retired)
+#ifdef SCAML_FIT_SPLIT
+        if (diag && J > 0 && upper_warp) split_put(dinvc, acc, t);
+#endif
         xblk_store(stage, xp, Xm, invl, I, J, nv, d, t.tid);  // stage is idle: x-block lives there
         __syncthreads();
+#ifdef SCAML_FIT_SPLIT
+        if (diag && J > 0 && t.rb == 1 && t.cb == 0) split_merge(acc, dinvc, t);
+#endif
         if (!(diag && upper_warp))
           assemble_tile<KIND>(acc, I, J, t, stage, d, nv, os, diag_add,
                               kcache ? kcache + ((size_t)(tri(I) + J) * 32) * kFitThreads + t.tid : nullptr);
@@ -1045,9 +1186,15 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
         LauumSrc src{W, I, J, NS};
         gemm_global(acc, src, stage, t, diag, diag, pig, zv);
         PROF_MARK(8);
+#ifdef SCAML_FIT_SPLIT
+        if (diag && upper_warp) split_put(dinvc, acc, t);  // dinvc is not used in phase D
+#endif
         xblk_store(stage, xp, Xm, invl, I, J, nv, d, t.tid);
         if (diag) red[t.tid] = pig;
         __syncthreads();
+#ifdef SCAML_FIT_SPLIT
+        if (diag && t.rb == 1 && t.cb == 0) split_merge(acc, dinvc, t);
+#endif
         if (diag) {
           if (t.tid < 64) av[I * kSB + t.tid] = red[t.tid] + red[64 + t.tid];
           __syncthreads();

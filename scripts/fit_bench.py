@@ -12,7 +12,12 @@ from scamlgp_b200.engine import Engine, SourceBatch
 
 M, R, n, d = (int(a) for a in sys.argv[1:5])
 kernel = int(sys.argv[5]) if len(sys.argv) > 5 else 0
-eng = Engine(torch.device("cuda:0"))
+lib = None
+if os.environ.get("SCAML_LIB"):  # A/B experiment builds (build.build_variant)
+    from scamlgp_b200._capi import ScamlLib
+
+    lib = ScamlLib(os.environ["SCAML_LIB"])
+eng = Engine(torch.device("cuda:0"), lib=lib)
 X, Y = O.synthetic_tasks(M, n, d, seed=0)
 th = O.sample_theta_raw(M, R, d, O.HyperSpec.source(kernel), seed=0).cuda().contiguous()
 batch = SourceBatch.from_padded(X.cuda(), Y.cuda())

@@ -18,6 +18,63 @@ from scamlgp_b200.fit import fit_sources
 from scamlgp_b200.sharded import ShardedSources
 
 
+def public_api_check(eng, rank, world, X, Y, steps=4):
+    """reference call sites that fan out: optimizer.py:128-133 (meta-fit), :176-185 (report), model.py:278-289 (caches),
+    model.py:364-375 (eval branch).  Every rank drives the same optimizer; rank 0 also runs the un-sharded one."""
+    from scamlgp_b200.optimizer import ScaMLGPBO
+    from scamlgp_b200.space import ContinuousParameter, Evaluation, Objective, ParameterSpace
+
+    M, d = 24, X.shape[-1]
+    space = ParameterSpace()
+    for k in range(d):
+        space.add(ContinuousParameter(f"x{k}", (0.0, 1.0)))
+    loss = Objective("loss", greater_is_better=False)
+    md = {f"t{i}": [Evaluation(configuration={f"x{k}": float(x[k]) for k in range(d)}, objectives={"loss": float(y)})
+                    for x, y in zip(X[i, :64], Y[i, :64])] for i in range(M)}
+    target = lambda c: float(O.hartmann6(torch.tensor([[c[f"x{k}"] for k in range(d)]], dtype=torch.float64),
+                                         torch.tensor([1.0, 1.2, 3.0, 3.2], dtype=torch.float64)))
+
+    probe = torch.rand(64, d, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
+
+    def run(group, follow=None):
+        """follow: configurations to EVALUATE instead of the optimizer's own proposals (so that two runs see the same
+        target data even where an acquisition optimum is nearly tied and a 1e-13 difference picks the other one)."""
+        opt = ScaMLGPBO(space, loss, md, seed=11, engine=eng, group=group, num_restarts_log_likelihood=2)
+        xs, posts = [], []
+        for k in range(steps):
+            spec = opt.generate_evaluation_specification()
+            xs.append([spec.configuration[f"x{j}"] for j in range(d)])
+            post = opt.model.posterior(probe)
+            posts.append(torch.stack([post.mean.reshape(-1).cpu(), post.variance.reshape(-1).cpu()]))
+            if follow is not None:
+                spec.configuration.update({f"x{j}": float(follow[k][j]) for j in range(d)})
+            opt.report(spec.create_evaluation(objectives={"loss": target(spec.configuration)}))
+        theta = torch.stack([torch.cat([g.covar_module.base_kernel.raw_lengthscale.reshape(-1),
+                                        g.covar_module.raw_outputscale.reshape(-1),
+                                        g.likelihood.raw_noise.reshape(-1)]) for g in opt.source_gps.values()])
+        return torch.tensor(xs, dtype=torch.float64), torch.stack(posts), theta, float(opt.model.last_fit.lml)
+
+    xs, posts, theta, lml = run(True)
+    # every rank proposed the same configurations
+    gx = [None] * world
+    dist.all_gather_object(gx, xs)
+    same = all(torch.equal(g, gx[0]) for g in gx)
+    ok = same
+    if rank == 0:
+        x1, posts1, theta1, lml1 = run(None, follow=xs)
+        rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+        close = [(xs[k] - x1[k]).abs().max().item() < 1e-6 for k in range(steps)]
+        checks = {"ranks agree bitwise": same, "meta-fit parameters bitwise": torch.equal(theta, theta1),
+                  "first proposal (prior-only model) 1e-9": rel(xs[0], x1[0]) < 1e-9,
+                  f"proposals equal to 1e-6 at {sum(close)}/{steps} steps (same data reported)": sum(close) >= steps - 1,
+                  "posterior before every report 1e-6": rel(posts, posts1) < 1e-6,
+                  "fitted target objective 1e-8": abs(lml - lml1) <= 1e-8 * abs(lml1)}
+        ok = all(checks.values())
+        print(f"ScaMLGPBO(group=True), world={world}, {M} meta-tasks, {steps} BO steps:", checks,
+              "posterior rel diff %.2e" % rel(posts, posts1), "OK" if ok else "FAILED", flush=True)
+    return ok
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -71,6 +128,9 @@ def main():
         }
         ok = all(checks.values())
         print(f"world={world}", checks, "OK" if ok else "FAILED", flush=True)
+    # ---- the public drop-in on sharded meta-tasks: ScaMLGPBO(group=True) proposes what a single GPU proposes ---- #
+    ok_api = public_api_check(eng, rank, world, X, Y)
+    ok = ok and ok_api
     flag = torch.tensor([int(ok)], device=dev)
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
