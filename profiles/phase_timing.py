@@ -13,7 +13,7 @@ from scamlgp_b200._capi import ScamlLib
 from scamlgp_b200.engine import Engine, SourceBatch
 
 NAMES = ["setup", "B gemm(update)", "B assemble(exp)+store", "B diag_factor", "B trsm+store", "C gemm1", "C gemm2+store",
-         "C z solve", "D gemm", "D grad epilogue", "final", " diag: chol#1 (warp0)", " diag: L10,D11,Tm", " diag: chol#2 rest (outputs)", " chain warp: load + 32 chol steps (x8)", " chain warp: logdet + 32 inv steps + outputs (x8)"]
+         "C z solve", "D gemm", "D grad epilogue", "final", " diag: chol#1 (warp0)", " diag: L10,D11,Tm", " diag: chol#2 rest (outputs)", " chain warp: 32 chol steps (x8)", " follower warp: 32 inverse steps incl. waits (x8)"]
 
 
 def main():

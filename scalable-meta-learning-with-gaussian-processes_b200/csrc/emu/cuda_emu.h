@@ -12,6 +12,7 @@
 // used for that).
 #pragma once
 #include <pthread.h>
+#include <sched.h>
 
 #include <cmath>
 #include <cstdint>
@@ -177,6 +178,7 @@ template <class T>
 inline T __ldg(const T* p) {
   return *p;
 }
+inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline double fma_emu(double a, double b, double c) { return std::fma(a, b, c); }

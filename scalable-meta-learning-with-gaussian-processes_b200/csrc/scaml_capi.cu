@@ -380,6 +380,7 @@ int scaml_target_lml_grad(const double* source_means, const double* source_covs,
   p.Wmat = ws + (size_t)R * n_t * n_t;
   p.meanw = ws + 2 * (size_t)R * n_t * n_t;
   p.alpha = p.meanw + (size_t)R * n_t;
+  p.big = (n_t >= scaml::kTgtBigFrom) ? ws + scaml::target_small_doubles(n_t, R) : nullptr;
   p.mu_all = mu_all, p.s_all = s_all;
   p.M = M, p.nt = n_t, p.d = d, p.R = R, p.w_prior = w_prior, p.w_p1 = w_p1, p.w_p2 = w_p2;
   p.spec = *spec;
@@ -406,6 +407,7 @@ int scaml_target_lml_grad_ladder(const double* source_means, const double* sourc
   p.Wmat = ws + (size_t)R * n_t * n_t;
   p.meanw = ws + 2 * (size_t)R * n_t * n_t;
   p.alpha = p.meanw + (size_t)R * n_t;
+  p.big = (n_t >= scaml::kTgtBigFrom) ? ws + scaml::target_small_doubles(n_t, R) : nullptr;
   p.mu_all = mu_all, p.s_all = s_all;
   p.M = M, p.nt = n_t, p.d = d, p.R = R, p.w_prior = w_prior, p.w_p1 = w_p1, p.w_p2 = w_p2;
   p.spec = *spec;
@@ -431,6 +433,7 @@ int scaml_target_factorize(const double* source_means, const double* source_covs
   p.meanw = ws + 2 * (size_t)n_t * n_t;
   p.alpha = alpha_t;
   p.grad_theta = p.meanw + n_t + n_t;  // scratch: the gradient is not part of this call's contract
+  p.big = (n_t >= scaml::kTgtBigFrom) ? ws + scaml::target_small_doubles(n_t, 1) + (d + 3) : nullptr;
   p.jitter = nullptr;
   p.lml = lml, p.grad_w = nullptr, p.info = info;
   p.linv_out = linv_t, p.theta_out = theta;

@@ -697,6 +697,118 @@ SCAML_DEVICE void inv_steps(double (&b)[kBS], int j0, const double* Lc, double* 
     for (int i = 1; i < W; ++i) b[i - 1] = fma(-lj[-i * kLd], b0, b[i]);
   }
 }
+// ---- the same factorisation as a two-warp pipeline (-DSCAML_FIT_FOLLOW; measured, NOT the default) ---------- //
+// Result on the B200 (profiles/r2_fit_follower_ab.txt): correct (all parity tests green) and 4 % faster with ONE CTA per
+// SM, but 1-3 % slower with the three co-resident CTAs the kernel runs with -- the chain step itself gets slower
+// (fence + flag store, a second warp on the tile's shared-memory rows) and the follower competes for the FP64 pipe
+// that the other CTAs' products need.
+// The inverse does not have to wait for the whole factor: with lane = COLUMN c of X = L^-1 and the pending sums
+// acc[r'] = delta(r', c) - sum_{k < r} L(r', k) X(k, c) kept in a rotating register window, row r of X is final as soon
+// as column r of L is (X(r, c) = acc[r] / L(r, r), then acc[r'] -= L(r', r) X(r, c) for r' > r) -- so a FOLLOWER warp
+// computes X one pivot step behind the CHAIN warp and the 32 inverse steps disappear from the critical path of every
+// diagonal block (they were 244 of 531 cycles per pivot, profiles/r2_fit_phase_cycles.txt).  Hand-shake: the chain warp
+// stores column k of L and 1 / L(k, k) to shared memory and publishes `k + 1` in a shared counter (fence + volatile
+// store by lane 0); the follower spins on the counter.  X is written directly in the three layouts the callers need
+// (no transpose buffer).
+SCAML_DEVICE void chain_publish(volatile int* prog, int v, int lane) {
+  if (lane == 0) {
+    __threadfence_block();
+    *prog = v;
+  }
+}
+SCAML_DEVICE void chain_wait(volatile int* prog, int v, int lane) {
+  if (lane == 0) {
+    while (*prog < v) {
+#ifdef SCAML_EMU
+      sched_yield();
+#endif
+    }
+    __threadfence_block();
+  }
+  __syncwarp();
+}
+template <int W>
+SCAML_DEVICE void chol_steps_pub(double (&a)[kBS], int k0, double* Lc, double* dg, volatile int* prog, int pbase,
+                                 int lane, int& fail, double& mydiag, double& dnext, double& rsnext) {
+#pragma unroll 1
+  for (int k = k0; k < k0 + 8; ++k) {
+    const double dkk = dnext, rs = rsnext;
+    if (lane == k) {
+      mydiag = dkk;
+      dg[k] = rs;
+    }
+    const double lrk = a[0] * rs;  // a[i] = A(lane, k + i)
+    Lc[k * kLd + lane] = lrk;
+    double dn = __shfl_sync(0xffffffffu, fma(-lrk, lrk, a[1]), (k + 1) & 31);
+    if (k + 1 < kBS) dn = checked_pivot(dn, k + 1, fail);
+    dnext = dn;
+    rsnext = rsqrt(dn);
+    __syncwarp();
+    chain_publish(prog, pbase + k + 1, lane);  // column k of L and dg[k] are complete
+    const double* lk = Lc + k * kLd + k;  // lk[j] = L(k + j, k)
+#pragma unroll
+    for (int j = 1; j < W; ++j) a[j - 1] = fma(-lrk, lk[j], a[j]);
+  }
+}
+template <int W>
+SCAML_DEVICE void inv_follow_steps(double (&a)[kBS], int r0, const double* Lc, const double* dg, volatile int* prog,
+                                   int pbase, double* XC, double* XRs, double* XRg, int lane) {
+#pragma unroll 1
+  for (int r = r0; r < r0 + 8; ++r) {
+    chain_wait(prog, pbase + r + 1, lane);
+    const double x = a[0] * dg[r];  // X(r, lane); a[i] = pending sum of row r + i (0 for lane > r)
+    XC[lane * kLd + r] = x;
+    if (XRs) XRs[r * kLd + lane] = x;
+    if (XRg) XRg[r * kBS + lane] = x;
+    const double* lk = Lc + r * kLd + r;  // lk[j] = L(r + j, r)
+#pragma unroll
+    for (int j = 1; j < W; ++j) a[j - 1] = fma(-x, lk[j], a[j]);
+  }
+}
+// chain warp: Cholesky of the tile in Dsm (C-layout padded), L -> Lc, 1 / L(k,k) -> dg[0..31]; returns the failing pivot
+SCAML_DEVICE int chol_32_pub(const double* Dsm, double* Lc, double* dg, volatile int* prog, int pbase, double* logdet,
+                             int lane) {
+#if defined(SCAML_PROF) && !defined(SCAML_PROF_GEMM)
+  const long long pc_a = clock64();
+#endif
+  double a[kBS];
+#pragma unroll
+  for (int c = 0; c < kBS; ++c) a[c] = Dsm[c * kLd + lane];
+  int fail = 0;
+  double mydiag = 1.0;
+  double dnext = checked_pivot(__shfl_sync(0xffffffffu, a[0], 0), 0, fail);
+  double rsnext = rsqrt(dnext);
+  chol_steps_pub<32>(a, 0, Lc, dg, prog, pbase, lane, fail, mydiag, dnext, rsnext);
+  chol_steps_pub<24>(a, 8, Lc, dg, prog, pbase, lane, fail, mydiag, dnext, rsnext);
+  chol_steps_pub<16>(a, 16, Lc, dg, prog, pbase, lane, fail, mydiag, dnext, rsnext);
+  chol_steps_pub<8>(a, 24, Lc, dg, prog, pbase, lane, fail, mydiag, dnext, rsnext);
+  double ld = log(mydiag);
+  ld = warp_sum(ld);
+  if (lane == 0) *logdet += ld;
+#if defined(SCAML_PROF) && !defined(SCAML_PROF_GEMM)
+  if (lane == 0) profsm[14] += clock64() - pc_a;  // chain warp: load + 32 Cholesky pivot steps + log det
+#endif
+  return fail;
+}
+// follower warp: X = L^-1 one step behind the chain warp
+SCAML_DEVICE void inv_32_follow(const double* Lc, const double* dg, volatile int* prog, int pbase, double* XC,
+                                double* XRs, double* XRg, int lane) {
+#if defined(SCAML_PROF) && !defined(SCAML_PROF_GEMM)
+  const long long pc_a = clock64();
+#endif
+  double a[kBS];
+#pragma unroll
+  for (int i = 0; i < kBS; ++i) a[i] = (i == lane) ? 1.0 : 0.0;
+  inv_follow_steps<32>(a, 0, Lc, dg, prog, pbase, XC, XRs, XRg, lane);
+  inv_follow_steps<24>(a, 8, Lc, dg, prog, pbase, XC, XRs, XRg, lane);
+  inv_follow_steps<16>(a, 16, Lc, dg, prog, pbase, XC, XRs, XRg, lane);
+  inv_follow_steps<8>(a, 24, Lc, dg, prog, pbase, XC, XRs, XRg, lane);
+  __syncwarp();
+#if defined(SCAML_PROF) && !defined(SCAML_PROF_GEMM)
+  if (lane == 0) profsm[15] += clock64() - pc_a;  // follower warp: 32 inverse steps incl. waiting for the chain warp
+#endif
+}
+
 SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* XC, double* XRs, double* XRg,
                              double* logdet, int lane) {
 #if defined(SCAML_PROF) && !defined(SCAML_PROF_GEMM)
@@ -803,7 +915,10 @@ SCAML_DEVICE void small_store_R(double* blk, int ld, const SAcc& o, const FThr& 
 #define DIAG_PROF_PASS
 #endif
 SCAML_DEVICE void diag_factor(double* stage, double* dinvc, double* wd00, double* wd10, double* wd11, double* logdet,
-                              int* flag, int pivot_base, const FThr& t, int chain_warp DIAG_PROF_ARGS) {
+                              int* flag, int pivot_base, const FThr& t, int chain_warp, double* dg DIAG_PROF_ARGS) {
+  // flag[3]: progress counter of the chain -> follower hand-shake (zeroed by the caller before its last barrier)
+  volatile int* prog = flag + 3;
+  const int inv_warp = (chain_warp + 1) & (kFitWarps - 1);
   double* T0 = stage;
   double* T1 = stage + kTileS;
   double* T2 = stage + 2 * kTileS;
@@ -811,11 +926,22 @@ SCAML_DEVICE void diag_factor(double* stage, double* dinvc, double* wd00, double
   double* V0 = dinvc;
   double* V1 = dinvc + kTileS;
   double* V2 = dinvc + 2 * kTileS;
+#ifdef SCAML_FIT_FOLLOW
+  if (t.warp == chain_warp) {
+    // L scratch = V1; X00: C-layout -> V0, R-layout -> T1 and workspace (written by the follower warp)
+    const int f = chol_32_pub(T0, V1, dg, prog, 0, logdet, t.lane);
+    if (f && t.lane == 0 && *flag == 0) *flag = pivot_base + f;
+  } else if (t.warp == inv_warp) {
+    inv_32_follow(V1, dg, prog, 0, V0, T1, wd00, t.lane);
+  }
+#else
+  (void)prog, (void)inv_warp, (void)dg;
   if (t.warp == chain_warp) {
     // L scratch = V1, transpose scratch = V2, X00: C-layout -> V0, R-layout -> T1 and workspace
     const int f = chol_inv_32(T0, V1, V2, V0, T1, wd00, logdet, t.lane);
     if (f && t.lane == 0 && *flag == 0) *flag = pivot_base + f;
   }
+#endif
   PROF_MARK(11);
   __syncthreads();
   SAcc o;
@@ -839,11 +965,21 @@ SCAML_DEVICE void diag_factor(double* stage, double* dinvc, double* wd00, double
   small_store_R(V1, kLd, o, t, 1.0);
   __syncthreads();
   PROF_MARK(12);
+#ifdef SCAML_FIT_FOLLOW
+  if (t.warp == chain_warp) {
+    // L scratch = T1 (X00 R-layout is dead)
+    const int f = chol_32_pub(T3, T1, dg + kBS, prog, kBS, logdet, t.lane);
+    if (f && t.lane == 0 && *flag == 0) *flag = pivot_base + kBS + f;
+  } else if (t.warp == inv_warp) {
+    inv_32_follow(T1, dg + kBS, prog, kBS, V2, nullptr, wd11, t.lane);
+  }
+#else
   if (t.warp == chain_warp) {
     // L scratch = T1 (X00 R-layout is dead), transpose scratch = T0 (D00 is dead)
     const int f = chol_inv_32(T3, T1, T0, V2, nullptr, wd11, logdet, t.lane);
     if (f && t.lane == 0 && *flag == 0) *flag = pivot_base + kBS + f;
   }
+#endif
   PROF_MARK(13);
   __syncthreads();
   // X10 = -X11 * Tm        (A[kk][r] = X11(r,kk) = C-layout X11 in V2, B = Tm R-layout in V1)
@@ -1078,11 +1214,12 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
                               kcache ? kcache + ((size_t)(tri(I) + J) * 32) * kFitThreads + t.tid : nullptr);
         __syncthreads();  // x-block consumed before C_in overwrites it
         if (!(diag && upper_warp)) store_tile_C(stage + (t.rb * 2 + t.cb) * kTileS, kLd, acc, t, 1.0);
+        if (diag && t.tid == 0) flag[3] = 0;  // chain -> follower progress counter of diag_factor
         __syncthreads();
         PROF_MARK(2);
         if (diag) {
           diag_factor(stage, dinvc, wtile_w(W, 2 * J, 2 * J), wtile_w(W, 2 * J + 1, 2 * J),
-                      wtile_w(W, 2 * J + 1, 2 * J + 1), &scal[0], flag, J * kSB, t, chain_warp DIAG_PROF_PASS);
+                      wtile_w(W, 2 * J + 1, 2 * J + 1), &scal[0], flag, J * kSB, t, chain_warp, red DIAG_PROF_PASS);
           PROF_MARK(3);
           if (*flag != 0 && !ABL(0x7fffffff)) {
             failed = true;

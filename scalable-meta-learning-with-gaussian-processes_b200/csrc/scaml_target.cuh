@@ -34,6 +34,7 @@ struct TargetParams {
   double* meanw;            // ws [R][nt]
   double* Wmat;             // ws [R][nt][nt]
   double* alpha;            // ws [R][nt]
+  double* big;              // ws [R][target_big_doubles]: K | L^-1 | scaled inputs of rows too large for shared memory
   double* linv_out;         // factorize: [nt][nt] row-major L^-1 (lower), or null
   double* theta_out;        // factorize: [P] constrained, or null
   double mu_all, s_all;
@@ -44,9 +45,23 @@ struct TargetParams {
   scaml_hyper_spec spec;
 };
 
-inline size_t target_workspace_doubles(int nt, int R) { return (size_t)R * (2 * (size_t)nt * nt + 2 * (size_t)nt); }
+inline size_t target_small_doubles(int nt, int R) { return (size_t)R * (2 * (size_t)nt * nt + 2 * (size_t)nt); }
 inline size_t target_smem_bytes(int nt, int d) {
   return sizeof(double) * (2 * (size_t)nt * (nt + 1) + 4 * (size_t)nt + (size_t)d * nt + 4 * kMaxP + 64 + 2 * kTgtThreads);
+}
+// n_t x n_t systems that do not fit 227 KB of shared memory (n_t > ~116) keep K, L^-1 and the scaled inputs in a
+// per-row global block (L2 resident: 2 x 5 MB at n_t = 800) -- same code, same order of operations, `BIG` variant
+constexpr int kTgtBigFrom = 100;   // workspace is sized with the block from here on (any d)
+constexpr int kTgtMaxPoints = 1024;
+#ifdef SCAML_EMU
+inline
+#else
+__host__ __device__ inline
+#endif
+size_t target_big_doubles(int nt) { return 2 * (size_t)nt * (nt + 1) + (size_t)kMaxP * nt; }
+inline size_t target_big_smem_bytes(int nt) { return sizeof(double) * (4 * (size_t)nt + 4 * kMaxP + 64 + 2 * kTgtThreads); }
+inline size_t target_workspace_doubles(int nt, int R) {
+  return target_small_doubles(nt, R) + (nt >= kTgtBigFrom ? (size_t)R * target_big_doubles(nt) : 0);
 }
 
 // (A) covw[r][a][b] = sum_i w_i^2 C[a][b][i] / s^2 ; meanw[r][a] = (sum_i w_i S[a][i] - mu) / s
@@ -88,18 +103,19 @@ SCAML_DEVICE double block_sum(double v, double* red) {
 }
 
 // (B) dense n_t x n_t part, one CTA per row r
-template <int KIND>
+template <int KIND, bool BIG>
 __global__ void __launch_bounds__(kTgtThreads) scaml_target_factor_kernel(const TargetParams p) {
   SCAML_DYN_SMEM(double, sm);
   const int tid = threadIdx.x, nt = p.nt, ld = nt + 1, d = p.d, P = d + 2, r = blockIdx.x;
-  double* K = sm;                 // nt x ld : K_y, then L (lower)
+  double* gbig = BIG ? p.big + (size_t)r * target_big_doubles(nt) : nullptr;
+  double* K = BIG ? gbig : sm;        // nt x ld : K_y, then L (lower)
   double* Li = K + (size_t)nt * ld;   // nt x ld : L^-1, then K^-1
-  double* rv = Li + (size_t)nt * ld;  // residual y - mean
+  double* rv = BIG ? sm : Li + (size_t)nt * ld;  // residual y - mean
   double* zv = rv + nt;
   double* al = zv + nt;
   double* dg = al + nt;           // 1 / L_kk
-  double* xs = dg + nt;           // [d][nt] scaled inputs
-  double* par = xs + (size_t)d * nt;  // th | lp | dlp | chain
+  double* xs = BIG ? Li + (size_t)nt * ld : dg + nt;  // [d][nt] scaled inputs
+  double* par = BIG ? dg + nt : xs + (size_t)d * nt;  // th | lp | dlp | chain
   double* th = par, *lp = par + kMaxP, *dlp = par + 2 * kMaxP, *chain = par + 3 * kMaxP;
   double* red = par + 4 * kMaxP;  // 64
   int* flag = reinterpret_cast<int*>(red + 32);
@@ -316,17 +332,20 @@ inline size_t target_post_smem_bytes(int nt, int d) {
   const int ld = nt | 1;
   return sizeof(double) * ((size_t)nt * ld + (size_t)nt * d + nt + (kPostThreads / 32) * (size_t)(2 * nt + d) + kMaxP);
 }
+// BIG (n_t too large for L_t^-1 in shared memory): L_t^-1 is read straight from global memory (L2), row stride n_t
+template <bool BIG>
 __global__ void __launch_bounds__(kPostThreads) scaml_target_posterior_kernel(const TargetPostParams p) {
   SCAML_DYN_SMEM(double, sm);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nt = p.nt, d = p.d, ld = nt | 1;
-  double* Li = sm;                        // nt x ld
-  double* xt = Li + (size_t)nt * ld;      // [nt][d] scaled
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nt = p.nt, d = p.d, ld = BIG ? nt : (nt | 1);
+  const double* Li = BIG ? p.linv : sm;   // nt x ld
+  double* xt = sm + (BIG ? 0 : (size_t)nt * ld);  // [nt][d] scaled
   double* al = xt + (size_t)nt * d;       // nt
   double* wk = al + nt;                   // per warp: k_s [nt] | x_b scaled [d] | L_t^-1 k_s [nt]
   double* th = wk + (kPostThreads / 32) * (size_t)(2 * nt + d);
   if (tid < d + 2) th[tid] = p.theta[tid];
   __syncthreads();
-  for (int i = tid; i < nt * nt; i += kPostThreads) Li[(i / nt) * ld + (i % nt)] = p.linv[i];
+  if (!BIG)
+    for (int i = tid; i < nt * nt; i += kPostThreads) sm[(i / nt) * ld + (i % nt)] = p.linv[i];
   for (int i = tid; i < nt * d; i += kPostThreads) xt[i] = p.Xt[i] / th[i % d];
   for (int i = tid; i < nt; i += kPostThreads) al[i] = p.alpha[i];
   __syncthreads();
@@ -375,42 +394,57 @@ __global__ void __launch_bounds__(kPostThreads) scaml_target_posterior_kernel(co
     }
   }
 }
-inline int launch_target_posterior(const TargetPostParams& p, int num_sms, void* stream) {
-  const size_t smem = target_post_smem_bytes(p.nt, p.d);
-  if (smem > 227 * 1024) return SCAML_E_SMEM;
-  long long gx = ((long long)p.B + kPostThreads / 32 - 1) / (kPostThreads / 32);
-  if (gx > 2LL * num_sms) gx = 2LL * num_sms;
+template <bool BIG>
+int launch_target_posterior_v(const TargetPostParams& p, size_t smem, long long gx, void* stream) {
 #ifdef SCAML_EMU
   (void)stream;
-  cuemu::launch(dim3(gx < 2 ? (unsigned)gx : 2u), dim3(kPostThreads), smem, scaml_target_posterior_kernel, p);
+  cuemu::launch(dim3(gx < 2 ? (unsigned)gx : 2u), dim3(kPostThreads), smem, scaml_target_posterior_kernel<BIG>, p);
   return 0;
 #else
   cudaError_t err =
-      cudaFuncSetAttribute(scaml_target_posterior_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(scaml_target_posterior_kernel<BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return (int)err;
-  scaml_target_posterior_kernel<<<(unsigned)gx, kPostThreads, smem, (cudaStream_t)stream>>>(p);
+  scaml_target_posterior_kernel<BIG><<<(unsigned)gx, kPostThreads, smem, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 #endif
 }
+inline int launch_target_posterior(const TargetPostParams& p, int num_sms, void* stream) {
+  size_t smem = target_post_smem_bytes(p.nt, p.d);
+  const bool big = smem > 227 * 1024;
+  if (big) smem -= sizeof(double) * (size_t)p.nt * (p.nt | 1);
+  if (smem > 227 * 1024 || p.nt > kTgtMaxPoints) return SCAML_E_SMEM;
+  long long gx = ((long long)p.B + kPostThreads / 32 - 1) / (kPostThreads / 32);
+  if (gx > 2LL * num_sms) gx = 2LL * num_sms;
+  return big ? launch_target_posterior_v<true>(p, smem, gx, stream) : launch_target_posterior_v<false>(p, smem, gx, stream);
+}
 
-template <int KIND>
-int launch_target_factor(const TargetParams& p, size_t smem, void* stream) {
+template <int KIND, bool BIG>
+int launch_target_factor_v(const TargetParams& p, size_t smem, void* stream) {
 #ifdef SCAML_EMU
   (void)stream;
-  cuemu::launch(dim3(p.R), dim3(kTgtThreads), smem, scaml_target_factor_kernel<KIND>, p);
+  cuemu::launch(dim3(p.R), dim3(kTgtThreads), smem, scaml_target_factor_kernel<KIND, BIG>, p);
   return 0;
 #else
-  cudaError_t err =
-      cudaFuncSetAttribute(scaml_target_factor_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t err = cudaFuncSetAttribute(scaml_target_factor_kernel<KIND, BIG>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return (int)err;
-  scaml_target_factor_kernel<KIND><<<p.R, kTgtThreads, smem, (cudaStream_t)stream>>>(p);
+  scaml_target_factor_kernel<KIND, BIG><<<p.R, kTgtThreads, smem, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 #endif
+}
+// smem = target_smem_bytes(nt, d) selects the shared-memory kernel, anything else (the BIG footprint) the global one
+template <int KIND>
+int launch_target_factor(const TargetParams& p, size_t smem, void* stream) {
+  if (smem == target_smem_bytes(p.nt, p.d)) return launch_target_factor_v<KIND, false>(p, smem, stream);
+  return launch_target_factor_v<KIND, true>(p, smem, stream);
 }
 
 inline int launch_target(const TargetParams& p, int num_sms, void* stream) {
-  const size_t smem = target_smem_bytes(p.nt, p.d);
-  if (smem > 227 * 1024) return SCAML_E_SMEM;
+  size_t smem = target_smem_bytes(p.nt, p.d);
+  if (smem > 227 * 1024) {  // K, L^-1 and the scaled inputs move to the per-row global block
+    if (p.nt < kTgtBigFrom || p.nt > kTgtMaxPoints || p.big == nullptr) return SCAML_E_SMEM;
+    smem = target_big_smem_bytes(p.nt);
+  }
   const long long items = (long long)p.nt * p.nt + p.nt;
   long long gx = (items + 7) / 8;
   if (gx > 8LL * num_sms) gx = 8LL * num_sms;
@@ -425,6 +459,7 @@ inline int launch_target(const TargetParams& p, int num_sms, void* stream) {
     if (p.grad_w) q.grad_w += (size_t)r * p.M;
     q.covw += (size_t)r * p.nt * p.nt, q.meanw += (size_t)r * p.nt, q.Wmat += (size_t)r * p.nt * p.nt,
         q.alpha += (size_t)r * p.nt;
+    if (p.big) q.big += (size_t)r * target_big_doubles(p.nt);
     cuemu::launch(dim3(2), dim3(kTgtThreads), 0, scaml_target_reduce_kernel, q);
     int rc;
     switch (p.spec.kernel) {

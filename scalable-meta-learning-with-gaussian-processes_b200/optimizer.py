@@ -1,3 +1,5 @@
+# The constructor signature and the `report` skeleton are derived from scamlgp/optimizer.py of
+# boschresearch/Scalable-Meta-Learning-with-Gaussian-Processes, Copyright (c) 2024 Robert Bosch GmbH, AGPL-3.0.
 """ScaMLGPBO -- mirror of the reference optimizer (scamlgp/optimizer.py:27-185) on the B200 engine.
 
 The reference derives from blackboxopt's `SingleObjectiveBOTorchOptimizer` (not in its tree, not
@@ -230,12 +232,11 @@ class ScaMLGPBO(_SingleObjectiveBase):
     def report(self, evaluations: Union[Evaluation, Iterable[Evaluation]]):
         """Book-keep the evaluations and refit the ScaML-GP target model (reference optimizer.py:156-185)."""
         _evals = evaluations if isinstance(evaluations, list) else [evaluations]
-        from .model import max_target_points
+        from .model import MAX_TARGET_POINTS
 
-        limit = max_target_points(self.source_gps.engine, len(self.search_space))
-        if int((~torch.isnan(self.losses)).sum()) + len(_evals) > limit:  # before any book-keeping is changed
-            raise NotImplementedError(f"more than {limit} target observations are not supported in this release "
-                                      "(shared-memory target-GP kernels); the optimizer state is unchanged")
+        if int((~torch.isnan(self.losses)).sum()) + len(_evals) > MAX_TARGET_POINTS:  # before any book-keeping changes
+            raise NotImplementedError(f"more than {MAX_TARGET_POINTS} target observations: exact inference is defined "
+                                      "up to that size (SURVEY A.5); the optimizer state is unchanged")
         super()._update_internal_evaluation_data(_evals)
         if len(self.X) < self.num_initial_random:
             return

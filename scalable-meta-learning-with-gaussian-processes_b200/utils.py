@@ -1,3 +1,7 @@
+# The interface pieces of this module that a drop-in must keep word for word -- the ValueError messages of
+# `validate_meta_data`, the prior-name -> parameter-name rule of `sample_all_priors` -- are derived from
+# scamlgp/utils.py of boschresearch/Scalable-Meta-Learning-with-Gaussian-Processes,
+# Copyright (c) 2024 Robert Bosch GmbH, AGPL-3.0.
 """Mirror of the reference's scamlgp/utils.py: restart driver, prior sampling, meta-data
 conversion/validation and the UCB acquisition, on the B200 engine.
 

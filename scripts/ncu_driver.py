@@ -1,0 +1,67 @@
+"""Launches every kernel whose roofline bench.py reports, twice each, at the bench's shapes -- the program the round's
+`ncu --set full` capture runs (profiles/r2_*_ncu_summary.txt, profiles/ncu_traffic.json):
+
+  scaml_fit_kernel<RBF>            config 3: 4096 tasks x R6 x n=256 x d=6
+  scaml_fit8_kernel<RBF>           config 4 block: 2048 tasks x R2 x n=512 x d=10
+  scaml_predict_kernel<RBF,64>     4096 fitted GPs x 18944 candidates (prior) and the CROSS variant (n_t = 32)
+  scaml_kmat_kernel<RBF>           4096 x 256 x 256 kernel matrices
+  scaml_cond_prepare_kernel<RBF>   K_m^-1 K_m(X_m, .) for 32 target inputs / 64 candidates
+
+  python scripts/ncu_driver.py            (plain run: must exit 0 before it is profiled)
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import datagen
+from scamlgp_b200 import HyperSpec
+from scamlgp_b200.engine import Engine, SourceBatch
+
+
+REPS = 1 if os.environ.get("SCAML_NCU_ONCE") else 2  # under ncu: one launch per kernel (the replays warm the caches)
+
+
+def main():
+    dev = torch.device("cuda:0")
+    eng = Engine(dev)
+    spec = HyperSpec.source()
+    M, R, n, d = 4096, 6, 256, 6
+    X, Y = datagen.synthetic_tasks(M, n, d, seed=0)
+    th = datagen.sample_theta_raw(M, R, d, spec, seed=0).to(dev).contiguous()
+    batch = SourceBatch.from_padded(X.to(dev), Y.to(dev))
+    for _ in range(REPS):
+        out = eng.lml_grad_raw(batch, th, spec)
+    assert int(out[2].abs().max()) == 0
+    fs = eng.factorize(batch, th[:, 0].contiguous(), spec)
+    w = torch.full((M,), 1.0 / M, dtype=torch.float64, device=dev)
+    g = torch.Generator().manual_seed(100)
+    Xc = torch.rand(2 * 148 * 64, d, dtype=torch.float64, generator=g).to(dev)
+    Xt = torch.rand(32, d, dtype=torch.float64, generator=g).to(dev)
+    for _ in range(REPS):
+        mean, var = eng.predict_weighted(fs, w, Xc)
+    for _ in range(REPS):
+        A = eng.cond_prepare(fs, Xt)
+    for _ in range(REPS):
+        U = eng.cond_prepare(fs, Xc[:64].contiguous())
+    for _ in range(REPS):
+        eng.predict_conditioned(fs, w, Xc, Xt, A)
+    thc = torch.rand(M, d + 2, dtype=torch.float64, device=dev) * 0.5 + 0.25
+    K = torch.empty(M, n, n, dtype=torch.float64, device=dev)
+    for _ in range(REPS):
+        eng.kernel_matrix(batch.X, thc, 0, out=K)
+    del K, fs, A, U
+    X4, Y4 = datagen.synthetic_tasks(2048, 512, 10, seed=1000)
+    t4 = datagen.sample_theta_raw(2048, 2, 10, spec, seed=1000).to(dev).contiguous()
+    b4 = SourceBatch.from_padded(X4.to(dev), Y4.to(dev))
+    for _ in range(REPS):
+        o4 = eng.lml_grad_raw(b4, t4, spec)
+    torch.cuda.synchronize()
+    assert int(o4[2].abs().max()) == 0 and bool(torch.isfinite(mean).all())
+    print("ncu_driver ok", flush=True)
+
+
+if __name__ == "__main__":
+    main()

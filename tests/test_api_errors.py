@@ -109,8 +109,8 @@ def test_model_errors_through_emulation(emu_engine):
     from scamlgp_b200.model import max_target_points
 
     assert max_target_points(emu_engine, 2) == 117 and max_target_points(emu_engine, 16) == 113  # 227 KB, grows with d
-    with pytest.raises(NotImplementedError, match="n_t <= 117 at d = 2"):
-        ScaMLGP(torch.rand(118, 2, dtype=DT), torch.rand(118, 1, dtype=DT), gps, engine=emu_engine)
+    with pytest.raises(NotImplementedError, match="n_t <= 800"):
+        ScaMLGP(torch.rand(801, 2, dtype=DT), torch.rand(801, 1, dtype=DT), gps, engine=emu_engine)
     with pytest.raises(ValueError):
         UpperConfidenceBound(model, maximize=True)
     # all restarts failing -> ModelFittingError (utils.py:207-212): NaN targets poison every row

@@ -183,7 +183,7 @@ def _oracle_target_value_and_grads(cache, w, th, ospec):
     return float(v.detach()), gw.numpy(), gt.numpy()
 
 
-@pytest.mark.parametrize("kernel,nt", [(0, 9), (3, 17), (1, 1)])
+@pytest.mark.parametrize("kernel,nt", [(0, 9), (3, 17), (1, 1), (0, 121)])  # 121 > the shared-memory limit: BIG variant
 def test_emu_target_lml_grad_matches_oracle(emu_lib, kernel, nt):
     """a7: target objective on the ScaMLGP training branch + gradient wrt weights and raw kernel params."""
     lib = emu_lib
@@ -373,3 +373,53 @@ def test_emu_source_jitter_ladder_inside_the_kernel_matches_the_host_ladder(emu_
 def test_gpu_source_jitter_ladder_inside_the_kernel_matches_the_host_ladder(engine):
     _source_ladder_case(engine)
     _source_ladder_case(engine, n=192)
+
+
+def _large_nt_case(eng, n_t, M=3, n=48, d=2, B=9):
+    """n_t beyond the shared-memory limit of the target-GP kernels (116 at small d; the reference is exact to 800,
+    model.py:359-384 + gpytorch's max_cholesky_size): objective, gradients, prediction state and conditioning run on
+    the global-memory variants and must match the oracle like the small case."""
+    from scamlgp_b200.engine import SourceBatch
+
+    dev = eng.device
+    pb = make_problem(M, 1, n, d, seed=19)
+    states = [O.factorize(pb["X"][m], pb["Y"][m], pb["th"][m, 0], pb["ospec"]) for m in range(M)]
+    g = torch.Generator().manual_seed(8)
+    Xt = torch.rand(n_t, d, dtype=torch.float64, generator=g)
+    Yt = torch.sin(4.0 * Xt).sum(1) + 0.1 * torch.randn(n_t, dtype=torch.float64, generator=g)
+    cache = O.build_target_cache(states, Xt, Yt)
+    ospec, cspec = O.HyperSpec.target(), HyperSpec.target()
+    w = torch.rand(M, dtype=torch.float64, generator=g) + 0.1
+    th = O.initial_theta_raw(d, ospec)
+    batch = SourceBatch.from_padded(pb["X"].to(dev), pb["Y"].to(dev))
+    fs = eng.factorize(batch, pb["th"][:, 0].contiguous().to(dev), pb["cspec"])
+    assert not eng.cond_supported(fs, n_t) or n_t <= 128
+    sm, sc = eng.predict_cross(fs, Xt.to(dev))
+    assert float((sm.cpu() - cache.source_means).abs().max()) < TOL_MEAN_VAR * float(cache.source_means.abs().max())
+    yt = cache.yt_std.to(dev).contiguous()
+    lml, gw, gt, info = eng.target_lml_grad_safe(sm, sc, Xt.to(dev), yt, w.reshape(1, -1).to(dev).contiguous(),
+                                                 th.reshape(1, -1).to(dev).contiguous(), cache.mu_all, cache.s_all, cspec)
+    v, ogw, ogt = _oracle_target_value_and_grads(cache, w, th, ospec)
+    assert int(info[0]) == 0 and abs(float(lml[0]) - v) < TOL_LML * abs(v)
+    assert np.abs(gw[0].cpu().numpy() - ogw).max() < TOL_GRAD * np.abs(ogw).max()
+    assert np.abs(gt[0].cpu().numpy() - ogt).max() < TOL_GRAD * max(np.abs(ogt).max(), np.abs(ogw).max())
+    ts = eng.target_factorize(sm, sc, Xt.to(dev), yt, w.to(dev), th.to(dev), cache.mu_all, cache.s_all, cspec)
+    Xc = torch.rand(B, d, dtype=torch.float64, generator=g)
+    pm, pv = eng.predict_weighted(fs, w.to(dev), Xc.to(dev))
+    _, cross = eng.predict_cross(fs, Xc.to(dev), Xt.to(dev), w=w.to(dev))
+    mean, var = eng.target_posterior(ts, pm, pv, cross, Xc.to(dev).contiguous())
+    om, ov = O.scaml_posterior(states, w, cache, th, ospec, Xc, prune_threshold=None)
+    assert float((mean.cpu() - om).abs().max()) < 1e-8 * float(om.abs().max())
+    assert float((var.cpu() - ov).abs().max()) < 1e-8 * float(ov.abs().max())
+
+
+def test_emu_target_kernels_beyond_the_shared_memory_limit(emu_lib):
+    from tests.emu_engine import EmuEngine
+
+    _large_nt_case(EmuEngine(emu_lib), 124)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_t", [130, 400])
+def test_gpu_target_kernels_beyond_the_shared_memory_limit(engine, n_t):
+    _large_nt_case(engine, n_t, M=6, n=96, d=3, B=200)
