@@ -634,12 +634,15 @@ def run_ours(args) -> None:
         # value + gradient: K_m^-1 k* (2 n^2), mix (2 n n_t), contraction n (5 d + 45), values from U (2 n (n_t + 1) + n (3d + 12))
         Fg = 2.0 * n * n + 2.0 * n * n_t + n * (5.0 * d + 45.0) + 2.0 * n * (n_t + 1) + n * (3.0 * d + 12.0)
         ach_g = float(Ml) * Bg * Fg / (ms_g / 3 * 1e-3) / 1e12
+        tr_c, st_c, tl_c = ncu_traffic("scaml_predict_kernel<RBF,64,CROSS>")
+        tr_p, st_p, tl_p = ncu_traffic("scaml_cond_prepare_kernel<RBF>")
         cond = {"n_t": n_t, "value": float(Ml) * B_SLICE * 2 / (ms_c * 1e-3), "unit": "points/s (this GPU's tasks)",
                 "ms_per_step": ms_c / 2, "prepare_ms": ms_prep, "candidates_per_step": B_SLICE,
                 "what": "weighted prior mean/variance + cross-covariance with n_t target inputs (fused)",
                 "roofline": {"bound": "tensor", "achieved": ach_c, "peak": peak, "unit": "TFLOP/s",
                              "frac": (ach_c / peak) if peak else None, "flops_per_point": Fc,
-                             "kernel": "scaml_predict_kernel<RBF,64,CROSS>", "traffic": None}}
+                             "kernel": "scaml_predict_kernel<RBF,64,CROSS>", "traffic": tr_c, "traffic_stale": st_c,
+                             "traffic_launch": tl_c}}
         acq = {"n_t": n_t, "candidates": Bg, "ms_per_step": ms_g / 3, "gpu_launches": nl_g // 3,
                "value": float(Ml) * Bg * 3 / (ms_g * 1e-3), "unit": "(task, candidate) gradients/s (this GPU's tasks)",
                "finite": grad_finite,
@@ -647,7 +650,9 @@ def run_ours(args) -> None:
                        "cond_prepare at the candidates, values from U, beta, DMMA mix, gradient contraction",
                "roofline": {"bound": "tensor", "achieved": ach_g, "peak": peak, "unit": "TFLOP/s",
                             "frac": (ach_g / peak) if peak else None, "flops_per_point": Fg,
-                            "kernel": "scaml_cond_prepare_kernel<RBF> (dominant) + grad kernels", "traffic": None}}
+                            "kernel": "scaml_cond_prepare_kernel<RBF> (dominant) + grad kernels", "traffic": tr_p,
+                            "traffic_stale": st_p, "traffic_launch": tl_p,
+                            "traffic_note": "DRAM bytes of the dominant kernel only (cond_prepare, 64-column panel)"}}
         return cond, acq
 
     # ---- config 4: 16384 tasks x n = 512 x d = 10 on the 8-warp blocked DMMA Cholesky kernel ---------------- #

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256, 4) scaml_kmat_kernel(const KmatParams p) 
   double* xa = sm;            // [d][64] rows of tile ti (scaled)
   double* xb = sm + d * kSB;  // [d][64] rows of tile tj
   double* T = xb + d * kSB;   // 64 x kTLd staging tile
+  double* invl = T + kSB * kTLd;  // [kMaxP] reciprocal lengthscales of the current task
   const int pairs = (p.nt * (p.nt + 1)) / 2;
   const bool vec_ok = (p.n_max % 2) == 0;
   for (long long it = blockIdx.x; it < p.items; it += gridDim.x) {
@@ -41,15 +42,31 @@ __global__ void __launch_bounds__(256, 4) scaml_kmat_kernel(const KmatParams p) 
     const int nv = p.n_valid ? p.n_valid[m] : p.n_max;
     const double* th = p.theta + (size_t)m * P;
     const double* Xm = p.X + (size_t)m * p.n_max * d;
-    __syncthreads();  // previous tile fully written out before xa / xb / T are overwritten
     // 128 points (64 rows of tile ti, 64 of tile tj) x d coordinates, scaled by the lengthscales:
-    // thread -> (point, coordinate parity); no runtime integer division
+    // thread -> (point, coordinate parity); no runtime integer division.  The raw coordinates are fetched into
+    // registers BEFORE the barrier (their latency overlaps the wait for the previous tile's stores) and scaled by
+    // reciprocal lengthscales (an FP64 division per element was 20 % of this kernel's stall samples,
+    // profiles/r2_kmat_kernel_source_hotspots.txt).
+    const int pt = t.tid & 127, kh = t.tid >> 7;
+    const int r = pt & 63;
+    const int ga = (pt < kSB) ? ti * kSB + r : tj * kSB + r;
+    double xq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int k = kh + 2 * u;
+      xq[u] = (k < d && ga < p.n_max) ? __ldg(Xm + (size_t)ga * d + k) : 0.0;
+    }
+    __syncthreads();  // previous tile fully written out before xa / xb / T / invl are overwritten
+    if (t.tid < d) invl[t.tid] = 1.0 / th[t.tid];
+    __syncthreads();
     {
-      const int pt = t.tid & 127, kh = t.tid >> 7;
-      const int r = pt & 63;
-      const int ga = (pt < kSB) ? ti * kSB + r : tj * kSB + r;
       double* dst = (pt < kSB) ? xa : xb;
-      for (int k = kh; k < d; k += 2) dst[k * kSB + r] = (ga < p.n_max) ? Xm[(size_t)ga * d + k] / th[k] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = kh + 2 * u;
+        if (k < d) dst[k * kSB + r] = xq[u] * invl[k];
+      }
+      for (int k = kh + 8; k < d; k += 2) dst[k * kSB + r] = (ga < p.n_max) ? __ldg(Xm + (size_t)ga * d + k) * invl[k] : 0.0;
     }
     __syncthreads();
     const double os = th[d], noise = th[d + 1];
@@ -147,7 +164,7 @@ inline int launch_kmat(const double* X, const int32_t* n_valid, const double* th
   p.X = X, p.n_valid = n_valid, p.theta = theta, p.K = K, p.M = M, p.n_max = n_max, p.d = d;
   p.nt = (n_max + kSB - 1) / kSB;
   p.items = (long long)M * ((p.nt * (p.nt + 1)) / 2);
-  const size_t smem = sizeof(double) * (2 * (size_t)d * kSB + (size_t)kSB * kTLd);
+  const size_t smem = sizeof(double) * (2 * (size_t)d * kSB + (size_t)kSB * kTLd + kMaxP);
   long long g = p.items;
 #ifdef SCAML_EMU
   if (g > 4) g = 4;

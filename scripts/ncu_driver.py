@@ -32,6 +32,15 @@ def main():
     X, Y = datagen.synthetic_tasks(M, n, d, seed=0)
     th = datagen.sample_theta_raw(M, R, d, spec, seed=0).to(dev).contiguous()
     batch = SourceBatch.from_padded(X.to(dev), Y.to(dev))
+    if os.environ.get("SCAML_NCU_ONLY") == "kmat":  # re-capture of the assembly kernel alone
+        thc = torch.rand(M, d + 2, dtype=torch.float64, device=dev) * 0.5 + 0.25
+        K = torch.empty(M, n, n, dtype=torch.float64, device=dev)
+        for _ in range(3):
+            eng.kernel_matrix(batch.X, thc, 0, out=K)
+        torch.cuda.synchronize()
+        assert bool(torch.isfinite(K[::512]).all())
+        print("ncu_driver ok (kmat)", flush=True)
+        return
     for _ in range(REPS):
         out = eng.lml_grad_raw(batch, th, spec)
     assert int(out[2].abs().max()) == 0
