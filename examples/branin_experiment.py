@@ -24,6 +24,8 @@ sys.path.insert(0, ROOT)
 from scamlgp_b200.engine import Engine  # noqa: E402
 from scamlgp_b200.optimizer import ScaMLGPBO  # noqa: E402
 from scamlgp_b200.space import ContinuousParameter, Evaluation, Objective, ParameterSpace  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from harness import compute_regrets  # noqa: E402  (restates scamlgp/benchmarking/plotting.py:21-53)
 
 
 def branin(x1, x2, a, b, c, r, s, t):
@@ -67,14 +69,14 @@ def main():
         t0 = time.perf_counter()
         opt = ScaMLGPBO(space, obj, md, seed=study, engine=eng, af_optimizer_kwargs={"method": args.af_method})
         t_fit.append(time.perf_counter() - t0)
-        best, curve = np.inf, []
+        values = []
         t0 = time.perf_counter()
         for _ in range(args.evals):
             spec = opt.generate_evaluation_specification()
             f = float(branin(spec.configuration["x1"], spec.configuration["x2"], **target))
             opt.report(spec.create_evaluation(objectives={"loss": f + rng.normal(0, args.noise)}))
-            best = min(best, f)
-            curve.append(best - fmin)
+            values.append({"loss": f})
+        curve = compute_regrets(False, "loss", fmin, values)
         t_step.append((time.perf_counter() - t0) / args.evals)
         reg.append([curve[m - 1] for m in marks])
         xr1, xr2 = rng.uniform(-5, 10, args.evals), rng.uniform(0, 15, args.evals)

@@ -21,6 +21,8 @@ sys.path.insert(0, ROOT)
 from scamlgp_b200.engine import Engine  # noqa: E402
 from scamlgp_b200.optimizer import ScaMLGPBO  # noqa: E402
 from scamlgp_b200.space import ContinuousParameter, Evaluation, Objective, ParameterSpace  # noqa: E402
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from harness import compute_regrets  # noqa: E402  (restates scamlgp/benchmarking/plotting.py:21-53)
 
 A = np.array([[10, 3, 17, 3.5, 1.7, 8], [0.05, 10, 17, 0.1, 8, 14], [3, 3.5, 1.7, 10, 17, 8], [17, 8, 0.05, 10, 0.1, 14]])
 P = 1e-4 * np.array([[1312, 1696, 5569, 124, 8283, 5886], [2329, 4135, 8307, 3736, 1004, 9991],
@@ -76,15 +78,15 @@ def main():
             t0 = time.perf_counter()
             opt = ScaMLGPBO(space, obj, md, seed=study, engine=eng, af_optimizer_kwargs={"method": method})
             t_fit.append(time.perf_counter() - t0)
-            best, curve = np.inf, []
+            values = []
             t0 = time.perf_counter()
             for _ in range(args.evals):
                 spec = opt.generate_evaluation_specification()
                 x = np.array([spec.configuration[f"x{j}"] for j in range(6)])
                 f = float(hartmann6(x, target)[0])
                 opt.report(spec.create_evaluation(objectives={"loss": f + rng.normal(0, args.noise)}))
-                best = min(best, f)
-                curve.append(best - fmin)
+                values.append({"loss": f})
+            curve = compute_regrets(False, "loss", fmin, values)
             t_step.append((time.perf_counter() - t0) / args.evals)
             reg.append([curve[m - 1] for m in marks])
             fr = np.minimum.accumulate(hartmann6(rng.random((args.evals, 6)), target)) - fmin
