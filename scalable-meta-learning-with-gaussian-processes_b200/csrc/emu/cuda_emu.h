@@ -44,6 +44,7 @@ namespace cuemu {
 struct BlockCtx {
   pthread_barrier_t bar;
   pthread_barrier_t wbar[64];
+  pthread_barrier_t nbar[8];  // named barriers 1..8 (bar.sync id, 128): groups of four warps
   alignas(16) unsigned char slot[64][32][16];
   unsigned char* dyn_smem = nullptr;
   int nthreads = 0;
@@ -70,6 +71,7 @@ inline dim3& gDim() {
 }
 inline void block_sync() { pthread_barrier_wait(&ctx()->bar); }
 inline void warp_sync() { pthread_barrier_wait(&ctx()->wbar[tIdx().x >> 5]); }
+inline void named_sync(int id) { pthread_barrier_wait(&ctx()->nbar[id - 1]); }  // 128 participants
 template <class T>
 inline T shfl(T v, int src) {
   static_assert(sizeof(T) <= 16, "shfl payload");
@@ -116,6 +118,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F kernel, A... args) {
       int cnt = (w == nw - 1 && (nt & 31)) ? (nt & 31) : 32;
       pthread_barrier_init(&c.wbar[w], nullptr, cnt);
     }
+    for (int i = 0; i < 8; ++i) pthread_barrier_init(&c.nbar[i], nullptr, nt < 128 ? nt : 128);
     void* mem = nullptr;
     if (posix_memalign(&mem, 1024, smem_bytes + 1024) != 0) abort();
     std::memset(mem, 0xCD, smem_bytes + 1024);  // poison: uninitialised smem reads show up as NaN-ish
@@ -139,6 +142,7 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, F kernel, A... args) {
       }
     pthread_barrier_destroy(&c.bar);
     for (int w = 0; w < nw; ++w) pthread_barrier_destroy(&c.wbar[w]);
+    for (int i = 0; i < 8; ++i) pthread_barrier_destroy(&c.nbar[i]);
     free(mem);
     ctx() = nullptr;
   }
@@ -184,6 +188,7 @@ inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline double fma_emu(double a, double b, double c) { return std::fma(a, b, c); }
 using std::exp;
 using std::fabs;
+using std::fmax;
 using std::isfinite;
 using std::lgamma;
 using std::log;

@@ -1,14 +1,27 @@
 // Weighted ScaML-GP prediction (K6-K9): for a tile of CT (64 or 32) candidates a CTA walks over the
-// tasks of its split.  Per task it (1) builds k*(X_m, candidates) once in shared memory (padded
-// k-major 32x32 tiles) together with the mean partials k*^T alpha, (2) streams the packed L_m^-1
-// tiles through a 3-stage cp.async pipeline (one barrier per 32-deep chunk, the pipeline does not
-// drain between the super-rows of a task) and forms V = L^-1 k* on the FP64 tensor cores
-// (mma.sync m8n8k4 -> DMMA; 8 warps, warp tile 32 x CT/4; the zero half of the diagonal tiles is
-// skipped), (3) folds  w_m (ybar_m + ystd_m k*^T alpha_m)  and  w_m^2 ystd_m^2 (s_m - ||V||^2)  into
-// per-candidate accumulators that stay in registers for the whole task loop -> the reduction over
-// tasks happens inside the kernel in a fixed order (deterministic, no atomics).
+// tasks of its split.  Per task it
+// (1) builds k*(X_m, candidates) once in shared memory (padded k-major 32x32 tiles) together with the
+//     mean partials k*^T alpha.  The squared distances come from the FP64 tensor cores as well:
+//     r^2 = |a|^2 + |c|^2 - 2 a.c on inputs centred on the task's first point and length-scaled (the
+//     quadratic expansion gpytorch itself evaluates), i.e. the accumulator is initialised
+//     with |a|^2 + |c|^2 and one DMMA per four input dimensions adds -2 a.c for an 8 x 8 block of
+//     pairs: 1/64 + 1 FP64 instructions per pair instead of 3 d (load, subtract, fma per dimension),
+//     which was what bound the assembly (issue slots, not the pipe).  Matern-1/2 keeps direct
+//     differences (exp(-r) is not smooth in r^2 at coincident points).
+// (2) streams the packed L_m^-1 tiles and forms V = L^-1 k* on the FP64 tensor cores (mma.sync
+//     m8n8k4 -> DMMA).  The 8 warps work as TWO independent groups of 4 (named barriers, own 3-stage
+//     cp.async ring each); group 0 owns the 32-row blocks 0, 3, 4, 7, ... of L^-1 and group 1 the blocks
+//     1, 2, 5, 6, ... -- row block r has r + 1 tiles, so both groups stream the same number of tiles
+//     (n_pad = 256: 18 each) where the former lock-step walk over (2I, 2I+1) pairs left the warps of the
+//     even blocks idle one step in every super-row; the zero half of the diagonal tiles is skipped.
+// (3) folds  w_m (ybar_m + ystd_m k*^T alpha_m)  and  w_m^2 ystd_m^2 (s_m - ||V||^2)  into
+//     per-candidate accumulators that stay in registers for the whole task loop -> the reduction over
+//     tasks happens inside the kernel in a fixed order (deterministic, no atomics).
 // Reference: _compute_target_prior, scamlgp/model.py:108-135; posterior A.7 of SURVEY.md.
 #pragma once
+#ifdef SCAML_PRED_PROF
+#include <cstdio>
+#endif
 #include "scaml_device.cuh"
 
 namespace scaml {
@@ -17,6 +30,7 @@ constexpr int kPLd = 36;               // padded row stride of a staged tile (co
 constexpr int kPTile = kBS * kPLd;     // 1152 doubles
 constexpr int kPStages = 3;
 constexpr int kPredThreads = 256;
+constexpr int kPGroupThreads = 128;  // one product group = 4 warps
 
 struct PredParams {
   const double* X;
@@ -38,24 +52,41 @@ struct PredParams {
   int n_tp;
 };
 
-// shared memory (doubles): kst | stage | [xst | alp | xcs] (aliased onto stage when alias) | xcr | red | vsq
+// shared memory (doubles): kst | rings | [auxA = xst] [auxB = xcs] | alp | xcr | red | vsq | invl, ctr (x2)
+// xst / xcs hold d + 2 rows (the scaled coordinates, then 1 | |a|^2 resp. |c|^2 | 1: the operand rows that put the
+// squared norms of r^2 = |a|^2 + |c|^2 - 2 a.c into the same tensor-core product) with strides n_pad + 4 / ct + 4
+// (== 4 mod 16 doubles: the DMMA fragment loads of the distance product are bank-conflict free).  The per-task
+// staging data is dead once k* is assembled, so it may share memory with the L^-1 rings (6 padded tiles, laid out
+// [g0 s0 | g0 s1 | g1 s0 | g1 s1 | g0 s2 | g1 s2]):
+//   alias 0  own memory
+//   alias 1  auxA on the two third-stage slots, which the pipeline does not touch before the product loop: the
+//            first two tiles of each group still stream in under the assembly
+//   alias 2  auxA and auxB on the rings; streaming starts after the assembly
+constexpr int kPAliasA = 2 * kPTile;
 #ifdef SCAML_EMU
 inline
 #else
 __host__ __device__ inline
 #endif
-size_t predict_aux_doubles(int n_pad, int d, int ct) { return (size_t)d * n_pad + n_pad + (size_t)d * ct; }
+size_t predict_auxA_doubles(int n_pad, int d) { return (size_t)(d + 2) * (n_pad + 4); }
+#ifdef SCAML_EMU
+inline
+#else
+__host__ __device__ inline
+#endif
+size_t predict_auxB_doubles(int d, int ct) { return (size_t)(d + 2) * (ct + 4); }
 inline size_t predict_smem_bytes(int n_pad, int d, int ct, int alias) {
   const size_t kst = (size_t)(n_pad / kBS) * (ct / kBS) * kPTile;
   const size_t stage = (size_t)kPStages * 2 * kPTile;
-  const size_t aux = predict_aux_doubles(n_pad, d, ct);
-  return sizeof(double) * (kst + stage + (alias ? 0 : aux) + (size_t)d * ct + 4 * ct + 2 * ct + 2 * kMaxP + 8);
+  const size_t aux = (alias == 0 ? predict_auxA_doubles(n_pad, d) : 0) + (alias <= 1 ? predict_auxB_doubles(d, ct) : 0);
+  return sizeof(double) * (kst + stage + aux + (size_t)n_pad + (size_t)d * ct + 4 * ct + 2 * ct + 4 * kMaxP + 8);
 }
-// candidate tile width / layout for (n_pad, d): widest tile that fits 227 KB, un-aliased if possible
+// candidate tile width / layout for (n_pad, d): widest tile that fits 227 KB, least aliasing first
 inline bool predict_config(int n_pad, int d, int* ct, int* alias) {
   for (int c = 64; c >= 32; c -= 32)
-    for (int a = 0; a <= 1; ++a) {
-      if (a && predict_aux_doubles(n_pad, d, c) > (size_t)kPStages * 2 * kPTile) continue;
+    for (int a = 0; a <= 2; ++a) {
+      if (a == 1 && predict_auxA_doubles(n_pad, d) > (size_t)kPAliasA) continue;
+      if (a == 2 && predict_auxA_doubles(n_pad, d) + predict_auxB_doubles(d, c) > (size_t)kPStages * 2 * kPTile) continue;
       if (predict_smem_bytes(n_pad, d, c, a) <= 227 * 1024) {
         *ct = c, *alias = a;
         return true;
@@ -102,24 +133,97 @@ SCAML_DEVICE void pred_issue(const double* Lm, const PChunk& c, double* st, int 
   ptile_async(st + kPTile, Lm + (size_t)(tri(2 * c.I + 1) + c.ck) * kTile, tid);
 }
 
+// ---- the prediction kernel's two product groups ---------------------------------------------------------- //
+// barrier over the 4 warps of group gi (hardware barrier 1 + gi; barrier 0 is __syncthreads)
+SCAML_DEVICE void group_sync(int gi) {
+#ifdef SCAML_EMU
+  cuemu::named_sync(1 + gi);
+#else
+  if (gi == 0) asm volatile("bar.sync 1, %0;\n" ::"n"(kPGroupThreads) : "memory");
+  else asm volatile("bar.sync 2, %0;\n" ::"n"(kPGroupThreads) : "memory");
+#endif
+}
+// ring slot s of group gi: [g0 s0 | g0 s1 | g1 s0 | g1 s1 | g0 s2 | g1 s2]
+SCAML_DEVICE double* gslot(double* stage, int gi, int s) {
+  return stage + (s < 2 ? 2 * gi + s : 4 + gi) * kPTile;
+}
+// one dense tile global -> padded shared rows by the 128 threads of a group: 4 x 16 B per thread
+SCAML_DEVICE void gtile_async(double* sdst, const double* gsrc, int gtid) {
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int c2 = gtid + u * kPGroupThreads;
+    const int row = c2 >> 4, j = c2 & 15;
+    cp_async16(sdst + row * kPLd + 2 * j, gsrc + row * kBS + 2 * j);
+  }
+}
+// walk of a group over its row blocks: group 0: r = 0, 3, 4, 7, ..; group 1: r = 1, 2, 5, 6, ..; tiles ck = 0 .. r
+struct GChunk {
+  int r, ck;
+  SCAML_DEVICE void next() {
+    if (++ck > r) {
+      r += (r & 1) ? 1 : 3;
+      ck = 0;
+    }
+  }
+};
+SCAML_DEVICE int group_tiles(int gi, int nb) {
+  int L = 0;
+  for (int r = gi; r < nb; r += (r & 1) ? 1 : 3) L += r + 1;
+  return L;
+}
+
+#ifdef SCAML_PRED_PROF  // diagnostics build: per-phase clock64 totals of CTA 0, printed by the kernel
+#define PPROF(ph)                                  \
+  do {                                             \
+    if (threadIdx.x == PPROF_TID) {                \
+      const long long now_ = clock64();            \
+      pprof[ph] += now_ - pprof_last;              \
+      pprof_last = now_;                           \
+    }                                              \
+  } while (0)
+#ifndef PPROF_TID
+#define PPROF_TID 0
+#endif
+#else
+#define PPROF(ph) \
+  do {            \
+  } while (0)
+#endif
+
 template <int KIND, int CT, bool CROSS>
 __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const PredParams p) {
-  constexpr int NJ = CT / 32;  // 8-column DMMA tiles per warp (warp tile: 32 rows x 8*NJ candidates)
+#ifdef SCAML_PRED_PROF
+  long long pprof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long pprof_last = clock64();
+#endif
+  constexpr int NJ = CT / 32;   // 8-column DMMA tiles per warp in the product (warp tile: 32 rows x 8*NJ candidates)
   constexpr int CBT = CT / 32;  // kst tile columns
+  constexpr int CS = CT + 4;    // row stride of the scaled candidates
+  constexpr int QN = kPredThreads / CT;  // row phases of the thread <-> candidate passes (4 for CT = 64, 8 for CT = 32)
+  // Matern-1/2 assembles k* from direct differences (thread <-> candidate), everything else through the tensor cores
+  constexpr bool kDirect = (KIND == SCAML_KERNEL_MATERN12);
   SCAML_DYN_SMEM(double, sm);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
-  const int rb = warp >> 2, col0 = (warp & 3) * 8 * NJ, cb = col0 >> 5, cin = col0 & 31;
-  const int d = p.d, P = d + 2, n_pad = p.n_pad;
+  const int gi = warp >> 2, gtid = tid & (kPGroupThreads - 1);  // product group, thread index inside it
+  const int col0 = (warp & 3) * 8 * NJ, cb = col0 >> 5, cin = col0 & 31;
+  const int d = p.d, P = d + 2, n_pad = p.n_pad, dp = (d + 3) & ~3, XS = n_pad + 4;
+  // the two norm rows ride in the padding of the contraction when there is room (d = 6: rows 6, 7 of 8); otherwise
+  // the accumulators are initialised with |a|^2 + |c|^2 (one FP64 add per pair, no extra DMMA)
+  const bool aug = (((d + 2) + 3) & ~3) == dp;
+  const int dk = aug ? d + 2 : d;
   double* kst = sm;                                                // (n_pad/32) x CBT padded tiles [a][c]
-  double* stage = kst + (size_t)(n_pad / kBS) * CBT * kPTile;      // kPStages x 2 padded tiles
-  double* aux = stage + (p.alias ? 0 : kPStages * 2 * kPTile);
-  double* xst = aux;                                               // [d][n_pad] scaled inputs of the task
-  double* alp = xst + (size_t)d * n_pad;                           // [n_pad]
-  double* xcs = alp + n_pad;                                       // [d][CT] scaled candidates
-  double* xcr = stage + kPStages * 2 * kPTile + (p.alias ? 0 : predict_aux_doubles(n_pad, d, CT));  // [d][CT] raw
+  double* stage = kst + (size_t)(n_pad / kBS) * CBT * kPTile;      // 2 groups x kPStages padded tiles
+  double* own = stage + kPStages * 2 * kPTile;                     // un-aliased staging data, then alp ..
+  const size_t nA = predict_auxA_doubles(n_pad, d), nB = predict_auxB_doubles(d, CT);
+  double* xst = (p.alias == 0) ? own : ((p.alias == 1) ? stage + 4 * kPTile : stage);  // [d+2][XS]
+  double* xcs = (p.alias == 0) ? own + nA : ((p.alias == 1) ? own : xst + nA);        // [d+2][CS]
+  double* alp = own + (p.alias == 0 ? nA : 0) + (p.alias <= 1 ? nB : 0);              // [n_pad]
+  double* xcr = alp + n_pad;                                       // [d][CT] raw candidates
   double* red = xcr + d * CT;                                      // 4 x CT mean partials
   double* vsq = red + 4 * CT;                                      // 2 x CT
-  double* invl2 = vsq + 2 * CT;                                    // 2 x kMaxP reciprocal lengthscales (task parity)
+  double* invl2 = vsq + 2 * CT;                                    // 2 x (kMaxP reciprocal lengthscales | kMaxP centre)
+  const double* nrm = xst + (size_t)(d + 1) * XS;                  // |a|^2 (row d + 1 of xst)
+  const double* ncs = xcs + (size_t)d * CS;                        // |c|^2 (row d of xcs)
   int tcount = 0;
   const long long lstride = (long long)tri(n_pad / kBS) * kTile;
   const int items = p.ntile * p.nsplit;
@@ -145,63 +249,112 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
     for (int i = 0; i < (CROSS ? 4 : 1); ++i)
 #pragma unroll
       for (int jj = 0; jj < (CROSS ? 4 : 1); ++jj) cx[i][jj][0] = cx[i][jj][1] = 0.0;
-    // inputs of the NEXT task (point `tid`, first kPreD dimensions, alpha) are fetched into registers while the
-    // tensor-core phase of the current task runs, so that the staging below does not wait on global memory
+    // Everything the NEXT task needs from global memory before its tiles -- its scalars, lengthscales, centre, point
+    // `tid` (first kPreD dimensions) and alpha -- is fetched into registers while the tensor-core phase of the
+    // current task runs, so that neither the task prologue nor the staging waits on L2
     constexpr int kPreD = 8;
-    int pre_m = -1;
-    double xpre[kPreD], apre = 0.0;
+    int pre_m = -1, nv_n = 0;
+    double xpre[kPreD], apre = 0.0, wm_n = 0.0, os_n = 0.0, ys_n = 0.0, yb_n = 0.0, th_n = 1.0, ctr_n = 0.0;
 #pragma unroll
     for (int k = 0; k < kPreD; ++k) xpre[k] = 0.0;
     for (int m = m_lo; m < m_hi; ++m) {
-      const double wm = p.w[m];
+      const bool have = (pre_m == m);
+      const double wm = have ? wm_n : p.w[m];
       if (wm == 0.0) continue;
-      const int nv = p.n_valid ? p.n_valid[m] : p.n_max;
-      const int NS = (nv + kSB - 1) / kSB, npt = NS * kSB;
-      const int L = NS * (NS + 1);  // flat chunks of this task
+      const int nv = have ? nv_n : (p.n_valid ? p.n_valid[m] : p.n_max);
+      const int NS = (nv + kSB - 1) / kSB, npt = NS * kSB, nb = 2 * NS;
+      const int L = group_tiles(gi, nb);  // tiles this group streams for this task
       const double* th = p.theta + (size_t)m * P;
-      const double os = th[d];
+      const double os = have ? os_n : th[d];
+      const double ys = have ? ys_n : p.ystd[m], yb = have ? yb_n : p.ybar[m];
       const double* Lm = p.linv + (size_t)m * lstride;
+      const double* Xm = p.X + (size_t)m * p.n_max * d;
       // x * (1/l) instead of x / l: an FP64 division is ~30 instructions per staged coordinate (<= 1 ulp apart)
-      double* invl = invl2 + (tcount & 1) * kMaxP;
+      double* invl = invl2 + (tcount & 1) * 2 * kMaxP;
+      double* ctr = invl + kMaxP;  // centre of the expansion: the task's first point (any point would do)
       ++tcount;
-      if (tid < d) invl[tid] = 1.0 / th[tid];
-      __syncthreads();  // previous task fully consumed (kst, stage, aux); invl visible
-      PChunk qi{0, 0};
+      if (tid < d) {
+        invl[tid] = 1.0 / (have ? th_n : th[tid]);
+        ctr[tid] = have ? ctr_n : Xm[tid];
+      }
+      __syncthreads();  // previous task fully consumed (kst, stage, aux); invl, ctr visible
+      PPROF(0);
+      GChunk qi{gi, 0};
       int issued = 0;
-      if (!p.alias) {  // start streaming L^-1 under the exp-heavy assembly below
-        for (; issued < 2 && issued < L; ++issued, qi.next()) {
-          pred_issue(Lm, qi, stage + (issued % kPStages) * 2 * kPTile, tid);
+      // start streaming L^-1 under the exp-heavy assembly below (always two commits: the wait<1> accounting of
+      // the product loop needs them even when the group has a single tile)
+      auto issue_first_two = [&]() {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (issued < L) {
+            gtile_async(gslot(stage, gi, issued % kPStages), Lm + (size_t)(tri(qi.r) + qi.ck) * kTile, gtid);
+            ++issued;
+            qi.next();
+          }
           cp_async_commit();
         }
-      }
+      };
+      if (p.alias <= 1) issue_first_two();
       {
-        const double* Xm = p.X + (size_t)m * p.n_max * d;
-        const bool have = (pre_m == m);
         if (tid < npt) {  // one point per thread: no runtime integer division
+          double nn = 0.0;
 #pragma unroll
           for (int k = 0; k < kPreD; ++k)
             if (k < d) {
-              const double v = have ? xpre[k] : ((tid < nv) ? Xm[(size_t)tid * d + k] : 0.0);
-              xst[k * n_pad + tid] = (tid < nv) ? v * invl[k] : 0.0;
+              const double x = have ? xpre[k] : ((tid < nv) ? Xm[(size_t)tid * d + k] : 0.0);
+              const double v = (tid < nv) ? (x - ctr[k]) * invl[k] : 0.0;
+              xst[k * XS + tid] = v;
+              nn = fma(v, v, nn);
             }
-          for (int k = kPreD; k < d; ++k) xst[k * n_pad + tid] = (tid < nv) ? Xm[(size_t)tid * d + k] * invl[k] : 0.0;
+          for (int k = kPreD; k < d; ++k) {
+            const double v = (tid < nv) ? (Xm[(size_t)tid * d + k] - ctr[k]) * invl[k] : 0.0;
+            xst[k * XS + tid] = v;
+            nn = fma(v, v, nn);
+          }
+          xst[d * XS + tid] = 1.0;
+          xst[(d + 1) * XS + tid] = nn;
           alp[tid] = have ? apre : p.alpha[(size_t)m * n_pad + tid];
         }
         for (int a = tid + kPredThreads; a < npt; a += kPredThreads) {
-          for (int k = 0; k < d; ++k) xst[k * n_pad + a] = (a < nv) ? Xm[(size_t)a * d + k] * invl[k] : 0.0;
+          double nn = 0.0;
+          for (int k = 0; k < d; ++k) {
+            const double v = (a < nv) ? (Xm[(size_t)a * d + k] - ctr[k]) * invl[k] : 0.0;
+            xst[k * XS + a] = v;
+            nn = fma(v, v, nn);
+          }
+          xst[d * XS + a] = 1.0;
+          xst[(d + 1) * XS + a] = nn;
           alp[a] = p.alpha[(size_t)m * n_pad + a];
         }
-        for (int i = tid; i < CT * d; i += kPredThreads) xcs[i] = xcr[i] * invl[i / CT];
+        if (tid < 4 * CT) {  // candidate c = tid / 4, dimensions k = tid % 4, + 4, ..; |c|^2 by a fixed-order quad sum
+          const int c = tid >> 2;
+          double nn = 0.0;
+          for (int k = tid & 3; k < d; k += 4) {
+            const double v = (xcr[k * CT + c] - ctr[k]) * invl[k];
+            xcs[k * CS + c] = -2.0 * v;
+            nn = fma(v, v, nn);
+          }
+          nn += __shfl_xor_sync(0xffffffffu, nn, 1);
+          nn += __shfl_xor_sync(0xffffffffu, nn, 2);
+          if ((tid & 3) == 0) {
+            xcs[d * CS + c] = nn;
+            xcs[(d + 1) * CS + c] = 1.0;
+          }
+        }
       }
       __syncthreads();
-      // ---- k*(X_m, candidates) and the mean partials -------------------------------- //
-      // a thread owns one candidate and walks the task's points 8 at a time: 8 independent distance / exp
-      // chains per thread keep the FP64 pipe busy (a single chain per thread is latency bound).
-      {
-        constexpr int QN = kPredThreads / CT;  // row phases (4 for CT = 64, 8 for CT = 32)
-        // rows per pass = QN * U must divide 64 (npt is a multiple of 64); CROSS keeps 32 more accumulators live
-        constexpr int U = (CT == 64 && !CROSS) ? 16 : 8;
-        static_assert((kPredThreads / CT) * U <= 64, "assembly pass must not run past the task's rows");
+      PPROF(1);
+      // ---- k*(X_m, candidates) and the mean partials k*^T alpha ------------------------- //
+      // every thread leaves the assembly with one or two folded partials (mu_lo, mu_hi) for columns red_col (+1) and a
+      // row of red[4][CT]: half of the threads store before the barrier, the other half add after it
+      double mu_lo = 0.0, mu_hi = 0.0;
+      int red_col = 0, red_row = 0, red_n = 1;
+      bool red_store = false, red_add = false;
+      if (kDirect) {
+        // a thread owns one candidate and walks the task's points 8 at a time: 8 independent distance / exp
+        // chains per thread keep the FP64 pipe busy (a single chain per thread is latency bound).
+        constexpr int U = 8;
+        static_assert(QN * U <= 64, "assembly pass must not run past the task's rows");
         const int c = tid % CT, q = tid / CT;
         double mu = 0.0;
         for (int a0 = q; a0 < npt; a0 += QN * U) {
@@ -209,8 +362,8 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
 #pragma unroll
           for (int u = 0; u < U; ++u) r2[u] = 0.0;
           for (int k = 0; k < d; ++k) {
-            const double xc = xcs[k * CT + c];
-            const double* xr = xst + k * n_pad + a0;
+            const double xc = -0.5 * xcs[k * CS + c];
+            const double* xr = xst + k * XS + a0;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
               const double df = xr[u * QN] - xc;
@@ -227,18 +380,125 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
             mu = fma(kv, alp[a], mu);
           }
         }
-        if (q < 4) red[q * CT + c] = mu;
-        if (QN > 4) {  // CT = 32: fold phases 4..7 onto 0..3 in a fixed order
-          __syncthreads();
-          if (q >= 4) red[(q - 4) * CT + c] += mu;
+        // fold the QN phases into red[4][CT] in a fixed order: phases 4..7 store before the barrier, 0..3 add after it
+        mu_lo = mu, red_col = c;
+        red_store = (QN == 4 || q >= 4), red_add = (QN > 4 && q < 4), red_n = 1;
+        red_row = q & 3;
+      } else {
+        // warp <-> 32-row block of the task (rbk = warp, warp + 8, ..); per (row block, 32-candidate half, RI 8-row
+        // groups) the lane holds the DMMA accumulator fragments of 8 RI pairs: rows 8 i2 + g, candidates 8 j + 2 t4 + e.
+        // Operand rows beyond dk (the contraction is padded to a multiple of 4) are selected to zero.
+        constexpr int RI = CROSS ? 1 : 2;  // CROSS keeps 32 more accumulators live: shorter exp batches
+        double mu[CBT * 8];  // [h][j][e] -> 8 h + 2 j + e : sum over this lane's rows of k* alpha
+#pragma unroll
+        for (int v = 0; v < CBT * 8; ++v) mu[v] = 0.0;
+#ifdef SCAML_PRED_NOASM
+        for (int rbk = warp; rbk < 0; rbk += 8) {
+#else
+        for (int rbk = warp; rbk < nb; rbk += 8) {
+#endif
+#pragma unroll
+          for (int h = 0; h < CBT; ++h) {
+            double nc[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const double2 v = *reinterpret_cast<const double2*>(ncs + 32 * h + 8 * j + 2 * t4);
+              nc[j][0] = aug ? 0.0 : v.x, nc[j][1] = aug ? 0.0 : v.y;
+            }
+            const double* bq = xcs + t4 * CS + 32 * h + g;
+#pragma unroll
+            for (int ip = 0; ip < 4 / RI; ++ip) {
+              const int arow = 32 * rbk + 8 * RI * ip + g;  // + 8 i2
+              double r2[8 * RI];  // [i2][j][e] -> 8 i2 + 2 j + e
+#pragma unroll
+              for (int i2 = 0; i2 < RI; ++i2) {
+                const double na = aug ? 0.0 : nrm[arow + 8 * i2];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) r2[8 * i2 + 2 * j] = na + nc[j][0], r2[8 * i2 + 2 * j + 1] = na + nc[j][1];
+              }
+              const double* aq = xst + t4 * XS + arow;
+              for (int ks = 0; ks < dp; ks += 4) {
+                const bool kin = (ks + t4 < dk);
+                double a[RI], b[4];
+#pragma unroll
+                for (int i2 = 0; i2 < RI; ++i2) a[i2] = kin ? aq[ks * XS + 8 * i2] : 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = kin ? bq[ks * CS + 8 * j] : 0.0;
+#pragma unroll
+                for (int i2 = 0; i2 < RI; ++i2)
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) dmma884s(r2[8 * i2 + 2 * j], r2[8 * i2 + 2 * j + 1], a[i2], b[j]);
+              }
+              // cancellation may leave r^2 = -1e-16 where gpytorch clamps to 0: exp(+5e-17) rounds to 1 all the
+              // same, and the Matern kernels clamp r^2 to >= 1e-30 themselves (an FP64 max is 7 instructions)
+#ifndef SCAML_PRED_NOEXP
+              kappa_n<KIND, 8 * RI, false>(r2, r2, r2);
+#endif
+              double* kt = kst + (size_t)(rbk * CBT + h) * kPTile + (8 * RI * ip + g) * kPLd + 2 * t4;
+#pragma unroll
+              for (int i2 = 0; i2 < RI; ++i2) {
+                const double osa = (arow + 8 * i2 < nv) ? os : 0.0, al = alp[arow + 8 * i2];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const double k0 = osa * r2[8 * i2 + 2 * j], k1 = osa * r2[8 * i2 + 2 * j + 1];
+                  *reinterpret_cast<double2*>(kt + 8 * i2 * kPLd + 8 * j) = make_double2(k0, k1);
+                  mu[8 * h + 2 * j] = fma(k0, al, mu[8 * h + 2 * j]);
+                  mu[8 * h + 2 * j + 1] = fma(k1, al, mu[8 * h + 2 * j + 1]);
+                }
+              }
+            }
+          }
+        }
+        // sum over the 8 row groups g (lane bits 2..4) by a halving butterfly: in every round a lane hands one half of
+        // its values to the partner and keeps the sums of the other half -- 8 + 4 + 2 shuffles (CT = 64) instead of
+        // 3 per value, a fixed pairwise order.  CT = 64 ends with columns 2 lane, 2 lane + 1 in the lane.
+        {
+          constexpr int NV = CBT * 8;
+          const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+          double s1[NV / 2];
+#pragma unroll
+          for (int v = 0; v < NV / 2; ++v) {
+            const double give = b4 ? mu[v] : mu[v + NV / 2], keep = b4 ? mu[v + NV / 2] : mu[v];
+            s1[v] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+          }
+          double s2[NV / 4];
+#pragma unroll
+          for (int v = 0; v < NV / 4; ++v) {
+            const double give = b3 ? s1[v] : s1[v + NV / 4], keep = b3 ? s1[v + NV / 4] : s1[v];
+            s2[v] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+          }
+          double s3[NV / 8];
+#pragma unroll
+          for (int v = 0; v < NV / 8; ++v) {
+            const double give = b2 ? s2[v] : s2[v + NV / 8], keep = b2 ? s2[v + NV / 8] : s2[v];
+            s3[v] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+          }
+          // value index bits, most significant first, were chosen by lane bits 4, 3, 2
+          if (CT == 64) {  // index = (h, j1, j0, e): h = b4, j = 2 b3 + b2, e = 0, 1 left -> columns 8 g + 2 t4 + e
+            mu_lo = s3[0], mu_hi = s3[NV / 8 - 1], red_n = 2, red_col = 2 * lane;
+          } else {         // index = (j1, j0, e): j = 2 b4 + b3, e = b2
+            mu_lo = s3[0], red_n = 1, red_col = 8 * (2 * (int)b4 + (int)b3) + 2 * t4 + (int)b2;
+          }
+          red_store = (warp >= 4), red_add = (warp < 4), red_row = warp & 3;
         }
       }
+      if (red_store) {
+        red[red_row * CT + red_col] = mu_lo;
+        if (red_n == 2) red[red_row * CT + red_col + 1] = mu_hi;
+      }
+      PPROF(2);
       __syncthreads();
+      PPROF(3);
+      if (p.alias == 2) issue_first_two();  // the staging data on the rings is dead (barrier above)
+      if (red_add) {
+        red[red_row * CT + red_col] += mu_lo;
+        if (red_n == 2) red[red_row * CT + red_col + 1] += mu_hi;
+      }
       if (CROSS) {
         // cx += (c_m k*)^T A_m : A-operand = k* (shared, this warp's 32-candidate tile column), B-operand = A_m
         // straight from L2 (each 4 x 8 fragment is 4 full 64-byte row segments), one k-step prefetched ahead
         const int njt = p.n_tp >> 3;
-        const double cm = wm * wm * p.ystd[m] * p.ystd[m];
+        const double cm = wm * wm * ys * ys;
         const double* Am = p.condA + (size_t)m * n_pad * p.n_tp + (size_t)t4 * p.n_tp + g;
         const double* ks = kst + (size_t)xt * kPTile + t4 * kPLd + g;
         // work items = (32-row block rbk of k*, column block jj of this warp); the 8 B-fragments of an item are
@@ -274,18 +534,22 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
           }
         }
       }
-      if (p.alias) {
-        for (; issued < 2 && issued < L; ++issued, qi.next()) {
-          pred_issue(Lm, qi, stage + (issued % kPStages) * 2 * kPTile, tid);
-          cp_async_commit();
-        }
-      }
       if (m + 1 < m_hi) {  // prefetch for the next task (lands during the product below)
         pre_m = m + 1;
-        const int nv1 = p.n_valid ? p.n_valid[m + 1] : p.n_max;
+        const double* th1 = p.theta + (size_t)(m + 1) * P;
         const double* X1 = p.X + (size_t)(m + 1) * p.n_max * d;
+        wm_n = p.w[m + 1];
+        nv_n = p.n_valid ? p.n_valid[m + 1] : p.n_max;
+        os_n = th1[d];
+        ys_n = p.ystd[m + 1];
+        yb_n = p.ybar[m + 1];
+        if (tid < d) {
+          th_n = th1[tid];
+          ctr_n = X1[tid];
+        }
+        // rows beyond the next task's n_valid are never used (staging masks them): no dependence on nv_n here
 #pragma unroll
-        for (int k = 0; k < kPreD; ++k) xpre[k] = (k < d && tid < nv1) ? X1[(size_t)tid * d + k] : 0.0;
+        for (int k = 0; k < kPreD; ++k) xpre[k] = (k < d && tid < p.n_max) ? X1[(size_t)tid * d + k] : 0.0;
         apre = (tid < n_pad) ? p.alpha[(size_t)(m + 1) * n_pad + tid] : 0.0;
       }
       // ---- V = L^-1 k*  on the FP64 tensor cores, column sums of squares ------------- //
@@ -297,22 +561,25 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-      PChunk qc{0, 0};
+      GChunk qc{gi, 0};
+      PPROF(4);
       for (int q = 0; q < L; ++q) {
         cp_async_wait<1>();
-        __syncthreads();  // chunk q visible to everyone; everyone has finished reading chunk q-1
+#ifndef SCAML_PRED_NOSYNC
+        group_sync(gi);  // tile q visible to the group; the group has finished reading tile q-1
+#endif
         if (issued < L) {
-          pred_issue(Lm, qi, stage + (issued % kPStages) * 2 * kPTile, tid);
+          gtile_async(gslot(stage, gi, issued % kPStages), Lm + (size_t)(tri(qi.r) + qi.ck) * kTile, gtid);
           ++issued;
           qi.next();
         }
         cp_async_commit();  // always commit (possibly empty): keeps the wait<1> accounting uniform
-        const int brow = 2 * qc.I + rb;  // 32-row block of L^-1 this warp multiplies
-        if (qc.ck <= brow) {
-          const bool dg = (qc.ck == brow);  // diagonal tile: L^-1(r, kk) = 0 for kk > r
-          const double* ar = stage + ((q % kPStages) * 2 + rb) * kPTile + t4 * kPLd + g;
+        const bool dg = (qc.ck == qc.r);  // diagonal tile: L^-1(r, kk) = 0 for kk > r
+#ifndef SCAML_PRED_NOPROD
+        {
+          const double* ar = gslot(stage, gi, q % kPStages) + t4 * kPLd + g;
           const double* br = kst + (qc.ck * CBT + cb) * kPTile + t4 * kPLd + cin + g;
-#pragma unroll 2
+#pragma unroll
           for (int s = 0; s < 8; ++s) {
             const double a[4] = {ar[0], ar[8], ar[16], ar[24]};
             double b[NJ];
@@ -328,7 +595,8 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
               }
           }
         }
-        if (qc.ck == 2 * qc.I + 1) {  // super-row complete: ||V_I||^2 per candidate column
+#endif
+        if (dg) {  // row block complete: ||V_r||^2 per candidate column
 #pragma unroll
           for (int j = 0; j < NJ; ++j)
 #pragma unroll
@@ -343,6 +611,7 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
         qc.next();
       }
       cp_async_wait<0>();
+      PPROF(5);
 #pragma unroll
       for (int j = 0; j < NJ; ++j)
 #pragma unroll
@@ -351,16 +620,16 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
           s += __shfl_xor_sync(0xffffffffu, s, 4);
           s += __shfl_xor_sync(0xffffffffu, s, 8);
           s += __shfl_xor_sync(0xffffffffu, s, 16);
-          if (g == 0) vsq[rb * CT + col0 + 8 * j + 2 * t4 + e] = s;
+          if (g == 0) vsq[gi * CT + col0 + 8 * j + 2 * t4 + e] = s;
         }
       __syncthreads();
       if (tid < CT) {
         const double mu = ((red[tid] + red[CT + tid]) + red[2 * CT + tid]) + red[3 * CT + tid];
         const double ssq = vsq[tid] + vsq[CT + tid];
-        const double ys = p.ystd[m];
-        macc = fma(wm, p.ybar[m] + ys * mu, macc);
+        macc = fma(wm, yb + ys * mu, macc);
         vacc = fma(wm * wm * ys * ys, os - ssq, vacc);
       }
+      PPROF(6);
     }
     if (CROSS) {
       const int njt = p.n_tp >> 3;
@@ -387,6 +656,11 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
       }
     }
   }
+#ifdef SCAML_PRED_PROF
+  if (blockIdx.x == 0 && threadIdx.x == PPROF_TID)
+    printf("pprof tid %d: top %lld staging %lld assembly %lld asmbar %lld mean+prefetch %lld product %lld tail %lld\n",
+           (int)threadIdx.x, pprof[0], pprof[1], pprof[2], pprof[3], pprof[4], pprof[5], pprof[6]);
+#endif
 }
 
 __global__ void scaml_predict_reduce_kernel(const double* part, double* mean, double* var, int nsplit, int B) {

@@ -220,7 +220,7 @@ def test_emu_target_lml_grad_matches_oracle(emu_lib, kernel, nt):
 
 def test_device_exp_is_accurate_to_two_ulp(emu_lib):
     """exp_nonpos (csrc/scaml_device.cuh) replaces libdevice exp in every kernel: < 2 ulp on [-707, 0] against
-    50-digit mpmath at sampled points and numpy elsewhere; flush-to-zero below, NaN propagates."""
+    50-digit mpmath at sampled points and numpy elsewhere; clamped to exp(-708) = 3.3e-308 below, NaN propagates."""
     import ctypes as C
 
     import mpmath
@@ -245,7 +245,7 @@ def test_device_exp_is_accurate_to_two_ulp(emu_lib):
     special = np.array([-707.5, -750.0, -1e6, -np.inf, np.nan])
     so = np.empty_like(special)
     f(special.ctypes.data, so.ctypes.data, special.size)
-    assert (so[:4] == 0.0).all() and np.isnan(so[4])
+    assert (so[:4] >= 0.0).all() and (so[:4] < 1e-307).all() and np.isnan(so[4])
 
 
 def test_emu_fused_conditioning_matches_cross_kernel_and_oracle(emu_lib):
