@@ -149,7 +149,11 @@ SCAML_DEVICE void fmma(Acc& acc, const double* __restrict__ Ap, const double* __
                        bool lower) {
   const double* ar = Ap + t.t4 * kLd + t.g;
   const double* br = Bp + t.t4 * kLd + t.g;
+#ifdef SCAML_FIT_UNROLL_FULL
+#pragma unroll
+#else
 #pragma unroll 2
+#endif
   for (int s = 0; s < NK4; ++s) {
     const double a[4] = {ar[0], ar[8], ar[16], ar[24]};
     const double b[4] = {br[0], br[8], br[16], br[24]};
@@ -651,6 +655,20 @@ SCAML_DEVICE void grad_tile(Acc& acc, int I, int J, const FThr& t, const double*
 // instruction stream: 10 % of the v3 stall samples were no_instruction).  The window shrinks every 8
 // pivots (32, 24, 16, 8 slots).  Slots that have rotated past the tile edge read a few doubles beyond
 // Lc's rows (still inside this CTA's shared memory) and only ever feed other dead slots.
+// 1 / sqrt(pivot).  libdevice's rsqrt() is a ~20-instruction dependent chain with slow-path branches, and it sits on the
+// critical path of every one of the n pivots of an evaluation.  -DSCAML_FAST_RSQRT: hardware seed (MUFU.RSQ64H, relative
+// error ~2^-22) + ONE cubic step  e = 1 - d y^2,  y <- y + y e (1/2 + 3/8 e)  (error (5/16) eps^3 + rounding: <= 2 ulp).
+SCAML_DEVICE double rsqrt_pivot(double d) {
+#if defined(SCAML_EMU) || !defined(SCAML_FAST_RSQRT)
+  return rsqrt(d);
+#else
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double t = d * y;
+  const double e = fma(-t, y, 1.0);
+  return fma(y * e, fma(0.375, e, 0.5), y);
+#endif
+}
 // pivot check shared by the chain: non-positive / non-finite pivot -> remember the first failure, continue with 1
 SCAML_DEVICE double checked_pivot(double dkk, int k, int& fail) {
   if (!(dkk > 0.0) || !(dkk < 1e300)) {
@@ -677,7 +695,7 @@ SCAML_DEVICE void chol_steps(double (&a)[kBS], int k0, double* Lc, int lane, int
     double dn = __shfl_sync(0xffffffffu, fma(-lrk, lrk, a[1]), (k + 1) & 31);
     if (k + 1 < kBS) dn = checked_pivot(dn, k + 1, fail);
     dnext = dn;
-    rsnext = rsqrt(dn);
+    rsnext = rsqrt_pivot(dn);
     __syncwarp();
     const double* lk = Lc + k * kLd + k;  // lk[j] = L(k + j, k)
 #pragma unroll
@@ -742,7 +760,7 @@ SCAML_DEVICE void chol_steps_pub(double (&a)[kBS], int k0, double* Lc, double* d
     double dn = __shfl_sync(0xffffffffu, fma(-lrk, lrk, a[1]), (k + 1) & 31);
     if (k + 1 < kBS) dn = checked_pivot(dn, k + 1, fail);
     dnext = dn;
-    rsnext = rsqrt(dn);
+    rsnext = rsqrt_pivot(dn);
     __syncwarp();
     chain_publish(prog, pbase + k + 1, lane);  // column k of L and dg[k] are complete
     const double* lk = Lc + k * kLd + k;  // lk[j] = L(k + j, k)
@@ -777,7 +795,7 @@ SCAML_DEVICE int chol_32_pub(const double* Dsm, double* Lc, double* dg, volatile
   int fail = 0;
   double mydiag = 1.0;
   double dnext = checked_pivot(__shfl_sync(0xffffffffu, a[0], 0), 0, fail);
-  double rsnext = rsqrt(dnext);
+  double rsnext = rsqrt_pivot(dnext);
   chol_steps_pub<32>(a, 0, Lc, dg, prog, pbase, lane, fail, mydiag, dnext, rsnext);
   chol_steps_pub<24>(a, 8, Lc, dg, prog, pbase, lane, fail, mydiag, dnext, rsnext);
   chol_steps_pub<16>(a, 16, Lc, dg, prog, pbase, lane, fail, mydiag, dnext, rsnext);
@@ -820,7 +838,7 @@ SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* 
   int fail = 0;
   double mydiag = 1.0, myrs = 1.0;
   double dnext = checked_pivot(__shfl_sync(0xffffffffu, a[0], 0), 0, fail);
-  double rsnext = rsqrt(dnext);
+  double rsnext = rsqrt_pivot(dnext);
   if (!ABL(32)) {
     chol_steps<32>(a, 0, Lc, lane, fail, mydiag, myrs, dnext, rsnext);
     chol_steps<24>(a, 8, Lc, lane, fail, mydiag, myrs, dnext, rsnext);
@@ -871,7 +889,11 @@ SCAML_DEVICE void small_gemm(SAcc& o, const double* A, const double* B, const FT
   const double* ar = A + t.t4 * kLd + 16 * (t.warp >> 1) + t.g;
   const double* br = B + t.t4 * kLd + 16 * (t.warp & 1) + t.g;
   if (ABL(256)) return;
+#ifdef SCAML_FIT_UNROLL_FULL
+#pragma unroll
+#else
 #pragma unroll 4
+#endif
   for (int s = 0; s < 8; ++s) {
     const double a0 = ar[0], a1 = ar[8], b0 = br[0], b1 = br[8];
     ar += 4 * kLd;

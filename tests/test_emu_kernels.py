@@ -107,9 +107,10 @@ def test_emu_factorize_and_weighted_prediction(emu_lib):
     assert rel_err(var, ov.numpy()) < TOL_MEAN_VAR
 
 
-def test_emu_kernel_matrix(emu_lib):
-    M, n, d = 2, 70, 3
-    pb = make_problem(M, 1, n, d, seed=2, n_valid=[70, 33])
+@pytest.mark.parametrize("n", [70, 200])  # whole-task kernel / tile kernel (the emulation build switches at 16 KB)
+def test_emu_kernel_matrix(emu_lib, n):
+    M, d = 2, 3 if n == 70 else 6
+    pb = make_problem(M, 1, n, d, seed=2, n_valid=[n, 33])
     theta = np.zeros((M, d + 2))
     for m in range(M):
         ls, os_, nz = O.split_theta(pb["th"][m, 0], pb["ospec"])
@@ -123,6 +124,7 @@ def test_emu_kernel_matrix(emu_lib):
             t = torch.tensor(theta[m])
             ref = O.kernel_matrix(pb["X"][m, :nv], pb["X"][m, :nv], t[:d], t[d], kernel) + t[d + 1] * torch.eye(nv, dtype=torch.float64)
             assert np.abs(K[m, :nv, :nv] - ref.numpy()).max() < 1e-14
+            assert np.array_equal(K[m], K[m].T)
             if nv < n:
                 assert np.array_equal(K[m, nv:, nv:], np.eye(n - nv))
                 assert (K[m, :nv, nv:] == 0).all() and (K[m, nv:, :nv] == 0).all()
