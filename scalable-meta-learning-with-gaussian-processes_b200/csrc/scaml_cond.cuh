@@ -36,15 +36,20 @@ inline size_t cond_prep_smem_bytes(int n_pad, int d, int pw) {
   return sizeof(double) * ((size_t)n_pad * (pw + 4) + (size_t)kPStages * 2 * kPTile + (size_t)d * n_pad +
                            (size_t)d * pw + kMaxP + 8);
 }
+// panel width: 8, 16, 32 or 64 columns (the kernel is instantiated per width) -- the narrowest that covers n_tp,
+// else the widest that fits shared memory; columns of a panel beyond n_tp are zero columns that are not stored
 inline int cond_panel_width(int n_pad, int d, int n_tp) {
-  for (int pw = 64; pw >= 8; pw >>= 1) {
-    const int w = pw < n_tp ? pw : n_tp;
-    if (cond_prep_smem_bytes(n_pad, d, w) <= 227 * 1024) return w;
-  }
+  int want = 8;
+  while (want < 64 && want < n_tp) want <<= 1;
+  for (int pw = want; pw >= 8; pw >>= 1)
+    if (cond_prep_smem_bytes(n_pad, d, pw) <= 227 * 1024) return pw;
   return 0;
 }
 
-template <int KIND>
+// NJT = 8-column blocks per panel (1 .. 8), a template parameter: the products below issue one DMMA per column
+// block, and a predicated-off DMMA (j >= njt at run time) would still hold the warp for its 16 issue cycles -- a
+// 32-column panel ran at the speed of a 64-column one.
+template <int KIND, int NJT>
 __global__ void __launch_bounds__(kPredThreads, 1) scaml_cond_prepare_kernel(const CondPrepParams p) {
   SCAML_DYN_SMEM(double, sm);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
@@ -60,7 +65,8 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_cond_prepare_kernel(con
     const int m = it / p.npanel, pn = it - m * p.npanel;
     if (p.skip_w != nullptr && p.skip_w[m] == 0.0) continue;  // uniform over the CTA
     const int j0 = pn * pw;
-    const int njt = ((p.n_tp - j0 < pw ? p.n_tp - j0 : pw) + 7) / 8;  // 8-column blocks of this panel
+    constexpr int njt = NJT;  // 8-column blocks of a panel; the columns of a last, narrower panel beyond n_tp are
+                              // zero columns of K (masked below) whose results are not stored
     const int nv = p.n_valid ? p.n_valid[m] : p.n_max;
     const int NS = (nv + kSB - 1) / kSB, npt = NS * kSB, NB = 2 * NS;
     const double* th = p.theta + (size_t)m * P;
@@ -77,15 +83,32 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_cond_prepare_kernel(con
       xts[i] = (j0 + j < p.n_t) ? p.Xt[(size_t)(j0 + j) * d + k] * invl[k] : 0.0;
     }
     __syncthreads();
-    // ---- K(X_m, X_t panel) -------------------------------------------------------------------------- //
-    for (int i = tid; i < npt * pw; i += kPredThreads) {
-      const int a = i / pw, j = i - a * pw;
-      double r2 = 0.0;
-      for (int k = 0; k < d; ++k) {
-        const double df = xst[k * n_pad + a] - xts[k * pw + j];
-        r2 = fma(df, df, r2);
+    // ---- K(X_m, X_t panel): thread <-> column j of the panel, rows in phases, 8 interleaved exp chains -------- //
+    {
+      constexpr int PW = 8 * NJT, QN = kPredThreads / PW, U = 8;
+      const int j = tid % PW, q = tid / PW;
+      const bool jin = (j0 + j < p.n_t);
+      for (int a0 = q; a0 < npt; a0 += QN * U) {
+        double r2[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) r2[u] = 0.0;
+        for (int k = 0; k < d; ++k) {
+          const double xt = xts[k * pw + j];
+          const double* xr = xst + k * n_pad + a0;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const double df = ((a0 + u * QN < npt) ? xr[u * QN] : 0.0) - xt;  // QN U > 64 for narrow panels
+            r2[u] = fma(df, df, r2[u]);
+          }
+        }
+        double kap[U];
+        kappa_n<KIND, U, false>(r2, kap, kap);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int a = a0 + u * QN;
+          if (a < npt) KV[(size_t)a * ld + j] = (a < nv && jin) ? os * kap[u] : 0.0;
+        }
       }
-      KV[(size_t)a * ld + j] = (a < nv && j0 + j < p.n_t) ? os * kappa_of<KIND>(r2) : 0.0;
     }
     __syncthreads();
     // ---- pass 1: V = L^-1 K, super-rows bottom-up so that V_I can overwrite the rows of K it no longer needs -- //
@@ -121,6 +144,7 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_cond_prepare_kernel(con
             const bool dg = (ck == brow);
             const double* ar = stage + ((q % kPStages) * 2 + rb) * kPTile + t4 * kPLd + 8 * ib + g;
             const double* br = KV + (size_t)(32 * ck + t4) * ld + g;
+#pragma unroll
             for (int s = 0; s < 8; ++s) {
               if (!dg || s < 2 * ib + 2) {  // diagonal tile: L^-1(r, kk) = 0 for kk > r
                 const double a = ar[0];
@@ -175,12 +199,13 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_cond_prepare_kernel(con
           // staged tile: row c (= column a of L^-1), entries r: A_op[a][r] = L^-1(r, a) = staged[a * kPLd + r]
           const double* ar = stage + (q % kPStages) * 2 * kPTile + (8 * ib + g) * kPLd + t4;
           const double* br = KV + (size_t)(32 * rbk + t4) * ld + 8 * jpar + g;
+#pragma unroll
           for (int s = 0; s < 8; ++s) {
             if (!dg || s >= 2 * ib) {  // diagonal tile: L^-1(r, a) = 0 for r < a
               const double a = ar[4 * s];
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (jpar + 2 * j < njt) dmma884(acc[j], a, br[16 * j]);
+              for (int j = 0; j < (NJT + 1) / 2; ++j)
+                if (NJT % 2 == 0 || jpar + 2 * j < njt) dmma884(acc[j], a, br[16 * j]);
             }
             br += 4 * ld;
           }
@@ -190,7 +215,7 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_cond_prepare_kernel(con
           double* dst = p.A + ((size_t)m * n_pad + a) * p.n_tp + j0 + 2 * t4;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (jpar + 2 * j < njt)
+            if (jpar + 2 * j < njt && j0 + 8 * (jpar + 2 * j) < p.n_tp)
               *reinterpret_cast<double2*>(dst + 8 * (jpar + 2 * j)) = make_double2(acc[j][0], acc[j][1]);
         }
       }
@@ -430,19 +455,28 @@ inline int launch_cond_caches(CondCachesParams p, int kernel, int num_sms, void*
   }
 }
 
-template <int KIND>
-int launch_cond_prepare_k(const CondPrepParams& p, int grid, size_t smem, void* stream) {
+template <int KIND, int NJT>
+int launch_cond_prepare_kn(const CondPrepParams& p, int grid, size_t smem, void* stream) {
 #ifdef SCAML_EMU
   (void)stream;
-  cuemu::launch(dim3(grid), dim3(kPredThreads), smem, scaml_cond_prepare_kernel<KIND>, p);
+  cuemu::launch(dim3(grid), dim3(kPredThreads), smem, scaml_cond_prepare_kernel<KIND, NJT>, p);
   return 0;
 #else
-  cudaError_t err =
-      cudaFuncSetAttribute(scaml_cond_prepare_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t err = cudaFuncSetAttribute(scaml_cond_prepare_kernel<KIND, NJT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (err != cudaSuccess) return (int)err;
-  scaml_cond_prepare_kernel<KIND><<<grid, kPredThreads, smem, (cudaStream_t)stream>>>(p);
+  scaml_cond_prepare_kernel<KIND, NJT><<<grid, kPredThreads, smem, (cudaStream_t)stream>>>(p);
   return (int)cudaGetLastError();
 #endif
+}
+template <int KIND>
+int launch_cond_prepare_k(const CondPrepParams& p, int grid, size_t smem, void* stream) {
+  switch (p.pw) {
+    case 8: return launch_cond_prepare_kn<KIND, 1>(p, grid, smem, stream);
+    case 16: return launch_cond_prepare_kn<KIND, 2>(p, grid, smem, stream);
+    case 32: return launch_cond_prepare_kn<KIND, 4>(p, grid, smem, stream);
+    default: return launch_cond_prepare_kn<KIND, 8>(p, grid, smem, stream);
+  }
 }
 
 inline int launch_cond_prepare(CondPrepParams p, int kernel, int num_sms, void* stream) {

@@ -144,9 +144,11 @@ SCAML_DEVICE void facc_zero(Acc& acc) {
 
 // acc(32x32) += A[kk][r] * B[kk][c] over NK4 steps of 4 kk.  Ap/Bp: padded k-major tiles (row
 // stride kLd) at their first kk row.  LOWER: skip the strictly-upper 8x8 tiles (diagonal tiles).
-template <int NK4>
-SCAML_DEVICE void fmma(Acc& acc, const double* __restrict__ Ap, const double* __restrict__ Bp, const FThr& t,
-                       bool lower) {
+// LOWER is a template parameter behind a warp-uniform branch, not a predicate on the DMMAs: a predicated-off
+// DMMA still holds the issuing warp for its 16 issue cycles (measured on the fused cross-covariance of the
+// prediction kernel), so predication saves pipe time but no warp time.
+template <int NK4, bool LOWER>
+SCAML_DEVICE void fmma_impl(Acc& acc, const double* __restrict__ Ap, const double* __restrict__ Bp, const FThr& t) {
   const double* ar = Ap + t.t4 * kLd + t.g;
   const double* br = Bp + t.t4 * kLd + t.g;
 #ifdef SCAML_FIT_UNROLL_FULL
@@ -163,26 +165,17 @@ SCAML_DEVICE void fmma(Acc& acc, const double* __restrict__ Ap, const double* __
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (j <= i || !lower) dmma884(acc[i][j], a[i], b[j]);
+        if (j <= i || !LOWER) dmma884(acc[i][j], a[i], b[j]);
   }
 }
-
-// The same product when an operand tile is triangular: the 8-row blocks that are identically zero in a k4-step are
-// skipped (a predicated-off DMMA costs an issue slot, not 16 cycles of the FP64 pipe).  kbase = index of the first kk
-// row of this call inside its 32 x 32 tile.  Modes (warp-uniform):
-//   1  operand[kk][x] != 0 only for x <= kk  (rows of L^-1, R-layout)      -> blocks  <= (kk0 + 3) / 8
-//   2  operand[kk][x] != 0 only for x >= kk  (D^-1 of a diagonal block, C-layout) -> blocks >= kk0 / 8
 template <int NK4>
-SCAML_DEVICE void fmma_tri(Acc& acc, const double* __restrict__ Ap, const double* __restrict__ Bp, const FThr& t,
-                           bool lower, int amode, int bmode, int kbase) {
+SCAML_DEVICE void fmma(Acc& acc, const double* __restrict__ Ap, const double* __restrict__ Bp, const FThr& t,
+                       bool lower) {
+#ifdef SCAML_FIT_PREDICATED_LOWER  // A/B: the round-1 form (one loop, predicated DMMAs)
   const double* ar = Ap + t.t4 * kLd + t.g;
   const double* br = Bp + t.t4 * kLd + t.g;
 #pragma unroll 2
   for (int s = 0; s < NK4; ++s) {
-    const int kk0 = kbase + 4 * s;
-    const int up = (kk0 + 3) >> 3, lo = kk0 >> 3;
-    const int ihi = (amode == 1) ? up : 3, ilo = (amode == 2) ? lo : 0;
-    const int jhi = (bmode == 1) ? up : 3, jlo = (bmode == 2) ? lo : 0;
     const double a[4] = {ar[0], ar[8], ar[16], ar[24]};
     const double b[4] = {br[0], br[8], br[16], br[24]};
     ar += 4 * kLd;
@@ -191,7 +184,74 @@ SCAML_DEVICE void fmma_tri(Acc& acc, const double* __restrict__ Ap, const double
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (i >= ilo && i <= ihi && j >= jlo && j <= jhi && (j <= i || !lower)) dmma884(acc[i][j], a[i], b[j]);
+        if (j <= i || !lower) dmma884(acc[i][j], a[i], b[j]);
+  }
+#else
+  if (lower) fmma_impl<NK4, true>(acc, Ap, Bp, t);
+  else fmma_impl<NK4, false>(acc, Ap, Bp, t);
+#endif
+}
+
+// The same product when an operand tile is triangular: the 8-row blocks that are identically zero in a k4-step are
+// not multiplied.  kbase = index of the first kk row of this call inside its 32 x 32 tile.  Modes:
+//   1  operand[kk][x] != 0 only for x <= kk  (rows of L^-1, R-layout)      -> blocks  <= (kk0 + 3) / 8
+//   2  operand[kk][x] != 0 only for x >= kk  (D^-1 of a diagonal block, C-layout) -> blocks >= kk0 / 8
+// Everything that selects a DMMA is a template parameter and the k loop is fully unrolled, so the skipped products
+// do not exist in the instruction stream (round 2 measured the same skipping with run-time predicates as a LOSS:
+// a predicated-off DMMA costs the warp the same 16 issue cycles as an executed one).
+template <int NK4, int AMODE, int BMODE, bool LOWER, int KBASE>
+SCAML_DEVICE void fmma_tri_impl(Acc& acc, const double* __restrict__ Ap, const double* __restrict__ Bp,
+                                const FThr& t) {
+  const double* ar = Ap + t.t4 * kLd + t.g;
+  const double* br = Bp + t.t4 * kLd + t.g;
+#pragma unroll
+  for (int s = 0; s < NK4; ++s) {
+    const int kk0 = KBASE + 4 * s;
+    const int up = (kk0 + 3) >> 3, lo = kk0 >> 3;
+    const int ihi = (AMODE == 1) ? up : 3, ilo = (AMODE == 2) ? lo : 0;
+    const int jhi = (BMODE == 1) ? up : 3, jlo = (BMODE == 2) ? lo : 0;
+    double a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = (i >= ilo && i <= ihi) ? ar[8 * i + 4 * s * kLd] : 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = (j >= jlo && j <= jhi) ? br[8 * j + 4 * s * kLd] : 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (i >= ilo && i <= ihi && j >= jlo && j <= jhi && (j <= i || !LOWER)) dmma884(acc[i][j], a[i], b[j]);
+  }
+}
+// streamed products: only the (amode, bmode, lower, kbase) combinations that occur are instantiated.  A diagonal K^-1
+// super-tile reads the triangular tiles L^-1(2I, 2I) / (2I+1, 2I+1) on both sides in roles (0,0) / (1,1) (which are
+// `lower` as well) and on one side in role (1,0); off the diagonal one operand at most is triangular.  A whole
+// 16-deep sub-chunk (NK4 = 4) starts at kbase 0 or 16, the halves of a split tile (NK4 = 2, never `lower`, one
+// triangular operand) at 0, 8, 16, 24.
+template <int KBASE>
+SCAML_DEVICE void fmma_tri4_k(Acc& acc, const double* __restrict__ Ap, const double* __restrict__ Bp, const FThr& t,
+                              int amode, int bmode) {
+  if (amode == 1 && bmode == 1) fmma_tri_impl<4, 1, 1, true, KBASE>(acc, Ap, Bp, t);
+  else if (amode == 1) fmma_tri_impl<4, 1, 0, false, KBASE>(acc, Ap, Bp, t);
+  else fmma_tri_impl<4, 0, 1, false, KBASE>(acc, Ap, Bp, t);
+}
+SCAML_DEVICE void fmma_tri4(Acc& acc, const double* __restrict__ Ap, const double* __restrict__ Bp, const FThr& t,
+                            int amode, int bmode, int kbase) {
+  if (kbase == 0) fmma_tri4_k<0>(acc, Ap, Bp, t, amode, bmode);  // warp-uniform
+  else fmma_tri4_k<16>(acc, Ap, Bp, t, amode, bmode);
+}
+template <int KBASE>
+SCAML_DEVICE void fmma_tri2_k(Acc& acc, const double* __restrict__ Ap, const double* __restrict__ Bp, const FThr& t,
+                              int amode) {
+  if (amode == 1) fmma_tri_impl<2, 1, 0, false, KBASE>(acc, Ap, Bp, t);
+  else fmma_tri_impl<2, 0, 1, false, KBASE>(acc, Ap, Bp, t);
+}
+SCAML_DEVICE void fmma_tri2(Acc& acc, const double* __restrict__ Ap, const double* __restrict__ Bp, const FThr& t,
+                            int amode, int kbase) {
+  switch (kbase) {  // warp-uniform
+    case 0: fmma_tri2_k<0>(acc, Ap, Bp, t, amode); break;
+    case 8: fmma_tri2_k<8>(acc, Ap, Bp, t, amode); break;
+    case 16: fmma_tri2_k<16>(acc, Ap, Bp, t, amode); break;
+    default: fmma_tri2_k<24>(acc, Ap, Bp, t, amode); break;
   }
 }
 
@@ -302,22 +362,25 @@ SCAML_DEVICE void stage_issue(const Src& src, int s, double* st, int tid) {
 
 // acc += sum over chunks; optional piggy-backed GEMV  pig[c] += sum_kk A[kk][c] * zv[zoff+kk]
 // (c = tid & 63 over the 64 A columns of the super-tile, kk-half = tid >> 6).
-// DIAG: super-tile on the diagonal -> roles (0,0), (1,1) compute the lower 8x8 tiles only (10 of 16), role (0,1) idles.
-// Two work-trimming variants are kept behind compile-time switches because they measured SLOWER on the B200
-// (profiles/r2_fit_split_tri_ab.txt: three co-resident CTAs keep the shared FP64 pipe fed, so shortening one role's
-// critical path buys nothing, while the extra predicates / merges cost issue slots):
-//   -DSCAML_FIT_SPLIT  the one full tile (1,0) is split along the contraction between its own warp and the idle
-//                      role's warp (40 / 32 / 32 / 40 DMMAs per step instead of 40 / 64 / 0 / 40), partial sums merged
-//                      by `split_merge` in a fixed order: -0.7 %
-//   -DSCAML_FIT_TRI    8-row blocks of triangular operand tiles that are identically zero in a k4-step are skipped
-//                      (predicated-off DMMAs, `fmma_tri`): -5 %
+// DIAG: super-tile on the diagonal -> roles (0,0), (1,1) compute the lower 8x8 tiles only (10 of 16); the one full
+// tile (1,0) is split along the contraction between its own warp and the warp of the idle role (0,1): 40 / 32 / 32 / 40
+// DMMAs per step instead of 40 / 64 / 0 / 40, partial sums merged by `split_merge` in a fixed order.
+// History of the two work-trimming variants (profiles/r2_fit_split_tri_ab.txt, r2_fit_predication.txt):
+//   * both LOST while the skipped products were predicated-off DMMAs (split -0.8 %, triangular skipping -3.6 %): a
+//     predicated-off DMMA holds the issuing warp for the same 16 issue cycles as an executed one, so roles (0,0) / (1,1)
+//     still took 64 DMMA slots per step and nothing got shorter.
+//   * with the skipping moved into template parameters behind warp-uniform branches (`fmma_impl`) the split pays:
+//     +2.1 % on top of +1.6 % from the templated lower-triangle product itself (-DSCAML_FIT_NOSPLIT is the A/B switch).
+//   * -DSCAML_FIT_TRI (zero 8-row blocks of triangular operand tiles left out of the instruction stream, `fmma_tri_impl`:
+//     8 % fewer DMMAs) still loses 1-3 %: the variants add ~2000 instructions to a 12 k-instruction kernel whose
+//     three co-resident CTAs sit in different phases (instruction-fetch stalls) -- kept off.
 // On return every thread has passed a __syncthreads after its last read of `stage`.
 template <class Src>
 SCAML_DEVICE void gemm_global(Acc& acc, const Src& src, double* stage, const FThr& t, bool diag, bool piggy,
                               double& pig, const double* zv) {
   const int n = 2 * src.count();
   if (n <= 0) return;
-#ifndef SCAML_FIT_SPLIT
+#ifdef SCAML_FIT_NOSPLIT
   const bool helper = false;
   if (diag && t.rb < t.cb) {  // A/B variant: role (0,1) idles, role (1,0) multiplies the whole tile
     stage_issue(src, 0, stage, t.tid);
@@ -378,10 +441,10 @@ SCAML_DEVICE void gemm_global(Acc& acc, const Src& src, double* stage, const FTh
       const double* bp = Bs + ecb * kHalfS + koff * kLd;
       const int kbase = (s & 1) * 16 + koff;
       if (split) {
-        if (amode | bmode) fmma_tri<2>(acc, ap, bp, t, false, amode, bmode, kbase);
+        if (amode | bmode) fmma_tri2(acc, ap, bp, t, amode, kbase);
         else fmma<2>(acc, ap, bp, t, false);
       } else {
-        if (amode | bmode) fmma_tri<4>(acc, ap, bp, t, lower, amode, bmode, kbase);
+        if (amode | bmode) fmma_tri4(acc, ap, bp, t, amode, bmode, kbase);
         else fmma<4>(acc, ap, bp, t, lower);
       }
     }
@@ -440,8 +503,8 @@ SCAML_DEVICE void gemm_smem_trsm(Acc& acc, const double* cin, const double* dinv
 #ifndef SCAML_FIT_TRI
     fmma<8>(acc, cin + (2 * t.rb + ck) * kTileS, dinvc + (t.cb + ck) * kTileS, t, false);
 #else
-    fmma_tri<8>(acc, cin + (2 * t.rb + ck) * kTileS, dinvc + (t.cb + ck) * kTileS, t, false, 0,
-                (t.cb + ck != 1) ? 2 : 0, 0);
+    if (t.cb + ck != 1) fmma_tri_impl<8, 0, 2, false, 0>(acc, cin + (2 * t.rb + ck) * kTileS, dinvc + (t.cb + ck) * kTileS, t);
+    else fmma<8>(acc, cin + (2 * t.rb + ck) * kTileS, dinvc + (t.cb + ck) * kTileS, t, false);
 #endif
   }
 }
@@ -456,8 +519,8 @@ SCAML_DEVICE void gemm_smem_trtri(Acc& acc, const double* dinvc, const double* s
 #ifndef SCAML_FIT_TRI
     fmma<8>(acc, dinvc + (t.rb + ck) * kTileS, sst + (2 * ck + t.cb) * kTileS, t, false);
 #else
-    fmma_tri<8>(acc, dinvc + (t.rb + ck) * kTileS, sst + (2 * ck + t.cb) * kTileS, t, false,
-                (t.rb + ck != 1) ? 2 : 0, 0, 0);
+    if (t.rb + ck != 1) fmma_tri_impl<8, 2, 0, false, 0>(acc, dinvc + (t.rb + ck) * kTileS, sst + (2 * ck + t.cb) * kTileS, t);
+    else fmma<8>(acc, dinvc + (t.rb + ck) * kTileS, sst + (2 * ck + t.cb) * kTileS, t, false);
 #endif
   }
 }
@@ -1223,12 +1286,12 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
         gemm_global(acc, src, stage, t, diag, false, pig, nullptr);
         PROF_MARK(1);
         // split tile (1,0) of a diagonal super-tile: dinvc is free here (all trsm of column J-1 have retired)
-#ifdef SCAML_FIT_SPLIT
+#ifndef SCAML_FIT_NOSPLIT
         if (diag && J > 0 && upper_warp) split_put(dinvc, acc, t);
 #endif
         xblk_store(stage, xp, Xm, invl, I, J, nv, d, t.tid);  // stage is idle: x-block lives there
         __syncthreads();
-#ifdef SCAML_FIT_SPLIT
+#ifndef SCAML_FIT_NOSPLIT
         if (diag && J > 0 && t.rb == 1 && t.cb == 0) split_merge(acc, dinvc, t);
 #endif
         if (!(diag && upper_warp))
@@ -1345,13 +1408,13 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
         LauumSrc src{W, I, J, NS};
         gemm_global(acc, src, stage, t, diag, diag, pig, zv);
         PROF_MARK(8);
-#ifdef SCAML_FIT_SPLIT
+#ifndef SCAML_FIT_NOSPLIT
         if (diag && upper_warp) split_put(dinvc, acc, t);  // dinvc is not used in phase D
 #endif
         xblk_store(stage, xp, Xm, invl, I, J, nv, d, t.tid);
         if (diag) red[t.tid] = pig;
         __syncthreads();
-#ifdef SCAML_FIT_SPLIT
+#ifndef SCAML_FIT_NOSPLIT
         if (diag && t.rb == 1 && t.cb == 0) split_merge(acc, dinvc, t);
 #endif
         if (diag) {

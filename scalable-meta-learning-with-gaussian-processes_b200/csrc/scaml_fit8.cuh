@@ -58,12 +58,12 @@ SCAML_DEVICE void acc_zero(Acc8& acc) {
 
 // acc(32 x 16) += A[kk][r] * B[kk][cin + c] over NK4 steps of 4 kk.  Ap/Bp: padded k-major tiles (row stride
 // kLd) at their first kk row.  LOWER: skip the strictly-upper 8x8 blocks (diagonal tiles).
-template <int NK4>
-SCAML_DEVICE void mma8(Acc8& acc, const double* __restrict__ Ap, const double* __restrict__ Bp, const Thr& t,
-                       bool lower) {
+// LOWER and the warp's first column block are template parameters behind warp-uniform branches: a predicated-off
+// DMMA still holds the issuing warp for its 16 issue cycles (see fmma in scaml_fit.cuh).
+template <int NK4, bool LOWER, int JJ0>
+SCAML_DEVICE void mma8_impl(Acc8& acc, const double* __restrict__ Ap, const double* __restrict__ Bp, const Thr& t) {
   const double* ar = Ap + t.t4 * kLd + t.g;
   const double* br = Bp + t.t4 * kLd + t.cin + t.g;
-  const int jj0 = t.cin >> 3;  // first 8-column block of this warp (0 or 2)
 #pragma unroll 2
   for (int s = 0; s < NK4; ++s) {
     const double a[4] = {ar[0], ar[8], ar[16], ar[24]};
@@ -74,8 +74,15 @@ SCAML_DEVICE void mma8(Acc8& acc, const double* __restrict__ Ap, const double* _
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 2; ++j)
-        if (!lower || jj0 + j <= i) dmma884(acc[i][j], a[i], b[j]);
+        if (!LOWER || JJ0 + j <= i) dmma884(acc[i][j], a[i], b[j]);
   }
+}
+template <int NK4>
+SCAML_DEVICE void mma8(Acc8& acc, const double* __restrict__ Ap, const double* __restrict__ Bp, const Thr& t,
+                       bool lower) {
+  if (!lower) mma8_impl<NK4, false, 0>(acc, Ap, Bp, t);
+  else if ((t.cin >> 3) == 0) mma8_impl<NK4, true, 0>(acc, Ap, Bp, t);  // first 8-column block of this warp: 0 or 2
+  else mma8_impl<NK4, true, 2>(acc, Ap, Bp, t);
 }
 
 // dense half tile (16 x 32 doubles, contiguous 4 KB) global -> padded shared rows: 16 B / thread

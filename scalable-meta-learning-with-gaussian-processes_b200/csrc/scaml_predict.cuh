@@ -495,44 +495,71 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
         if (red_n == 2) red[red_row * CT + red_col + 1] += mu_hi;
       }
       if (CROSS) {
-        // cx += (c_m k*)^T A_m : A-operand = k* (shared, this warp's 32-candidate tile column), B-operand = A_m
-        // straight from L2 (each 4 x 8 fragment is 4 full 64-byte row segments), one k-step prefetched ahead
+        // cx += (c_m k*)^T A_m : A-operand = k* (shared, this warp's 32-candidate tile column), B-operand = A_m.
+        // A_m streams through the two third-stage ring slots -- idle until the product loop -- as [32 rows of one row
+        // block] x [W = 8 JS target columns] tiles (row stride W + 4), double-buffered when two fit (W = 32), fetched
+        // with cp.async by the whole CTA; in a tile every warp owns ONE 8-column block (jw) and the accumulator set
+        // jj = column chunk.  (Round 1 read the B fragments straight from L2 with one item of register prefetch:
+        // latency bound, 27 k cycles per task and candidate tile against 8 k of DMMA work.)
+        constexpr int W = 8 * JS, LDW = W + 4, NBUF = (2 * kPTile) / (32 * LDW);
+        static_assert(NBUF >= 1, "a CROSS tile must fit the two spare ring slots");
+        double* xbuf = stage + 4 * kPTile;
         const int njt = p.n_tp >> 3;
+        const int nchunk = (p.n_tp + W - 1) / W, nitems = nb * nchunk;
         const double cm = wm * wm * ys * ys;
-        const double* Am = p.condA + (size_t)m * n_pad * p.n_tp + (size_t)t4 * p.n_tp + g;
-        const double* ks = kst + (size_t)xt * kPTile + t4 * kPLd + g;
-        // work items = (32-row block rbk of k*, column block jj of this warp); the 8 B-fragments of an item are
-        // fetched while the previous item's 32 DMMAs run (double-buffered registers): L2 latency is hidden
-        const int nrb = npt >> 5;
-        const int njw = (njt > jw) ? (njt - jw + JS - 1) / JS : 0;  // column blocks jw, jw+JS, .. owned by this warp
-        const int nitems = nrb * njw;
-        double bcur[8], bnxt[8];
-        auto fetch = [&](int item, double (&b)[8]) {
-          const int rbk = item / njw, jj = item - rbk * njw;
-          const double* src = Am + (size_t)(32 * rbk) * p.n_tp + 8 * (jw + JS * jj);
+        const double* Am = p.condA + (size_t)m * n_pad * p.n_tp;
+        auto issue_item = [&](int item) {
+          const int rbk = item / nchunk, c = item - rbk * nchunk;
+          double* dst = xbuf + (NBUF == 2 ? (item & 1) : 0) * 32 * LDW;
+          const double* src = Am + (size_t)(32 * rbk) * p.n_tp + W * c;
 #pragma unroll
-          for (int s = 0; s < 8; ++s) b[s] = __ldg(src + (size_t)(4 * s) * p.n_tp);
+          for (int u = 0; u < (16 * W) / kPredThreads; ++u) {
+            const int pc = tid + u * kPredThreads;
+            const int row = pc / (W / 2), j2 = pc - row * (W / 2);
+            if (W * c + 2 * j2 < p.n_tp) cp_async16(dst + row * LDW + 2 * j2, src + (size_t)row * p.n_tp + 2 * j2);
+          }
+          cp_async_commit();
         };
-        if (nitems > 0) fetch(0, bnxt);
+        const double* ks = kst + (size_t)xt * kPTile + t4 * kPLd + g;
+        if (nitems > 0) issue_item(0);
         for (int item = 0; item < nitems; ++item) {
-#pragma unroll
-          for (int s = 0; s < 8; ++s) bcur[s] = bnxt[s];
-          if (item + 1 < nitems) fetch(item + 1, bnxt);
-          const int rbk = item / njw, jj = item - rbk * njw;
-          const double* kr = ks + (size_t)rbk * CBT * kPTile;
-#pragma unroll
-          for (int s = 0; s < 8; ++s) {
-            const double a[4] = {cm * kr[0], cm * kr[8], cm * kr[16], cm * kr[24]};
-            kr += 4 * kPLd;
-            // jj is warp-uniform but not a compile-time constant: select the accumulator set by unrolled compare
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (q == jj) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) dmma884(cx[i][q], a[i], bcur[s]);
-              }
+          cp_async_wait<0>();
+          __syncthreads();  // tile `item` visible; every warp has finished the tile before it
+          if (NBUF == 2 && item + 1 < nitems) issue_item(item + 1);
+          const int rbk = item / nchunk, jj = item - rbk * nchunk;
+          if (jw + JS * jj < njt) {
+            const double* kr = ks + (size_t)rbk * CBT * kPTile;
+            const double* br = xbuf + (NBUF == 2 ? (item & 1) : 0) * 32 * LDW + t4 * LDW + 8 * jw + g;
+            // jj is warp-uniform but not a compile-time constant, and the accumulators must be indexed statically to
+            // stay in registers: one copy of the loop per set behind a uniform branch.  (Selecting the set by
+            // predicate inside ONE loop issued 16 DMMAs per step, 12 of them predicated off -- and a predicated-off
+            // DMMA still holds the warp for its 16 issue cycles: the fused cross-covariance ran at a quarter of
+            // the tensor-core rate.)
+#define SCAML_CX_LOOP(Q)                                                  \
+  _Pragma("unroll") for (int s = 0; s < 8; ++s) {                         \
+    const double a[4] = {kr[0], kr[8], kr[16], kr[24]};                   \
+    const double b = cm * br[0];                                          \
+    kr += 4 * kPLd;                                                       \
+    br += 4 * LDW;                                                        \
+    _Pragma("unroll") for (int i = 0; i < 4; ++i) dmma884(cx[i][Q], a[i], b); \
+  }
+            if (jj == 0) {
+              SCAML_CX_LOOP(0)
+            } else if (jj == 1) {
+              SCAML_CX_LOOP(1)
+            } else if (jj == 2) {
+              SCAML_CX_LOOP(2)
+            } else {
+              SCAML_CX_LOOP(3)
+            }
+#undef SCAML_CX_LOOP
+          }
+          if (NBUF == 1 && item + 1 < nitems) {
+            __syncthreads();
+            issue_item(item + 1);
           }
         }
+        __syncthreads();  // the spare slots go back to the product groups
       }
       if (m + 1 < m_hi) {  // prefetch for the next task (lands during the product below)
         pre_m = m + 1;

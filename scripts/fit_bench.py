@@ -36,4 +36,4 @@ for _ in range(3):
 ms = sorted(ts)[1]
 F = float(n) ** 3 + float(n) ** 2 * (2.5 * d + 10.0)
 print(f"M={M} R={R} n={n} d={d} kernel={kernel}: {ms:.3f} ms  {M*R/ms*1e3:.0f} evals/s  {M*R*F/ms/1e9:.2f} TFLOP/s algorithmic  "
-      f"info!=0: {int((out[2] != 0).sum())}", flush=True)
+      f"info!=0: {int((out[2] != 0).sum())}  sum(lml)={float(out[0].sum()):.12e} sum|grad|={float(out[1].abs().sum()):.12e}", flush=True)
