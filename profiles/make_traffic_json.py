@@ -22,9 +22,9 @@ KERNELS = {
                                   ["scaml_predict.cuh"]),
     "scaml_predict_kernel<RBF,64,CROSS>": ("scaml_predict_kernel<0, 64, 1>", None,
                                            "4096 GPs x 18944 candidates, n_t = 32", ["scaml_predict.cuh"]),
-    "scaml_cond_prepare_kernel<RBF>": ("scaml_cond_prepare_kernel<0>", None, "4096 GPs, 64-column panel (candidates)",
+    "scaml_cond_prepare_kernel<RBF>": ("scaml_cond_prepare_kernel<0, 8>", None, "4096 GPs, 64-column panel (candidates)",
                                        ["scaml_cond.cuh", "scaml_predict.cuh"]),
-    "scaml_kmat_kernel<RBF>": ("scaml_kmat_kernel<0>", None, "4096 tasks x 256 x 256", ["scaml_kmat.cuh", "scaml_tile256.cuh"]),
+    "scaml_kmat_kernel<RBF>": ("scaml_kmat_task_kernel<0>", None, "4096 tasks x 256 x 256", ["scaml_kmat.cuh"]),
 }
 
 
