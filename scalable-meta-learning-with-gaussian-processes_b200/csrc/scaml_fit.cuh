@@ -151,11 +151,7 @@ template <int NK4, bool LOWER>
 SCAML_DEVICE void fmma_impl(Acc& acc, const double* __restrict__ Ap, const double* __restrict__ Bp, const FThr& t) {
   const double* ar = Ap + t.t4 * kLd + t.g;
   const double* br = Bp + t.t4 * kLd + t.g;
-#ifdef SCAML_FIT_UNROLL_FULL
-#pragma unroll
-#else
 #pragma unroll 2
-#endif
   for (int s = 0; s < NK4; ++s) {
     const double a[4] = {ar[0], ar[8], ar[16], ar[24]};
     const double b[4] = {br[0], br[8], br[16], br[24]};
@@ -952,11 +948,7 @@ SCAML_DEVICE void small_gemm(SAcc& o, const double* A, const double* B, const FT
   const double* ar = A + t.t4 * kLd + 16 * (t.warp >> 1) + t.g;
   const double* br = B + t.t4 * kLd + 16 * (t.warp & 1) + t.g;
   if (ABL(256)) return;
-#ifdef SCAML_FIT_UNROLL_FULL
-#pragma unroll
-#else
 #pragma unroll 4
-#endif
   for (int s = 0; s < 8; ++s) {
     const double a0 = ar[0], a1 = ar[8], b0 = br[0], b1 = br[8];
     ar += 4 * kLd;

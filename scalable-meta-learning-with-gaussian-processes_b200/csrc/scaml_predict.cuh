@@ -392,11 +392,7 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
         double mu[CBT * 8];  // [h][j][e] -> 8 h + 2 j + e : sum over this lane's rows of k* alpha
 #pragma unroll
         for (int v = 0; v < CBT * 8; ++v) mu[v] = 0.0;
-#ifdef SCAML_PRED_NOASM
-        for (int rbk = warp; rbk < 0; rbk += 8) {
-#else
         for (int rbk = warp; rbk < nb; rbk += 8) {
-#endif
 #pragma unroll
           for (int h = 0; h < CBT; ++h) {
             double nc[4][2];
@@ -431,9 +427,7 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
               }
               // cancellation may leave r^2 = -1e-16 where gpytorch clamps to 0: exp(+5e-17) rounds to 1 all the
               // same, and the Matern kernels clamp r^2 to >= 1e-30 themselves (an FP64 max is 7 instructions)
-#ifndef SCAML_PRED_NOEXP
               kappa_n<KIND, 8 * RI, false>(r2, r2, r2);
-#endif
               double* kt = kst + (size_t)(rbk * CBT + h) * kPTile + (8 * RI * ip + g) * kPLd + 2 * t4;
 #pragma unroll
               for (int i2 = 0; i2 < RI; ++i2) {
@@ -592,9 +586,7 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
       PPROF(4);
       for (int q = 0; q < L; ++q) {
         cp_async_wait<1>();
-#ifndef SCAML_PRED_NOSYNC
         group_sync(gi);  // tile q visible to the group; the group has finished reading tile q-1
-#endif
         if (issued < L) {
           gtile_async(gslot(stage, gi, issued % kPStages), Lm + (size_t)(tri(qi.r) + qi.ck) * kTile, gtid);
           ++issued;
@@ -602,7 +594,6 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
         }
         cp_async_commit();  // always commit (possibly empty): keeps the wait<1> accounting uniform
         const bool dg = (qc.ck == qc.r);  // diagonal tile: L^-1(r, kk) = 0 for kk > r
-#ifndef SCAML_PRED_NOPROD
         {
           const double* ar = gslot(stage, gi, q % kPStages) + t4 * kPLd + g;
           const double* br = kst + (qc.ck * CBT + cb) * kPTile + t4 * kPLd + cin + g;
@@ -622,7 +613,6 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
               }
           }
         }
-#endif
         if (dg) {  // row block complete: ||V_r||^2 per candidate column
 #pragma unroll
           for (int j = 0; j < NJ; ++j)
