@@ -164,84 +164,73 @@ SCAML_DEVICE double dbl_make(int hi, int lo) { return __hiloint2double(hi, lo); 
 SCAML_DEVICE double exp2_tab(int j) { return __ldg(kExp2Tab + j); }
 #endif
 
-#ifndef SCAML_EXP_POLY
 // U independent exponentials, written step-major so that the U dependent chains are interleaved in the
 // instruction stream (in[u] <= 0; out may alias in).  Range handling is ONE clamp of the argument to >= -708
 // (compare + two selects; NaN fails the compare and propagates through the FP64 chain, its low word is 0 on
 // the GPU so that n = 0): below -708 the function returns exp(-708) = 3.3e-308 instead of a denormal or 0 --
 // 18 instructions per value instead of 25 with per-value flush / NaN selects (the k* assemblies are bound by
 // issue slots, not by the FP64 pipe).
-template <int U>
+// TAB = false: table-free variant, x = n ln2 + r, degree-13 polynomial (17 FP64 instructions, no load) for kernels
+// whose load / store pipe is the scarce resource (kernel-matrix assembly).
+template <int U, bool TAB = true>
 SCAML_DEVICE void exp_nonpos_n(const double (&in)[U], double (&out)[U]) {
   const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
   double r[U], p[U], tab[U];
   int n[U];
+  if (TAB) {
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const double x = (in[u] < -708.0) ? -708.0 : in[u];
-    const double t = fma(x, 92.33248261689366, kMagic);  // 64 / ln 2
-    const int k = dbl_lo(t);                             // round(64 x / ln 2) = 64 n + j, n >= -1022
-    tab[u] = exp2_tab(k & 63);
-    n[u] = k >> 6;
-    const double kf = t - kMagic;
-    // ln2/64 split: the high part has 35 significant bits, so kf * hi is exact for |kf| < 2^17
-    r[u] = fma(kf, -0x1.1cf79abc9e3b4p-42, fma(kf, -0x1.62e42fef80000p-7, x));
-    p[u] = fma(8.3333333333333332177e-03, r[u], 4.1666666666666664354e-02);  // 1/5!, 1/4!
+    for (int u = 0; u < U; ++u) {
+      const double x = (in[u] < -708.0) ? -708.0 : in[u];
+      const double t = fma(x, 92.33248261689366, kMagic);  // 64 / ln 2
+      const int k = dbl_lo(t);                             // round(64 x / ln 2) = 64 n + j, n >= -1022
+      tab[u] = exp2_tab(k & 63);
+      n[u] = k >> 6;
+      const double kf = t - kMagic;
+      // ln2/64 split: the high part has 35 significant bits, so kf * hi is exact for |kf| < 2^17
+      r[u] = fma(kf, -0x1.1cf79abc9e3b4p-42, fma(kf, -0x1.62e42fef80000p-7, x));
+      p[u] = fma(8.3333333333333332177e-03, r[u], 4.1666666666666664354e-02);  // 1/5!, 1/4!
 #ifdef SCAML_EMU
-    if (x != x) n[u] = 0;  // host NaNs keep their payload: low word not necessarily 0
+      if (x != x) n[u] = 0;  // host NaNs keep their payload: low word not necessarily 0
 #endif
-  }
+    }
 #pragma unroll
-  for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], 1.6666666666666665741e-01);
+    for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], 1.6666666666666665741e-01);
 #pragma unroll
-  for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], 0.5);
+    for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], 0.5);
 #pragma unroll
-  for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], 1.0);
+    for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], 1.0);
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const double q = fma(tab[u], p[u] * r[u], tab[u]);  // T (1 + r poly): in [0.99, 2); NaN for NaN
-    out[u] = dbl_make(dbl_hi(q) + n[u] * 1048576, dbl_lo(q));
+    for (int u = 0; u < U; ++u) {
+      const double q = fma(tab[u], p[u] * r[u], tab[u]);  // T (1 + r poly): in [0.99, 2); NaN for NaN
+      out[u] = dbl_make(dbl_hi(q) + n[u] * 1048576, dbl_lo(q));
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double x = (in[u] < -708.0) ? -708.0 : in[u];
+      const double t = fma(x, 1.4426950408889634074, kMagic);
+      n[u] = dbl_lo(t);  // round(x / ln 2) >= -1022
+      const double nf = t - kMagic;
+      r[u] = fma(nf, -1.90821492927058770002e-10, fma(nf, -6.93147180369123816490e-01, x));
+      p[u] = fma(1.6059043836821614599e-10, r[u], 2.0876756987868098979e-09);  // 1/13!, 1/12!
+#ifdef SCAML_EMU
+      if (x != x) n[u] = 0;
+#endif
+    }
+    const double c[11] = {2.5052108385441718775e-08, 2.7557319223985890653e-07, 2.7557319223985892511e-06,
+                          2.4801587301587301566e-05, 1.9841269841269841253e-04, 1.3888888888888889419e-03,
+                          8.3333333333333332177e-03, 4.1666666666666664354e-02, 1.6666666666666665741e-01, 0.5, 1.0};
+#pragma unroll
+    for (int k = 0; k < 11; ++k)
+#pragma unroll
+      for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], c[k]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double q = fma(p[u], r[u], 1.0);  // in [0.7, 1.42]
+      out[u] = dbl_make(dbl_hi(q) + n[u] * 1048576, dbl_lo(q));
+    }
   }
 }
-#else  // A/B variant: table-free degree-13 polynomial (17 FP64 instructions per value)
-// U independent exponentials, written step-major so that the U dependent chains are interleaved in the
-// instruction stream (in[u] <= 0; out may alias in).
-template <int U>
-SCAML_DEVICE void exp_nonpos_n(const double (&in)[U], double (&out)[U]) {
-  const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: adding it rounds to the nearest integer
-  double r[U], p[U];
-  int n[U], xh[U], xl[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const double x = in[u];
-    xh[u] = dbl_hi(x);
-    xl[u] = dbl_lo(x);
-    const double t = fma(x, 1.4426950408889634074, kMagic);
-    n[u] = dbl_lo(t);
-    const double nf = t - kMagic;
-    r[u] = fma(nf, -1.90821492927058770002e-10, fma(nf, -6.93147180369123816490e-01, x));
-    p[u] = fma(1.6059043836821614599e-10, r[u], 2.0876756987868098979e-09);  // 1/13!, 1/12!
-  }
-  const double c[11] = {2.5052108385441718775e-08, 2.7557319223985890653e-07, 2.7557319223985892511e-06,
-                        2.4801587301587301566e-05, 1.9841269841269841253e-04, 1.3888888888888889419e-03,
-                        8.3333333333333332177e-03, 4.1666666666666664354e-02, 1.6666666666666665741e-01, 0.5, 1.0};
-#pragma unroll
-  for (int k = 0; k < 11; ++k)
-#pragma unroll
-    for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], c[k]);
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const double q = fma(p[u], r[u], 1.0);
-    int hi = dbl_hi(q) + n[u] * 1048576, lo = dbl_lo(q);
-    // |x| >= 707 (incl. -inf / NaN): 0, or NaN for NaN -- selects only, no branch
-    const bool big = ((unsigned)xh[u] & 0x7fffffffu) >= 0x40861800u;
-    const bool neg = in[u] < 0.0;  // false for NaN
-    hi = big ? (neg ? 0 : xh[u]) : hi;
-    lo = big ? (neg ? 0 : xl[u]) : lo;
-    out[u] = dbl_make(hi, lo);
-  }
-}
-#endif
 SCAML_DEVICE double exp_nonpos(double x) {
   const double in[1] = {x};
   double out[1];
@@ -292,7 +281,7 @@ SCAML_DEVICE void kappa_pair(double r2, double& k, double& kd) {
 }
 
 // U kernel values at once (independent chains interleaved): k[u] = kappa(r2[u]), kd[u] = -2 dkappa/dr^2
-template <int KIND, int U, bool WITH_KD>
+template <int KIND, int U, bool WITH_KD, bool TAB = true>
 SCAML_DEVICE void kappa_n(const double (&r2)[U], double (&k)[U], double (&kd)[U]) {
   double arg[U], r[U], e[U];
 #pragma unroll
@@ -306,7 +295,7 @@ SCAML_DEVICE void kappa_n(const double (&r2)[U], double (&k)[U], double (&kd)[U]
                                                  : -2.2360679774997896964 * r[u];
     }
   }
-  exp_nonpos_n<U>(arg, e);
+  exp_nonpos_n<U, TAB>(arg, e);
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     if (KIND == SCAML_KERNEL_RBF) {

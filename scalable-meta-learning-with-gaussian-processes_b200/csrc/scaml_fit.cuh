@@ -415,7 +415,8 @@ SCAML_DEVICE void gemm_global(Acc& acc, const Src& src, double* stage, const FTh
     const long long pc0 = clock64();
 #endif
     // ONE barrier per step: after it sub-chunk s is visible to everyone and everyone has finished reading
-    // sub-chunk s-1, whose buffer the prefetch of s+1 may therefore overwrite.
+    // sub-chunk s-1, whose buffer the prefetch of s+1 may therefore overwrite.  (A third buffer in phase D -- dinvc is
+    // idle there -- with the prefetch two steps ahead measured -0.3 %: profiles/r2_fit_predication.txt.)
     cp_async_wait<0>();
     __syncthreads();
     if (s + 1 < n) stage_issue(src, s + 1, stage + ((s + 1) & 1) * 4 * kHalfS, t.tid);
@@ -886,6 +887,93 @@ SCAML_DEVICE void inv_32_follow(const double* Lc, const double* dg, volatile int
 #endif
 }
 
+// ---- X = L^-1 of a 32 x 32 lower-triangular factor, blocked 8 x 8 (default; -DSCAML_FIT_SWEEPINV: the sweep) -------- //
+// The substitution sweep above is 32 dependent steps of up to 31 broadcast loads + FMAs on ONE warp while the other
+// three warps of the CTA wait.  Blocked:  X_aa = L_aa^-1  for the four diagonal blocks at once (lane = 8 a + j solves
+// column j of block a: 7 dependent rows), then the sub-diagonals one after the other,
+//     X_ab = -X_aa (sum_{c = b}^{a-1} L_ac X_cb),        a - b = 1, 2, 3  (3, 2, 1 independent blocks each),
+// with every 8 x 8 x 8 product as two DMMAs: 32 DMMAs and ~40 dependent steps instead of 32 x 31 FMAs in 32 steps.
+// The sum S leaves the accumulator layout through a 64-double scratch per block to become the B operand of X_aa S.
+// Lc: L (C-layout padded).  myrs: lane k holds 1 / L(k, k).  Outputs as for the sweep: XC (C-layout padded), XRs
+// (R-layout padded, optional), XRg (R-layout dense global, optional), zeros above the diagonal.  Pz: >= 192 doubles.
+SCAML_DEVICE void inv_32_blocked(const double* Lc, double* Pz, double* XC, double* XRs, double* XRg, int lane,
+                                 double myrs) {
+  const int a = lane >> 3, j = lane & 7;
+  const int g = lane >> 2, t4 = lane & 3;
+  // diagonal blocks: column j of X_aa by forward substitution (rows above j stay 0)
+  {
+    double x[8];
+    const double* La = Lc + (8 * a) * kLd + 8 * a;  // La[k * kLd + r] = L_aa(r, k)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const double rsr = __shfl_sync(0xffffffffu, myrs, 8 * a + r);
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < r; ++k) {
+        if (k & 1) s1 = fma(La[k * kLd + r], x[k], s1);
+        else s0 = fma(La[k * kLd + r], x[k], s0);
+      }
+      x[r] = (r < j) ? 0.0 : ((r == j) ? rsr : -(s0 + s1) * rsr);
+    }
+    double* xc = XC + (8 * a + j) * kLd + 8 * a;
+#pragma unroll
+    for (int r = 0; r < 8; r += 2) *reinterpret_cast<double2*>(xc + r) = make_double2(x[r], x[r + 1]);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (XRs) XRs[(8 * a + r) * kLd + 8 * a + j] = x[r];
+      if (XRg) XRg[(8 * a + r) * kBS + 8 * a + j] = x[r];
+    }
+    // zeros above the block diagonal: block (a, bb), bb > a, column j of it
+    for (int bb = a + 1; bb < 4; ++bb) {
+      double* zc = XC + (8 * bb + j) * kLd + 8 * a;
+#pragma unroll
+      for (int r = 0; r < 8; r += 2) *reinterpret_cast<double2*>(zc + r) = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (XRs) XRs[(8 * a + r) * kLd + 8 * bb + j] = 0.0;
+        if (XRg) XRg[(8 * a + r) * kBS + 8 * bb + j] = 0.0;
+      }
+    }
+  }
+  __syncwarp();
+  // sub-diagonals: the blocks of one sub-diagonal are independent
+#pragma unroll
+  for (int dlt = 1; dlt < 4; ++dlt) {
+    double R[3][2];
+#pragma unroll
+    for (int b = 0; b + dlt < 4; ++b) {
+      const int aa = b + dlt;
+      double S[2] = {0.0, 0.0};
+#pragma unroll
+      for (int c = b; c < aa; ++c)
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2)  // S += L_ac X_cb : A[row][k] = L(8 aa + row, 8 c + k), B[k][col] = X(8 c + k, 8 b + col)
+          dmma884(S, Lc[(8 * c + 4 * s2 + t4) * kLd + 8 * aa + g], XC[(8 * b + g) * kLd + 8 * c + 4 * s2 + t4]);
+      *reinterpret_cast<double2*>(Pz + 64 * b + 8 * g + 2 * t4) = make_double2(S[0], S[1]);  // S(g, 2 t4 + e)
+    }
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b + dlt < 4; ++b) {
+      const int aa = b + dlt;
+      R[b][0] = R[b][1] = 0.0;
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2)  // R = X_aa S : A[row][k] = X(8 aa + row, 8 aa + k), B[k][col] = S(k, col)
+        dmma884(R[b], XC[(8 * aa + 4 * s2 + t4) * kLd + 8 * aa + g], Pz[64 * b + 8 * (4 * s2 + t4) + g]);
+    }
+    __syncwarp();  // S consumed before the next sub-diagonal overwrites the scratch
+#pragma unroll
+    for (int b = 0; b + dlt < 4; ++b) {
+      const int aa = b + dlt;
+      const double v0 = -R[b][0], v1 = -R[b][1];  // X_ab(g, 2 t4 + e)
+      XC[(8 * b + 2 * t4) * kLd + 8 * aa + g] = v0;
+      XC[(8 * b + 2 * t4 + 1) * kLd + 8 * aa + g] = v1;
+      if (XRs) *reinterpret_cast<double2*>(XRs + (8 * aa + g) * kLd + 8 * b + 2 * t4) = make_double2(v0, v1);
+      if (XRg) *reinterpret_cast<double2*>(XRg + (8 * aa + g) * kBS + 8 * b + 2 * t4) = make_double2(v0, v1);
+    }
+    __syncwarp();  // X of this sub-diagonal visible to the next one
+  }
+}
+
 SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* XC, double* XRs, double* XRg,
                              double* logdet, int lane) {
 #if defined(SCAML_PROF) && !defined(SCAML_PROF_GEMM)
@@ -911,6 +999,10 @@ SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* 
   double ld = log(mydiag);
   ld = warp_sum(ld);
   if (lane == 0) *logdet += ld;
+#ifndef SCAML_FIT_SWEEPINV
+  __syncwarp();
+  inv_32_blocked(Lc, Pz, XC, XRs, XRg, lane, myrs);
+#else
   // inverse, row `lane` of X = L^-1 by a backward column sweep on L^T
   double b[kBS];
 #pragma unroll
@@ -931,6 +1023,7 @@ SCAML_DEVICE int chol_inv_32(const double* Dsm, double* Lc, double* Pz, double* 
     }
   }
   __syncwarp();
+#endif
 #if defined(SCAML_PROF) && !defined(SCAML_PROF_GEMM)
   if (lane == 0) profsm[15] += clock64() - pc_b;  // chain warp: log det + 32 inverse steps + transposed outputs
 #endif

@@ -330,7 +330,13 @@ __global__ void __launch_bounds__(256, 3) scaml_kmat_task_kernel(const KmatParam
             for (int j = 0; j < 2; ++j) dmma884s(kv[4 * i + 2 * j], kv[4 * i + 2 * j + 1], a[i], b[j]);
         }
       }
+#ifdef SCAML_KMAT_TABEXP
       kappa_n<KIND, 16, false>(kv, kv, kv);  // 16 independent exponentials, interleaved
+#else
+      // table-free exp: this kernel's scarce resource is the load / store pipe (78 % busy with the table variant, a
+      // third of it table lookups), not the FP64 pipe
+      kappa_n<KIND, 16, false, false>(kv, kv, kv);
+#endif
       // blocks off the diagonal tiles and fully inside the valid range need no per-element masks: warp-uniform
       const bool interior = (ti != tj) && (r0 + 32 <= nv);
       if (interior) {

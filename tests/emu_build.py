@@ -29,7 +29,8 @@ def build_emu(force: bool = False) -> str:
         if all(os.path.getmtime(d) <= t for d in _sources()):
             return EMU_LIB
     tmp = EMU_LIB + f".{os.getpid()}.tmp"  # several test processes may build at once: write, then rename
-    cmd = ["g++", "-std=c++17", "-O2", "-mfma", "-DSCAML_EMU", "-x", "c++", "-fPIC", "-shared", "-pthread",
+    extra = os.environ.get("SCAML_EMU_DEFS", "").split()  # A/B experiment switches, e.g. "-DSCAML_FIT_BLOCKINV"
+    cmd = ["g++", "-std=c++17", "-O2", "-mfma", "-DSCAML_EMU"] + extra + ["-x", "c++", "-fPIC", "-shared", "-pthread",
            "-o", tmp, "scaml_capi.cu"]
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
