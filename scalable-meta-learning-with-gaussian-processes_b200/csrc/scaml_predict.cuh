@@ -202,6 +202,12 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
   constexpr int QN = kPredThreads / CT;  // row phases of the thread <-> candidate passes (4 for CT = 64, 8 for CT = 32)
   // Matern-1/2 assembles k* from direct differences (thread <-> candidate), everything else through the tensor cores
   constexpr bool kDirect = (KIND == SCAML_KERNEL_MATERN12);
+  // RBF: the tensor-core product delivers the ARGUMENT of the exponential, log(s) - r^2 / 2, directly -- operand scales
+  // (a . c instead of -2 a . c, norms times -1/2) and log(outputscale) in the norm row of the task's points -- so the
+  // exponential IS the scaled kernel value: no multiply by -1/2, none by the outputscale, and the rows beyond n_valid
+  // get -1e4 there (exp -> 3e-308, whose square underflows to 0) instead of a select per pair
+  constexpr bool kArg = (KIND == SCAML_KERNEL_RBF);
+  constexpr double kCs = kArg ? 1.0 : -2.0, kNs = kArg ? -0.5 : 1.0;
   SCAML_DYN_SMEM(double, sm);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
   const int gi = warp >> 2, gtid = tid & (kPGroupThreads - 1);  // product group, thread index inside it
@@ -277,6 +283,7 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
         invl[tid] = 1.0 / (have ? th_n : th[tid]);
         ctr[tid] = have ? ctr_n : Xm[tid];
       }
+      const double nadd = kArg ? log(os) : 0.0;  // uniform; the norm row below carries it into every argument
       __syncthreads();  // previous task fully consumed (kst, stage, aux); invl, ctr visible
       PPROF(0);
       GChunk qi{gi, 0};
@@ -312,7 +319,7 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
             nn = fma(v, v, nn);
           }
           xst[d * XS + tid] = 1.0;
-          xst[(d + 1) * XS + tid] = nn;
+          xst[(d + 1) * XS + tid] = (kArg && tid >= nv) ? -1e4 : fma(kNs, nn, nadd);
           alp[tid] = have ? apre : p.alpha[(size_t)m * n_pad + tid];
         }
         for (int a = tid + kPredThreads; a < npt; a += kPredThreads) {
@@ -323,7 +330,7 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
             nn = fma(v, v, nn);
           }
           xst[d * XS + a] = 1.0;
-          xst[(d + 1) * XS + a] = nn;
+          xst[(d + 1) * XS + a] = (kArg && a >= nv) ? -1e4 : fma(kNs, nn, nadd);
           alp[a] = p.alpha[(size_t)m * n_pad + a];
         }
         if (tid < 4 * CT) {  // candidate c = tid / 4, dimensions k = tid % 4, + 4, ..; |c|^2 by a fixed-order quad sum
@@ -331,13 +338,13 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
           double nn = 0.0;
           for (int k = tid & 3; k < d; k += 4) {
             const double v = (xcr[k * CT + c] - ctr[k]) * invl[k];
-            xcs[k * CS + c] = -2.0 * v;
+            xcs[k * CS + c] = kCs * v;
             nn = fma(v, v, nn);
           }
           nn += __shfl_xor_sync(0xffffffffu, nn, 1);
           nn += __shfl_xor_sync(0xffffffffu, nn, 2);
           if ((tid & 3) == 0) {
-            xcs[d * CS + c] = nn;
+            xcs[d * CS + c] = kNs * nn;
             xcs[(d + 1) * CS + c] = 1.0;
           }
         }
@@ -362,7 +369,7 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
 #pragma unroll
           for (int u = 0; u < U; ++u) r2[u] = 0.0;
           for (int k = 0; k < d; ++k) {
-            const double xc = -0.5 * xcs[k * CS + c];
+            const double xc = -0.5 * xcs[k * CS + c];  // kDirect is a Matern kernel: scale -2
             const double* xr = xst + k * XS + a0;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -427,14 +434,16 @@ __global__ void __launch_bounds__(kPredThreads, 1) scaml_predict_kernel(const Pr
               }
               // cancellation may leave r^2 = -1e-16 where gpytorch clamps to 0: exp(+5e-17) rounds to 1 all the
               // same, and the Matern kernels clamp r^2 to >= 1e-30 themselves (an FP64 max is 7 instructions)
-              kappa_n<KIND, 8 * RI, false>(r2, r2, r2);
+              if (kArg) exp_nonpos_n<8 * RI>(r2, r2);  // r2 holds log(s) - r^2 / 2 (<= log s; the exp takes small positive arguments)
+              else kappa_n<KIND, 8 * RI, false>(r2, r2, r2);
               double* kt = kst + (size_t)(rbk * CBT + h) * kPTile + (8 * RI * ip + g) * kPLd + 2 * t4;
 #pragma unroll
               for (int i2 = 0; i2 < RI; ++i2) {
                 const double osa = (arow + 8 * i2 < nv) ? os : 0.0, al = alp[arow + 8 * i2];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const double k0 = osa * r2[8 * i2 + 2 * j], k1 = osa * r2[8 * i2 + 2 * j + 1];
+                  const double k0 = kArg ? r2[8 * i2 + 2 * j] : osa * r2[8 * i2 + 2 * j];
+                  const double k1 = kArg ? r2[8 * i2 + 2 * j + 1] : osa * r2[8 * i2 + 2 * j + 1];
                   *reinterpret_cast<double2*>(kt + 8 * i2 * kPLd + 8 * j) = make_double2(k0, k1);
                   mu[8 * h + 2 * j] = fma(k0, al, mu[8 * h + 2 * j]);
                   mu[8 * h + 2 * j + 1] = fma(k1, al, mu[8 * h + 2 * j + 1]);

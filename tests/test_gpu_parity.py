@@ -149,6 +149,8 @@ def test_factorize_and_weighted_prediction(engine):
     (320, 6, 0, [320, 257, 100]),    # 32-candidate tiles (k* of 64 candidates no longer fits shared memory)
     (512, 10, 3, [512, 400, 1]),     # config-4 shape: 32-candidate tiles, task staging aliased onto the L^-1 stages
     (256, 20, 2, [256, 130, 64]),    # 64-candidate tiles, aliased staging (large d)
+    (256, 6, 1, [256, 130, 64]),     # Matern-1/2: k* from direct differences (not smooth in r^2), no tensor-core distances
+    (192, 7, 0, [192, 77, 3]),       # d = 7: the norm rows do not fit the contraction's padding (accumulator-init path)
 ])
 def test_weighted_prediction_other_layouts(engine, n, d, kernel, nvs):
     M, B = len(nvs), 150
