@@ -76,6 +76,11 @@ class ContinuousParameter:
         lo, hi = self.bounds
         return (float(v) - lo) / (hi - lo)
 
+    def to_num_array(self, v: np.ndarray) -> np.ndarray:
+        """`to_num` on a float array (same operations in the same order: bit-identical to the scalar path)."""
+        lo, hi = self.bounds
+        return (v - lo) / (hi - lo)
+
     def from_num(self, u: float):
         lo, hi = self.bounds
         return lo + min(max(float(u), 0.0), 1.0) * (hi - lo)
@@ -90,6 +95,10 @@ class IntegerParameter(ContinuousParameter):
     def to_num(self, v) -> float:
         lo, hi = self.bounds
         return (float(v) - lo + 0.5) / (hi - lo + 1.0)
+
+    def to_num_array(self, v: np.ndarray) -> np.ndarray:
+        lo, hi = self.bounds
+        return (v - lo + 0.5) / (hi - lo + 1.0)
 
     def from_num(self, u: float):
         lo, hi = self.bounds
@@ -171,7 +180,16 @@ class ParameterSpace:
         out = np.full((len(configs), len(self._params)), np.nan)
         for i, p in enumerate(self._params):
             name, conv = p.name, p.to_num
-            out[:, i] = [conv(v) if (v := c.get(name)) is not None else np.nan for c in configs]
+            col = [c.get(name) for c in configs]
+            if type(p) in (ContinuousParameter, IntegerParameter):
+                # numeric parameters: one vectorised transform per column (the meta-data of 4096 tasks x 256 points
+                # are 6 million values: a Python call per value was 3 of the 5 s of ScaMLGPBO's construction)
+                try:
+                    out[:, i] = p.to_num_array(np.array(col, dtype=float))
+                    continue
+                except (TypeError, ValueError):
+                    pass  # inactive (None) or non-numeric entries: value by value below
+            out[:, i] = [conv(v) if v is not None else np.nan for v in col]
         return out
 
     def from_numerical(self, vec) -> Dict[str, Any]:
