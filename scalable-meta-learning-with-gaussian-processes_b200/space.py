@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import json
 import math
+import operator
 import time
 from dataclasses import dataclass, field
 from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tuple
@@ -178,6 +179,18 @@ class ParameterSpace:
     def to_numerical_batch(self, configs: Sequence[Dict[str, Any]]) -> np.ndarray:
         """[n, d] numerical representation of many configurations (column-wise: one pass per parameter)."""
         out = np.full((len(configs), len(self._params)), np.nan)
+        if len(configs) and all(type(p) in (ContinuousParameter, IntegerParameter) for p in self._params):
+            # all-numeric space, every parameter present in every configuration: ONE array conversion
+            try:
+                names = [p.name for p in self._params]
+                get = operator.itemgetter(*names)
+                rows = list(map(get, configs)) if len(names) > 1 else [(get(c),) for c in configs]
+                raw = np.array(rows, dtype=float)
+                for i, p in enumerate(self._params):
+                    out[:, i] = p.to_num_array(raw[:, i])
+                return out
+            except (KeyError, TypeError, ValueError):
+                pass  # conditional / inactive parameters: column by column below
         for i, p in enumerate(self._params):
             name, conv = p.name, p.to_num
             col = [c.get(name) for c in configs]
