@@ -16,7 +16,7 @@ reported beside it under `weak_scaling`.
 
 Further legs on the same line: `posterior` (second half of the metric, config 5: weighted mean + variance of the
 4096 base GPs at 1 Mi candidates, tasks sharded, candidates replicated, one all_reduce over [2, B]), `config4`
-(16384 tasks x n=512 x d=10 on the 8-warp blocked DMMA Cholesky kernel), `kernel_matrix` (stand-alone assembly,
+(16384 tasks x n=512 x d=10, blocked DMMA Cholesky), `kernel_matrix` (stand-alone assembly,
 HBM-bound), `conditioned` and `acq_grad` (target-GP conditioning and analytic candidate gradients).
 `--metric posterior` prints the posterior leg as its own line (same contract) so that the driver can pair it with
 `--impl reference --metric posterior`.
@@ -683,7 +683,7 @@ def run_ours(args) -> None:
                             "traffic_note": "DRAM bytes of the dominant kernel only (cond_prepare, 64-column panel)"}}
         return cond, acq
 
-    # ---- config 4: 16384 tasks x n = 512 x d = 10 on the 8-warp blocked DMMA Cholesky kernel ---------------- #
+    # ---- config 4: 16384 tasks x n = 512 x d = 10, blocked DMMA Cholesky (4-warp kernel, 2 CTAs/SM at this n) ---- #
     def config4_bench():
         nblocks = C4_TASKS // C4_BLOCK
         if nblocks % world != 0:
@@ -712,16 +712,16 @@ def run_ours(args) -> None:
         F4 = algorithmic_flops(C4_N, C4_D)
         ach = float(M4) * C4_R * F4 / (ms4 / 3 * 1e-3) / 1e12
         peak = peaks.get("dfma", 0.0) or None
-        traffic, stale, tl = ncu_traffic("scaml_fit8_kernel<RBF>")
+        traffic, stale, tl = ncu_traffic("scaml_fit_kernel<RBF> config4")
         out = {"metric": "meta-task LML+grad evals/s (n=512,d=10)", "value": float(C4_TASKS) * C4_R * 3 / (ms4 * 1e-3),
                "unit": "evals/s", "ms_per_step": ms4 / 3, "steps": 3, "n_gpus": world, "scaling": "strong",
                "config": {"workload": f"config4: {C4_TASKS} meta-tasks in total x n={C4_N} x d={C4_D}, R={C4_R} rows/task, "
-                                      "blocked DMMA Cholesky (8-warp kernel), tasks block-partitioned over the GPUs",
+                                      "blocked DMMA Cholesky (4-warp kernel, 2 CTAs/SM), tasks block-partitioned over the GPUs",
                           "tasks_per_gpu": M4, "all_info_zero": bool(ok4)},
                "gpu_launches": nl4,
                "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                             "frac": (ach / peak) if peak else None, "flops_per_eval": F4,
-                            "kernel": "scaml_fit8_kernel<RBF>", "traffic": traffic, "traffic_stale": stale,
+                            "kernel": "scaml_fit_kernel<RBF> (4-warp; n = 512: 2 CTAs/SM)", "traffic": traffic, "traffic_stale": stale,
                             "traffic_launch": tl}}
         del b4, t4, o4
         return out

@@ -18,7 +18,7 @@ NAMES = ["setup", "B gemm(update)", "B assemble(exp)+store", "B diag_factor", "B
 
 def main():
     M, R, n, d = (int(a) for a in (sys.argv[1:5] + ["1184", "2", "256", "6"][len(sys.argv) - 1:]))
-    lib = ScamlLib(build.build_prof())
+    lib = ScamlLib(os.environ["SCAML_LIB"] if os.environ.get("SCAML_LIB") else build.build_prof())
     import ctypes as C
 
     eng = Engine(torch.device("cuda:0"), lib=lib)

@@ -126,7 +126,10 @@ namespace {
 // Two variants of the fit kernel (same algorithm, same results): 4-warp CTAs, three per SM (scaml_fit.cuh), and
 // 8-warp CTAs, two per SM (scaml_fit8.cuh).  Measured on B200 (profiles/r1_fit_variants.txt): the 4-warp
 // kernel wins up to n = 320 (RBF 722k vs 652k evals/s, Matern-5/2 626k vs 604k at n = 256), the 8-warp kernel
-// for larger tasks (118k vs 110k at n = 512, d = 10).  SCAML_FIT_IMPL=4|8 forces one (A/B runs).
+// for larger tasks (118k vs 110k at n = 512, d = 10).  Round 2: with the lower-triangle skipping as a template
+// parameter and the split of the diagonal super-tiles' full tile (scaml_fit.cuh) the 4-warp kernel also wins at
+// n = 512 (126.9k vs 121.9k evals/s for 2048 x R2 x 512 x 10; a tie at n = 384; 484k vs 424k at n = 320), so the
+// 8-warp kernel is left for tasks beyond 512 points.  SCAML_FIT_IMPL=4|8 forces one (A/B runs).
 }  // namespace
 __attribute__((visibility("hidden"))) int scaml_detail_dispatch_fit8(const scaml::FitParams& p, int grid, size_t smem,
                                                                    void* stream);
@@ -138,7 +141,7 @@ bool use_fit8(int n_pad, int kernel) {
     if (v == 8) return true;
   }
   (void)kernel;
-  return n_pad >= 384;
+  return n_pad > 512;
 }
 
 int dispatch_fit(const scaml::FitParams& p, int grid, size_t smem, void* stream) {

@@ -2,7 +2,7 @@
 `ncu --set full` capture runs (profiles/r2_*_ncu_summary.txt, profiles/ncu_traffic.json):
 
   scaml_fit_kernel<RBF>            config 3: 4096 tasks x R6 x n=256 x d=6
-  scaml_fit8_kernel<RBF>           config 4 block: 2048 tasks x R2 x n=512 x d=10
+  scaml_fit_kernel<RBF>            config 4 block: 2048 tasks x R2 x n=512 x d=10 (2 CTAs/SM: grid 296)
   scaml_predict_kernel<RBF,64>     4096 fitted GPs x 18944 candidates (prior) and the CROSS variant (n_t = 32)
   scaml_kmat_kernel<RBF>           4096 x 256 x 256 kernel matrices
   scaml_cond_prepare_kernel<RBF>   K_m^-1 K_m(X_m, .) for 32 target inputs / 64 candidates
