@@ -104,12 +104,14 @@ inline long long fit_ws_doubles_host(int n_pad, int d) {
   const int NS = n_pad / kSB;
   return fit_tile_doubles_host(n_pad) + (long long)((NS * (NS + 1)) / 2) * kSB * kSB * 2;  // kappa and kd
 }
-// shared memory (doubles): stage 4608 | dinvc 3456 | y,z,alpha 3*n_pad | red 128 |
+// shared memory (doubles): stage 4608 | dinvc 3456 | z,alpha 2*n_pad | red 128 |
 //                          gsm 4*kMaxP | par 4*kMaxP+8 | flags 2
+// (y is read from global memory where the forward substitution needs it, 64 values per super-row: keeping a copy here
+//  cost 4 KB at n = 512 and with it the third co-resident CTA for every n_pad in 384 .. 512)
 inline size_t fit_smem_bytes(int n_pad, int d) {
   (void)d;
   return sizeof(double) *
-         (size_t)(kStage + 3 * kTileS + 3 * (size_t)n_pad + 128 + kFitWarps * kMaxP + 5 * kMaxP + 8 + 2);
+         (size_t)(kStage + 3 * kTileS + 2 * (size_t)n_pad + 128 + kFitWarps * kMaxP + 5 * kMaxP + 8 + 2);
 }
 
 // per-thread coordinates: warp (rb, cb) owns one 32x32 tile of the 64x64 super-tile as a 4x4
@@ -1252,8 +1254,7 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
   const int d = p.d, P = p.d + 2, n_pad_max = p.n_pad;
   double* stage = sm;             // 2 stages x 4 padded half tiles | 4 full padded tiles (C_in / S / diag)
   double* dinvc = stage + kStage;  // 3 padded tiles
-  double* yv = dinvc + 3 * kTileS;
-  double* zv = yv + n_pad_max;
+  double* zv = dinvc + 3 * kTileS;
   double* av = zv + n_pad_max;
   double* red = av + n_pad_max;  // 128
   double* gsm = red + 128;       // kFitWarps * kMaxP
@@ -1341,11 +1342,7 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
     __syncthreads();
     const double os = th[d];
     const double* Xm = p.X + (size_t)m * p.n_max * d;
-    {
-      const double* ym = p.y + (size_t)m * p.n_max;
-      for (int i = t.tid; i < n_pad; i += kFitThreads) yv[i] = (i < nv) ? ym[i] : 0.0;
-    }
-    __syncthreads();
+    const double* ym = p.y + (size_t)m * p.n_max;
 
     Acc acc;
     double pig = 0.0;
@@ -1447,7 +1444,10 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
       // z_I = D_I^-1 (y_I - sum_{K<I} L(I,K) z_K)
       red[t.tid] = pig;
       __syncthreads();
-      if (t.tid < 64) av[t.tid] = yv[I * kSB + t.tid] - (red[t.tid] + red[64 + t.tid]);  // av: scratch here
+      if (t.tid < 64) {
+        const int iy = I * kSB + t.tid;
+        av[t.tid] = ((iy < nv) ? __ldg(ym + iy) : 0.0) - (red[t.tid] + red[64 + t.tid]);  // av: scratch here
+      }
       __syncthreads();
       dinv_matvec(zv + I * kSB, dinvc, av, red, t);
       PROF_MARK(7);
