@@ -16,8 +16,9 @@ COMMON = ["scaml_device.cuh"]
 # bench key -> (kernel-name substring, template filter, launch description, source files)
 KERNELS = {
     "scaml_fit_kernel<RBF>": ("scaml_fit_kernel<0>", None, "config3: 4096 tasks x R=6 x n=256 x d=6", ["scaml_fit.cuh"]),
-    # the same kernel at config 4's shape: told apart by its grid (n = 512: 2 CTAs per SM -> 296 CTAs; config 3: 444)
-    "scaml_fit_kernel<RBF> config4": ("scaml_fit_kernel<0>", 296, "config4 block: 2048 tasks x R=2 x n=512 x d=10",
+    # the same kernel at config 4's shape (same grid: 3 CTAs per SM at both shapes): told apart by the launch order of
+    # scripts/ncu_driver.py -- config 3, the factorize-mode launch (< 10 ms), then config 4
+    "scaml_fit_kernel<RBF> config4": ("scaml_fit_kernel<0>", "second", "config4 block: 2048 tasks x R=2 x n=512 x d=10",
                                       ["scaml_fit.cuh"]),
     "scaml_predict_kernel<RBF>": ("scaml_predict_kernel<0, 64, 0>", None, "4096 GPs x 18944 candidates",
                                   ["scaml_predict.cuh"]),
@@ -44,6 +45,7 @@ def scale(unit):
 def main(paths):
     out = {"source": "ncu --set full --clock-control none, one launch each at the bench's shapes (scripts/ncu_driver.py; "
                      "summaries profiles/r2_*_ncu_summary.txt)"}
+    fit_long = {}  # (capture, launch id) -> index among the long fit-kernel launches of that capture
     for path in paths:
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], dict(zip(rows[0], rows[1]))
@@ -62,11 +64,12 @@ def main(paths):
                     continue  # pass not collected (nan)
                 if key == "scaml_fit_kernel<RBF>" and ms < 10.0:
                     continue  # the factorize-mode launch of the same kernel
-                grid = int(float(d.get("launch__grid_size", "0").replace(",", "") or 0))
-                if key == "scaml_fit_kernel<RBF>" and grid == 296:
-                    continue  # config-4 launch: its own entry
-                if KERNELS[key][1] is not None and grid != KERNELS[key][1]:
-                    continue
+                if sub == "scaml_fit_kernel<0>":
+                    if ms < 10.0:
+                        continue  # the factorize-mode launch
+                    nth = fit_long.setdefault((path, d["ID"]), len({k for k in fit_long if k[0] == path}))
+                    if (key == "scaml_fit_kernel<RBF>") != (nth == 0):
+                        continue  # first long launch of a capture = config 3, second = config 4
                 files = COMMON + srcs
                 out[key] = {"dram_bytes_read": rd, "dram_bytes_write": wr, "duration_ms_under_ncu": ms, "launch": launch,
                             "sources": files, "source_sha16": sha16(files)}
