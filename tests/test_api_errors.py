@@ -168,3 +168,31 @@ def test_acquisition_optimiser_falls_back_without_gradient_support():
     base.acquisition_function_factory = lambda model: _AF()
     spec = base.generate_evaluation_specification()
     assert abs(spec.configuration["x"] - 0.5) < 0.05 and len(calls) == 1
+
+
+def test_to_numerical_batch_vector_paths_equal_the_scalar_conversion():
+    """ParameterSpace.to_numerical_batch (the meta-data conversion of metadata_to_numerical, reference
+    scamlgp/utils.py:98-106) has a one-shot array path for all-numeric spaces and a per-column path otherwise; both
+    must give exactly what the value-by-value `to_numerical` gives, including inactive (None / missing) entries."""
+    import numpy as np
+
+    from scamlgp_b200.space import CategoricalParameter, ContinuousParameter, IntegerParameter, ParameterSpace
+
+    rng = np.random.default_rng(0)
+    num = ParameterSpace()
+    for k in range(4):
+        num.add(ContinuousParameter(f"x{k}", (-1.0, 3.0)))
+    num.add(IntegerParameter("i", (2, 11)))
+    cfgs = [{**{f"x{k}": float(rng.uniform(-1, 3)) for k in range(4)}, "i": int(rng.integers(2, 12))} for _ in range(200)]
+    ref = np.stack([num.to_numerical(c) for c in cfgs])
+    assert np.array_equal(num.to_numerical_batch(cfgs), ref)            # one array conversion
+    cfgs[7]["x2"] = None
+    del cfgs[9]["i"]
+    ref = np.stack([num.to_numerical(c) for c in cfgs])
+    assert np.array_equal(num.to_numerical_batch(cfgs), ref, equal_nan=True)   # falls back column by column
+    mixed = ParameterSpace()
+    mixed.add(ContinuousParameter("lr", (1e-4, 1.0)))
+    mixed.add(CategoricalParameter("opt", ["sgd", "adam", "lion"]))
+    cfgs = [{"lr": float(rng.uniform(1e-4, 1)), "opt": ["sgd", "adam", "lion"][int(rng.integers(0, 3))]} for _ in range(50)]
+    ref = np.stack([mixed.to_numerical(c) for c in cfgs])
+    assert np.array_equal(mixed.to_numerical_batch(cfgs), ref)
