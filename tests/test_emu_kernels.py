@@ -69,10 +69,16 @@ def test_emu_reports_non_psd_pivot_and_jitter_recovers(emu_lib):
     assert abs(lml[0, 0] - float(v)) < 1e-6 * abs(float(v))  # cond ~ 1e8+: loose tolerance, see DESIGN.md
 
 
-def test_emu_factorize_and_weighted_prediction(emu_lib):
+@pytest.mark.parametrize("n,d,kernel,nvs", [
+    (128, 3, 0, [128, 77, 5]),   # RBF, d = 3: tensor-core distances, norm rows inside the contraction's padding
+    (70, 7, 0, [70, 64, 9]),     # d = 7: no room for the norm rows -> accumulators initialised with |a|^2 + |c|^2
+    (70, 3, 1, [70, 33, 2]),     # Matern-1/2: k* from direct differences (thread <-> candidate path)
+    (70, 4, 3, [70, 65, 1]),     # Matern-5/2 through the tensor-core distances (r^2, not the folded RBF argument)
+])
+def test_emu_factorize_and_weighted_prediction(emu_lib, n, d, kernel, nvs):
     lib = emu_lib
-    M, n, d, B = 3, 128, 3, 70
-    pb = make_problem(M, 2, n, d, seed=5, n_valid=[128, 77, 5])
+    M, B = 3, 70
+    pb = make_problem(M, 2, n, d, seed=5, n_valid=nvs, kernel=kernel)
     th = pb["th"][:, 1].contiguous()
     X = np.ascontiguousarray(pb["X"].numpy())
     y = np.ascontiguousarray(pb["yt"].numpy())
@@ -101,7 +107,7 @@ def test_emu_factorize_and_weighted_prediction(emu_lib):
     pws = np.zeros(pwb // 8 + 8)
     Xcn, wn = np.ascontiguousarray(Xc.numpy()), w.numpy().copy()
     lib.predict_weighted(P(X), P(pb["nv"]), P(theta), P(linv), P(alpha), P(pb["ybar"]), P(pb["ystd"]), P(wn), P(Xcn),
-                         P(mean), P(var), P(pws), pwb, M, n, d, B, 0)
+                         P(mean), P(var), P(pws), pwb, M, n, d, B, kernel)
     om, ov = O.scaml_prior_predict(states, w, Xc)
     assert rel_err(mean, om.numpy()) < TOL_MEAN_VAR
     assert rel_err(var, ov.numpy()) < TOL_MEAN_VAR
