@@ -213,17 +213,18 @@ def test_pipeline_on_gpu(engine, M, n, d, n_t, ragged):
 
 
 @pytest.mark.gpu
-def test_batched_lbfgs_reaches_scipy_lbfgsb_optimum(engine):
+@pytest.mark.parametrize("M,n,d,seed", [(12, 64, 6, 4), (8, 32, 2, 7), (4, 128, 4, 9), (6, 48, 10, 11)])
+def test_batched_lbfgs_reaches_scipy_lbfgsb_optimum(engine, M, n, d, seed):
     """The reference optimises with scipy L-BFGS-B (botorch fit_gpytorch_mll, utils.py:175); from the same
-    start our lock-step L-BFGS must end at an objective at least as good (up to the ftol both use)."""
+    start our lock-step L-BFGS must end at an objective at least as good (up to the ftol both use).  Shapes: the
+    Hartmann-6 family of config 2, the Branin shape of config 1 (d = 2, n = 32), a longer task and a d = 10 one."""
     from scipy.optimize import minimize
 
     from scamlgp_b200._capi import HyperSpec
     from scamlgp_b200.engine import SourceBatch
     from scamlgp_b200.fit import fit_sources
 
-    M, n, d = 12, 64, 6
-    X, Y = O.synthetic_tasks(M, n, d, seed=4)
+    X, Y = O.synthetic_tasks(M, n, d, seed=seed)
     ospec = O.HyperSpec.source()
     th0 = O.initial_theta_raw(d, ospec)
     batch = SourceBatch.from_padded(X.cuda(), Y.cuda())
