@@ -56,6 +56,9 @@ def main():
     ap.add_argument("--evals", type=int, default=40)
     ap.add_argument("--procs", type=int, default=8)
     ap.add_argument("--first", type=int, default=0, help="oracle arm: first study seed (results are merged into the JSON)")
+    ap.add_argument("--save", default=None, help="product arm: also write the per-study regrets (product, random search) "
+                    "to this JSON; --compare PATH re-prints the table from it against the oracle JSON without a GPU")
+    ap.add_argument("--compare", default=None)
     args = ap.parse_args()
     path = os.path.join(ROOT, "profiles", f"r2_bo_oracle_{args.bench}.json")
     marks = [m for m in (5, 10, 20, 40) if m <= args.evals]
@@ -76,14 +79,20 @@ def main():
         print(table(f"oracle loop (CPU, {len(out['regrets'])} studies)", list(out["regrets"].values()), marks))
         print(f"  {out['seconds_per_study']:.1f} s per study (1 thread)")
         return
-    import torch
-
-    from scamlgp_b200.engine import Engine
-
-    eng = Engine(torch.device("cuda:0"))
     ref = json.load(open(path)) if os.path.exists(path) else None
     prod, rs, secs = [], [], []
-    for s in range(args.studies):
+    if args.compare:
+        saved = json.load(open(args.compare))
+        prod, rs, secs = saved["product"], saved["random_search"], saved["seconds"]
+        args.studies, args.evals = len(prod), saved["evals"]
+        marks = [m for m in (5, 10, 20, 40) if m <= args.evals]
+    else:
+        import torch
+
+        from scamlgp_b200.engine import Engine
+
+        eng = Engine(torch.device("cuda:0"))
+    for s in range(0 if args.compare else args.studies):
         st = make_study(args.bench, s)
         t0 = time.perf_counter()
         prod.append(harness.run_product_study(st, eng, args.evals, s, af_optimizer_kwargs=dict(AF)))
@@ -92,6 +101,10 @@ def main():
         lo, hi = st2.bounds[:, 0], st2.bounds[:, 1]
         xs = lo + st2.rng.random((args.evals, len(lo))) * (hi - lo)
         rs.append(harness.compute_regrets(False, "loss", st2.optimum, [{"loss": st2.objective(x)} for x in xs]))
+    if args.save:
+        with open(args.save, "w") as f:
+            json.dump({"bench": args.bench, "evals": args.evals, "af": AF, "product": [list(map(float, r)) for r in prod],
+                       "random_search": [list(map(float, r)) for r in rs], "seconds": secs}, f)
     print(f"{args.bench}: {args.studies} studies x {args.evals} evaluations, identical seeds in every arm; simple regret "
           "(compute_regrets)")
     print(table("ScaMLGPBO on the B200", prod, marks))
