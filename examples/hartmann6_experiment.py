@@ -54,6 +54,7 @@ def main():
     ap.add_argument("--studies", type=int, default=4)
     ap.add_argument("--evals", type=int, default=40)
     ap.add_argument("--noise", type=float, default=0.1)
+    ap.add_argument("--methods", default="lbfgsb,batched", help="acquisition optimisers to run (comma-separated)")
     args = ap.parse_args()
     eng = Engine(torch.device("cuda:0"))
     space = ParameterSpace()
@@ -62,7 +63,7 @@ def main():
     obj = Objective("loss", False)
     marks = [m for m in (10, 20, 40, 80) if m <= args.evals]
     print(f"Hartmann-6, {args.tasks} meta-tasks x {args.points} points, noise {args.noise}, {args.studies} studies")
-    for method in ("lbfgsb", "batched"):
+    for method in args.methods.split(","):
         reg, reg_rs, t_fit, t_step = [], [], [], []
         for study in range(args.studies):
             rng = np.random.default_rng(study)

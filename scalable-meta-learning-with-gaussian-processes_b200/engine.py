@@ -94,6 +94,12 @@ class SourceBatch:
         M = len(tasks)
         d = tasks[0][0].shape[-1]
         n_max = max([int(t[0].shape[-2]) for t in tasks] + [int(n_max or 0)])
+        if all(int(t[0].shape[-2]) == n_max and t[0].dim() == 2 for t in tasks):
+            # every task has n_max points (the usual meta-data layout): two stacks instead of 2 M row-block copies
+            X = torch.stack([t[0].detach() for t in tasks]).to("cpu", torch.float64)
+            Y = torch.stack([t[1].detach().reshape(-1) for t in tasks]).to("cpu", torch.float64)
+            b = SourceBatch.from_padded(X.to(device), Y.to(device))
+            return b
         X = torch.zeros(M, n_max, d, dtype=torch.float64)
         Y = torch.zeros(M, n_max, dtype=torch.float64)
         nv = torch.zeros(M, dtype=torch.int32)

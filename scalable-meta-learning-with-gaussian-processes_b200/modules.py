@@ -254,6 +254,10 @@ class _CallableTensor(torch.Tensor):
     """botorch 0.7.3's SupervisedDataset exposes X / Y both as attributes with `.shape` and as callables
     (`task_data.X()`, scamlgp/model.py:180-181 vs `data.X.shape`, utils.py:117-118)."""
 
+    # attribute reads (`.shape`) and arithmetic on the container's tensors take the plain-Tensor path: without this every
+    # `task_data.X.shape` of validate_meta_data went through the __torch_function__ protocol (75 ms at 4096 tasks)
+    __torch_function__ = torch._C._disabled_torch_function_impl
+
     def __call__(self):
         return self.as_subclass(torch.Tensor)
 
