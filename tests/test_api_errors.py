@@ -196,3 +196,27 @@ def test_to_numerical_batch_vector_paths_equal_the_scalar_conversion():
     cfgs = [{"lr": float(rng.uniform(1e-4, 1)), "opt": ["sgd", "adam", "lion"][int(rng.integers(0, 3))]} for _ in range(50)]
     ref = np.stack([mixed.to_numerical(c) for c in cfgs])
     assert np.array_equal(mixed.to_numerical_batch(cfgs), ref)
+
+
+def test_dataset_tensors_and_uniform_upload_fast_paths():
+    """botorch's SupervisedDataset exposes X / Y as attributes with `.shape` AND as callables (reference model.py:180-181
+    vs utils.py:117-118); the stand-in keeps both, and the stacked upload of uniform tasks equals the row-block copies of
+    the ragged path."""
+    from scamlgp_b200.engine import SourceBatch
+    from scamlgp_b200.modules import SupervisedDataset
+
+    g = torch.Generator().manual_seed(0)
+    X = torch.rand(5, 7, 3, dtype=torch.float64, generator=g)
+    Y = torch.rand(5, 7, 1, dtype=torch.float64, generator=g)
+    ds = SupervisedDataset(X[0], Y[0])
+    assert ds.X.shape == (7, 3) and ds.Y.shape == (7, 1)
+    assert type(ds.X()) is torch.Tensor and torch.equal(ds.X(), X[0]) and torch.equal(ds.Y(), Y[0])
+    assert type(ds.X + 1.0) is torch.Tensor  # arithmetic leaves the container type
+    tasks = [(X[i], Y[i]) for i in range(5)]
+    fast = SourceBatch.from_ragged(tasks, "cpu")
+    slow = SourceBatch.from_ragged(tasks, "cpu", n_max=8)  # padded by one row: the general path
+    assert fast.uniform and not slow.uniform
+    assert torch.equal(fast.X, slow.X[:, :7]) and torch.equal(fast.Y_raw, slow.Y_raw[:, :7])
+    assert torch.equal(fast.n_valid, slow.n_valid)
+    assert torch.allclose(fast.y, slow.y[:, :7], rtol=0, atol=1e-15)
+    assert torch.allclose(fast.ybar, slow.ybar, rtol=0, atol=1e-15) and torch.allclose(fast.ystd, slow.ystd, rtol=0, atol=1e-15)
