@@ -49,8 +49,9 @@ def _nvcc() -> str:
 PARTS = (0, 1, 2, 3)  # scaml_capi.cu is compiled once per part (see its header), in parallel
 
 
-def _compile_parts(extra, out: str, verbose: bool = False) -> None:
-    """nvcc -c per part (parallel processes) + scaml_microbench.cu, then one link."""
+def _compile_parts(extra, out: str, verbose: bool = False, parts=PARTS) -> None:
+    """nvcc -c per part (parallel processes) + scaml_microbench.cu, then one link.  parts=(None,): one translation unit
+    (SCAML_PART undefined)."""
     from concurrent.futures import ThreadPoolExecutor
 
     nvcc = _nvcc()
@@ -58,10 +59,10 @@ def _compile_parts(extra, out: str, verbose: bool = False) -> None:
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
     jobs = []
-    for part in PARTS:
+    for part in parts:
         obj = os.path.join(objdir, f"{tag}_part{part}.o")
         jobs.append((obj, [nvcc] + NVCC_COMPILE_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) +
-                     [f"-DSCAML_PART={part}", "-c", "-o", obj, "scaml_capi.cu"]))
+                     ([f"-DSCAML_PART={part}"] if part is not None else []) + ["-c", "-o", obj, "scaml_capi.cu"]))
     obj = os.path.join(objdir, f"{tag}_microbench.o")
     jobs.append((obj, [nvcc] + NVCC_COMPILE_FLAGS + extra + ["-c", "-o", obj, "scaml_microbench.cu"]))
 
@@ -106,7 +107,9 @@ def build_ablate(force: bool = False) -> str:
     deps = [os.path.join(CSRC, s) for s in CUDA_SOURCES + HEADERS]
     if not force and _newer(out, deps):
         return out
-    _compile_parts(["-DSCAML_ABLATE"], out)
+    # one translation unit: the ablation switch is a __device__ variable, and with it nvcc gives the file-scope helpers
+    # of scaml_capi.cu external linkage under a name derived from the FILE name -- the four parts would collide
+    _compile_parts(["-DSCAML_ABLATE"], out, parts=(None,))
     return out
 
 

@@ -64,6 +64,9 @@ inline int pad64(int n) { return ((n + 63) / 64) * 64; }
 // persistent grid of the fit kernels: CTAs per SM allowed by shared memory (<= 3)
 int fit_ctas_per_sm(int n_pad, int d) {
   const size_t s = scaml::fit_smem_bytes(n_pad, d) + 1024;
+#ifdef SCAML_FIT_PROBE4
+  if (4 * s <= 228 * 1024) return 4;
+#endif
   if (3 * s <= 228 * 1024) return 3;
   return (2 * s <= 228 * 1024) ? 2 : 1;
 }

@@ -108,10 +108,19 @@ inline long long fit_ws_doubles_host(int n_pad, int d) {
 //                          gsm 4*kMaxP | par 4*kMaxP+8 | flags 2
 // (y is read from global memory where the forward substitution needs it, 64 values per super-row: keeping a copy here
 //  cost 4 KB at n = 512 and with it the third co-resident CTA for every n_pad in 384 .. 512)
+// -DSCAML_FIT_PROBE4: TIMING-ONLY probe build (WRONG results by design, experiments only -- scripts/fit_probe4.sh): what
+// would a fourth co-resident CTA buy?  The D^-1 tiles alias the staging area (44 KB of shared memory per CTA instead of
+// 72 KB), the kernel is compiled for 128 registers (__launch_bounds__(128, 4)) and pivot failures are ignored, so the
+// instruction stream and the memory traffic of an evaluation stay what they are while four CTAs fit an SM.
+#ifdef SCAML_FIT_PROBE4
+constexpr int kFitDinvTiles = 0, kFitMinCtas = 4;
+#else
+constexpr int kFitDinvTiles = 3, kFitMinCtas = 3;
+#endif
 inline size_t fit_smem_bytes(int n_pad, int d) {
   (void)d;
-  return sizeof(double) *
-         (size_t)(kStage + 3 * kTileS + 2 * (size_t)n_pad + 128 + kFitWarps * kMaxP + 5 * kMaxP + 8 + 2);
+  return sizeof(double) * (size_t)(kStage + kFitDinvTiles * kTileS + 2 * (size_t)n_pad + 128 + kFitWarps * kMaxP +
+                                   5 * kMaxP + 8 + 2);
 }
 
 // per-thread coordinates: warp (rb, cb) owns one 32x32 tile of the 64x64 super-tile as a 4x4
@@ -420,7 +429,7 @@ SCAML_DEVICE void gemm_global(Acc& acc, const Src& src, double* stage, const FTh
     // sub-chunk s-1, whose buffer the prefetch of s+1 may therefore overwrite.  (A third buffer in phase D -- dinvc is
     // idle there -- with the prefetch two steps ahead measured -0.3 %: profiles/r2_fit_predication.txt.)
     cp_async_wait<0>();
-    __syncthreads();
+    if (!ABL(131072)) __syncthreads();  // (ablation bit 131072: what do the per-step barriers of the streamed products cost?)
     if (s + 1 < n) stage_issue(src, s + 1, stage + ((s + 1) & 1) * 4 * kHalfS, t.tid);
 #ifdef SCAML_PROF
     const long long pc1 = clock64();
@@ -1248,13 +1257,13 @@ __global__ void __launch_bounds__(kSchedThreads) scaml_fit_schedule_kernel(const
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitParams p) {
+__global__ void __launch_bounds__(kFitThreads, kFitMinCtas) scaml_fit_kernel(const FitParams p) {
   SCAML_DYN_SMEM(double, sm);
   FThr t = make_fthr();
   const int d = p.d, P = p.d + 2, n_pad_max = p.n_pad;
   double* stage = sm;             // 2 stages x 4 padded half tiles | 4 full padded tiles (C_in / S / diag)
-  double* dinvc = stage + kStage;  // 3 padded tiles
-  double* zv = dinvc + 3 * kTileS;
+  double* dinvc = stage + (kFitDinvTiles ? kStage : 0);  // 3 padded tiles (probe build: aliased with `stage`)
+  double* zv = stage + kStage + kFitDinvTiles * kTileS;
   double* av = zv + n_pad_max;
   double* red = av + n_pad_max;  // 128
   double* gsm = red + 128;       // kFitWarps * kMaxP
@@ -1267,7 +1276,14 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
   double* scal = par + 5 * kMaxP;  // [0] logdet
   int* flag = reinterpret_cast<int*>(scal + 8);
 
+#ifdef SCAML_FIT_PROBE_HOTWS
+  // TIMING-ONLY probe (WRONG results): the co-resident CTAs of an SM share ONE workspace slot per SM-slot pair modulo 32,
+  // so the whole tile / kappa workspace of the grid is 32 slots (~20 MB) and stays L2-resident -- what does the DRAM
+  // spill of the 270 MB workspace cost?
+  double* W = p.workspace + (size_t)(blockIdx.x & 31) * p.ws_stride;
+#else
   double* W = p.workspace + (size_t)blockIdx.x * p.ws_stride;
+#endif
   // kappa cache behind the tiles; the mapping thread -> slot depends on the thread id only, so the warp-role
   // rotation (which is per evaluation) does not matter
   double2* kcache = (p.kcache && p.mode == kModeLmlGrad)
@@ -1388,10 +1404,12 @@ __global__ void __launch_bounds__(kFitThreads, 3) scaml_fit_kernel(const FitPara
           diag_factor(stage, dinvc, wtile_w(W, 2 * J, 2 * J), wtile_w(W, 2 * J + 1, 2 * J),
                       wtile_w(W, 2 * J + 1, 2 * J + 1), &scal[0], flag, J * kSB, t, chain_warp, red DIAG_PROF_PASS);
           PROF_MARK(3);
+#if !defined(SCAML_FIT_PROBE4) && !defined(SCAML_FIT_PROBE_HOTWS)
           if (*flag != 0 && !ABL(0x7fffffff)) {
             failed = true;
             break;
           }
+#endif
         } else {
           // L(I,J) = C * D^-T : A chunk kb2 = C tiles (rb,kb2); B[kk][c] = D^-1(c,kk)
           facc_zero(acc);
