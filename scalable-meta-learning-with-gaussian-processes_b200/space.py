@@ -255,6 +255,9 @@ def sort_numerical(X: torch.Tensor, Y: torch.Tensor):
     if X.shape[0] <= 1:
         return X, Y
     A = np.concatenate([X.numpy().astype(float), Y.numpy().astype(float)], axis=1)
+    if not np.isnan(A).any():  # the usual case (no inactive parameters, no missing objectives): the columns are the keys
+        idx = torch.as_tensor(np.lexsort(A.T[::-1]).copy())
+        return X[idx], Y[idx]
     keys = []
     for j in range(A.shape[1] - 1, -1, -1):  # lexsort: last key is the primary one
         col = A[:, j]

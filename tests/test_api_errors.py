@@ -220,3 +220,25 @@ def test_dataset_tensors_and_uniform_upload_fast_paths():
     assert torch.equal(fast.n_valid, slow.n_valid)
     assert torch.allclose(fast.y, slow.y[:, :7], rtol=0, atol=1e-15)
     assert torch.allclose(fast.ybar, slow.ybar, rtol=0, atol=1e-15) and torch.allclose(fast.ystd, slow.ystd, rtol=0, atol=1e-15)
+
+
+def test_sort_numerical_fast_path_equals_the_general_path_and_ignores_the_report_order():
+    """Deterministic, report-order independent arrangement of the meta-data (reference utils.py:98-106 sorts the
+    evaluations): the NaN-free shortcut gives the order of the general (NaN-aware) path, ties included."""
+    import numpy as np
+
+    from scamlgp_b200 import space as S
+
+    g = np.random.default_rng(0)
+    for _ in range(40):
+        n, d = int(g.integers(2, 40)), int(g.integers(1, 5))
+        X = torch.tensor(np.round(g.random((n, d)), 1))  # coarse grid: many ties
+        Y = torch.tensor(np.round(g.random((n, 1)), 1))
+        a = S.sort_numerical(X, Y)
+        Xn = torch.cat([X, torch.full((1, d), float("nan"), dtype=torch.float64)])  # a NaN row forces the general path
+        Yn = torch.cat([Y, torch.zeros(1, 1, dtype=torch.float64)])
+        b = S.sort_numerical(Xn, Yn)
+        assert torch.equal(a[0], b[0][:-1]) and torch.equal(a[1], b[1][:-1]) and bool(torch.isnan(b[0][-1]).all())
+        p = torch.as_tensor(g.permutation(n))
+        c = S.sort_numerical(X[p], Y[p])
+        assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
