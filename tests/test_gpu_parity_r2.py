@@ -162,3 +162,21 @@ def test_one_mi_candidates_properties(engine):
     om, ov = O.scaml_prior_predict(states, w.cpu(), Xc[idx.cuda()].cpu())
     assert rel_err(mean[idx.cuda()].cpu().numpy(), om.numpy()) < TOL_MEAN_VAR
     assert rel_err(var[idx.cuda()].cpu().numpy(), ov.numpy()) < TOL_MEAN_VAR
+
+
+@pytest.mark.parametrize("M,R,n,d", [(1332, 2, 256, 6), (444, 2, 512, 10)])
+def test_lml_grad_is_bit_reproducible_at_full_occupancy(engine, M, R, n, d):
+    """Several waves of the persistent grid with dynamic work distribution: which CTA evaluates which row, with which
+    warp -> role rotation and next to which neighbours differs from launch to launch; every output bit must not
+    (scripts/fit_determinism.py is the long form: 180 launches at the bench's shapes)."""
+    from scamlgp_b200.engine import SourceBatch
+
+    X, Y = datagen.synthetic_tasks(M, n, d, seed=21)
+    spec = HyperSpec.source()
+    th = datagen.sample_theta_raw(M, R, d, spec, seed=21).cuda().contiguous()
+    batch = SourceBatch.from_padded(X.cuda(), Y.cuda())
+    l0, g0, i0 = (t.clone() for t in engine.lml_grad_raw(batch, th, spec))
+    assert int(i0.abs().max()) == 0
+    for _ in range(6):
+        l, g, i = engine.lml_grad_raw(batch, th, spec)
+        assert torch.equal(l, l0) and torch.equal(g, g0) and torch.equal(i, i0)
