@@ -508,7 +508,7 @@ SCAML_DEVICE void gemm_smem_trsm(Acc& acc, const double* cin, const double* dinv
   for (int ck = 0; ck < 2; ++ck) {
     if (t.cb < ck) continue;
     // D^-1 tiles (0,0) and (1,1) are lower triangular: B[kk][c] = D^-1(c, kk) vanishes for c < kk
-#if !defined(SCAML_FIT_TRI) && !defined(SCAML_FIT_TRI_SMEM)
+#ifndef SCAML_FIT_TRI
     fmma<8>(acc, cin + (2 * t.rb + ck) * kTileS, dinvc + (t.cb + ck) * kTileS, t, false);
 #else
     if (t.cb + ck != 1) fmma_tri_impl<8, 0, 2, false, 0>(acc, cin + (2 * t.rb + ck) * kTileS, dinvc + (t.cb + ck) * kTileS, t);
@@ -524,7 +524,7 @@ SCAML_DEVICE void gemm_smem_trtri(Acc& acc, const double* dinvc, const double* s
   for (int ck = 0; ck < 2; ++ck) {
     if (t.rb < ck) continue;
     // A[kk][r] = D^-1(r, kk) vanishes for r < kk on the triangular tiles (0,0), (1,1)
-#if !defined(SCAML_FIT_TRI) && !defined(SCAML_FIT_TRI_SMEM)
+#ifndef SCAML_FIT_TRI
     fmma<8>(acc, dinvc + (t.rb + ck) * kTileS, sst + (2 * ck + t.cb) * kTileS, t, false);
 #else
     if (t.rb + ck != 1) fmma_tri_impl<8, 2, 0, false, 0>(acc, dinvc + (t.rb + ck) * kTileS, sst + (2 * ck + t.cb) * kTileS, t);
